@@ -1,0 +1,334 @@
+"""Float64 CPU restatement of DenseMatcher's correspondence hot path (numpy/scipy).
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package.  Importers:
+``tests/``, ``__graft_entry__.smoke()``, ``bench.py`` (``cpu_baseline`` leg and
+``--impl reference``).
+
+Every function cites the reference file:line (relative to the upstream repo
+root, JunzheJosephZhu/DenseMatcher @ 96da493) whose arithmetic it restates.
+
+Parity pinning
+--------------
+The reference ships no golden vectors or runnable tests for this path
+(SURVEY.md section 4), so this oracle is pinned against *outputs of the
+reference itself*: ``oracle/make_goldens.py`` imports the unmodified reference
+from ``/root/reference`` (authoring container only), runs its ``knn_query``,
+``FM_to_p2p``, ``p2p_to_FM``, ``icp_refine``, ``FunctionalMapping.fit`` and
+``compute_surface_map`` on seeded inputs and stores the results in
+``tests/golden/*.npz``; ``tests/test_oracle_vs_golden.py`` replays them against
+this file on every CPU test run.
+
+Third-party arithmetic the reference delegates to (not under /root/reference):
+scikit-learn ``NearestNeighbors(algorithm='kd_tree')`` (unpinned upstream,
+1.9.0 here), ``scipy.linalg.lstsq`` / ``svd`` / ``scipy.optimize.minimize``
+(unpinned, 1.18.1 here).  ``knn_query`` below makes the same sklearn call; the
+brute-force ``nn_argmax`` formulation is proven equal to it in the golden tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+
+__all__ = [
+    "knn_query", "nn_argmax", "knn_bruteforce", "project", "fmap_c00", "ev_sqdiff",
+    "fmap_solve_closed_form", "fmap_energy", "fm_to_p2p", "dense_argmax_override",
+    "p2p_to_fm", "zoomout_refine", "icp_refine", "surface_map_arrays",
+]
+
+
+# --------------------------------------------------------------------------------------
+# nearest neighbours
+# --------------------------------------------------------------------------------------
+def knn_query(X, Y, k=1, return_distance=False, n_jobs=1):
+    """For every row of ``Y`` the Euclidean-nearest row(s) of ``X`` via a kd-tree.
+
+    Same third-party call as densematcher/pyFM/spectral/nn_utils.py:28-30
+    (leaf_size=40, kd_tree), same squeeze for k == 1 (:32-34) and the same return
+    convention (:36-38).
+    """
+    from sklearn.neighbors import NearestNeighbors
+
+    nbrs = NearestNeighbors(n_neighbors=k, leaf_size=40, algorithm="kd_tree", n_jobs=n_jobs).fit(X)
+    d, idx = nbrs.kneighbors(Y)
+    if k == 1:
+        d, idx = d.squeeze(), idx.squeeze()
+    return (d, idx) if return_distance else idx
+
+
+def nn_argmax(Y, X, col_scale=None, col_bias=None, axis=1, chunk=1024):
+    """``argmax`` over ``j`` (axis=1) or ``i`` (axis=0) of ``<Y[i], X[j]> * s[j] + b[j]`` in float64.
+
+    The single primitive behind the three NN flavours of the reference
+    (SURVEY.md fact 2): cosine on unit rows (model.py:169 + nn_utils.py:4-38),
+    Euclidean 1-NN (s=1, b=-|x|^2/2; nn_utils.py:4-38) and the dense
+    ``mapped_indicator`` argmax (functional_map.py:49-50).  Ties go to the lowest
+    index (numpy ``argmax``), which is also what exact duplicate rows produce.
+    Returns int64.
+    """
+    Y = np.asarray(Y, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    s = None if col_scale is None else np.asarray(col_scale, dtype=np.float64)
+    b = None if col_bias is None else np.asarray(col_bias, dtype=np.float64)
+    if axis == 1:
+        out = np.empty(Y.shape[0], dtype=np.int64)
+        for lo in range(0, Y.shape[0], chunk):
+            S = Y[lo:lo + chunk] @ X.T
+            if s is not None:
+                S *= s[None, :]
+            if b is not None:
+                S += b[None, :]
+            out[lo:lo + chunk] = S.argmax(axis=1)
+        return out
+    S = Y @ X.T
+    if s is not None:
+        S *= s[None, :]
+    if b is not None:
+        S += b[None, :]
+    return S.argmax(axis=0).astype(np.int64)
+
+
+def knn_bruteforce(X, Y):
+    """1-NN of each row of ``Y`` among rows of ``X`` (Euclidean) without a tree.
+
+    argmin_j |y - x_j|^2 == argmax_j (<y, x_j> - |x_j|^2 / 2); equals ``knn_query``
+    (nn_utils.py:4-38) away from exact distance ties.
+    """
+    X = np.asarray(X, dtype=np.float64)
+    return nn_argmax(Y, X, None, -0.5 * np.einsum("ij,ij->i", X, X))
+
+
+# --------------------------------------------------------------------------------------
+# spectral projection and the functional-map solve
+# --------------------------------------------------------------------------------------
+def project(Phi, area, F, k=None):
+    """``Phi[:, :k].T @ (area[:, None] * F)``: coefficients of ``F`` in the LBO basis.
+
+    densematcher/pyFM/mesh/trimesh.py:533-556 (``TriMesh.project``) and the same
+    contraction inside the fit, optimize/base_functions.py:526-532, with the lumped
+    (diagonal) mass matrix ``A = diag(area)``.
+    """
+    Phi = np.asarray(Phi, dtype=np.float64)
+    if k is not None:
+        Phi = Phi[:, :k]
+    return Phi.T @ (np.asarray(area, dtype=np.float64)[:, None] * np.asarray(F, dtype=np.float64))
+
+
+def fmap_c00(Phi1, Phi2, area1, area2):
+    """The pinned entry ``C[0, 0]``: sign(Phi1[0,0] * Phi2[0,0]) * sqrt(area2 / area1).
+
+    densematcher/pyFM/functional.py:654-658 (``get_x0``); ``area`` is the sum of
+    the lumped vertex areas (mesh/trimesh.py:206-221).
+    """
+    sgn = np.sign(Phi1[0, 0] * Phi2[0, 0])
+    return float(sgn * np.sqrt(np.sum(area2) / np.sum(area1)))
+
+
+def ev_sqdiff(evals1, evals2):
+    """(k2, k1) squared differences of eigenvalues scaled by the largest one.
+
+    densematcher/pyFM/functional.py:403-405.
+    """
+    evals1 = np.asarray(evals1, dtype=np.float64)
+    evals2 = np.asarray(evals2, dtype=np.float64)
+    scale = max(evals1.max(), evals2.max())
+    return np.square(evals1[None, :] / scale - evals2[:, None] / scale)
+
+
+def fmap_energy(C, A, B, Delta, w_descr, w_lap):
+    """w_descr * 1/2 |C A - B|^2 + w_lap * 1/2 sum C^2 * Delta.
+
+    optimize/base_functions.py:31-56 (descriptor preservation) and :79-102
+    (Laplacian commutativity), weighted as in ``energy_func_std`` :536-544.
+    """
+    r = C @ A - B
+    return 0.5 * w_descr * float(np.sum(r * r)) + 0.5 * w_lap * float(np.sum(C * C * Delta))
+
+
+def fmap_solve_closed_form(A, B, evals1, evals2, c00, w_descr, w_lap):
+    """Exact minimiser of the reference's descriptor + Laplacian energy.
+
+    The reference minimises ``fmap_energy`` with L-BFGS-B from ``x0`` (zeros except
+    ``x0[0, 0] = c00``) while zeroing the gradient of column 0
+    (functional.py:441,477; base_functions.py:759), i.e. column 0 stays
+    ``c00 * e_0``.  With only those two terms the rows of ``C`` decouple
+    (SURVEY.md App. A.3):
+
+        c_i[1:] (w_d Abar Abar^T + w_l diag(Delta[i, 1:])) = w_d (B_i - C[i,0] A_0) Abar^T
+
+    ``A``: (k1, d), ``B``: (k2, d).  Returns (k2, k1) float64.
+    """
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    k1, k2 = A.shape[0], B.shape[0]
+    Delta = ev_sqdiff(np.asarray(evals1)[:k1], np.asarray(evals2)[:k2])
+    C = np.zeros((k2, k1))
+    C[0, 0] = c00
+    Abar = A[1:]
+    G = w_descr * (Abar @ Abar.T)
+    R = w_descr * ((B - C[:, :1] * A[:1]) @ Abar.T)  # (k2, k1-1)
+    for i in range(k2):
+        M = G + w_lap * np.diag(Delta[i, 1:])
+        C[i, 1:] = scipy.linalg.solve(M, R[i], assume_a="pos")
+    return C
+
+
+# --------------------------------------------------------------------------------------
+# functional map <-> point-to-point map
+# --------------------------------------------------------------------------------------
+def fm_to_p2p(C, Phi1, Phi2, a1=None, nn="brute", want_indicator=True):
+    """(p2p_21, p2p_12, mapped_indicator) as the *modified* reference FM_to_p2p.
+
+    densematcher/pyFM/spectral/convert.py:126-147:
+      p2p_12 = knn(tree = Phi2[:, :k2] @ C, query = Phi1[:, :k1])          (:134-136)
+      p2p_21 = knn(tree = Phi1[:, :k1] @ C.T, query = Phi2[:, :k2])        (:138-140)
+      mapped_indicator = Phi2 @ C @ Phi1.T @ A1                            (:144)
+    ``use_adj`` is ignored upstream, so it is not a parameter here.  ``a1`` is the
+    diagonal of A1.  ``nn='tree'`` uses the sklearn kd-tree exactly as the
+    reference; ``'brute'`` the float64 argmax form (identical results away from
+    exact ties, 25x faster).
+    """
+    C = np.asarray(C, dtype=np.float64)
+    k2, k1 = C.shape
+    assert k1 <= Phi1.shape[1] and k2 <= Phi2.shape[1]
+    P1 = np.asarray(Phi1, dtype=np.float64)[:, :k1]
+    P2 = np.asarray(Phi2, dtype=np.float64)[:, :k2]
+    find = knn_query if nn == "tree" else knn_bruteforce
+    emb2 = P2 @ C
+    p2p_12 = find(emb2, P1)
+    emb1 = P1 @ C.T
+    p2p_21 = find(emb1, P2)
+    MI = None
+    if want_indicator:
+        MI = (emb2 @ P1.T) * np.asarray(a1, dtype=np.float64)[None, :]
+    return np.asarray(p2p_21, dtype=np.int64), np.asarray(p2p_12, dtype=np.int64), MI
+
+
+def dense_argmax_override(MI, eta=None):
+    """(argmax over axis 1, argmax over axis 0) of ``mapped_indicator * eta[:, None]``.
+
+    densematcher/functional_map.py:49-50 and :76-77; ``eta`` is all ones
+    (functional.py:483).
+    """
+    if eta is not None:
+        MI = MI * np.asarray(eta)[:, None]
+    return MI.argmax(axis=1).astype(np.int64), MI.argmax(axis=0).astype(np.int64)
+
+
+def p2p_to_fm(p2p_21, Phi1, Phi2, A2=None):
+    """Functional map induced by a vertex map.
+
+    densematcher/pyFM/spectral/convert.py:39-51: pull back ``Phi1[p2p_21]`` (or
+    ``P @ Phi1`` for a matrix map), then ``Phi2.T @ (A2 .)`` when the target mass
+    is given (1-D, sparse or dense), else least squares ``lstsq(Phi2, pullback)``.
+    """
+    Phi1 = np.asarray(Phi1, dtype=np.float64)
+    Phi2 = np.asarray(Phi2, dtype=np.float64)
+    pb = Phi1[np.asarray(p2p_21), :] if np.asarray(p2p_21).ndim == 1 else p2p_21 @ Phi1
+    if A2 is None:
+        return scipy.linalg.lstsq(Phi2, pb)[0]
+    if A2.shape[0] != Phi2.shape[0]:
+        raise ValueError("Can't compute exact pseudo inverse with subsampled eigenvectors")
+    if getattr(A2, "ndim", 2) == 1:
+        return Phi2.T @ (np.asarray(A2)[:, None] * pb)
+    return Phi2.T @ (A2 @ pb)
+
+
+def _steps(step):
+    try:
+        s1, s2 = step
+    except TypeError:
+        s1 = s2 = step
+    return int(s1), int(s2)
+
+
+def zoomout_refine(FM_12, Phi1, Phi2, nit=10, step=1, A2=None, subsample=None,
+                   return_p2p=False, nn="brute"):
+    """ZoomOut with *upstream pyFM* semantics.
+
+    The shipped call ``spectral.FM_to_p2p(FM_12, evects1, evects2, n_jobs=...)``
+    (densematcher/pyFM/refine/zoomout.py:40,112) no longer matches the modified
+    ``FM_to_p2p`` signature (convert.py:96) and raises TypeError (SURVEY.md fact
+    3), so the loop structure follows zoomout.py:7-115 while the conversion is the
+    un-modified upstream one it was written against:
+        p2p_21 = knn(tree = Phi1[:, :k1] @ C.T, query = Phi2[:, :k2])
+    then ``C <- p2p_to_FM(p2p_21, Phi1[:, :k1+s1], Phi2[:, :k2+s2], A2)`` (:42).
+    With ``subsample=(sub1, sub2)`` rows are restricted and the map is solved by
+    least squares (:104-105).
+    """
+    C = np.array(FM_12, dtype=np.float64, copy=True)
+    s1, s2 = _steps(step)
+    k2_0, k1_0 = C.shape
+    assert k1_0 + nit * s1 <= Phi1.shape[1], "Not enough eigenvectors on source"
+    assert k2_0 + nit * s2 <= Phi2.shape[1], "Not enough eigenvectors on target"
+    find = knn_query if nn == "tree" else knn_bruteforce
+    E1, E2, area = Phi1, Phi2, A2
+    if subsample is not None:
+        E1, E2, area = Phi1[subsample[0]], Phi2[subsample[1]], None
+    for _ in range(nit):
+        k2, k1 = C.shape
+        p = find(E1[:, :k1] @ C.T, E2[:, :k2])
+        C = p2p_to_fm(p, E1[:, :k1 + s1], E2[:, :k2 + s2], A2=area)
+    if return_p2p:
+        k2, k1 = C.shape
+        return C, np.asarray(find(Phi1[:, :k1] @ C.T, Phi2[:, :k2]), dtype=np.int64)
+    return C
+
+
+def icp_refine(FM_12, Phi1, Phi2, nit=10, tol=1e-10, return_p2p=False, nn="brute"):
+    """Spectral ICP.
+
+    densematcher/pyFM/refine/icp.py:36-40 per iteration: p2p_21 from
+    ``FM_to_p2p`` (the knn of :138-140 in convert.py), ``C = lstsq(Phi2[:, :k2],
+    Phi1[p2p_21, :k1])``, then the nearest (partial) isometry ``U @ eye(k2, k1) @
+    Vt`` of its SVD.  ``nit`` in (None, 0) iterates until the max-abs change is
+    <= ``tol`` (icp.py:84-94), at most 10000 times (:82).
+    """
+    C = np.array(FM_12, dtype=np.float64, copy=True)
+    k2, k1 = C.shape
+    P1 = np.asarray(Phi1, dtype=np.float64)[:, :k1]
+    P2 = np.asarray(Phi2, dtype=np.float64)[:, :k2]
+    find = knn_query if nn == "tree" else knn_bruteforce
+    fixed = nit is not None and nit > 0
+    for _ in range(nit if fixed else 10000):
+        p = find(P1 @ C.T, P2)
+        U, _, Vt = scipy.linalg.svd(scipy.linalg.lstsq(P2, P1[p])[0])
+        C_new = U @ np.eye(k2, k1) @ Vt
+        done = (not fixed) and np.max(np.abs(C - C_new)) <= tol
+        C = C_new
+        if done:
+            break
+    if return_p2p:
+        return C, np.asarray(find(P1 @ C.T, P2), dtype=np.int64)
+    return C
+
+
+# --------------------------------------------------------------------------------------
+# the driver, on arrays
+# --------------------------------------------------------------------------------------
+def surface_map_arrays(Phi1, evals1, a1, Phi2, evals2, a2, c1, c2, n_ev, w_descr, w_lap,
+                       icp_nit=10, nn="brute"):
+    """Array-level restatement of ``compute_surface_map`` with descr+lap energy.
+
+    densematcher/functional_map.py:44-78: preprocess (basis truncated to ``n_ev``,
+    functional.py:294-295 + trimesh.py:520-523), fit (closed form, see
+    ``fmap_solve_closed_form``), ``get_p2p`` (kd-tree pair, exposed as
+    ``*_adjoint``, :48), dense-argmax override (:49-50), ``icp_refine`` (:71,
+    nit=10), second ``get_p2p`` + override (:75-77).  The Hungarian assignment
+    (:57,:78) and the precise map (:62) are outside the hot path.
+    """
+    k = int(n_ev)
+    P1, P2 = np.asarray(Phi1, np.float64)[:, :k], np.asarray(Phi2, np.float64)[:, :k]
+    l1, l2 = np.asarray(evals1, np.float64)[:k], np.asarray(evals2, np.float64)[:k]
+    A = project(P1, a1, c1)
+    B = project(P2, a2, c2)
+    C = fmap_solve_closed_form(A, B, l1, l2, fmap_c00(P1, P2, a1, a2), w_descr, w_lap)
+    out = {"A": A, "B": B, "C": C}
+    p21_adj, p12_adj, MI = fm_to_p2p(C, P1, P2, a1, nn=nn)
+    out["p2p_21_adjoint"], out["p2p_12_adjoint"] = p21_adj, p12_adj
+    out["p2p_21"], out["p2p_12"] = dense_argmax_override(MI)
+    C_icp = icp_refine(C, P1, P2, nit=icp_nit, nn=nn)
+    out["C_icp"] = C_icp
+    p21_adj, p12_adj, MI = fm_to_p2p(C_icp, P1, P2, a1, nn=nn)
+    out["p2p_21_icp_adjoint"], out["p2p_12_icp_adjoint"] = p21_adj, p12_adj
+    out["p2p_21_icp"], out["p2p_12_icp"] = dense_argmax_override(MI)
+    return out

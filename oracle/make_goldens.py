@@ -1,0 +1,176 @@
+"""Mint tests/golden/*.npz by running the UNMODIFIED reference (authoring container only).
+
+    python -m oracle.make_goldens            # writes tests/golden/
+
+TEST INFRASTRUCTURE ONLY.  Needs /root/reference (see oracle/ref_shim.py); the
+resulting small fixtures are committed so that the CPU and GPU test-suites can
+replay the reference's answers where the reference itself cannot travel.
+
+Every array named ``ref_*`` was produced by reference code; everything else is an
+input (or can be regenerated from the recorded seed).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import dm_oracle as orc, meshgen, ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def cfg1_features(seed, n, d):
+    """BASELINE.json config 1 inputs: standard normal rows, unit-normalised, fp32."""
+    return meshgen.random_unit_features(n, d, np.random.default_rng(seed))
+
+
+def golden_nn(ref):
+    # --- cfg1: N = M = 2000, d = 384, unit rows; only seeds + answers are stored.
+    F1 = cfg1_features(1000, 2000, 384)
+    F2 = cfg1_features(1001, 2000, 384)
+    t = time.perf_counter()
+    p21 = ref.knn_query(F1, F2)          # for each vertex of mesh 2 its NN on mesh 1
+    p12 = ref.knn_query(F2, F1)
+    dt = time.perf_counter() - t
+    np.savez_compressed(
+        os.path.join(OUT, "nn_cfg1.npz"), seed1=1000, seed2=1001, n1=2000, n2=2000, d=384,
+        checksum1=np.float64(F1.astype(np.float64).sum()), checksum2=np.float64(F2.astype(np.float64).sum()),
+        ref_p2p_21=p21.astype(np.int64), ref_p2p_12=p12.astype(np.int64), ref_seconds=dt)
+    assert np.array_equal(p21, orc.nn_argmax(F2, F1)), "cosine argmax != kd-tree on unit rows"
+    print(f"nn_cfg1: reference knn_query x2 took {dt:.2f}s")
+
+    # --- small, ragged, NON-unit rows with distances (k = 1 return_distance path).
+    rng = np.random.default_rng(7)
+    X = (rng.standard_normal((257, 48)) * rng.uniform(0.2, 3.0, size=(257, 1))).astype(np.float32)
+    Y = (rng.standard_normal((193, 48)) * rng.uniform(0.2, 3.0, size=(193, 1))).astype(np.float32)
+    d, m = ref.knn_query(X, Y, return_distance=True)
+    d3, m3 = ref.knn_query(X, Y, k=3, return_distance=True)
+    np.savez_compressed(os.path.join(OUT, "nn_small.npz"), X=X, Y=Y, ref_match=m.astype(np.int64),
+                        ref_dist=d, ref_match_k3=m3.astype(np.int64), ref_dist_k3=d3)
+
+
+def ref_lbo(ref, V, F, K):
+    W = ref.laplacian.cotangent_weights(V, F)
+    A = ref.laplacian.dia_area_mat(V, F)
+    evals, Phi = ref.laplacian.laplacian_spectrum(W, sp.csc_matrix(A), K)
+    return evals, Phi, np.asarray(A.diagonal()), W
+
+
+def golden_fm(ref):
+    V0, F = meshgen.icosphere(3)                                   # 642 vertices
+    V1 = meshgen.deform(V0, (1.0, 1.3, 0.7))
+    V2 = meshgen.deform(V0, (1.2, 0.8, 1.0), bump=0.15, phase=(0.3, 1.1))
+    # compute_surface_map reads float32 vertices (functional_map.py:17-18)
+    V1 = V1.astype(np.float32).astype(np.float64)
+    V2 = V2.astype(np.float32).astype(np.float64)
+
+    # (i) operator check: meshgen's own cotangent / mass / spectrum vs the reference's
+    ev_r, Phi_r, a_r, W_r = ref_lbo(ref, V1, F, 40)
+    W_m, a_m = meshgen.cotan_stiffness(V1, F), meshgen.lumped_area(V1, F)
+    assert abs(W_r - W_m).max() < 1e-10 and np.abs(a_r - a_m).max() < 1e-14
+    ev_m, _, _ = meshgen.lbo_basis(V1, F, 40)
+    assert np.allclose(ev_r, ev_m, rtol=1e-7, atol=1e-8)
+
+    # (ii) the driver end-to-end, descr + lap energy (notebook cell 11 weights)
+    k, d = 20, 32
+    rng = np.random.default_rng(2000)
+    ev1, Phi1, a1, _ = ref_lbo(ref, V1, F, 40)
+    ev2, Phi2, a2, _ = ref_lbo(ref, V2, F, 40)
+    coef = rng.standard_normal((30, d))
+    c1 = Phi1[:, :30] @ coef + 0.02 * rng.standard_normal((642, d))
+    c2 = Phi2[:, :30] @ coef + 0.02 * rng.standard_normal((642, d))
+    c1 = (c1 / np.linalg.norm(c1, axis=1, keepdims=True)).astype(np.float32)
+    c2 = (c2 / np.linalg.norm(c2, axis=1, keepdims=True)).astype(np.float32)
+    fit_params = dict(w_descr=1e4, w_lap=1e3, w_dcomm=0, w_orient=0, w_area=0, w_conformal=0, w_p2p=0,
+                      w_stochastic=0, w_ent=0, w_range01=0, w_sumto1=0, optinit="zeros", maxiter=5000)
+    t = time.perf_counter()
+    res = ref.compute_surface_map(ref_shim.DuckMesh(V1, F), ref_shim.DuckMesh(V2, F), c1, c2, n_ev=k,
+                                  optimizer="L-BFGS-B", maxiter=5000, fit_params=fit_params)
+    dt = time.perf_counter() - t
+    (p21, p12, _h, _hp, p21_icp, p12_icp, hung_icp, model, m1, m2,
+     p21_adj, p12_adj, p21_icp_adj, p12_icp_adj) = res
+    E1, E2 = np.array(m1.eigenvectors), np.array(m2.eigenvectors)
+    l1, l2 = np.array(m1.eigenvalues), np.array(m2.eigenvalues)
+    A1d, A2d = np.asarray(m1.A.diagonal()), np.asarray(m2.A.diagonal())
+    C_lbfgs, C_icp = np.array(model._FM_base), np.array(model._FM_icp)
+
+    # (iii) reference primitives on the float64 closed-form C (the parity oracle for C)
+    A = orc.project(E1, A1d, c1)
+    B = orc.project(E2, A2d, c2)
+    C_cf = orc.fmap_solve_closed_form(A, B, l1, l2, orc.fmap_c00(E1, E2, A1d, A2d), 1e4, 1e3)
+    relF = np.linalg.norm(C_lbfgs - C_cf) / np.linalg.norm(C_cf)
+    print(f"fm_pair: reference compute_surface_map {dt:.1f}s; relF(L-BFGS C, closed form) = {relF:.2e}")
+    r21, r12, MI = ref.FM_to_p2p(C_cf, E1, E2, m1.A)
+    C_area = ref.p2p_to_FM(r21, E1, E2, A2=A2d)
+    C_area_sp = ref.p2p_to_FM(r21, E1, E2, A2=m2.A)
+    C_lstsq = ref.p2p_to_FM(r21, E1, E2)
+    C_icp_cf, p_icp_cf = ref.icp_refine(C_cf, E1, E2, m1.A, nit=10, return_p2p=True)
+    assert np.allclose(C_area, C_area_sp)
+    np.savez_compressed(
+        os.path.join(OUT, "fm_pair_ico3.npz"),
+        Phi1=E1, evals1=l1, area1=A1d, Phi2=E2, evals2=l2, area2=A2d, c1=c1, c2=c2, k=k,
+        w_descr=1e4, w_lap=1e3,
+        ref_C_lbfgs=C_lbfgs, ref_C_icp=C_icp, ref_p2p_21=p21, ref_p2p_12=p12,
+        ref_p2p_21_icp=p21_icp, ref_p2p_12_icp=p12_icp, ref_p2p_21_adjoint=p21_adj,
+        ref_p2p_12_adjoint=p12_adj, ref_p2p_21_icp_adjoint=p21_icp_adj,
+        ref_p2p_12_icp_adjoint=p12_icp_adj,
+        C_closed_form=C_cf, ref_relF_lbfgs_vs_closed_form=relF,
+        ref_cf_p2p_21=r21, ref_cf_p2p_12=r12, ref_cf_MI_argmax1=MI.argmax(1), ref_cf_MI_argmax0=MI.argmax(0),
+        ref_cf_MI_sum=MI.sum(), ref_cf_MI_fro=np.linalg.norm(MI), ref_cf_MI_corner=MI[:8, :8],
+        ref_cf_C_area=C_area, ref_cf_C_lstsq=C_lstsq, ref_cf_C_icp=C_icp_cf, ref_cf_p2p_icp=p_icp_cf,
+        ref_seconds=dt)
+
+    # (iv) ZoomOut, upstream semantics, composed from the reference's own primitives
+    #      (the shipped zoomout_refine raises TypeError, fact 3)
+    try:
+        ref.zoomout_refine(C_cf[:10, :10], Phi1, Phi2, nit=1)
+        broken = False
+    except TypeError:
+        broken = True
+
+    def zo(C, P1, P2, area2, nit, s1, s2):
+        for _ in range(nit):
+            kk2, kk1 = C.shape
+            p = ref.knn_query(P1[:, :kk1] @ C.T, P2[:, :kk2])
+            C = ref.p2p_to_FM(p, P1[:, :kk1 + s1], P2[:, :kk2 + s2], A2=area2)
+        kk2, kk1 = C.shape
+        return C, ref.knn_query(P1[:, :kk1] @ C.T, P2[:, :kk2])
+
+    A12 = orc.project(Phi1[:, :12], a1, c1)
+    B12 = orc.project(Phi2[:, :12], a2, c2)
+    C0 = orc.fmap_solve_closed_form(A12, B12, ev1, ev2, orc.fmap_c00(Phi1, Phi2, a1, a2), 1e4, 1e3)
+    C_zo, p_zo = zo(C0, Phi1, Phi2, a2, 14, 1, 1)                  # 12 -> 26
+    C_zo_r, p_zo_r = zo(C0, Phi1, Phi2, a2, 9, 2, 3)               # (12,12) -> (39,30)
+    sub1 = np.random.default_rng(5).choice(642, 300, replace=False)
+    sub2 = np.random.default_rng(6).choice(642, 280, replace=False)
+    C_sub = C0
+    for _ in range(6):
+        kk2, kk1 = C_sub.shape
+        p = ref.knn_query(Phi1[sub1][:, :kk1] @ C_sub.T, Phi2[sub2][:, :kk2])
+        C_sub = ref.p2p_to_FM(p, Phi1[sub1][:, :kk1 + 1], Phi2[sub2][:, :kk2 + 1], A2=None)
+    np.savez_compressed(
+        os.path.join(OUT, "zoomout_ico3.npz"), Phi1=Phi1, Phi2=Phi2, area1=a1, area2=a2, evals1=ev1,
+        evals2=ev2, C0=C0, ref_C_zo=C_zo, ref_p2p_zo=p_zo, ref_C_zo_rect=C_zo_r, ref_p2p_zo_rect=p_zo_r,
+        sub1=sub1, sub2=sub2, ref_C_zo_sub=C_sub, ref_shipped_zoomout_raises_typeerror=broken)
+    print(f"zoomout: shipped reference zoomout_refine broken = {broken}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    golden_nn(ref)
+    golden_fm(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

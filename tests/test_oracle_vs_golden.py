@@ -1,0 +1,158 @@
+"""Pin the CPU oracle (oracle/dm_oracle.py) against answers produced by the reference itself.
+
+The fixtures in tests/golden/ were minted by oracle/make_goldens.py from the
+unmodified reference (knn_query, FM_to_p2p, p2p_to_FM, icp_refine,
+compute_surface_map); arrays named ``ref_*`` are reference outputs.
+"""
+import numpy as np
+import pytest
+
+from oracle import dm_oracle as orc, meshgen
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_cfg1_inputs_regenerate(golden_nn_cfg1):
+    g = golden_nn_cfg1
+    F1 = meshgen.random_unit_features(int(g["n1"]), int(g["d"]), np.random.default_rng(int(g["seed1"])))
+    F2 = meshgen.random_unit_features(int(g["n2"]), int(g["d"]), np.random.default_rng(int(g["seed2"])))
+    assert F1.astype(np.float64).sum() == g["checksum1"]
+    assert F2.astype(np.float64).sum() == g["checksum2"]
+
+
+def test_nn_cfg1_cosine_argmax_equals_reference_kdtree(golden_nn_cfg1):
+    g = golden_nn_cfg1
+    F1 = meshgen.random_unit_features(2000, 384, np.random.default_rng(int(g["seed1"])))
+    F2 = meshgen.random_unit_features(2000, 384, np.random.default_rng(int(g["seed2"])))
+    # Euclidean form (exact restatement of knn_query) ...
+    assert np.array_equal(orc.knn_bruteforce(F1, F2), g["ref_p2p_21"])
+    assert np.array_equal(orc.knn_bruteforce(F2, F1), g["ref_p2p_12"])
+    # ... and the cosine form the north star names (rows are unit norm, model.py:169)
+    assert np.array_equal(orc.nn_argmax(F2, F1), g["ref_p2p_21"])
+    # column-argmax of the same score matrix gives the reverse map on unit rows
+    assert np.array_equal(orc.nn_argmax(F2, F1, axis=0), g["ref_p2p_12"])
+
+
+def test_nn_small_nonunit_rows_and_distances(golden_nn_small):
+    g = golden_nn_small
+    X, Y = g["X"], g["Y"]
+    assert np.array_equal(orc.knn_bruteforce(X, Y), g["ref_match"])
+    d, m = orc.knn_query(X, Y, return_distance=True)
+    assert np.array_equal(m, g["ref_match"]) and np.allclose(d, g["ref_dist"], rtol=0, atol=1e-12)
+    d3, m3 = orc.knn_query(X, Y, k=3, return_distance=True)
+    assert np.array_equal(m3, g["ref_match_k3"]) and m3.shape == (193, 3)
+    best = np.linalg.norm(Y.astype(np.float64) - X.astype(np.float64)[m], axis=1)
+    assert np.allclose(best, g["ref_dist"], atol=1e-12)
+
+
+def test_nn_duplicate_rows_lowest_index():
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((64, 16)).astype(np.float32)
+    X[40] = X[7]
+    X[41] = X[7]
+    Y = X[[7, 40, 41, 3]]
+    assert orc.nn_argmax(Y, X).tolist() == [7, 7, 7, 3]
+    assert orc.knn_bruteforce(X, Y).tolist() == [7, 7, 7, 3]
+
+
+def test_closed_form_matches_reference_lbfgs(golden_fm):
+    g = golden_fm
+    k = int(g["k"])
+    A = orc.project(g["Phi1"], g["area1"], g["c1"], k)
+    B = orc.project(g["Phi2"], g["area2"], g["c2"], k)
+    c00 = orc.fmap_c00(g["Phi1"], g["Phi2"], g["area1"], g["area2"])
+    C = orc.fmap_solve_closed_form(A, B, g["evals1"], g["evals2"], c00, float(g["w_descr"]), float(g["w_lap"]))
+    assert relF(C, g["C_closed_form"]) < 1e-12
+    # the reference's L-BFGS-B run (fp32 energy) agrees to its own optimiser noise
+    assert relF(g["ref_C_lbfgs"], C) < 1e-3
+    assert C[0, 0] == pytest.approx(c00) and np.all(C[1:, 0] == 0)
+    # stationarity: gradient of the free block vanishes
+    Delta = orc.ev_sqdiff(g["evals1"][:k], g["evals2"][:k])
+    grad = float(g["w_descr"]) * (C @ A - B) @ A.T + float(g["w_lap"]) * C * Delta
+    assert np.abs(grad[:, 1:]).max() < 1e-6 * np.abs(float(g["w_descr"]) * B @ A.T).max()
+    e0 = orc.fmap_energy(C, A, B, Delta, float(g["w_descr"]), float(g["w_lap"]))
+    assert e0 <= orc.fmap_energy(g["ref_C_lbfgs"], A, B, Delta, float(g["w_descr"]), float(g["w_lap"])) * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("nn", ["brute", "tree"])
+def test_fm_to_p2p_matches_reference(golden_fm, nn):
+    g = golden_fm
+    p21, p12, MI = orc.fm_to_p2p(g["C_closed_form"], g["Phi1"], g["Phi2"], g["area1"], nn=nn)
+    assert np.array_equal(p21, g["ref_cf_p2p_21"])
+    assert np.array_equal(p12, g["ref_cf_p2p_12"])
+    assert np.allclose(MI[:8, :8], g["ref_cf_MI_corner"], rtol=1e-12, atol=1e-14)
+    assert MI.sum() == pytest.approx(float(g["ref_cf_MI_sum"]), rel=1e-10)
+    assert np.linalg.norm(MI) == pytest.approx(float(g["ref_cf_MI_fro"]), rel=1e-12)
+    a1, a0 = orc.dense_argmax_override(MI, np.ones(MI.shape[0]))
+    assert np.array_equal(a1, g["ref_cf_MI_argmax1"]) and np.array_equal(a0, g["ref_cf_MI_argmax0"])
+
+
+def test_dense_argmax_is_a_scaled_score_argmax(golden_fm):
+    """the dense override equals argmax_j S_ij a1[j] / argmax_i S_ij."""
+    g = golden_fm
+    C, P1, P2, a1 = g["C_closed_form"], g["Phi1"], g["Phi2"], g["area1"]
+    assert np.array_equal(orc.nn_argmax(P2 @ C, P1, col_scale=a1), g["ref_cf_MI_argmax1"])
+    assert np.array_equal(orc.nn_argmax(P2 @ C, P1, axis=0), g["ref_cf_MI_argmax0"])
+
+
+def test_p2p_to_fm_matches_reference(golden_fm):
+    g = golden_fm
+    p = g["ref_cf_p2p_21"]
+    assert relF(orc.p2p_to_fm(p, g["Phi1"], g["Phi2"], A2=g["area2"]), g["ref_cf_C_area"]) < 1e-13
+    import scipy.sparse as sp
+    assert relF(orc.p2p_to_fm(p, g["Phi1"], g["Phi2"], A2=sp.diags(g["area2"]).tocsc()), g["ref_cf_C_area"]) < 1e-13
+    assert relF(orc.p2p_to_fm(p, g["Phi1"], g["Phi2"]), g["ref_cf_C_lstsq"]) < 1e-12
+    with pytest.raises(ValueError):
+        orc.p2p_to_fm(p, g["Phi1"], g["Phi2"], A2=g["area2"][:-1])
+
+
+def test_icp_matches_reference(golden_fm):
+    g = golden_fm
+    C, p = orc.icp_refine(g["C_closed_form"], g["Phi1"], g["Phi2"], nit=10, return_p2p=True)
+    assert relF(C, g["ref_cf_C_icp"]) < 1e-10
+    assert np.array_equal(p, g["ref_cf_p2p_icp"])
+    assert np.allclose(C @ C.T, np.eye(C.shape[0]), atol=1e-10)
+
+
+def test_surface_map_arrays_vs_reference_driver(golden_fm):
+    """End to end vs compute_surface_map.  C differs by the reference's L-BFGS noise, so index
+    maps may differ on a handful of vertices; the bound here is 1 %."""
+    g = golden_fm
+    out = orc.surface_map_arrays(g["Phi1"], g["evals1"], g["area1"], g["Phi2"], g["evals2"], g["area2"],
+                                 g["c1"], g["c2"], int(g["k"]), float(g["w_descr"]), float(g["w_lap"]))
+    assert relF(out["C"], g["ref_C_lbfgs"]) < 1e-3
+    n = len(g["ref_p2p_21"])
+    for key in ("p2p_21", "p2p_12", "p2p_21_adjoint", "p2p_12_adjoint"):
+        assert np.count_nonzero(out[key] != g["ref_" + key]) <= 0.01 * n, key
+    for key in ("p2p_21_icp", "p2p_12_icp", "p2p_21_icp_adjoint", "p2p_12_icp_adjoint"):
+        assert np.count_nonzero(out[key] != g["ref_" + key]) <= 0.05 * n, key
+
+
+def test_zoomout_upstream_semantics(golden_zo):
+    g = golden_zo
+    assert bool(g["ref_shipped_zoomout_raises_typeerror"])
+    for nn in ("brute", "tree"):
+        C, p = orc.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=14, step=1, A2=g["area2"],
+                                  return_p2p=True, nn=nn)
+        assert C.shape == (26, 26) and relF(C, g["ref_C_zo"]) < 1e-12
+        assert np.array_equal(p, g["ref_p2p_zo"])
+    C, p = orc.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=9, step=(2, 3), A2=g["area2"], return_p2p=True)
+    assert C.shape == (39, 30) and relF(C, g["ref_C_zo_rect"]) < 1e-12
+    assert np.array_equal(p, g["ref_p2p_zo_rect"])
+    C = orc.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=6, step=1, A2=g["area2"],
+                           subsample=(g["sub1"], g["sub2"]))
+    assert relF(C, g["ref_C_zo_sub"]) < 1e-10
+    with pytest.raises(AssertionError):
+        orc.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=40, step=1, A2=g["area2"])
+
+
+def test_meshgen_basis_is_area_orthonormal():
+    V, F = meshgen.icosphere(2)
+    ev, Phi, a = meshgen.lbo_basis(meshgen.deform(V, (1, 1.2, 0.8)), F, 25)
+    assert np.allclose(Phi.T @ (a[:, None] * Phi), np.eye(25), atol=1e-8)
+    assert abs(ev[0]) < 1e-6 and np.all(np.diff(ev) > -1e-9)
+    ev, Phi, a = meshgen.synthetic_basis(500, 30, np.random.default_rng(0))
+    assert np.allclose(Phi.T @ (a[:, None] * Phi), np.eye(30), atol=1e-9)
+    assert np.allclose(Phi[:, 0], Phi[0, 0])
