@@ -1,0 +1,226 @@
+// Internal declarations shared by the translation units of libdm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <float.h>
+#include "../../include/dm_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdm_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace dm {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define DM_FAIL(code, ...)      \
+  do {                          \
+    ::dm::set_error(__VA_ARGS__); \
+    return (code);              \
+  } while (0)
+#define DM_CUDA_OK(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) DM_FAIL(DM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define DM_LAUNCH_OK(what)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) DM_FAIL(DM_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---------------------------------------------------------------- workspace carving
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  size_t bytes() const { return (off + 255) & ~size_t(255); }
+};
+
+// ---------------------------------------------------------------- top-2 tracking
+struct Top2 {
+  float m1;
+  int i1;
+  float m2;
+  int pad;
+};
+__device__ __forceinline__ Top2 top2_init() {
+  Top2 t;
+  t.m1 = -INFINITY;
+  t.i1 = 0x7fffffff;
+  t.m2 = -INFINITY;
+  t.pad = 0;
+  return t;
+}
+// candidates arrive in ascending index order inside one thread: strict '>' keeps the lowest index
+__device__ __forceinline__ void top2_push(Top2& t, float v, int idx) {
+  if (v > t.m1) {
+    t.m2 = t.m1;
+    t.m1 = v;
+    t.i1 = idx;
+  } else if (v > t.m2) {
+    t.m2 = v;
+  }
+}
+// union of two disjoint candidate sets; equal maxima -> lower index, and the gap becomes 0
+__device__ __forceinline__ void top2_merge(Top2& a, float bm1, int bi1, float bm2) {
+  float lo = fminf(a.m1, bm1);
+  bool takeb = (bm1 > a.m1) || (bm1 == a.m1 && bi1 < a.i1);
+  float m2 = fmaxf(fmaxf(a.m2, bm2), lo);
+  if (takeb) {
+    a.m1 = bm1;
+    a.i1 = bi1;
+  }
+  a.m2 = m2;
+}
+
+__device__ __forceinline__ void store_index(void* out, int64_t pos, int v, bool i64) {
+  if (i64)
+    static_cast<int64_t*>(out)[pos] = v;
+  else
+    static_cast<int32_t*>(out)[pos] = v;
+}
+__device__ __forceinline__ int64_t load_index(const void* in, int64_t pos, bool i64) {
+  return i64 ? static_cast<const int64_t*>(in)[pos] : static_cast<const int32_t*>(in)[pos];
+}
+
+// ---------------------------------------------------------------- the NN problem, device view
+constexpr int kMaxEpi = 2;
+
+// One argmax epilogue after preparation: fp32 and fp64 copies of scale/bias over the reduced-over side,
+// per-pair maxima for the error bound, and where the result goes.
+struct EpiDev {
+  const float* sf;   // scale, fp32            [rows of reduced-over side]
+  const float* bf;   // bias, fp32
+  const double* sd;  // scale, fp64 (recheck)
+  const double* bd;  // bias, fp64
+  const float* G;    // per pair: max_j |v_j| * |scale_j|
+  const float* Bm;   // per pair: max_j |bias_j|
+  void* out;
+};
+
+struct FlagEntry {  // one result that must be re-evaluated in float64
+  int pair;
+  int local;  // local index of the kept-side row inside the pair
+  int epi;    // epilogue number; bit 8 set = column epilogue
+  int pad;
+};
+
+struct NNProblem {
+  // fp32 operands for the fast score pass
+  const float* Y;
+  int64_t ldY;
+  const float* X;
+  int64_t ldX;
+  // operands for the float64 re-evaluation (either the same fp32 data or float64 originals)
+  const void* Y64;
+  int64_t ldY64;
+  int y64_is_double;
+  const void* X64;
+  int64_t ldX64;
+  int x64_is_double;
+  const int64_t* q_off;
+  const int64_t* db_off;
+  int64_t total_q, total_db;
+  int max_q, max_db;
+  int n_pairs, d;
+  int d_fast;  // inner dimension of the fp32 operands (>= d; extra columns are zero on the database side)
+  int n_row, n_col;
+  EpiDev row[kMaxEpi];
+  EpiDev col[kMaxEpi];
+  const float* norm_q;   // |y_i| (fp32, rounded up)
+  const float* norm_db;  // |x_j|
+  float eps;             // relative error bound of one score: |S~ - S| <= eps |y| |x|
+  int i64_out;
+  int recheck_all;
+  // scratch
+  Top2* col_partial;  // [n_col][n_pairs * max_rt][max_db]
+  int max_rt;         // row tiles per pair upper bound
+  int rt_rows;        // rows per row tile (engine dependent)
+  FlagEntry* flags;
+  unsigned int* counters;  // [0] = number of flagged entries, [1] rows flagged, [2] cols flagged
+};
+
+// Writes the fp32-grade argmax and, when the top-2 gap is inside the rounding-error bound of the score
+// pass, queues the result for the float64 re-evaluation.  |s~ - s| <= eps |y||x||scale| + 4u(|s| + |bias|)
+// for each of the two candidates (u = 2^-24), hence the threshold below (with 2x slack on the u term).
+__device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E, bool is_col, int epi, int pair,
+                                            int64_t gpos, int local, float own_norm, const Top2& s) {
+  const int idx = (s.i1 == 0x7fffffff) ? 0 : s.i1;
+  store_index(E.out, gpos, idx, P.i64_out != 0);
+  if (P.flags == nullptr) return;
+  const float thr = 2.f * P.eps * own_norm * E.G[pair] + 9.6e-7f * (fabsf(s.m1) + E.Bm[pair]);
+  const bool safe = (s.m1 - s.m2) > thr;  // NaN -> not safe
+  if (!safe || P.recheck_all) {
+    const unsigned slot = atomicAdd(&P.counters[0], 1u);
+    FlagEntry f;
+    f.pair = pair;
+    f.local = local;
+    f.epi = epi | (is_col ? 256 : 0);
+    f.pad = 0;
+    P.flags[slot] = f;
+    atomicAdd(&P.counters[is_col ? 2 : 1], 1u);
+  }
+}
+
+// engines (nn_ffma.cu, nn_tc.cu)
+int nn_ffma_launch(const NNProblem& P, cudaStream_t st);
+int nn_ffma_debug_scores(const float* Y, int64_t ldY, int nq, const float* X, int64_t ldX, int ndb, int d,
+                         float* S, int64_t ldS, cudaStream_t st);
+constexpr int kFfmaRowTile = 128;
+
+// shared stages (nn_common.cu)
+struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of one side
+  int scale_mode, bias_mode;
+  const double* scale;
+  const double* bias;
+  float* sf;
+  float* bf;
+  double* sd;
+  double* bd;
+  float* G;
+  float* Bm;
+};
+// norms + derived scale/bias + per-pair maxima for one side; M is float or double
+int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, cudaStream_t st);
+int nn_col_finalize(const NNProblem& P, cudaStream_t st);
+int nn_recheck(const NNProblem& P, cudaStream_t st);
+
+// full driver used by the extern "C" entry points and by the FM kernels
+struct NNRequest {
+  const float* Y;
+  int64_t ldY;
+  const float* X;
+  int64_t ldX;
+  const double* Y64;  // optional float64 originals (else nullptr -> use Y)
+  int64_t ldY64;
+  const double* X64;
+  int64_t ldX64;
+  const int64_t* q_off;
+  const int64_t* db_off;
+  int64_t total_q, total_db;
+  int max_q, max_db, n_pairs, d;
+  int d_fast;  // 0 -> d
+  dm_nn_epi row[kMaxEpi];
+  int n_row;
+  dm_nn_epi col[kMaxEpi];
+  int n_col;
+  int flags;
+};
+size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
+                          int n_col, int flags);
+int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st);
+
+int num_sms();
+int cvt_f64_f32(const double* src, int64_t lds, int64_t rows, int d, float* dst, int ldd, cudaStream_t st);
+
+}  // namespace dm

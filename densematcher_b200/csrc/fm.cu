@@ -1,0 +1,462 @@
+// Functional-map stages: spectral projection, the closed-form C solve, FM -> p2p (four index outputs
+// from one score pass), p2p -> FM and the ZoomOut ladder.  Everything that enters C is float64; the
+// N x N x k score pass runs through the fused NN engine with the float64 near-tie re-evaluation.
+#include "dm_internal.cuh"
+#include "gemm64.cuh"
+
+namespace dm {
+namespace {
+
+// bias[j] = -1/2 |row_j|^2 over the first d columns (float64), one warp per row
+__global__ void __launch_bounds__(256)
+    neg_half_sqnorm_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int d, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double* r = M + row * ld;
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) s = fma(r[k], r[k], s);
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+  if (lane == 0) out[row] = -0.5 * s;
+}
+
+// One CTA per (pair, row i of C): solve (w_d Abar Abar^T + w_l diag(Delta_i)) c = w_d Abar (B_i - c_i0 A_0)^T
+// by an in-shared-memory Cholesky factorisation (float64).
+__global__ void __launch_bounds__(256)
+    fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ ev1,
+                      const double* __restrict__ ev2, const double* __restrict__ c00, double wd, double wl, int k1,
+                      int k2, double* __restrict__ C, int* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int n = k1 - 1, ldm = n + 1;
+  double* Mx = sm;             // [n][ldm]
+  double* rhs = sm + n * ldm;  // [n]
+  __shared__ double s_scale;
+  __shared__ int s_bad;
+  const int b = blockIdx.x / k2, i = blockIdx.x % k2;
+  const int t = threadIdx.x;
+  const double* aat = AAt + int64_t(b) * k1 * k1;
+  const double* bat = BAt + int64_t(b) * k2 * k1;
+  const double* l1 = ev1 + int64_t(b) * k1;
+  const double* l2 = ev2 + int64_t(b) * k2;
+  if (t == 0) {
+    double m = -INFINITY;
+    for (int j = 0; j < k1; ++j) m = fmax(m, l1[j]);
+    for (int j = 0; j < k2; ++j) m = fmax(m, l2[j]);
+    s_scale = m;
+    s_bad = 0;
+  }
+  __syncthreads();
+  const double scale = s_scale;
+  const double ci0 = (i == 0) ? c00[b] : 0.0;
+  const double l2i = l2[i] / scale;
+  for (int e = t; e < n * n; e += blockDim.x) {
+    const int r = e / n, c = e % n;
+    double v = wd * aat[int64_t(r + 1) * k1 + (c + 1)];
+    if (r == c) {
+      const double df = l1[c + 1] / scale - l2i;
+      v += wl * (df * df);
+    }
+    Mx[r * ldm + c] = v;
+  }
+  for (int r = t; r < n; r += blockDim.x) rhs[r] = wd * (bat[int64_t(i) * k1 + r + 1] - ci0 * aat[r + 1]);
+  __syncthreads();
+  // right-looking Cholesky, lower triangle
+  for (int j = 0; j < n; ++j) {
+    if (t == 0) {
+      const double dj = Mx[j * ldm + j];
+      if (!(dj > 0.0)) s_bad = 1;
+      Mx[j * ldm + j] = sqrt(dj);
+    }
+    __syncthreads();
+    const double inv = 1.0 / Mx[j * ldm + j];
+    for (int r = j + 1 + t; r < n; r += blockDim.x) Mx[r * ldm + j] *= inv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int e = t; e < m * m; e += blockDim.x) {
+      const int r = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= r) Mx[r * ldm + c] = fma(-Mx[r * ldm + j], Mx[c * ldm + j], Mx[r * ldm + c]);
+    }
+    __syncthreads();
+  }
+  // forward substitution L y = rhs
+  for (int j = 0; j < n; ++j) {
+    if (t == 0) rhs[j] /= Mx[j * ldm + j];
+    __syncthreads();
+    const double yj = rhs[j];
+    for (int r = j + 1 + t; r < n; r += blockDim.x) rhs[r] = fma(-Mx[r * ldm + j], yj, rhs[r]);
+    __syncthreads();
+  }
+  // back substitution L^T x = y
+  for (int j = n - 1; j >= 0; --j) {
+    if (t == 0) rhs[j] /= Mx[j * ldm + j];
+    __syncthreads();
+    const double xj = rhs[j];
+    for (int r = t; r < j; r += blockDim.x) rhs[r] = fma(-Mx[j * ldm + r], xj, rhs[r]);
+    __syncthreads();
+  }
+  double* Ci = C + (int64_t(b) * k2 + i) * k1;
+  if (t == 0) {
+    Ci[0] = ci0;
+    if (s_bad) atomicExch(status, 1);
+  }
+  for (int r = t; r < n; r += blockDim.x) Ci[r + 1] = rhs[r];
+}
+
+int neg_half_sqnorm(const double* M, int64_t ld, int64_t rows, int d, double* out, cudaStream_t st) {
+  if (rows <= 0) return DM_OK;
+  neg_half_sqnorm_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(M, ld, rows, d, out);
+  DM_LAUNCH_OK("neg_half_sqnorm_kernel");
+  return DM_OK;
+}
+
+int pad4(int x) { return (x + 3) / 4 * 4; }
+
+// ---- p2p -> FM (internal, with split-K workspace)
+constexpr int kP2PChunk = 256;
+size_t p2p_to_fm_ws(int n_pairs, int max_n2, int k1, int k2) {
+  const int ks = (max_n2 + kP2PChunk - 1) / kP2PChunk;
+  Carver c(nullptr);
+  if (ks > 1) c.take<double>(size_t(ks) * n_pairs * k1 * k2);
+  return c.bytes();
+}
+int p2p_to_fm_run(const void* p2p, int p2p_i64, const double* Phi1, int64_t ld1, const int64_t* off1,
+                  const double* Phi2, int64_t ld2, const int64_t* off2, int max_n2, const double* area2, int n_pairs,
+                  int k1, int k2, double* C, void* ws, cudaStream_t st) {
+  if (n_pairs <= 0 || k1 <= 0 || k2 <= 0) return DM_OK;
+  const int ks = (max_n2 + kP2PChunk - 1) / kP2PChunk;
+  GemmProblem G;
+  G.A.d = Phi2, G.A.ld = ld2, G.A.off = off2, G.A.trans = 1, G.A.kscale = area2;
+  G.B.d = Phi1, G.B.ld = ld1, G.B.off = off1, G.B.trans = 1, G.B.gather = p2p, G.B.gather_i64 = p2p_i64,
+  G.B.gather_off = off2;
+  G.M = k2, G.N = k1, G.maxM = k2, G.maxN = k1, G.maxK = max_n2, G.n_batch = n_pairs;
+  G.ldc = k1, G.c_batch_stride = int64_t(k1) * k2;
+  int rc;
+  if (ks <= 1) {
+    G.C = C;
+    return gemm64_launch(G, st);
+  }
+  Carver c(ws);
+  double* part = c.take<double>(size_t(ks) * n_pairs * k1 * k2);
+  G.C = part, G.ksplit = ks, G.kchunk = kP2PChunk, G.split_stride = int64_t(n_pairs) * k1 * k2;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  return sum_partials_launch(part, ks, G.split_stride, G.split_stride, C, st);
+}
+
+// ---- p2p_21 of a functional map, upstream pyFM semantics (the ZoomOut / ICP inner conversion):
+//      knn(tree = Phi1[:, :k1] C^T, query = Phi2[:, :k2])
+struct P2P21Scratch {
+  double* emb1;  // [total_n1, lde]
+  float* Xf;     // [total_n1, ldf]
+  void* nn_ws;
+  size_t nn_ws_bytes;
+  int lde, ldf;
+};
+int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
+              int max_n1, const double* Phi2, int64_t ld2, const float* Phi2f, int ldPhi2f, const int64_t* off2,
+              int64_t total_n2, int max_n2, int n_pairs, void* p2p_out, int flags, const P2P21Scratch& S,
+              cudaStream_t st) {
+  int rc;
+  GemmProblem G;
+  G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
+  G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 0;
+  G.N = k2, G.K = k1, G.maxM = max_n1, G.maxN = k2, G.maxK = k1, G.n_batch = n_pairs;
+  G.C = S.emb1, G.ldc = S.lde, G.c_off = off1;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  const int dfast = pad4(k2);
+  if ((rc = cvt_f64_f32(S.emb1, S.lde, total_n1, k2, S.Xf, S.ldf, st))) return rc;
+  // Xf columns k2..dfast must be zero: cvt writes ldf columns per row, zero beyond k2
+  NNRequest R{};
+  R.Y = Phi2f, R.ldY = ldPhi2f, R.X = S.Xf, R.ldX = S.ldf;
+  R.Y64 = Phi2, R.ldY64 = ld2, R.X64 = S.emb1, R.ldX64 = S.lde;
+  R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
+  R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = k2, R.d_fast = dfast;
+  R.n_row = 1, R.n_col = 0;
+  R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NEG_HALF_SQNORM, nullptr, nullptr, p2p_out};
+  R.flags = flags;
+  return nn_run(R, S.nn_ws, S.nn_ws_bytes, st);
+}
+
+}  // namespace
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" {
+
+// ------------------------------------------------------------------ projection
+size_t dm_project_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int d) {
+  (void)total_n;
+  const int ks = (max_n + 255) / 256;
+  Carver c(nullptr);
+  if (ks > 1) c.take<double>(size_t(ks) * n_meshes * k * d);
+  return c.bytes();
+}
+
+int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
+               const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d, double* out,
+               void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_meshes < 0 || k <= 0 || d <= 0 || total_n < 0 || max_n < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_meshes == 0) return DM_OK;
+  if (!Phi || !area || !F || !row_off || !out) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ldPhi < k || ldF < d) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
+  const size_t need = dm_project_workspace_bytes(n_meshes, total_n, max_n, k, d);
+  if (need > workspace_bytes || (need && !workspace)) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ks = (max_n + 255) / 256;
+  GemmProblem G;
+  G.A.d = Phi, G.A.ld = ldPhi, G.A.off = row_off, G.A.trans = 1, G.A.kscale = area;
+  G.B.f = F, G.B.ld = ldF, G.B.off = row_off, G.B.trans = 1;
+  G.M = k, G.N = d, G.maxM = k, G.maxN = d, G.maxK = max_n, G.n_batch = n_meshes;
+  G.ldc = d, G.c_batch_stride = int64_t(k) * d;
+  if (ks <= 1) {
+    G.C = out;
+    return gemm64_launch(G, st);
+  }
+  Carver c(workspace);
+  double* part = c.take<double>(size_t(ks) * n_meshes * k * d);
+  G.C = part, G.ksplit = ks, G.kchunk = 256, G.split_stride = int64_t(n_meshes) * k * d;
+  int rc;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  return sum_partials_launch(part, ks, G.split_stride, G.split_stride, out, st);
+}
+
+// ------------------------------------------------------------------ closed-form C
+size_t dm_fmap_solve_workspace_bytes(int n_pairs, int k1, int k2, int d) {
+  (void)d;
+  Carver c(nullptr);
+  c.take<double>(size_t(n_pairs) * k1 * k1);
+  c.take<double>(size_t(n_pairs) * k2 * k1);
+  c.take<int>(4);
+  return c.bytes();
+}
+
+int dm_fmap_solve(const double* A, const double* B, const double* evals1, const double* evals2, const double* c00,
+                  double w_descr, double w_lap, int n_pairs, int k1, int k2, int d, double* C, void* workspace,
+                  size_t workspace_bytes, dm_stream_t stream) {
+  if (n_pairs < 0 || k1 < 2 || k2 < 1 || d <= 0) DM_FAIL(DM_ERR_BADARG, "bad size (need k1 >= 2)");
+  if (n_pairs == 0) return DM_OK;
+  if (!A || !B || !evals1 || !evals2 || !c00 || !C) DM_FAIL(DM_ERR_BADARG, "null argument");
+  const size_t need = dm_fmap_solve_workspace_bytes(n_pairs, k1, k2, d);
+  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  const int n = k1 - 1;
+  const size_t shm = sizeof(double) * (size_t(n) * (n + 1) + n);
+  if (shm > 227 * 1024) DM_FAIL(DM_ERR_UNSUPPORTED, "k1 = %d too large for the in-shared-memory Cholesky (max ~168)", k1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  double* AAt = c.take<double>(size_t(n_pairs) * k1 * k1);
+  double* BAt = c.take<double>(size_t(n_pairs) * k2 * k1);
+  int* status = c.take<int>(4);
+  DM_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
+  int rc;
+  GemmProblem G;
+  G.A.d = A, G.A.ld = d, G.A.batch_stride = int64_t(k1) * d, G.A.trans = 0;
+  G.B = G.A;
+  G.M = k1, G.N = k1, G.K = d, G.maxM = k1, G.maxN = k1, G.maxK = d, G.n_batch = n_pairs;
+  G.C = AAt, G.ldc = k1, G.c_batch_stride = int64_t(k1) * k1;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
+  G.M = k2, G.maxM = k2, G.C = BAt, G.c_batch_stride = int64_t(k2) * k1;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  if (shm > 48 * 1024)
+    DM_CUDA_OK(cudaFuncSetAttribute(fmap_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm)));
+  fmap_solve_kernel<<<unsigned(n_pairs) * k2, 256, shm, st>>>(AAt, BAt, evals1, evals2, c00, w_descr, w_lap, k1, k2, C,
+                                                              status);
+  DM_LAUNCH_OK("fmap_solve_kernel");
+  return DM_OK;
+}
+
+// ------------------------------------------------------------------ FM -> p2p
+size_t dm_fm_to_p2p_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1,
+                                    int k2, int flags) {
+  Carver c(nullptr);
+  c.take<double>(size_t(total_n2) * k1);        // emb2 = Phi2 C
+  c.take<double>(size_t(total_n1) * k2);        // emb1 = Phi1 C^T
+  c.take<double>(size_t(total_n1));             // -1/2 |emb1|^2
+  c.take<float>(size_t(total_n2) * pad4(k1));   // fp32 emb2
+  c.take<float>(size_t(total_n1) * pad4(k1));   // fp32 Phi1
+  c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k1, 2, 2, flags));
+  return c.bytes();
+}
+
+int dm_fm_to_p2p(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1,
+                 int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2,
+                 int max_n2, const double* area1, int n_pairs, void* p2p_21, void* p2p_12, void* dense_21,
+                 void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_pairs < 0 || k1 <= 0 || k2 <= 0 || total_n1 < 0 || total_n2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0) return DM_OK;
+  if (!C || !Phi1 || !Phi2 || !off1 || !off2) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ld1 < k1 || ld2 < k2) DM_FAIL(DM_ERR_BADARG, "eigenbasis has fewer columns than the functional map");
+  if (dense_21 && !area1) DM_FAIL(DM_ERR_BADARG, "dense_21 needs area1");
+  if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) DM_FAIL(DM_ERR_BADARG, "no output requested");
+  const size_t need = dm_fm_to_p2p_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k1, k2, flags);
+  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  double* emb2 = c.take<double>(size_t(total_n2) * k1);
+  double* emb1 = c.take<double>(size_t(total_n1) * k2);
+  double* bias1 = c.take<double>(size_t(total_n1));
+  const int ldf = pad4(k1);
+  float* Yf = c.take<float>(size_t(total_n2) * ldf);
+  float* Xf = c.take<float>(size_t(total_n1) * ldf);
+  const size_t nn_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k1, 2, 2, flags);
+  char* nn_ws = c.take<char>(nn_bytes);
+  int rc;
+  // emb2 = Phi2[:, :k2] C   (convert.py:134)
+  {
+    GemmProblem G;
+    G.A.d = Phi2, G.A.ld = ld2, G.A.off = off2, G.A.trans = 0;
+    G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 1;
+    G.N = k1, G.K = k2, G.maxM = max_n2, G.maxN = k1, G.maxK = k2, G.n_batch = n_pairs;
+    G.C = emb2, G.ldc = k1, G.c_off = off2;
+    if ((rc = gemm64_launch(G, st))) return rc;
+  }
+  if (p2p_21) {  // |emb1_j|^2 with emb1 = Phi1[:, :k1] C^T   (convert.py:138)
+    GemmProblem G;
+    G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
+    G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 0;
+    G.N = k2, G.K = k1, G.maxM = max_n1, G.maxN = k2, G.maxK = k1, G.n_batch = n_pairs;
+    G.C = emb1, G.ldc = k2, G.c_off = off1;
+    if ((rc = gemm64_launch(G, st))) return rc;
+    if ((rc = neg_half_sqnorm(emb1, k2, total_n1, k2, bias1, st))) return rc;
+  }
+  if ((rc = cvt_f64_f32(emb2, k1, total_n2, k1, Yf, ldf, st))) return rc;
+  if ((rc = cvt_f64_f32(Phi1, ld1, total_n1, k1, Xf, ldf, st))) return rc;
+  NNRequest R{};
+  R.Y = Yf, R.ldY = ldf, R.X = Xf, R.ldX = ldf;
+  R.Y64 = emb2, R.ldY64 = k1, R.X64 = Phi1, R.ldX64 = ld1;
+  R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
+  R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = k1, R.d_fast = ldf;
+  R.n_row = 0, R.n_col = 0;
+  if (p2p_21) R.row[R.n_row++] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_ARRAY, nullptr, bias1, p2p_21};
+  if (dense_21) R.row[R.n_row++] = dm_nn_epi{DM_SCALE_ARRAY, DM_BIAS_NONE, area1, nullptr, dense_21};
+  if (p2p_12) R.col[R.n_col++] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NEG_HALF_SQNORM, nullptr, nullptr, p2p_12};
+  if (dense_12) R.col[R.n_col++] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, dense_12};
+  R.flags = flags;
+  return nn_run(R, nn_ws, nn_bytes, st);
+}
+
+size_t dm_mapped_indicator_workspace_bytes(int n1, int k2) {
+  Carver c(nullptr);
+  c.take<double>(size_t(n1 > 0 ? n1 : 0) * (k2 > 0 ? k2 : 0));
+  return c.bytes();
+}
+
+int dm_mapped_indicator(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, int n1, const double* Phi2,
+                        int64_t ld2, int n2, const double* area1, double* MI, int64_t ldMI, void* workspace,
+                        size_t workspace_bytes, dm_stream_t stream) {
+  if (k1 <= 0 || k2 <= 0 || n1 < 0 || n2 < 0 || ldMI < n1) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n1 == 0 || n2 == 0) return DM_OK;
+  if (!C || !Phi1 || !Phi2 || !area1 || !MI) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ld1 < k1 || ld2 < k2) DM_FAIL(DM_ERR_BADARG, "eigenbasis has fewer columns than the functional map");
+  if (!workspace || dm_mapped_indicator_workspace_bytes(n1, k2) > workspace_bytes)
+    DM_FAIL(DM_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  double* W = c.take<double>(size_t(n1) * k2);  // W = Phi1 C^T  [n1, k2];  MI = Phi2 W^T diag(area1)
+  int rc;
+  GemmProblem G;
+  G.A.d = Phi1, G.A.ld = ld1, G.A.rows = n1, G.A.trans = 0;
+  G.B.d = C, G.B.ld = k1, G.B.rows = k2, G.B.trans = 0;
+  G.M = n1, G.N = k2, G.K = k1, G.maxM = n1, G.maxN = k2, G.maxK = k1, G.n_batch = 1;
+  G.C = W, G.ldc = k2;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  GemmProblem H;
+  H.A.d = Phi2, H.A.ld = ld2, H.A.rows = n2, H.A.trans = 0;
+  H.B.d = W, H.B.ld = k2, H.B.rows = n1, H.B.trans = 0;
+  H.M = n2, H.N = n1, H.K = k2, H.maxM = n2, H.maxN = n1, H.maxK = k2, H.n_batch = 1;
+  H.C = MI, H.ldc = ldMI, H.c_colscale = area1;
+  return gemm64_launch(H, st);
+}
+
+// ------------------------------------------------------------------ p2p -> FM
+size_t dm_p2p_to_fm_workspace_bytes(int n_pairs, int max_n2, int k1, int k2) {
+  return p2p_to_fm_ws(n_pairs, max_n2, k1, k2);
+}
+
+int dm_p2p_to_fm(const void* p2p_21, const double* Phi1, int64_t ld1, const int64_t* off1, const double* Phi2,
+                 int64_t ld2, const int64_t* off2, int max_n2, const double* area2, int n_pairs, int k1, int k2,
+                 double* C, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_pairs < 0 || k1 <= 0 || k2 <= 0 || max_n2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0) return DM_OK;
+  if (!p2p_21 || !Phi1 || !Phi2 || !off1 || !off2 || !C) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ld1 < k1 || ld2 < k2) DM_FAIL(DM_ERR_BADARG, "eigenbasis has fewer columns than requested");
+  const size_t need = p2p_to_fm_ws(n_pairs, max_n2, k1, k2);
+  if (need > workspace_bytes || (need && !workspace)) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  return p2p_to_fm_run(p2p_21, (flags & DM_I64_OUT) ? 1 : 0, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs,
+                       k1, k2, C, workspace, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ ZoomOut
+size_t dm_zoomout_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1_0,
+                                  int k2_0, int nit, int step1, int step2, int flags) {
+  const int k1m = k1_0 + nit * step1, k2m = k2_0 + nit * step2;
+  Carver c(nullptr);
+  c.take<double>(size_t(n_pairs) * k1m * k2m);  // C ping
+  c.take<double>(size_t(n_pairs) * k1m * k2m);  // C pong
+  c.take<double>(size_t(total_n1) * k2m);       // emb1
+  c.take<float>(size_t(total_n1) * pad4(k2m));  // fp32 emb1
+  c.take<float>(size_t(total_n2) * pad4(k2m));  // fp32 Phi2
+  c.take<int32_t>(size_t(total_n2) * 2);        // p2p (int32 or int64)
+  c.take<char>(p2p_to_fm_ws(n_pairs, max_n2, k1m, k2m));
+  c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags));
+  return c.bytes();
+}
+
+int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int step2, const double* Phi1, int64_t ld1,
+               const int64_t* off1, int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2,
+               int64_t total_n2, int max_n2, const double* area2, int n_pairs, double* C_out, void* p2p_out, int flags,
+               void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_pairs < 0 || k1_0 <= 0 || k2_0 <= 0 || nit < 0 || step1 < 0 || step2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0) return DM_OK;
+  if (!C0 || !Phi1 || !Phi2 || !off1 || !off2 || !area2 || !C_out) DM_FAIL(DM_ERR_BADARG, "null argument");
+  const int k1m = k1_0 + nit * step1, k2m = k2_0 + nit * step2;
+  if (ld1 < k1m) DM_FAIL(DM_ERR_BADARG, "Not enough eigenvectors on source : %d are needed when %lld are provided", k1m, (long long)ld1);
+  if (ld2 < k2m) DM_FAIL(DM_ERR_BADARG, "Not enough eigenvectors on target : %d are needed when %lld are provided", k2m, (long long)ld2);
+  const size_t need = dm_zoomout_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k1_0, k2_0, nit, step1, step2, flags);
+  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  double* Cbuf[2];
+  Cbuf[0] = c.take<double>(size_t(n_pairs) * k1m * k2m);
+  Cbuf[1] = c.take<double>(size_t(n_pairs) * k1m * k2m);
+  P2P21Scratch S;
+  S.lde = k2m, S.ldf = pad4(k2m);
+  S.emb1 = c.take<double>(size_t(total_n1) * k2m);
+  S.Xf = c.take<float>(size_t(total_n1) * S.ldf);
+  float* Phi2f = c.take<float>(size_t(total_n2) * S.ldf);
+  void* p2p = c.take<int32_t>(size_t(total_n2) * 2);
+  const size_t pf_bytes = p2p_to_fm_ws(n_pairs, max_n2, k1m, k2m);
+  void* pf_ws = c.take<char>(pf_bytes);
+  S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags);
+  S.nn_ws = c.take<char>(S.nn_ws_bytes);
+  const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
+  int rc;
+  if ((rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
+  const double* Ccur = C0;
+  int k1 = k1_0, k2 = k2_0;
+  for (int it = 0; it < nit; ++it) {
+    // the fp32 copy of emb1 is re-made with the current width; stale columns beyond k2 are zeroed by cvt
+    if ((rc = p2p21_run(Ccur, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2, total_n2,
+                        max_n2, n_pairs, p2p, flags, S, st)))
+      return rc;
+    double* Cnext = (it == nit - 1) ? C_out : Cbuf[it & 1];
+    if ((rc = p2p_to_fm_run(p2p, i64, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs, k1 + step1, k2 + step2,
+                            Cnext, pf_ws, st)))
+      return rc;
+    Ccur = Cnext;
+    k1 += step1, k2 += step2;
+  }
+  if (nit == 0)
+    DM_CUDA_OK(cudaMemcpyAsync(C_out, C0, sizeof(double) * size_t(n_pairs) * k1 * k2, cudaMemcpyDeviceToDevice, st));
+  if (p2p_out) {
+    if ((rc = p2p21_run(nit == 0 ? C0 : C_out, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2,
+                        total_n2, max_n2, n_pairs, p2p_out, flags, S, st)))
+      return rc;
+  }
+  return DM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+// Stages shared by both score engines: operand preparation (norms, scale/bias, error-bound maxima),
+// column finalisation, the float64 near-tie re-evaluation, and the driver that strings them together.
+#include <stdarg.h>
+#include <stdio.h>
+#include "dm_internal.cuh"
+
+namespace dm {
+
+// ---------------------------------------------------------------- error string
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+namespace {
+
+__device__ __forceinline__ int find_pair(const int64_t* off, int n_pairs, int64_t row) {
+  int lo = 0, hi = n_pairs;  // off[lo] <= row < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= row)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+struct SpecArr {
+  SideEpiSpec s[kMaxEpi];
+};
+
+// one warp per row: |row| in float64, then the epilogue scale/bias derived from it
+template <typename T>
+__global__ void __launch_bounds__(256)
+    prep_side_kernel(const T* __restrict__ M, int64_t ld, const int64_t* __restrict__ off, int n_pairs, int64_t total,
+                     int d, float* __restrict__ norm_out, SpecArr specs, int n_specs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= total) return;
+  const T* r = M + row * ld;
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) {
+    const double v = double(r[k]);
+    s = fma(v, v, s);
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+  if (lane != 0) return;
+  const double nrm = sqrt(s);
+  const float nf = __double2float_ru(nrm) * 1.0000005f;
+  norm_out[row] = nf;
+  const int p = find_pair(off, n_pairs, row);
+  for (int e = 0; e < n_specs; ++e) {
+    const SideEpiSpec& S = specs.s[e];
+    double sc = 1.0, bi = 0.0;
+    if (S.scale_mode == DM_SCALE_ARRAY)
+      sc = S.scale[row];
+    else if (S.scale_mode == DM_SCALE_INVNORM)
+      sc = 1.0 / fmax(nrm, 1e-30);
+    if (S.bias_mode == DM_BIAS_ARRAY)
+      bi = S.bias[row];
+    else if (S.bias_mode == DM_BIAS_NEG_HALF_SQNORM)
+      bi = -0.5 * s;
+    S.sd[row] = sc;
+    S.bd[row] = bi;
+    const float scf = float(sc), bif = float(bi);
+    S.sf[row] = scf;
+    S.bf[row] = bif;
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned int*>(S.G + p), __float_as_uint(nf * fabsf(scf) * 1.0000005f));
+    atomicMax(reinterpret_cast<unsigned int*>(S.Bm + p), __float_as_uint(fabsf(bif)));
+  }
+}
+
+__global__ void __launch_bounds__(256) col_finalize_kernel(const NNProblem P) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per_epi = int64_t(P.n_pairs) * P.max_db;
+  if (idx >= per_epi * P.n_col) return;
+  const int c = int(idx / per_epi);
+  const int64_t rem = idx % per_epi;
+  const int p = int(rem / P.max_db), j = int(rem % P.max_db);
+  const int64_t d0 = P.db_off[p];
+  const int nd = int(P.db_off[p + 1] - d0);
+  if (j >= nd) return;
+  const int nq = int(P.q_off[p + 1] - P.q_off[p]);
+  const int nrt = (nq + P.rt_rows - 1) / P.rt_rows;
+  const Top2* part = P.col_partial + ((int64_t(c) * P.n_pairs + p) * P.max_rt) * P.max_db + j;
+  Top2 m = top2_init();
+  for (int rt = 0; rt < nrt; ++rt) {
+    const Top2 o = part[int64_t(rt) * P.max_db];
+    top2_merge(m, o.m1, o.i1, o.m2);
+  }
+  emit_result(P, P.col[c], true, c, p, d0 + j, j, P.norm_db[d0 + j], m);
+}
+
+// ---------------------------------------------------------------- float64 re-evaluation
+constexpr int RC_THREADS = 256;
+
+template <typename TM>
+__device__ __forceinline__ double dot64(const double* __restrict__ vec, const TM* __restrict__ r, int d);
+
+template <>
+__device__ __forceinline__ double dot64<float>(const double* __restrict__ vec, const float* __restrict__ r, int d) {
+  double s = 0.0;
+  int k = 0;
+  if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+    for (; k + 4 <= d; k += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(r + k));
+      s = fma(vec[k + 0], double(v.x), s);
+      s = fma(vec[k + 1], double(v.y), s);
+      s = fma(vec[k + 2], double(v.z), s);
+      s = fma(vec[k + 3], double(v.w), s);
+    }
+  }
+  for (; k < d; ++k) s = fma(vec[k], double(__ldg(r + k)), s);
+  return s;
+}
+template <>
+__device__ __forceinline__ double dot64<double>(const double* __restrict__ vec, const double* __restrict__ r, int d) {
+  double s = 0.0;
+  int k = 0;
+  if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+    for (; k + 2 <= d; k += 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(r + k));
+      s = fma(vec[k + 0], v.x, s);
+      s = fma(vec[k + 1], v.y, s);
+    }
+  }
+  for (; k < d; ++k) s = fma(vec[k], __ldg(r + k), s);
+  return s;
+}
+
+// argmax_j  dot(vec, mat[j]) * sc[j] + bi[j]  over n candidate rows, float64, lowest index on ties.
+// One CTA; each thread walks candidates t, t+256, ... (ascending, so strict '>' keeps the lowest index).
+template <typename TV, typename TM>
+__device__ int scan64(double* vec, double* sbest, int* sidx, const TV* __restrict__ v, const TM* __restrict__ mat,
+                      int64_t ldm, int n, int d, const double* __restrict__ sc, const double* __restrict__ bi) {
+  const int t = threadIdx.x;
+  for (int k = t; k < d; k += RC_THREADS) vec[k] = double(v[k]);
+  __syncthreads();
+  double best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int j = t; j < n; j += RC_THREADS) {
+    const double s = dot64<TM>(vec, mat + int64_t(j) * ldm, d);
+    const double val = __dadd_rn(__dmul_rn(s, sc[j]), bi[j]);  // same two roundings as numpy's S *= s; S += b
+    if (val > best) {
+      best = val;
+      besti = j;
+    }
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, sh);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, sh);
+    if (ob > best || (ob == best && oi < besti)) {
+      best = ob;
+      besti = oi;
+    }
+  }
+  if ((t & 31) == 0) {
+    sbest[t >> 5] = best;
+    sidx[t >> 5] = besti;
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < RC_THREADS / 32; ++w)
+      if (sbest[w] > best || (sbest[w] == best && sidx[w] < besti)) {
+        best = sbest[w];
+        besti = sidx[w];
+      }
+    sidx[0] = besti;
+  }
+  __syncthreads();
+  const int res = sidx[0];
+  __syncthreads();
+  return res;
+}
+
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(RC_THREADS) recheck_kernel(const NNProblem P) {
+  extern __shared__ double vec[];
+  __shared__ double sbest[RC_THREADS / 32];
+  __shared__ int sidx[RC_THREADS / 32];
+  const unsigned count = P.counters[0];
+  const TY* Y = static_cast<const TY*>(P.Y64);
+  const TX* X = static_cast<const TX*>(P.X64);
+  for (unsigned f = blockIdx.x; f < count; f += gridDim.x) {
+    const FlagEntry e = P.flags[f];
+    const int p = e.pair, epi = e.epi & 255;
+    const bool is_col = (e.epi & 256) != 0;
+    const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
+    const int nq = int(P.q_off[p + 1] - q0), nd = int(P.db_off[p + 1] - d0);
+    int res;
+    if (!is_col) {
+      const EpiDev& E = P.row[epi];
+      res = scan64<TY, TX>(vec, sbest, sidx, Y + (q0 + e.local) * P.ldY64, X + d0 * P.ldX64, P.ldX64, nd, P.d,
+                           E.sd + d0, E.bd + d0);
+      if (threadIdx.x == 0) store_index(E.out, q0 + e.local, res == 0x7fffffff ? 0 : res, P.i64_out != 0);
+    } else {
+      const EpiDev& E = P.col[epi];
+      res = scan64<TX, TY>(vec, sbest, sidx, X + (d0 + e.local) * P.ldX64, Y + q0 * P.ldY64, P.ldY64, nq, P.d,
+                           E.sd + q0, E.bd + q0);
+      if (threadIdx.x == 0) store_index(E.out, d0 + e.local, res == 0x7fffffff ? 0 : res, P.i64_out != 0);
+    }
+  }
+}
+
+}  // namespace
+
+int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, cudaStream_t st) {
+  if (total <= 0) return DM_OK;
+  SpecArr arr;
+  for (int e = 0; e < kMaxEpi; ++e) arr.s[e] = specs && e < n_specs ? specs[e] : SideEpiSpec{};
+  for (int e = 0; e < n_specs; ++e) {
+    DM_CUDA_OK(cudaMemsetAsync(specs[e].G, 0, sizeof(float) * n_pairs, st));
+    DM_CUDA_OK(cudaMemsetAsync(specs[e].Bm, 0, sizeof(float) * n_pairs, st));
+  }
+  const int wpb = 8;
+  const unsigned grid = unsigned((total + wpb - 1) / wpb);
+  if (is_double)
+    prep_side_kernel<double><<<grid, wpb * 32, 0, st>>>(static_cast<const double*>(M), ld, off, n_pairs, total, d,
+                                                        norm_out, arr, n_specs);
+  else
+    prep_side_kernel<float><<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(M), ld, off, n_pairs, total, d,
+                                                       norm_out, arr, n_specs);
+  DM_LAUNCH_OK("prep_side_kernel");
+  return DM_OK;
+}
+
+int nn_col_finalize(const NNProblem& P, cudaStream_t st) {
+  if (P.n_col == 0 || P.total_db <= 0) return DM_OK;
+  const int64_t n = int64_t(P.n_pairs) * P.max_db * P.n_col;
+  col_finalize_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(P);
+  DM_LAUNCH_OK("col_finalize_kernel");
+  return DM_OK;
+}
+
+int nn_recheck(const NNProblem& P, cudaStream_t st) {
+  if (P.flags == nullptr) return DM_OK;
+  const size_t shm = sizeof(double) * size_t(P.d);
+  if (shm > 200 * 1024) DM_FAIL(DM_ERR_UNSUPPORTED, "inner dimension %d too large for the float64 re-evaluation", P.d);
+  const int grid = num_sms() * 8;
+#define DM_RC(TY, TX)                                                                                         \
+  do {                                                                                                        \
+    if (shm > 48 * 1024)                                                                                      \
+      DM_CUDA_OK(cudaFuncSetAttribute(recheck_kernel<TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
+    recheck_kernel<TY, TX><<<grid, RC_THREADS, shm, st>>>(P);                                                 \
+  } while (0)
+  if (P.y64_is_double && P.x64_is_double)
+    DM_RC(double, double);
+  else if (P.y64_is_double)
+    DM_RC(double, float);
+  else if (P.x64_is_double)
+    DM_RC(float, double);
+  else
+    DM_RC(float, float);
+#undef DM_RC
+  DM_LAUNCH_OK("recheck_kernel");
+  return DM_OK;
+}
+
+// ---------------------------------------------------------------- driver
+namespace {
+struct NNLayout {
+  unsigned int* counters;
+  float *norm_q, *norm_db;
+  struct Arr {
+    float *sf, *bf;
+    double *sd, *bd;
+    float *G, *Bm;
+  } row[kMaxEpi], col[kMaxEpi];
+  Top2* col_partial;
+  FlagEntry* flags;
+  size_t bytes;
+};
+
+int pick_rt_rows(int /*d*/, int /*flags*/) { return kFfmaRowTile; }
+
+NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
+               int n_col, int flags) {
+  Carver c(ws);
+  NNLayout L;
+  L.counters = c.take<unsigned int>(64);
+  L.norm_q = c.take<float>(total_q);
+  L.norm_db = c.take<float>(total_db);
+  for (int e = 0; e < n_row; ++e) {
+    L.row[e].sf = c.take<float>(total_db);
+    L.row[e].bf = c.take<float>(total_db);
+    L.row[e].sd = c.take<double>(total_db);
+    L.row[e].bd = c.take<double>(total_db);
+    L.row[e].G = c.take<float>(n_pairs);
+    L.row[e].Bm = c.take<float>(n_pairs);
+  }
+  for (int e = 0; e < n_col; ++e) {
+    L.col[e].sf = c.take<float>(total_q);
+    L.col[e].bf = c.take<float>(total_q);
+    L.col[e].sd = c.take<double>(total_q);
+    L.col[e].bd = c.take<double>(total_q);
+    L.col[e].G = c.take<float>(n_pairs);
+    L.col[e].Bm = c.take<float>(n_pairs);
+  }
+  const int rt_rows = pick_rt_rows(d, flags);
+  const int max_rt = (max_q + rt_rows - 1) / rt_rows;
+  L.col_partial = c.take<Top2>(size_t(n_col) * n_pairs * max_rt * max_db);
+  L.flags = c.take<FlagEntry>((flags & DM_NO_RECHECK) ? 0 : size_t(n_row) * total_q + size_t(n_col) * total_db);
+  L.bytes = c.bytes();
+  return L;
+}
+}  // namespace
+
+size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
+                          int n_col, int flags) {
+  return carve(nullptr, n_pairs, total_q, total_db, max_q, max_db, d, n_row, n_col, flags).bytes;
+}
+
+int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (R.n_pairs < 0 || R.d <= 0 || R.total_q < 0 || R.total_db < 0 || R.max_q < 0 || R.max_db < 0)
+    DM_FAIL(DM_ERR_BADARG, "negative size");
+  if (R.n_row < 0 || R.n_row > kMaxEpi || R.n_col < 0 || R.n_col > kMaxEpi || R.n_row + R.n_col == 0)
+    DM_FAIL(DM_ERR_BADARG, "need 1..%d row and/or column epilogues", kMaxEpi);
+  if (R.n_pairs == 0 || (R.total_q == 0 && R.total_db == 0)) return DM_OK;
+  if (!R.Y || !R.X || !R.q_off || !R.db_off) DM_FAIL(DM_ERR_BADARG, "null operand");
+  if (R.ldY < R.d || R.ldX < R.d || (R.d_fast > 0 && (R.d_fast < R.d || R.ldY < R.d_fast || R.ldX < R.d_fast)))
+    DM_FAIL(DM_ERR_BADARG, "leading dimension smaller than d");
+  if ((R.flags & DM_ENGINE_FFMA) && (R.flags & DM_ENGINE_TC)) DM_FAIL(DM_ERR_BADARG, "both engines forced");
+  for (int e = 0; e < R.n_row + R.n_col; ++e) {
+    const dm_nn_epi& E = e < R.n_row ? R.row[e] : R.col[e - R.n_row];
+    if (!E.out) DM_FAIL(DM_ERR_BADARG, "epilogue %d has no output", e);
+    if (E.scale_mode == DM_SCALE_ARRAY && !E.scale) DM_FAIL(DM_ERR_BADARG, "epilogue %d: scale array missing", e);
+    if (E.bias_mode == DM_BIAS_ARRAY && !E.bias) DM_FAIL(DM_ERR_BADARG, "epilogue %d: bias array missing", e);
+    if (E.scale_mode < 0 || E.scale_mode > 2 || E.bias_mode < 0 || E.bias_mode > 2)
+      DM_FAIL(DM_ERR_BADARG, "epilogue %d: bad mode", e);
+  }
+  if (!ws) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
+  if (reinterpret_cast<uintptr_t>(ws) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  NNLayout L = carve(ws, R.n_pairs, R.total_q, R.total_db, R.max_q, R.max_db, R.d, R.n_row, R.n_col, R.flags);
+  if (L.bytes > ws_bytes)
+    DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.bytes, ws_bytes);
+
+  DM_CUDA_OK(cudaMemsetAsync(L.counters, 0, 64 * sizeof(unsigned int), st));
+
+  NNProblem P{};
+  P.Y = R.Y, P.ldY = R.ldY, P.X = R.X, P.ldX = R.ldX;
+  P.Y64 = R.Y64 ? static_cast<const void*>(R.Y64) : R.Y, P.ldY64 = R.Y64 ? R.ldY64 : R.ldY, P.y64_is_double = R.Y64 != nullptr;
+  P.X64 = R.X64 ? static_cast<const void*>(R.X64) : R.X, P.ldX64 = R.X64 ? R.ldX64 : R.ldX, P.x64_is_double = R.X64 != nullptr;
+  P.q_off = R.q_off, P.db_off = R.db_off;
+  P.total_q = R.total_q, P.total_db = R.total_db, P.max_q = R.max_q, P.max_db = R.max_db;
+  P.n_pairs = R.n_pairs, P.d = R.d, P.n_row = R.n_row, P.n_col = R.n_col;
+  P.d_fast = R.d_fast > 0 ? R.d_fast : R.d;
+  P.norm_q = L.norm_q, P.norm_db = L.norm_db;
+  P.i64_out = (R.flags & DM_I64_OUT) ? 1 : 0;
+  P.recheck_all = (R.flags & DM_RECHECK_ALL) ? 1 : 0;
+  P.col_partial = L.col_partial;
+  P.rt_rows = pick_rt_rows(R.d, R.flags);
+  P.max_rt = (R.max_q + P.rt_rows - 1) / P.rt_rows;
+  P.flags = (R.flags & DM_NO_RECHECK) ? nullptr : L.flags;
+  P.counters = L.counters;
+  // fp32 FMA chain of length d (+ the fp32 rounding of float64 originals): gamma_d = d u / (1 - d u)
+  P.eps = float((double(R.d) + 4.0) * 5.9604644775390625e-08 * 1.01);
+
+  SideEpiSpec rs[kMaxEpi], cs[kMaxEpi];
+  for (int e = 0; e < R.n_row; ++e) {
+    rs[e] = SideEpiSpec{R.row[e].scale_mode, R.row[e].bias_mode, R.row[e].scale, R.row[e].bias, L.row[e].sf,
+                        L.row[e].bf,         L.row[e].sd,        L.row[e].bd,    L.row[e].G,    L.row[e].Bm};
+    P.row[e] = EpiDev{L.row[e].sf, L.row[e].bf, L.row[e].sd, L.row[e].bd, L.row[e].G, L.row[e].Bm, R.row[e].out};
+  }
+  for (int e = 0; e < R.n_col; ++e) {
+    cs[e] = SideEpiSpec{R.col[e].scale_mode, R.col[e].bias_mode, R.col[e].scale, R.col[e].bias, L.col[e].sf,
+                        L.col[e].bf,         L.col[e].sd,        L.col[e].bd,    L.col[e].G,    L.col[e].Bm};
+    P.col[e] = EpiDev{L.col[e].sf, L.col[e].bf, L.col[e].sd, L.col[e].bd, L.col[e].G, L.col[e].Bm, R.col[e].out};
+  }
+  int rc;
+  if (!(R.flags & DM_SKIP_PREP)) {
+    // database side carries the row epilogues' scale/bias, query side the column epilogues'
+    if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row, st)))
+      return rc;
+    if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col, st)))
+      return rc;
+  }
+  if ((rc = nn_ffma_launch(P, st))) return rc;
+  if (R.flags & DM_SKIP_FINISH) return DM_OK;
+  if ((rc = nn_col_finalize(P, st))) return rc;
+  if ((rc = nn_recheck(P, st))) return rc;
+  return DM_OK;
+}
+
+}  // namespace dm

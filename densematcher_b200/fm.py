@@ -1,0 +1,271 @@
+"""Device-level API of the functional-map stages (torch CUDA tensors in / out, batched over pairs).
+
+Mirrors, stage by stage, what ``FunctionalMapping.fit`` / ``get_p2p`` / ``zoomout_refine`` /
+``icp_refine`` do in the reference (densematcher/pyFM/functional.py:201-219, :352-487, :564-617),
+but for a ragged batch of mesh pairs at once and without ever leaving the GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .nn import Workspace, as_offsets, default_workspace
+
+__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "PairBatch"]
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _f64(t):
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if t.dim() == 2 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.dim() != 2 and not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _offsets(off, total, dev):
+    """-> (device offsets, host offsets, max rows)."""
+    if off is None:
+        off = [0, total]
+    od, oh = as_offsets(off, dev)
+    if oh[0] != 0 or oh[-1] != total or np.any(np.diff(oh) < 0):
+        raise ValueError("offsets do not cover the rows")
+    return od, oh, int(np.diff(oh).max()) if len(oh) > 1 else 0
+
+
+def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = None):
+    """out[m] = Phi_m[:, :k]^T diag(area_m) F_m -> [n_meshes, k, d] float64.
+    (optimize/base_functions.py:526-532; TriMesh.project mesh/trimesh.py:533-556)"""
+    lib = _lib.load()
+    dev = Phi.device
+    Phi, area = _f64(Phi), _f64(area)
+    if F.dtype != torch.float32:
+        F = F.to(torch.float32)
+    if F.stride(1) != 1:
+        F = F.contiguous()
+    total = Phi.shape[0]
+    k = Phi.shape[1] if k is None else int(k)
+    if k > Phi.shape[1]:
+        raise ValueError("not enough eigenvectors")
+    d = F.shape[1]
+    od, oh, max_n = _offsets(off, total, dev)
+    n_m = len(oh) - 1
+    out = torch.empty(n_m, k, d, dtype=torch.float64, device=dev)
+    need = lib.dm_project_workspace_bytes(n_m, total, max_n, k, d)
+    ws = (workspace or default_workspace(dev, "fm")).get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_project(Phi.data_ptr(), Phi.stride(0), area.data_ptr(), F.data_ptr(), F.stride(0), od.data_ptr(),
+                            total, max_n, n_m, k, d, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_project")
+    return out
+
+
+def fmap_solve(A, B, evals1, evals2, c00, w_descr, w_lap, workspace: Optional[Workspace] = None):
+    """Closed-form minimiser of the descriptor + Laplacian energy, column 0 pinned.
+    A [P,k1,d], B [P,k2,d], evals1 [P,k1], evals2 [P,k2], c00 [P] -> C [P,k2,k1] float64.
+    (FunctionalMapping.fit pyFM/functional.py:352-487 with only w_descr / w_lap active)"""
+    lib = _lib.load()
+    dev = A.device
+    A, B = _f64(A).contiguous(), _f64(B).contiguous()
+    evals1, evals2, c00 = _f64(evals1).contiguous(), _f64(evals2).contiguous(), _f64(c00).contiguous()
+    P, k1, d = A.shape
+    k2 = B.shape[1]
+    if B.shape[0] != P or B.shape[2] != d or evals1.shape != (P, k1) or evals2.shape != (P, k2) or c00.shape != (P,):
+        raise ValueError("shape mismatch in fmap_solve")
+    C = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
+    need = lib.dm_fmap_solve_workspace_bytes(P, k1, k2, d)
+    ws = (workspace or default_workspace(dev, "fm")).get(need)
+    with torch.cuda.device(dev):
+        rc = lib.dm_fmap_solve(A.data_ptr(), B.data_ptr(), evals1.data_ptr(), evals2.data_ptr(), c00.data_ptr(),
+                               float(w_descr), float(w_lap), P, k1, k2, d, C.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream(dev))
+    _lib.check(rc, "dm_fmap_solve")
+    return C
+
+
+def fm_to_p2p(C, Phi1, Phi2, area1=None, off1=None, off2=None, want=("p2p_21", "p2p_12", "dense_21", "dense_12"),
+              flags=0, out_dtype=torch.int64, workspace: Optional[Workspace] = None):
+    """All index outputs of FM_to_p2p + the dense-argmax override from one score pass.
+    C [P,k2,k1]; Phi1 [total_n1, >=k1]; Phi2 [total_n2, >=k2]; area1 [total_n1].
+    Returns a dict of LOCAL index tensors.  (pyFM/spectral/convert.py:96-147; functional_map.py:49-50)"""
+    lib = _lib.load()
+    dev = C.device
+    C = _f64(C)
+    if C.dim() == 2:
+        C = C[None]
+    C = C.contiguous()
+    Phi1, Phi2 = _f64(Phi1), _f64(Phi2)
+    P, k2, k1 = C.shape
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    if k1 > Phi1.shape[1] or k2 > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")  # convert.py:129-132
+    o1, o1h, max1 = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P:
+        raise ValueError("offsets / batch mismatch")
+    if out_dtype == torch.int64:
+        flags |= _lib.DM_I64_OUT
+    outs = {}
+    for name in want:
+        n = n2 if name.endswith("_21") else n1
+        outs[name] = torch.empty(n, dtype=out_dtype, device=dev)
+    a1 = _f64(area1).contiguous() if area1 is not None else None
+    if "dense_21" in outs and a1 is None:
+        raise ValueError("dense_21 needs area1")
+    need = lib.dm_fm_to_p2p_workspace_bytes(P, n1, n2, max1, max2, k1, k2, flags)
+    ws = (workspace or default_workspace(dev, "fm")).get(need)
+    g = lambda nm: outs[nm].data_ptr() if nm in outs else None
+    with torch.cuda.device(dev):
+        rc = lib.dm_fm_to_p2p(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1, max1,
+                              Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2,
+                              a1.data_ptr() if a1 is not None else None, P, g("p2p_21"), g("p2p_12"), g("dense_21"),
+                              g("dense_12"), flags, ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_fm_to_p2p")
+    return outs
+
+
+def mapped_indicator(C, Phi1, Phi2, area1):
+    """Phi2 C Phi1^T A1 for ONE pair, float64 [n2, n1] (convert.py:144) -- API parity only."""
+    lib = _lib.load()
+    dev = C.device
+    C, Phi1, Phi2, area1 = _f64(C).contiguous(), _f64(Phi1), _f64(Phi2), _f64(area1).contiguous()
+    k2, k1 = C.shape
+    if k1 > Phi1.shape[1] or k2 > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    MI = torch.empty(n2, n1, dtype=torch.float64, device=dev)
+    need = lib.dm_mapped_indicator_workspace_bytes(n1, k2)
+    ws = default_workspace(dev, "fm").get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_mapped_indicator(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), n1, Phi2.data_ptr(),
+                                     Phi2.stride(0), n2, area1.data_ptr(), MI.data_ptr(), MI.stride(0), ws.data_ptr(),
+                                     ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_mapped_indicator")
+    return MI
+
+
+def p2p_to_fm(p2p_21, Phi1, Phi2, area2=None, off1=None, off2=None, k1=None, k2=None,
+              workspace: Optional[Workspace] = None):
+    """C[p] = Phi2[:, :k2]^T (area2 * Phi1[p2p_21, :k1]) -> [P,k2,k1] float64 (convert.py:39-48).
+    ``area2=None`` gives the un-weighted product Phi2^T Phi1[p] (the normal-equation right-hand side)."""
+    lib = _lib.load()
+    dev = Phi1.device
+    Phi1, Phi2 = _f64(Phi1), _f64(Phi2)
+    k1 = Phi1.shape[1] if k1 is None else int(k1)
+    k2 = Phi2.shape[1] if k2 is None else int(k2)
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    o1, o1h, _ = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    P = len(o2h) - 1
+    if p2p_21.dtype not in (torch.int32, torch.int64):
+        p2p_21 = p2p_21.to(torch.int64)
+    p2p_21 = p2p_21.contiguous()
+    if p2p_21.numel() != n2:
+        raise ValueError("p2p_21 must have one entry per target vertex")
+    flags = _lib.DM_I64_OUT if p2p_21.dtype == torch.int64 else 0
+    a2 = _f64(area2).contiguous() if area2 is not None else None
+    C = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
+    need = lib.dm_p2p_to_fm_workspace_bytes(P, max2, k1, k2)
+    ws = (workspace or default_workspace(dev, "fm")).get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_p2p_to_fm(p2p_21.data_ptr(), Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), Phi2.data_ptr(),
+                              Phi2.stride(0), o2.data_ptr(), max2, a2.data_ptr() if a2 is not None else None, P, k1, k2,
+                              C.data_ptr(), flags, ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_p2p_to_fm")
+    return C
+
+
+def zoomout(C0, Phi1, Phi2, area2, nit, step=1, off1=None, off2=None, return_p2p=False, flags=0,
+            out_dtype=torch.int64, workspace: Optional[Workspace] = None):
+    """ZoomOut ladder with upstream pyFM semantics (pyFM/refine/zoomout.py:7-115).
+    C0 [P,k2,k1] -> C [P,k2+nit*s2,k1+nit*s1] (and the final p2p_21, local ids)."""
+    lib = _lib.load()
+    dev = C0.device
+    C0 = _f64(C0)
+    if C0.dim() == 2:
+        C0 = C0[None]
+    C0 = C0.contiguous()
+    Phi1, Phi2, area2 = _f64(Phi1), _f64(Phi2), _f64(area2).contiguous()
+    try:
+        s1, s2 = step
+    except TypeError:
+        s1 = s2 = step
+    s1, s2 = int(s1), int(s2)
+    P, k2, k1 = C0.shape
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    assert k1 + nit * s1 <= Phi1.shape[1], \
+        f"Not enough eigenvectors on source : {k1 + nit * s1} are needed when {Phi1.shape[1]} are provided"
+    assert k2 + nit * s2 <= Phi2.shape[1], \
+        f"Not enough eigenvectors on target : {k2 + nit * s2} are needed when {Phi2.shape[1]} are provided"
+    o1, o1h, max1 = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P:
+        raise ValueError("offsets / batch mismatch")
+    if out_dtype == torch.int64:
+        flags |= _lib.DM_I64_OUT
+    C = torch.empty(P, k2 + nit * s2, k1 + nit * s1, dtype=torch.float64, device=dev)
+    p2p = torch.empty(n2, dtype=out_dtype, device=dev) if return_p2p else None
+    need = lib.dm_zoomout_workspace_bytes(P, n1, n2, max1, max2, k1, k2, nit, s1, s2, flags)
+    ws = (workspace or default_workspace(dev, "fm")).get(need)
+    with torch.cuda.device(dev):
+        rc = lib.dm_zoomout(C0.data_ptr(), k1, k2, nit, s1, s2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1,
+                            max1, Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, area2.data_ptr(), P,
+                            C.data_ptr(), p2p.data_ptr() if p2p is not None else None, flags, ws.data_ptr(), ws.numel(),
+                            _stream(dev))
+    _lib.check(rc, "dm_zoomout")
+    return (C, p2p) if return_p2p else C
+
+
+def icp(C0, Phi1, Phi2, nit=10, off1=None, off2=None, return_p2p=False, flags=0, out_dtype=torch.int64,
+        workspace: Optional[Workspace] = None):
+    """Spectral ICP (pyFM/refine/icp.py:10-107).  C0 [P,k2,k1] -> refined C (and its p2p_21)."""
+    lib = _lib.load()
+    dev = C0.device
+    C0 = _f64(C0)
+    if C0.dim() == 2:
+        C0 = C0[None]
+    C0 = C0.contiguous()
+    Phi1, Phi2 = _f64(Phi1), _f64(Phi2)
+    P, k2, k1 = C0.shape
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    if k1 > Phi1.shape[1] or k2 > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    o1, o1h, max1 = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    if out_dtype == torch.int64:
+        flags |= _lib.DM_I64_OUT
+    C = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
+    p2p = torch.empty(n2, dtype=out_dtype, device=dev) if return_p2p else None
+    need = lib.dm_icp_workspace_bytes(P, n1, n2, max1, max2, k1, k2, flags)
+    ws = (workspace or default_workspace(dev, "fm")).get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_icp(C0.data_ptr(), k1, k2, int(nit), Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1, max1,
+                        Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, P, C.data_ptr(),
+                        p2p.data_ptr() if p2p is not None else None, flags, ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_icp")
+    return (C, p2p) if return_p2p else C
+
+
+class PairBatch:
+    """A ragged batch of mesh pairs resident in HBM: packed features, eigenbases and offsets.
+
+    This is the data layout of the hot path: every per-vertex array of all pairs is
+    stacked row-wise; ``off1`` / ``off2`` delimit the pairs."""
+
+    def __init__(self, F1, F2, off1, off2, Phi1=None, Phi2=None, evals1=None, evals2=None, area1=None, area2=None):
+        self.F1, self.F2 = F1, F2
+        dev = F1.device
+        self.off1, self.off1_h = as_offsets(off1, dev)
+        self.off2, self.off2_h = as_offsets(off2, dev)
+        self.max1 = int(np.diff(self.off1_h).max())
+        self.max2 = int(np.diff(self.off2_h).max())
+        self.n_pairs = len(self.off1_h) - 1
+        self.Phi1, self.Phi2, self.evals1, self.evals2, self.area1, self.area2 = Phi1, Phi2, evals1, evals2, area1, area2

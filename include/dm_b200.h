@@ -1,0 +1,234 @@
+/*
+ * dm_b200.h -- C ABI of libdm_b200.so: the B200 (sm_100a) implementation of the
+ * DenseMatcher correspondence hot path (feature NN / functional-map solve /
+ * FM->p2p / ZoomOut / spectral ICP).
+ *
+ * The reference has no FFI layer: its boundary is Python call signatures over
+ * numpy arrays.  Each entry point below therefore cites
+ * the reference *Python function* (file:line, relative to the upstream repo root
+ * JunzheJosephZhu/DenseMatcher @ 96da493) whose arithmetic it replaces; the
+ * ctypes binding a maintainer would add on the reference side is shown in
+ * INTEGRATION.md and lives in densematcher_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h (host);
+ *   - matrices are row-major with a leading dimension in ELEMENTS;
+ *   - a batch of mesh pairs is "ragged-packed": the rows of all pairs are
+ *     stacked in one matrix and an int64 offsets array of n_pairs+1 entries
+ *     (device) delimits pair p as rows off[p] .. off[p+1]-1;
+ *   - all calls are stream-ordered and asynchronous w.r.t. the host, never
+ *     synchronise, never allocate: the caller owns every buffer including the
+ *     workspace, whose size the matching *_workspace_bytes call returns;
+ *   - no global state except a thread-local error string; thread-safe;
+ *   - return value: 0 = OK, <0 = one of DM_ERR_*; never throws.
+ *   - index outputs are int32, or int64 when DM_I64_OUT is set (the reference
+ *     returns int64, nn_utils.py:30 / numpy argmax).
+ */
+#ifndef DM_B200_H
+#define DM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_VERSION 100
+
+typedef void* dm_stream_t; /* a cudaStream_t */
+
+enum {
+  DM_OK = 0,
+  DM_ERR_BADARG = -1,
+  DM_ERR_ALIGN = -2,
+  DM_ERR_WORKSPACE = -3,
+  DM_ERR_CUDA = -4,
+  DM_ERR_UNSUPPORTED = -5
+};
+
+/* flags */
+enum {
+  DM_I64_OUT = 1 << 0,      /* index outputs are int64 instead of int32 */
+  DM_NO_RECHECK = 1 << 1,   /* skip the float64 near-tie re-evaluation (results are then only fp32-grade) */
+  DM_ENGINE_FFMA = 1 << 2,  /* force the CUDA-core fp32 score kernel */
+  DM_ENGINE_TC = 1 << 3,    /* force the tcgen05 split-bf16 tensor-core score kernel */
+  DM_RECHECK_ALL = 1 << 4,  /* testing: send every row through the float64 path */
+  DM_SKIP_PREP = 1 << 5,    /* profiling: reuse the operand preparation a previous identical call left in the workspace */
+  DM_SKIP_FINISH = 1 << 6   /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
+};
+
+/* how the per-element scale / bias of one argmax epilogue is obtained */
+enum { DM_SCALE_NONE = 0, DM_SCALE_ARRAY = 1, DM_SCALE_INVNORM = 2 };
+enum { DM_BIAS_NONE = 0, DM_BIAS_ARRAY = 1, DM_BIAS_NEG_HALF_SQNORM = 2 };
+
+/*
+ * One fused argmax epilogue over the score matrix S = Y X^T of a pair.
+ * A ROW epilogue reduces over database rows j:  out[i] = argmax_j S_ij * scale[j] + bias[j]
+ * A COL epilogue reduces over query rows i:     out[j] = argmax_i S_ij * scale[i] + bias[i]
+ * scale/bias are indexed by the reduced-over side (packed like that side's matrix),
+ * float64 because the near-tie re-evaluation is done in float64 like the reference.
+ *   cosine NN on unit rows (model.py:169 + nn_utils.py:4-38):  NONE / NONE
+ *   cosine NN on arbitrary rows:                                INVNORM / NONE
+ *   Euclidean 1-NN == knn_query (nn_utils.py:4-38):             NONE / NEG_HALF_SQNORM
+ *   dense mapped-indicator argmax (functional_map.py:49-50):    ARRAY (= vertex areas) / NONE
+ * Ties resolve to the lowest index (numpy argmax).
+ */
+typedef struct dm_nn_epi {
+  int32_t scale_mode;
+  int32_t bias_mode;
+  const double* scale; /* DM_SCALE_ARRAY only */
+  const double* bias;  /* DM_BIAS_ARRAY only */
+  void* out;           /* [rows of the kept side] int32 | int64 */
+} dm_nn_epi;
+
+const char* dm_last_error(void);
+int dm_version(void);
+/* "sm_100a;tc=1;..." -- what the library was compiled with */
+const char* dm_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused similarity + argmax (never materialises S).
+ * Replaces: knn_query  densematcher/pyFM/spectral/nn_utils.py:4-38  (k = 1)
+ *           dense argmax override  densematcher/functional_map.py:49-50, :76-77
+ * Y: queries  [total_q,  d] (ld = ldY), pair p = rows q_off[p]..q_off[p+1]
+ * X: database [total_db, d] (ld = ldX), pair p = rows db_off[p]..db_off[p+1]
+ * max_q / max_db: upper bounds of the per-pair row counts (host knowledge; sizes the grid).
+ * Up to 2 row and 2 column epilogues share one pass over S.
+ * Scores are evaluated in fp32-grade arithmetic; rows whose top-2 gap is below a rigorous
+ * rounding-error bound are re-evaluated in float64 so that the index equals the float64
+ * argmax of the reference.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d,
+                             int n_row_epi, int n_col_epi, int flags);
+
+int dm_nn_argmax_f32(const float* Y, int64_t ldY, const int64_t* q_off, int64_t total_q, int max_q,
+                     const float* X, int64_t ldX, const int64_t* db_off, int64_t total_db, int max_db,
+                     int n_pairs, int d,
+                     const dm_nn_epi* row_epi_h, int n_row_epi,
+                     const dm_nn_epi* col_epi_h, int n_col_epi,
+                     int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* Same for float64 operands (the spectral embeddings of FM_to_p2p are float64 in the reference,
+ * convert.py:134-140): the score pass runs on an fp32 copy made in the workspace, the near-tie
+ * re-evaluation on the float64 originals. */
+size_t dm_nn_f64_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d,
+                                 int n_row_epi, int n_col_epi, int flags);
+int dm_nn_argmax_f64(const double* Y, int64_t ldY, const int64_t* q_off, int64_t total_q, int max_q,
+                     const double* X, int64_t ldX, const int64_t* db_off, int64_t total_db, int max_db,
+                     int n_pairs, int d,
+                     const dm_nn_epi* row_epi_h, int n_row_epi,
+                     const dm_nn_epi* col_epi_h, int n_col_epi,
+                     int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* counters of the last call that used `workspace`: out_h[0] = row results re-evaluated in float64,
+ * out_h[1] = column results re-evaluated, out_h[2] = their sum, out_h[3] reserved.
+ * Synchronises the stream (diagnostics only). */
+int dm_nn_read_stats(const void* workspace, int64_t* out_h, dm_stream_t stream);
+
+/* Testing aid: materialise the fp32-grade score matrix of ONE pair as the selected engine computes it
+ * (S_out [nq, ldS]); used to measure the engine's rounding error against float64. */
+int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, int64_t ldX, int ndb, int d,
+                           float* S_out, int64_t ldS, int flags, void* workspace, size_t workspace_bytes,
+                           dm_stream_t stream);
+
+/* Euclidean distance of matched rows: dist[i] = | Y[i] - X[idx[i]] |_2 in float64
+ * (the `dists` return of knn_query, nn_utils.py:30-38).  idx is int32|int64 per flags, global row ids into X. */
+int dm_match_dist_f32(const float* Y, int64_t ldY, const float* X, int64_t ldX, const void* idx, int64_t n,
+                      int d, double* dist, int flags, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectral projection  out[m] = Phi_m[:, :k]^T diag(area_m) F_m     (k x d per mesh, float64 out)
+ * Replaces: optimize/base_functions.py:526-532, TriMesh.project mesh/trimesh.py:533-556.
+ * Phi [total_n, ldPhi] float64, area [total_n] float64, F [total_n, ldF] float32, meshes ragged-packed
+ * by row_off.  Products are formed in fp32 split arithmetic with float64 accumulation across row blocks.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_project_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int d);
+int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
+               const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d,
+               double* out /* [n_meshes, k, d] */, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Functional-map solve: exact minimiser of  w_descr/2 |C A - B|^2 + w_lap/2 sum C^2 Delta  with column 0
+ * pinned to c00 * e_0 -- the energy FunctionalMapping.fit minimises with L-BFGS-B when only the
+ * descriptor and Laplacian terms are active (pyFM/functional.py:352-487, :629-660;
+ * optimize/base_functions.py:31-56, :79-102, :480-763).  Rows decouple into k2 SPD systems (float64
+ * Cholesky).  A [n_pairs,k1,d], B [n_pairs,k2,d], evals1 [n_pairs,k1], evals2 [n_pairs,k2], c00 [n_pairs].
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_fmap_solve_workspace_bytes(int n_pairs, int k1, int k2, int d);
+int dm_fmap_solve(const double* A, const double* B, const double* evals1, const double* evals2,
+                  const double* c00, double w_descr, double w_lap, int n_pairs, int k1, int k2, int d,
+                  double* C /* [n_pairs, k2, k1] */, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FM -> point-to-point maps, all four index outputs from one pass over S = (Phi2 C) Phi1^T.
+ * Replaces: FM_to_p2p  pyFM/spectral/convert.py:96-147 and the override functional_map.py:49-50.
+ *   p2p_21     [total_n2]  argmin_j | Phi2[i] - (Phi1 C^T)[j] |     (convert.py:138-140)
+ *   p2p_12     [total_n1]  argmin_i | Phi1[j] - (Phi2 C)[i] |       (convert.py:134-136)
+ *   dense_21   [total_n2]  argmax_j (Phi2 C Phi1^T A1)_ij           (functional_map.py:49)
+ *   dense_12   [total_n1]  argmax_i (Phi2 C Phi1^T A1)_ij           (functional_map.py:50)
+ * any output pointer may be NULL.  C [n_pairs, k2, k1] float64; Phi1 [total_n1, ld1] uses columns :k1,
+ * Phi2 [total_n2, ld2] uses columns :k2.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_fm_to_p2p_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2,
+                                    int k1, int k2, int flags);
+int dm_fm_to_p2p(const double* C, int k1, int k2,
+                 const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1,
+                 const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                 const double* area1, int n_pairs,
+                 void* p2p_21, void* p2p_12, void* dense_21, void* dense_12,
+                 int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* mapped_indicator = Phi2 C Phi1^T A1 of ONE pair, float64 [n2, n1] (convert.py:144); API parity only
+ * (the index outputs above never materialise it). */
+size_t dm_mapped_indicator_workspace_bytes(int n1, int k2);
+int dm_mapped_indicator(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, int n1,
+                        const double* Phi2, int64_t ld2, int n2, const double* area1,
+                        double* MI, int64_t ldMI, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * p2p -> FM with the target mass:  C = Phi2[:, :k2]^T (area2 * Phi1[p2p_21, :k1])   float64
+ * Replaces: p2p_to_FM  pyFM/spectral/convert.py:39-48 (A2 given; area2 == NULL means unit weights,
+ * i.e. the Phi2^T Phi1[p] factor of the lstsq branch :51).  p2p_21 holds LOCAL vertex ids
+ * (int32 | int64 per flags).  Deterministic split-K over the vertices.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_p2p_to_fm_workspace_bytes(int n_pairs, int max_n2, int k1, int k2);
+int dm_p2p_to_fm(const void* p2p_21, const double* Phi1, int64_t ld1, const int64_t* off1,
+                 const double* Phi2, int64_t ld2, const int64_t* off2, int max_n2,
+                 const double* area2, int n_pairs, int k1, int k2,
+                 double* C /* [n_pairs, k2, k1] */, int flags, void* workspace, size_t workspace_bytes,
+                 dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ZoomOut ladder (upstream pyFM semantics; pyFM/refine/zoomout.py:7-115, the shipped call at :40 is
+ * broken): nit times  p = p2p_21(C);  C <- Phi2[:, :k2+s2]^T A2 Phi1[p, :k1+s1].
+ * C0 [n_pairs, k2_0, k1_0] -> C_out [n_pairs, k2_0+nit*s2, k1_0+nit*s1]; p2p_out (optional) is the final
+ * p2p_21 of the refined map.  Runs the whole ladder stream-ordered without host synchronisation.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_zoomout_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2,
+                                  int k1_0, int k2_0, int nit, int step1, int step2, int flags);
+int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int step2,
+               const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1,
+               const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+               const double* area2, int n_pairs,
+               double* C_out, void* p2p_out,
+               int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectral ICP (pyFM/refine/icp.py:10-107, driven by FunctionalMapping.icp_refine functional.py:564-586):
+ * nit times  p = p2p_21(C);  C = lstsq(Phi2[:, :k2], Phi1[p, :k1]);  C <- U I V^T of its SVD.
+ * The least squares is solved through the (once-factorised) Gram matrix Phi2^T Phi2 and the orthogonal
+ * polar factor through a one-sided Jacobi SVD, all float64.  p2p_out (optional) = p2p_21 of the result.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_icp_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1,
+                              int k2, int flags);
+int dm_icp(const double* C0, int k1, int k2, int nit,
+           const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1,
+           const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+           int n_pairs, double* C_out, void* p2p_out,
+           int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM_B200_H */

@@ -1,0 +1,124 @@
+"""GPU parity of the functional-map stages against the oracle and the reference-minted goldens.
+Index outputs bit-exact; C within 1e-4 relative Frobenius (north star), in practice ~1e-12."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dm_oracle as orc, meshgen
+
+pytestmark = pytest.mark.gpu
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope="module")
+def fm():
+    from densematcher_b200 import fm as _fm
+    return _fm
+
+
+def test_projection_and_closed_form_solve(fm, golden_fm):
+    g = golden_fm
+    k = int(g["k"])
+    A = fm.project(dev(g["Phi1"]), dev(g["area1"]), dev(g["c1"]), k=k)[0].cpu().numpy()
+    B = fm.project(dev(g["Phi2"]), dev(g["area2"]), dev(g["c2"]), k=k)[0].cpu().numpy()
+    assert relF(A, orc.project(g["Phi1"], g["area1"], g["c1"], k)) < 1e-12
+    assert relF(B, orc.project(g["Phi2"], g["area2"], g["c2"], k)) < 1e-12
+    c00 = orc.fmap_c00(g["Phi1"], g["Phi2"], g["area1"], g["area2"])
+    C = fm.fmap_solve(dev(A)[None], dev(B)[None], dev(g["evals1"][:k])[None], dev(g["evals2"][:k])[None],
+                      dev(np.array([c00])), float(g["w_descr"]), float(g["w_lap"]))[0].cpu().numpy()
+    assert relF(C, g["C_closed_form"]) < 1e-9          # bar: 1e-4 (north star)
+    assert relF(C, g["ref_C_lbfgs"]) < 1e-3            # the reference's own L-BFGS noise
+    assert C[0, 0] == c00 and np.all(C[1:, 0] == 0)
+
+
+def test_fm_to_p2p_four_outputs(fm, golden_fm):
+    g = golden_fm
+    out = fm.fm_to_p2p(dev(g["C_closed_form"]), dev(g["Phi1"]), dev(g["Phi2"]), dev(g["area1"]))
+    assert np.array_equal(out["p2p_21"].cpu().numpy(), g["ref_cf_p2p_21"])
+    assert np.array_equal(out["p2p_12"].cpu().numpy(), g["ref_cf_p2p_12"])
+    assert np.array_equal(out["dense_21"].cpu().numpy(), g["ref_cf_MI_argmax1"])
+    assert np.array_equal(out["dense_12"].cpu().numpy(), g["ref_cf_MI_argmax0"])
+    MI = fm.mapped_indicator(dev(g["C_closed_form"]), dev(g["Phi1"]), dev(g["Phi2"]), dev(g["area1"])).cpu().numpy()
+    assert np.allclose(MI[:8, :8], g["ref_cf_MI_corner"], rtol=1e-11, atol=1e-13)
+    assert np.linalg.norm(MI) == pytest.approx(float(g["ref_cf_MI_fro"]), rel=1e-12)
+
+
+def test_reference_facing_FM_to_p2p_and_p2p_to_FM(golden_fm):
+    import scipy.sparse as sp
+    from densematcher_b200.pyFM import spectral
+    g = golden_fm
+    A1 = sp.diags(g["area1"]).tocsc()
+    p21, p12, MI = spectral.FM_to_p2p(g["C_closed_form"], g["Phi1"], g["Phi2"], A1)
+    assert p21.dtype == np.int64 and MI.shape == (642, 642)
+    assert np.array_equal(p21, g["ref_cf_p2p_21"]) and np.array_equal(p12, g["ref_cf_p2p_12"])
+    assert np.array_equal(MI.argmax(1), g["ref_cf_MI_argmax1"]) and np.array_equal(MI.argmax(0), g["ref_cf_MI_argmax0"])
+    with pytest.raises(AssertionError):
+        spectral.FM_to_p2p(g["C_closed_form"], g["Phi1"][:, :5], g["Phi2"], A1)
+    p = g["ref_cf_p2p_21"]
+    assert relF(spectral.p2p_to_FM(p, g["Phi1"], g["Phi2"], A2=g["area2"]), g["ref_cf_C_area"]) < 1e-12
+    assert relF(spectral.p2p_to_FM(p, g["Phi1"], g["Phi2"], A2=sp.diags(g["area2"]).tocsc()), g["ref_cf_C_area"]) < 1e-12
+    assert relF(spectral.p2p_to_FM(p, g["Phi1"], g["Phi2"]), g["ref_cf_C_lstsq"]) < 1e-9
+    with pytest.raises(ValueError):
+        spectral.p2p_to_FM(p, g["Phi1"], g["Phi2"], A2=g["area2"][:-1])
+
+
+def test_zoomout_upstream_semantics(golden_zo):
+    from densematcher_b200.pyFM import refine
+    g = golden_zo
+    C, p = refine.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=14, step=1, A2=g["area2"], return_p2p=True)
+    assert C.shape == (26, 26) and relF(C, g["ref_C_zo"]) < 1e-11
+    assert np.array_equal(p, g["ref_p2p_zo"])
+    C, p = refine.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=9, step=(2, 3), A2=g["area2"], return_p2p=True)
+    assert C.shape == (39, 30) and relF(C, g["ref_C_zo_rect"]) < 1e-11
+    assert np.array_equal(p, g["ref_p2p_zo_rect"])
+    C = refine.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=6, step=1, A2=g["area2"],
+                              subsample=(g["sub1"], g["sub2"]))
+    assert relF(C, g["ref_C_zo_sub"]) < 1e-8
+    with pytest.raises(AssertionError):
+        refine.zoomout_refine(g["C0"], g["Phi1"], g["Phi2"], nit=40, step=1, A2=g["area2"])
+
+
+def test_batched_pairs_equal_single_pairs(fm):
+    """A ragged batch of 3 pairs through one call == three single-pair oracle runs (C and all index maps)."""
+    rng = np.random.default_rng(42)
+    meshes = []
+    for sub, scale in ((2, (1, 1.2, 0.8)), (3, (1.1, 0.9, 1.0)), (2, (0.9, 1.0, 1.3))):
+        V, F = meshgen.icosphere(sub)
+        meshes.append(meshgen.lbo_basis(meshgen.deform(V, scale, bump=0.1, phase=(0.2, 0.7)), F, 24))
+    pairs = [(0, 1), (1, 2), (2, 0)]
+    k, d = 12, 40
+    Phi1 = np.concatenate([meshes[a][1] for a, _ in pairs]); Phi2 = np.concatenate([meshes[b][1] for _, b in pairs])
+    ar1 = np.concatenate([meshes[a][2] for a, _ in pairs]); ar2 = np.concatenate([meshes[b][2] for _, b in pairs])
+    o1 = np.concatenate([[0], np.cumsum([meshes[a][1].shape[0] for a, _ in pairs])])
+    o2 = np.concatenate([[0], np.cumsum([meshes[b][1].shape[0] for _, b in pairs])])
+    F1 = meshgen.random_unit_features(int(o1[-1]), d, rng); F2 = meshgen.random_unit_features(int(o2[-1]), d, rng)
+    A = fm.project(dev(Phi1), dev(ar1), dev(F1), o1, k=k)
+    B = fm.project(dev(Phi2), dev(ar2), dev(F2), o2, k=k)
+    ev1 = np.stack([meshes[a][0][:k] for a, _ in pairs]); ev2 = np.stack([meshes[b][0][:k] for _, b in pairs])
+    c00 = np.array([orc.fmap_c00(meshes[a][1], meshes[b][1], meshes[a][2], meshes[b][2]) for a, b in pairs])
+    C = fm.fmap_solve(A, B, dev(ev1), dev(ev2), dev(c00), 1e4, 1e3)
+    out = fm.fm_to_p2p(C, dev(Phi1[:, :k]), dev(Phi2[:, :k]), dev(ar1), o1, o2)
+    Cz, pz = fm.zoomout(C, dev(Phi1), dev(Phi2), dev(ar2), nit=8, step=1, off1=o1, off2=o2, return_p2p=True)
+    for i, (a, b) in enumerate(pairs):
+        s1, s2 = slice(o1[i], o1[i + 1]), slice(o2[i], o2[i + 1])
+        Ao, Bo = orc.project(Phi1[s1], ar1[s1], F1[s1], k), orc.project(Phi2[s2], ar2[s2], F2[s2], k)
+        Co = orc.fmap_solve_closed_form(Ao, Bo, ev1[i], ev2[i], c00[i], 1e4, 1e3)
+        assert relF(C[i].cpu().numpy(), Co) < 1e-9
+        Cg = C[i].cpu().numpy()
+        p21, p12, MI = orc.fm_to_p2p(Cg, Phi1[s1, :k], Phi2[s2, :k], ar1[s1])
+        assert np.array_equal(out["p2p_21"][s2].cpu().numpy(), p21)
+        assert np.array_equal(out["p2p_12"][s1].cpu().numpy(), p12)
+        d21, d12 = orc.dense_argmax_override(MI)
+        assert np.array_equal(out["dense_21"][s2].cpu().numpy(), d21)
+        assert np.array_equal(out["dense_12"][s1].cpu().numpy(), d12)
+        Czo, pzo = orc.zoomout_refine(Cg, Phi1[s1], Phi2[s2], nit=8, step=1, A2=ar2[s2], return_p2p=True)
+        assert relF(Cz[i].cpu().numpy(), Czo) < 1e-10
+        assert np.array_equal(pz[s2].cpu().numpy(), pzo)
