@@ -336,13 +336,13 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (R.n_row < 0 || R.n_row > kMaxEpi || R.n_col < 0 || R.n_col > kMaxEpi || R.n_row + R.n_col == 0)
     DM_FAIL(DM_ERR_BADARG, "need 1..%d row and/or column epilogues", kMaxEpi);
   if (R.n_pairs == 0 || (R.total_q == 0 && R.total_db == 0)) return DM_OK;
-  if (!R.Y || !R.X || !R.q_off || !R.db_off) DM_FAIL(DM_ERR_BADARG, "null operand");
+  if ((R.total_q > 0 && !R.Y) || (R.total_db > 0 && !R.X) || !R.q_off || !R.db_off) DM_FAIL(DM_ERR_BADARG, "null operand");
   if (R.ldY < R.d || R.ldX < R.d || (R.d_fast > 0 && (R.d_fast < R.d || R.ldY < R.d_fast || R.ldX < R.d_fast)))
     DM_FAIL(DM_ERR_BADARG, "leading dimension smaller than d");
   if ((R.flags & DM_ENGINE_FFMA) && (R.flags & DM_ENGINE_TC)) DM_FAIL(DM_ERR_BADARG, "both engines forced");
   for (int e = 0; e < R.n_row + R.n_col; ++e) {
     const dm_nn_epi& E = e < R.n_row ? R.row[e] : R.col[e - R.n_row];
-    if (!E.out) DM_FAIL(DM_ERR_BADARG, "epilogue %d has no output", e);
+    if (!E.out && (e < R.n_row ? R.total_q : R.total_db) > 0) DM_FAIL(DM_ERR_BADARG, "epilogue %d has no output", e);
     if (E.scale_mode == DM_SCALE_ARRAY && !E.scale) DM_FAIL(DM_ERR_BADARG, "epilogue %d: scale array missing", e);
     if (E.bias_mode == DM_BIAS_ARRAY && !E.bias) DM_FAIL(DM_ERR_BADARG, "epilogue %d: bias array missing", e);
     if (E.scale_mode < 0 || E.scale_mode > 2 || E.bias_mode < 0 || E.bias_mode > 2)

@@ -142,7 +142,12 @@ def nn_argmax(Y: torch.Tensor, X: torch.Tensor, q_off=None, db_off=None, *, row_
         raise ValueError("need between 1 and 2 row and/or column epilogues")
     row_out = [torch.empty(total_q, dtype=out_dtype, device=dev) for _ in range(n_row)]
     col_out = [torch.empty(total_db, dtype=out_dtype, device=dev) for _ in range(n_col)]
-    if n_pairs == 0 or (total_q == 0 and total_db == 0):
+    if n_pairs == 0 or total_q == 0 or total_db == 0:
+        # nothing to search (or nothing to search in): index outputs are empty / zero, no launch
+        if total_db == 0 and total_q > 0 and n_row:
+            raise ValueError("empty database: no nearest neighbour exists")
+        for t in row_out + col_out:
+            t.zero_()
         return (row_out, col_out, (0, 0)) if return_stats else (row_out, col_out)
     keep = []
     RowArr = _lib.NNEpi * max(n_row, 1)
