@@ -49,6 +49,7 @@ SIGNATURES = {
     "dm_nn_argmax_f64": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int,
                                  C.POINTER(NNEpi), c_int, C.POINTER(NNEpi), c_int, c_int, c_vp, c_sz, c_vp]),
     "dm_nn_read_stats": (c_int, [c_vp, C.POINTER(c_i64), c_vp]),
+    "dm_nn_debug_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_nn_debug_scores_f32": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_vp,
                                        c_sz, c_vp]),
     "dm_match_dist_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),

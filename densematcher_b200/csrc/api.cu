@@ -24,6 +24,10 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) dist[row] = sqrt(s);
 }
 
+__global__ void set_single_pair_offsets(int64_t* q_off, int64_t nq, int64_t* db_off, int64_t ndb) {
+  q_off[0] = 0, q_off[1] = nq, db_off[0] = 0, db_off[1] = ndb;
+}
+
 __global__ void __launch_bounds__(256)
     cvt_f64_f32_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int d, float* __restrict__ dst,
                        int ldd) {
@@ -51,11 +55,7 @@ extern "C" {
 const char* dm_last_error(void) { return dm::last_error(); }
 int dm_version(void) { return DM_VERSION; }
 const char* dm_build_info(void) {
-  return "libdm_b200 " __DATE__ " sm_100a engines=ffma"
-#ifdef DM_HAVE_TC
-         ",tcgen05"
-#endif
-      ;
+  return "libdm_b200 " __DATE__ " sm_100a engines=tcgen05(split-bf16,default),ffma";
 }
 
 size_t dm_nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d,
@@ -90,9 +90,11 @@ size_t dm_nn_f64_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db,
   const size_t inner = dm_nn_workspace_bytes(n_pairs, total_q, total_db, max_q, max_db, d, n_row_epi, n_col_epi, flags);
   const size_t ldd = size_t((d + 3) / 4 * 4);
   Carver c(nullptr);
-  c.take<float>(size_t(total_q) * ldd);
-  c.take<float>(size_t(total_db) * ldd);
-  c.take<char>(inner);
+  c.take<char>(inner);  // first, so that dm_nn_read_stats finds the counters at the start of the workspace
+  if (!nn_use_tc(flags)) {  // the CUDA-core engine runs on fp32 copies; the tensor-core engine splits the originals
+    c.take<float>(size_t(total_q) * ldd);
+    c.take<float>(size_t(total_db) * ldd);
+  }
   return c.bytes();
 }
 
@@ -112,13 +114,16 @@ int dm_nn_argmax_f64(const double* Y, int64_t ldY, const int64_t* q_off, int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ldd = (d + 3) / 4 * 4;
   Carver c(workspace);
-  float* Yf = c.take<float>(size_t(total_q) * ldd);
-  float* Xf = c.take<float>(size_t(total_db) * ldd);
   const size_t inner = dm_nn_workspace_bytes(n_pairs, total_q, total_db, max_q, max_db, d, n_row_epi, n_col_epi, flags);
   char* inner_ws = c.take<char>(inner);
+  float *Yf = nullptr, *Xf = nullptr;
   int rc;
-  if ((rc = cvt_f64_f32(Y, ldY, total_q, d, Yf, ldd, st))) return rc;
-  if ((rc = cvt_f64_f32(X, ldX, total_db, d, Xf, ldd, st))) return rc;
+  if (!nn_use_tc(flags)) {
+    Yf = c.take<float>(size_t(total_q) * ldd);
+    Xf = c.take<float>(size_t(total_db) * ldd);
+    if ((rc = cvt_f64_f32(Y, ldY, total_q, d, Yf, ldd, st))) return rc;
+    if ((rc = cvt_f64_f32(X, ldX, total_db, d, Xf, ldd, st))) return rc;
+  }
   NNRequest R{};
   R.Y = Yf, R.ldY = ldd, R.X = Xf, R.ldX = ldd;
   R.Y64 = Y, R.ldY64 = ldY, R.X64 = X, R.ldX64 = ldX;
@@ -139,19 +144,55 @@ int dm_nn_read_stats(const void* workspace, int64_t* out_h, dm_stream_t stream) 
   out_h[0] = c[1];
   out_h[1] = c[2];
   out_h[2] = c[0];
-  out_h[3] = c[3];
+  out_h[3] = c[3];  // results that needed the full float64 scan (the others were decided between two candidates)
   return DM_OK;
+}
+
+size_t dm_nn_debug_workspace_bytes(int nq, int ndb, int d, int flags) {
+  if (nq < 0 || ndb < 0 || d <= 0) return 0;
+  Carver c(nullptr);
+  if (nn_use_tc(flags)) {
+    const size_t kp = size_t(nn_tc_kp(d));
+    c.take<int64_t>(4);
+    c.take<float>(size_t(nq));
+    c.take<float>(size_t(ndb));
+    c.take<uint16_t>(size_t(nq) * kp);
+    c.take<uint16_t>(size_t(nq) * kp);
+    c.take<uint16_t>(size_t(ndb) * kp);
+    c.take<uint16_t>(size_t(ndb) * kp);
+  }
+  return c.bytes();
 }
 
 int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, int64_t ldX, int ndb, int d,
                            float* S_out, int64_t ldS, int flags, void* workspace, size_t workspace_bytes,
                            dm_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   if (!Y || !X || !S_out || nq < 0 || ndb < 0 || d <= 0 || ldY < d || ldX < d || ldS < ndb)
     DM_FAIL(DM_ERR_BADARG, "bad argument");
-  if (flags & DM_ENGINE_TC) DM_FAIL(DM_ERR_UNSUPPORTED, "tcgen05 engine not built");
-  return nn_ffma_debug_scores(Y, ldY, nq, X, ldX, ndb, d, S_out, ldS, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!nn_use_tc(flags)) return nn_ffma_debug_scores(Y, ldY, nq, X, ldX, ndb, d, S_out, ldS, st);
+  if (nq == 0 || ndb == 0) return DM_OK;
+  const size_t need = dm_nn_debug_workspace_bytes(nq, ndb, d, flags);
+  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  const int kp = nn_tc_kp(d);
+  Carver c(workspace);
+  int64_t* off = c.take<int64_t>(4);
+  float* nqv = c.take<float>(size_t(nq));
+  float* ndv = c.take<float>(size_t(ndb));
+  uint16_t* yh = c.take<uint16_t>(size_t(nq) * kp);
+  uint16_t* yl = c.take<uint16_t>(size_t(nq) * kp);
+  uint16_t* xh = c.take<uint16_t>(size_t(ndb) * kp);
+  uint16_t* xl = c.take<uint16_t>(size_t(ndb) * kp);
+  set_single_pair_offsets<<<1, 1, 0, st>>>(off, nq, off + 2, ndb);
+  DM_LAUNCH_OK("set_single_pair_offsets");
+  int rc;
+  if ((rc = nn_prep_side(Y, 0, ldY, off, 1, nq, d, nqv, nullptr, 0, yh, yl, kp, st))) return rc;
+  if ((rc = nn_prep_side(X, 0, ldX, off + 2, 1, ndb, d, ndv, nullptr, 0, xh, xl, kp, st))) return rc;
+  NNProblem P{};
+  P.q_off = off, P.db_off = off + 2, P.total_q = nq, P.total_db = ndb, P.max_q = nq, P.max_db = ndb;
+  P.n_pairs = 1, P.d = d, P.kp = kp, P.rt_rows = kFfmaRowTile, P.max_rt = (nq + kFfmaRowTile - 1) / kFfmaRowTile;
+  return nn_tc_launch(P, yh, yl, xh, xl, S_out, ldS, st);
 }
 
 int dm_match_dist_f32(const float* Y, int64_t ldY, const float* X, int64_t ldX, const void* idx, int64_t n, int d,

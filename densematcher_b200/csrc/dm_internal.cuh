@@ -45,42 +45,48 @@ struct Carver {
   size_t bytes() const { return (off + 255) & ~size_t(255); }
 };
 
-// ---------------------------------------------------------------- top-2 tracking
-struct Top2 {
+// ---------------------------------------------------------------- top-3 tracking
+// Running (best, runner-up, third) of a candidate set: indices of the first two, value of the third.
+// The third value bounds every candidate other than i1 / i2, which is what lets the float64
+// re-evaluation look at two rows instead of the whole database (emit_result below).
+struct Top3 {
   float m1;
   int i1;
   float m2;
-  int pad;
-};
-__device__ __forceinline__ Top2 top2_init() {
-  Top2 t;
-  t.m1 = -INFINITY;
-  t.i1 = 0x7fffffff;
-  t.m2 = -INFINITY;
-  t.pad = 0;
+  int i2;
+  float m3;
+};  // 20 B: a stride of 5 words is conflict-free in shared memory
+constexpr int kNoIdx = 0x7fffffff;
+__device__ __forceinline__ Top3 top3_init() {
+  Top3 t;
+  t.m1 = t.m2 = t.m3 = -INFINITY;
+  t.i1 = t.i2 = kNoIdx;
   return t;
 }
-// candidates arrive in ascending index order inside one thread: strict '>' keeps the lowest index
-__device__ __forceinline__ void top2_push(Top2& t, float v, int idx) {
-  if (v > t.m1) {
-    t.m2 = t.m1;
-    t.m1 = v;
-    t.i1 = idx;
-  } else if (v > t.m2) {
-    t.m2 = v;
-  }
+// candidates arrive in ascending index order inside one thread: strict '>' keeps the lowest index. Branch-free.
+__device__ __forceinline__ void top3_push(Top3& t, float v, int idx) {
+  const bool c1 = v > t.m1, c2 = v > t.m2;
+  t.m3 = fmaxf(t.m3, fminf(t.m2, v));
+  t.i2 = c1 ? t.i1 : (c2 ? idx : t.i2);
+  t.m2 = fmaxf(t.m2, fminf(t.m1, v));
+  t.i1 = c1 ? idx : t.i1;
+  t.m1 = fmaxf(t.m1, v);
 }
-// union of two disjoint candidate sets; equal maxima -> lower index, and the gap becomes 0
-__device__ __forceinline__ void top2_merge(Top2& a, float bm1, int bi1, float bm2) {
-  float lo = fminf(a.m1, bm1);
-  bool takeb = (bm1 > a.m1) || (bm1 == a.m1 && bi1 < a.i1);
-  float m2 = fmaxf(fmaxf(a.m2, bm2), lo);
-  if (takeb) {
-    a.m1 = bm1;
-    a.i1 = bi1;
-  }
-  a.m2 = m2;
+// union of two disjoint candidate sets; equal values -> lower index first
+__device__ __forceinline__ void top3_merge(Top3& a, float bm1, int bi1, float bm2, int bi2, float bm3) {
+  const bool bfirst = (bm1 > a.m1) || (bm1 == a.m1 && bi1 < a.i1);
+  const float hm1 = bfirst ? bm1 : a.m1, hm2 = bfirst ? bm2 : a.m2, hm3 = bfirst ? bm3 : a.m3;
+  const int hi1 = bfirst ? bi1 : a.i1, hi2 = bfirst ? bi2 : a.i2;
+  const float lm1 = bfirst ? a.m1 : bm1, lm2 = bfirst ? a.m2 : bm2;
+  const int li1 = bfirst ? a.i1 : bi1;
+  const bool slo = (lm1 > hm2) || (lm1 == hm2 && li1 < hi2);
+  a.m1 = hm1;
+  a.i1 = hi1;
+  a.m2 = slo ? lm1 : hm2;
+  a.i2 = slo ? li1 : hi2;
+  a.m3 = slo ? fmaxf(hm2, lm2) : fmaxf(hm3, lm1);
 }
+__device__ __forceinline__ void top3_merge(Top3& a, const Top3& b) { top3_merge(a, b.m1, b.i1, b.m2, b.i2, b.m3); }
 
 __device__ __forceinline__ void store_index(void* out, int64_t pos, int v, bool i64) {
   if (i64)
@@ -111,8 +117,11 @@ struct FlagEntry {  // one result that must be re-evaluated in float64
   int pair;
   int local;  // local index of the kept-side row inside the pair
   int epi;    // epilogue number; bit 8 set = column epilogue
-  int pad;
+  int mode;   // kFlagFull: scan every candidate; kFlagCand: only c1 / c2 can be the argmax
+  int c1, c2; // local indices on the reduced-over side (kFlagCand)
+  int pad0, pad1;
 };
+constexpr int kFlagFull = 0, kFlagCand = 1;
 
 struct NNProblem {
   // fp32 operands for the fast score pass
@@ -133,6 +142,7 @@ struct NNProblem {
   int max_q, max_db;
   int n_pairs, d;
   int d_fast;  // inner dimension of the fp32 operands (>= d; extra columns are zero on the database side)
+  int kp;      // inner dimension of the bf16 split operands of the tensor-core engine (d rounded up to 64)
   int n_row, n_col;
   EpiDev row[kMaxEpi];
   EpiDev col[kMaxEpi];
@@ -142,32 +152,38 @@ struct NNProblem {
   int i64_out;
   int recheck_all;
   // scratch
-  Top2* col_partial;  // [n_col][n_pairs * max_rt][max_db]
+  Top3* col_partial;  // [n_col][n_pairs * max_rt][max_db]
   int max_rt;         // row tiles per pair upper bound
   int rt_rows;        // rows per row tile (engine dependent)
   FlagEntry* flags;
-  unsigned int* counters;  // [0] = number of flagged entries, [1] rows flagged, [2] cols flagged
+  unsigned int* counters;  // [0] = number of flagged entries, [1] rows flagged, [2] cols flagged, [3] full scans
 };
 
 // Writes the fp32-grade argmax and, when the top-2 gap is inside the rounding-error bound of the score
 // pass, queues the result for the float64 re-evaluation.  |s~ - s| <= eps |y||x||scale| + 4u(|s| + |bias|)
-// for each of the two candidates (u = 2^-24), hence the threshold below (with 2x slack on the u term).
+// for every candidate (u = 2^-24), hence the threshold below (with 2x slack on the u term).  When the
+// third-best score is outside that window only the two leaders can be the float64 argmax.
 __device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E, bool is_col, int epi, int pair,
-                                            int64_t gpos, int local, float own_norm, const Top2& s) {
-  const int idx = (s.i1 == 0x7fffffff) ? 0 : s.i1;
+                                            int64_t gpos, int local, float own_norm, const Top3& s) {
+  const int idx = (s.i1 == kNoIdx) ? 0 : s.i1;
   store_index(E.out, gpos, idx, P.i64_out != 0);
   if (P.flags == nullptr) return;
   const float thr = 2.f * P.eps * own_norm * E.G[pair] + 9.6e-7f * (fabsf(s.m1) + E.Bm[pair]);
   const bool safe = (s.m1 - s.m2) > thr;  // NaN -> not safe
   if (!safe || P.recheck_all) {
+    const bool two = !P.recheck_all && (s.m1 - s.m3) > thr && s.i2 != kNoIdx;
     const unsigned slot = atomicAdd(&P.counters[0], 1u);
     FlagEntry f;
     f.pair = pair;
     f.local = local;
     f.epi = epi | (is_col ? 256 : 0);
-    f.pad = 0;
+    f.mode = two ? kFlagCand : kFlagFull;
+    f.c1 = s.i1;
+    f.c2 = s.i2;
+    f.pad0 = f.pad1 = 0;
     P.flags[slot] = f;
     atomicAdd(&P.counters[is_col ? 2 : 1], 1u);
+    if (!two) atomicAdd(&P.counters[3], 1u);
   }
 }
 
@@ -176,6 +192,11 @@ int nn_ffma_launch(const NNProblem& P, cudaStream_t st);
 int nn_ffma_debug_scores(const float* Y, int64_t ldY, int nq, const float* X, int64_t ldX, int ndb, int d,
                          float* S, int64_t ldS, cudaStream_t st);
 constexpr int kFfmaRowTile = 128;
+// tcgen05 engine: bf16 split operands [rows, kp] prepared by nn_prep_side; dbgS != nullptr materialises the scores
+int nn_tc_kp(int d);
+int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, float* dbgS,
+                 int64_t ldS, cudaStream_t st);
+inline bool nn_use_tc(int flags) { return !(flags & DM_ENGINE_FFMA); }
 
 // shared stages (nn_common.cu)
 struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of one side
@@ -191,7 +212,7 @@ struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of
 };
 // norms + derived scale/bias + per-pair maxima for one side; M is float or double
 int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
-                 float* norm_out, const SideEpiSpec* specs, int n_specs, cudaStream_t st);
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi, void* lo, int kp, cudaStream_t st);
 int nn_col_finalize(const NNProblem& P, cudaStream_t st);
 int nn_recheck(const NNProblem& P, cudaStream_t st);
 

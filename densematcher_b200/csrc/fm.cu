@@ -164,10 +164,11 @@ int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, 
   G.C = S.emb1, G.ldc = S.lde, G.c_off = off1;
   if ((rc = gemm64_launch(G, st))) return rc;
   const int dfast = pad4(k2);
-  if ((rc = cvt_f64_f32(S.emb1, S.lde, total_n1, k2, S.Xf, S.ldf, st))) return rc;
+  const bool tc = nn_use_tc(flags);  // the tensor-core engine splits the float64 operands itself
+  if (!tc && (rc = cvt_f64_f32(S.emb1, S.lde, total_n1, k2, S.Xf, S.ldf, st))) return rc;
   // Xf columns k2..dfast must be zero: cvt writes ldf columns per row, zero beyond k2
   NNRequest R{};
-  R.Y = Phi2f, R.ldY = ldPhi2f, R.X = S.Xf, R.ldX = S.ldf;
+  R.Y = tc ? nullptr : Phi2f, R.ldY = ldPhi2f, R.X = tc ? nullptr : S.Xf, R.ldX = S.ldf;
   R.Y64 = Phi2, R.ldY64 = ld2, R.X64 = S.emb1, R.ldX64 = S.lde;
   R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
   R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = k2, R.d_fast = dfast;
@@ -321,10 +322,13 @@ int dm_fm_to_p2p(const double* C, int k1, int k2, const double* Phi1, int64_t ld
     if ((rc = gemm64_launch(G, st))) return rc;
     if ((rc = neg_half_sqnorm(emb1, k2, total_n1, k2, bias1, st))) return rc;
   }
-  if ((rc = cvt_f64_f32(emb2, k1, total_n2, k1, Yf, ldf, st))) return rc;
-  if ((rc = cvt_f64_f32(Phi1, ld1, total_n1, k1, Xf, ldf, st))) return rc;
+  const bool tc = nn_use_tc(flags);  // the tensor-core engine splits the float64 operands itself
+  if (!tc) {
+    if ((rc = cvt_f64_f32(emb2, k1, total_n2, k1, Yf, ldf, st))) return rc;
+    if ((rc = cvt_f64_f32(Phi1, ld1, total_n1, k1, Xf, ldf, st))) return rc;
+  }
   NNRequest R{};
-  R.Y = Yf, R.ldY = ldf, R.X = Xf, R.ldX = ldf;
+  R.Y = tc ? nullptr : Yf, R.ldY = ldf, R.X = tc ? nullptr : Xf, R.ldX = ldf;
   R.Y64 = emb2, R.ldY64 = k1, R.X64 = Phi1, R.ldX64 = ld1;
   R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
   R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = k1, R.d_fast = ldf;
@@ -434,7 +438,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   S.nn_ws = c.take<char>(S.nn_ws_bytes);
   const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
   int rc;
-  if ((rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
+  if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
   const double* Ccur = C0;
   int k1 = k1_0, k2 = k2_0;
   for (int it = 0; it < nit; ++it) {

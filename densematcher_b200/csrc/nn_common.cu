@@ -2,6 +2,7 @@
 // column finalisation, the float64 near-tie re-evaluation, and the driver that strings them together.
 #include <stdarg.h>
 #include <stdio.h>
+#include <cuda_bf16.h>
 #include "dm_internal.cuh"
 
 namespace dm {
@@ -49,15 +50,29 @@ struct SpecArr {
 template <typename T>
 __global__ void __launch_bounds__(256)
     prep_side_kernel(const T* __restrict__ M, int64_t ld, const int64_t* __restrict__ off, int n_pairs, int64_t total,
-                     int d, float* __restrict__ norm_out, SpecArr specs, int n_specs) {
+                     int d, float* __restrict__ norm_out, SpecArr specs, int n_specs, __nv_bfloat16* __restrict__ hi,
+                     __nv_bfloat16* __restrict__ lo, int kp) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= total) return;
   const T* r = M + row * ld;
   double s = 0.0;
-  for (int k = lane; k < d; k += 32) {
-    const double v = double(r[k]);
-    s = fma(v, v, s);
+  if (hi) {
+    // split representation for the tensor-core engine: v = hi + lo + O(2^-18 |v|), zero-padded to kp columns
+    __nv_bfloat16* h = hi + row * kp;
+    __nv_bfloat16* l = lo + row * kp;
+    for (int k = lane; k < kp; k += 32) {
+      const double v = k < d ? double(r[k]) : 0.0;
+      s = fma(v, v, s);
+      const __nv_bfloat16 vh = __float2bfloat16_rn(float(v));
+      h[k] = vh;
+      l[k] = __float2bfloat16_rn(float(v - double(__bfloat162float(vh))));
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      const double v = double(r[k]);
+      s = fma(v, v, s);
+    }
   }
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
@@ -100,12 +115,9 @@ __global__ void __launch_bounds__(256) col_finalize_kernel(const NNProblem P) {
   if (j >= nd) return;
   const int nq = int(P.q_off[p + 1] - P.q_off[p]);
   const int nrt = (nq + P.rt_rows - 1) / P.rt_rows;
-  const Top2* part = P.col_partial + ((int64_t(c) * P.n_pairs + p) * P.max_rt) * P.max_db + j;
-  Top2 m = top2_init();
-  for (int rt = 0; rt < nrt; ++rt) {
-    const Top2 o = part[int64_t(rt) * P.max_db];
-    top2_merge(m, o.m1, o.i1, o.m2);
-  }
+  const Top3* part = P.col_partial + ((int64_t(c) * P.n_pairs + p) * P.max_rt) * P.max_db + j;
+  Top3 m = top3_init();
+  for (int rt = 0; rt < nrt; ++rt) top3_merge(m, part[int64_t(rt) * P.max_db]);
   emit_result(P, P.col[c], true, c, p, d0 + j, j, P.norm_db[d0 + j], m);
 }
 
@@ -202,6 +214,7 @@ __global__ void __launch_bounds__(RC_THREADS) recheck_kernel(const NNProblem P) 
   const TX* X = static_cast<const TX*>(P.X64);
   for (unsigned f = blockIdx.x; f < count; f += gridDim.x) {
     const FlagEntry e = P.flags[f];
+    if (e.mode != kFlagFull) continue;  // block-uniform
     const int p = e.pair, epi = e.epi & 255;
     const bool is_col = (e.epi & 256) != 0;
     const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
@@ -221,10 +234,56 @@ __global__ void __launch_bounds__(RC_THREADS) recheck_kernel(const NNProblem P) 
   }
 }
 
+// Two-candidate re-evaluation: one warp per flagged result computes the two float64 scores with the same
+// rounding sequence for both (so exact duplicates tie exactly and resolve to the lower index).
+template <typename TV, typename TM>
+__device__ __forceinline__ double warp_dot64(const TV* __restrict__ v, const TM* __restrict__ r, int d, int lane) {
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) s = fma(double(v[k]), double(r[k]), s);
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+  return s;
+}
+
+template <typename TY, typename TX>
+__global__ void __launch_bounds__(256) recheck_cand_kernel(const NNProblem P) {
+  const unsigned count = P.counters[0];
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
+  const TY* Y = static_cast<const TY*>(P.Y64);
+  const TX* X = static_cast<const TX*>(P.X64);
+  for (unsigned f = warp; f < count; f += nwarp) {
+    const FlagEntry e = P.flags[f];
+    if (e.mode != kFlagCand) continue;  // warp-uniform
+    const int p = e.pair, epi = e.epi & 255;
+    const bool is_col = (e.epi & 256) != 0;
+    const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
+    const int lo = min(e.c1, e.c2), hi = max(e.c1, e.c2);
+    double vlo, vhi;
+    const EpiDev& E = is_col ? P.col[epi] : P.row[epi];
+    if (!is_col) {
+      const TY* y = Y + (q0 + e.local) * P.ldY64;
+      vlo = warp_dot64(y, X + (d0 + lo) * P.ldX64, P.d, lane);
+      vhi = warp_dot64(y, X + (d0 + hi) * P.ldX64, P.d, lane);
+      vlo = __dadd_rn(__dmul_rn(vlo, E.sd[d0 + lo]), E.bd[d0 + lo]);
+      vhi = __dadd_rn(__dmul_rn(vhi, E.sd[d0 + hi]), E.bd[d0 + hi]);
+    } else {
+      const TX* x = X + (d0 + e.local) * P.ldX64;
+      vlo = warp_dot64(x, Y + (q0 + lo) * P.ldY64, P.d, lane);
+      vhi = warp_dot64(x, Y + (q0 + hi) * P.ldY64, P.d, lane);
+      vlo = __dadd_rn(__dmul_rn(vlo, E.sd[q0 + lo]), E.bd[q0 + lo]);
+      vhi = __dadd_rn(__dmul_rn(vhi, E.sd[q0 + hi]), E.bd[q0 + hi]);
+    }
+    if (lane == 0) store_index(E.out, (is_col ? d0 : q0) + e.local, (vhi > vlo) ? hi : lo, P.i64_out != 0);
+  }
+}
+
 }  // namespace
 
 int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
-                 float* norm_out, const SideEpiSpec* specs, int n_specs, cudaStream_t st) {
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi_v, void* lo_v, int kp, cudaStream_t st) {
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(hi_v);
+  __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(lo_v);
   if (total <= 0) return DM_OK;
   SpecArr arr;
   for (int e = 0; e < kMaxEpi; ++e) arr.s[e] = specs && e < n_specs ? specs[e] : SideEpiSpec{};
@@ -236,10 +295,10 @@ int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, i
   const unsigned grid = unsigned((total + wpb - 1) / wpb);
   if (is_double)
     prep_side_kernel<double><<<grid, wpb * 32, 0, st>>>(static_cast<const double*>(M), ld, off, n_pairs, total, d,
-                                                        norm_out, arr, n_specs);
+                                                        norm_out, arr, n_specs, hi, lo, kp);
   else
     prep_side_kernel<float><<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(M), ld, off, n_pairs, total, d,
-                                                       norm_out, arr, n_specs);
+                                                       norm_out, arr, n_specs, hi, lo, kp);
   DM_LAUNCH_OK("prep_side_kernel");
   return DM_OK;
 }
@@ -273,6 +332,16 @@ int nn_recheck(const NNProblem& P, cudaStream_t st) {
     DM_RC(float, float);
 #undef DM_RC
   DM_LAUNCH_OK("recheck_kernel");
+  const int cgrid = num_sms() * 4;
+  if (P.y64_is_double && P.x64_is_double)
+    recheck_cand_kernel<double, double><<<cgrid, 256, 0, st>>>(P);
+  else if (P.y64_is_double)
+    recheck_cand_kernel<double, float><<<cgrid, 256, 0, st>>>(P);
+  else if (P.x64_is_double)
+    recheck_cand_kernel<float, double><<<cgrid, 256, 0, st>>>(P);
+  else
+    recheck_cand_kernel<float, float><<<cgrid, 256, 0, st>>>(P);
+  DM_LAUNCH_OK("recheck_cand_kernel");
   return DM_OK;
 }
 
@@ -286,12 +355,13 @@ struct NNLayout {
     double *sd, *bd;
     float *G, *Bm;
   } row[kMaxEpi], col[kMaxEpi];
-  Top2* col_partial;
+  Top3* col_partial;
   FlagEntry* flags;
+  uint16_t *yh, *yl, *xh, *xl;  // bf16 split operands of the tensor-core engine [rows, kp]
   size_t bytes;
 };
 
-int pick_rt_rows(int /*d*/, int /*flags*/) { return kFfmaRowTile; }
+int pick_rt_rows(int /*d*/, int /*flags*/) { return kFfmaRowTile; }  // both engines tile 128 query rows per CTA
 
 NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                int n_col, int flags) {
@@ -318,8 +388,16 @@ NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max
   }
   const int rt_rows = pick_rt_rows(d, flags);
   const int max_rt = (max_q + rt_rows - 1) / rt_rows;
-  L.col_partial = c.take<Top2>(size_t(n_col) * n_pairs * max_rt * max_db);
+  L.col_partial = c.take<Top3>(size_t(n_col) * n_pairs * max_rt * max_db);
   L.flags = c.take<FlagEntry>((flags & DM_NO_RECHECK) ? 0 : size_t(n_row) * total_q + size_t(n_col) * total_db);
+  L.yh = L.yl = L.xh = L.xl = nullptr;
+  if (nn_use_tc(flags)) {
+    const size_t kp = size_t(nn_tc_kp(d));
+    L.yh = c.take<uint16_t>(size_t(total_q) * kp);
+    L.yl = c.take<uint16_t>(size_t(total_q) * kp);
+    L.xh = c.take<uint16_t>(size_t(total_db) * kp);
+    L.xl = c.take<uint16_t>(size_t(total_db) * kp);
+  }
   L.bytes = c.bytes();
   return L;
 }
@@ -336,8 +414,12 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (R.n_row < 0 || R.n_row > kMaxEpi || R.n_col < 0 || R.n_col > kMaxEpi || R.n_row + R.n_col == 0)
     DM_FAIL(DM_ERR_BADARG, "need 1..%d row and/or column epilogues", kMaxEpi);
   if (R.n_pairs == 0 || (R.total_q == 0 && R.total_db == 0)) return DM_OK;
-  if ((R.total_q > 0 && !R.Y) || (R.total_db > 0 && !R.X) || !R.q_off || !R.db_off) DM_FAIL(DM_ERR_BADARG, "null operand");
-  if (R.ldY < R.d || R.ldX < R.d || (R.d_fast > 0 && (R.d_fast < R.d || R.ldY < R.d_fast || R.ldX < R.d_fast)))
+  const bool tc = nn_use_tc(R.flags);
+  // the tensor-core engine reads the float64 originals when they are given; the CUDA-core engine needs fp32 operands
+  const bool haveY = R.Y || (tc && R.Y64), haveX = R.X || (tc && R.X64);
+  if ((R.total_q > 0 && !haveY) || (R.total_db > 0 && !haveX) || !R.q_off || !R.db_off) DM_FAIL(DM_ERR_BADARG, "null operand");
+  if ((R.Y && R.ldY < R.d) || (R.X && R.ldX < R.d) || (R.Y64 && R.ldY64 < R.d) || (R.X64 && R.ldX64 < R.d) ||
+      (!tc && R.d_fast > 0 && (R.d_fast < R.d || R.ldY < R.d_fast || R.ldX < R.d_fast)))
     DM_FAIL(DM_ERR_BADARG, "leading dimension smaller than d");
   if ((R.flags & DM_ENGINE_FFMA) && (R.flags & DM_ENGINE_TC)) DM_FAIL(DM_ERR_BADARG, "both engines forced");
   for (int e = 0; e < R.n_row + R.n_col; ++e) {
@@ -372,8 +454,13 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   P.max_rt = (R.max_q + P.rt_rows - 1) / P.rt_rows;
   P.flags = (R.flags & DM_NO_RECHECK) ? nullptr : L.flags;
   P.counters = L.counters;
-  // fp32 FMA chain of length d (+ the fp32 rounding of float64 originals): gamma_d = d u / (1 - d u)
-  P.eps = float((double(R.d) + 4.0) * 5.9604644775390625e-08 * 1.01);
+  P.kp = nn_tc_kp(R.d);
+  if (tc)
+    // split-bf16 truncation 3 * 2^-18 (+5%) plus one fp32 rounding (with 2x slack) per accumulated MMA
+    P.eps = float(1.2e-5 + (3.0 * (P.kp / 16) + 2.0) * 2.384185791015625e-07);
+  else
+    // fp32 FMA chain of length d (+ the fp32 rounding of float64 originals): gamma_d = d u / (1 - d u)
+    P.eps = float((double(R.d) + 4.0) * 5.9604644775390625e-08 * 1.01);
 
   SideEpiSpec rs[kMaxEpi], cs[kMaxEpi];
   for (int e = 0; e < R.n_row; ++e) {
@@ -389,12 +476,18 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   int rc;
   if (!(R.flags & DM_SKIP_PREP)) {
     // database side carries the row epilogues' scale/bias, query side the column epilogues'
-    if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row, st)))
+    if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row,
+                           L.xh, L.xl, P.kp, st)))
       return rc;
-    if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col, st)))
+    if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col,
+                           L.yh, L.yl, P.kp, st)))
       return rc;
   }
-  if ((rc = nn_ffma_launch(P, st))) return rc;
+  if (tc) {
+    if ((rc = nn_tc_launch(P, L.yh, L.yl, L.xh, L.xl, nullptr, 0, st))) return rc;
+  } else {
+    if ((rc = nn_ffma_launch(P, st))) return rc;
+  }
   if (R.flags & DM_SKIP_FINISH) return DM_OK;
   if ((rc = nn_col_finalize(P, st))) return rc;
   if ((rc = nn_recheck(P, st))) return rc;

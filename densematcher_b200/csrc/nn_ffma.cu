@@ -104,15 +104,17 @@ __global__ void __launch_bounds__(NT, 2) nn_ffma_kernel(const NNProblem P) {
   const int64_t d0 = P.db_off[p];
   const int nd = int(P.db_off[p + 1] - d0);
 
-  __shared__ __align__(16) float smem[2 * 2 * BK * BM];  // 32 KB of tiles, re-used for the column reduction
-  __shared__ Top2 rowstate[NR > 0 ? NR : 1][BM];
-  Top2(*red)[BN] = reinterpret_cast<Top2(*)[BN]>(smem);  // [16][BN] x 16 B = 32 KB
+  // 32 KB of tiles, re-used (and sized) for the column reduction: [16][BN] x 20 B = 40 KB
+  __shared__ __align__(16) float smem[16 * BN * sizeof(Top3) / sizeof(float)];
+  static_assert(sizeof(smem) >= 2 * 2 * BK * BM * sizeof(float), "tile buffers must fit");
+  __shared__ Top3 rowstate[NR > 0 ? NR : 1][BM];
+  Top3(*red)[BN] = reinterpret_cast<Top3(*)[BN]>(smem);
 
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int lrow = t & 127;
   if (t < BM)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) rowstate[r][t] = top2_init();
+    for (int r = 0; r < NR; ++r) rowstate[r][t] = top3_init();
 
   const bool yvalid = row0 + lrow < nq;
   const float* Yrow = P.Y + (q0 + row0 + (yvalid ? lrow : 0)) * P.ldY;
@@ -136,19 +138,21 @@ __global__ void __launch_bounds__(NT, 2) nn_ffma_kernel(const NNProblem P) {
       }
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
-        Top2 s = top2_init();
+        Top3 s = top3_init();
 #pragma unroll
-        for (int b = 0; b < 8; ++b) top2_push(s, fmaf(acc[a][b], cs[b], cb[b]), col0 + sub_idx(tx, b));
+        for (int b = 0; b < 8; ++b) top3_push(s, fmaf(acc[a][b], cs[b], cb[b]), col0 + sub_idx(tx, b));
 #pragma unroll
         for (int sh = 1; sh < 16; sh <<= 1) {
           const float om1 = __shfl_xor_sync(0xffffffffu, s.m1, sh);
           const int oi1 = __shfl_xor_sync(0xffffffffu, s.i1, sh);
           const float om2 = __shfl_xor_sync(0xffffffffu, s.m2, sh);
-          top2_merge(s, om1, oi1, om2);
+          const int oi2 = __shfl_xor_sync(0xffffffffu, s.i2, sh);
+          const float om3 = __shfl_xor_sync(0xffffffffu, s.m3, sh);
+          top3_merge(s, om1, oi1, om2, oi2, om3);
         }
         if (tx == 0) {
-          Top2 cur = rowstate[r][sub_idx(ty, a)];
-          top2_merge(cur, s.m1, s.i1, s.m2);
+          Top3 cur = rowstate[r][sub_idx(ty, a)];
+          top3_merge(cur, s);
           rowstate[r][sub_idx(ty, a)] = cur;
         }
       }
@@ -167,19 +171,16 @@ __global__ void __launch_bounds__(NT, 2) nn_ffma_kernel(const NNProblem P) {
       }
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
-        Top2 s = top2_init();
+        Top3 s = top3_init();
 #pragma unroll
-        for (int a = 0; a < 8; ++a) top2_push(s, fmaf(acc[a][b], rs[a], rb[a]), row0 + sub_idx(ty, a));
+        for (int a = 0; a < 8; ++a) top3_push(s, fmaf(acc[a][b], rs[a], rb[a]), row0 + sub_idx(ty, a));
         red[ty][sub_idx(tx, b)] = s;
       }
       __syncthreads();
       if (t < BN) {
-        Top2 m = red[0][t];
+        Top3 m = red[0][t];
 #pragma unroll
-        for (int y = 1; y < 16; ++y) {
-          const Top2 o = red[y][t];
-          top2_merge(m, o.m1, o.i1, o.m2);
-        }
+        for (int y = 1; y < 16; ++y) top3_merge(m, red[y][t]);
         const int j = col0 + t;
         if (j < nd)
           P.col_partial[((int64_t(c) * P.n_pairs + p) * P.max_rt + rt) * P.max_db + j] = m;

@@ -1,0 +1,456 @@
+// tcgen05 engine of the fused similarity + argmax pass (sm_100a).
+//
+// S = Y X^T is never written.  Each CTA owns 128 query rows of one mesh pair and sweeps the pair's
+// database in tiles of 256 columns.  fp32-grade scores come from THREE bf16 tensor-core passes over a
+// split representation v = hi + lo (hi = bf16(v), lo = bf16(v - hi)):
+//     S ~= Yhi Xhi^T + Yhi Xlo^T + Ylo Xhi^T          (|error| <= 3 * 2^-18 |y||x| + accumulation)
+// accumulated in fp32 in tensor memory.  Operand tiles are staged by TMA (128-byte swizzle) through a
+// 2-stage mbarrier ring; one thread issues tcgen05.mma; the accumulator is double-buffered in TMEM
+// (2 x 256 columns) so that the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue.  An epilogue thread owns one accumulator row (TMEM lane): the row epilogues are a
+// purely sequential top-3 scan over the columns (no shuffles); the column epilogues transpose each
+// 32x32 block through a padded shared-memory patch, scan 32 rows per lane, merge the four warps in
+// shared memory and write one partial per (row tile, column) for nn_col_finalize.
+//
+// Replaces the kd-tree search of knn_query (densematcher/pyFM/spectral/nn_utils.py:28-30) and the dense
+// argmax of functional_map.py:49-50; exactness versus the float64 reference is restored by the
+// near-tie re-evaluation in nn_common.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "dm_internal.cuh"
+
+namespace dm {
+namespace {
+
+constexpr int TM_ROWS = 128;  // query rows per CTA (UMMA M)
+constexpr int TN = 256;       // database columns per accumulator tile (UMMA N)
+constexpr int TBK = 64;       // K elements per pipeline stage (one 128-byte swizzle row of bf16)
+constexpr int STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int CCH = 32;  // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
+
+constexpr uint32_t SZ_Y = TM_ROWS * TBK * 2;  // 16 KB per half
+constexpr uint32_t SZ_X = TN * TBK * 2;       // 32 KB per half
+constexpr uint32_t STAGE_BYTES = 2 * SZ_Y + 2 * SZ_X;
+constexpr uint32_t OFF_PATCH = STAGES * STAGE_BYTES;
+constexpr uint32_t PATCH_BYTES = 32 * 33 * 4;
+constexpr uint32_t OFF_COLRED = OFF_PATCH + kEpiWarps * PATCH_BYTES;            // [2][kMaxEpi][4 warps][32] Top3
+constexpr uint32_t COLRED_BYTES = 2 * kMaxEpi * kEpiWarps * CCH * sizeof(Top3);
+constexpr uint32_t OFF_ROWSB = OFF_COLRED + COLRED_BYTES;                       // [kMaxEpi][2][TN] float
+constexpr uint32_t ROWSB_BYTES = kMaxEpi * 2 * TN * 4;
+constexpr uint32_t OFF_COLSB = OFF_ROWSB + ROWSB_BYTES;                         // [kMaxEpi][2][TM_ROWS] float
+constexpr uint32_t COLSB_BYTES = kMaxEpi * 2 * TM_ROWS * 4;
+constexpr uint32_t OFF_BAR = OFF_COLSB + COLSB_BYTES;                           // mbarriers + tmem pointer
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;                           // + alignment slack
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr >> 4) & 0x3FFF);
+  d |= uint64_t(1) << 16;            // leading byte offset (unused for swizzled K-major), 16 B
+  d |= uint64_t(1024 >> 4) << 32;    // stride byte offset between 8-row groups
+  d |= uint64_t(1) << 46;            // descriptor version
+  d |= uint64_t(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+// kind::f16, A = B = bf16 (K-major), D = fp32, M = 128, N = TN
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM_ROWS >> 4) << 24);
+
+struct TcMaps {
+  CUtensorMap yh, yl, xh, xl;
+};
+
+struct DebugOut {
+  float* S;
+  int64_t ldS;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int NR, int NC, bool DEBUG>
+__global__ void __launch_bounds__(kThreads, 1)
+    nn_tc_kernel(const __grid_constant__ TcMaps maps, const NNProblem P, const DebugOut dbg) {
+  const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
+  const int64_t q0 = P.q_off[p];
+  const int nq = int(P.q_off[p + 1] - q0);
+  const int row0 = rt * TM_ROWS;
+  if (row0 >= nq) return;
+  const int64_t d0 = P.db_off[p];
+  const int nd = int(P.db_off[p + 1] - d0);
+  const int n_ct = (nd + TN - 1) / TN;
+  const int n_kc = P.kp / TBK;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_full = sbase + OFF_BAR;               // [STAGES]
+  const uint32_t bar_empty = bar_full + 8 * STAGES;        // [STAGES]
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;       // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + OFF_BAR + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.yh) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.yl) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.xh) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.xl) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      const int yrow = int(q0 + row0);
+      for (int ct = 0; ct < n_ct; ++ct) {
+        const int xrow = int(d0 + int64_t(ct) * TN);
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sb = sbase + stage * STAGE_BYTES, fb = bar_full + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_2d(sb, &maps.yh, kc * TBK, yrow, fb);
+          tma_load_2d(sb + SZ_Y, &maps.yl, kc * TBK, yrow, fb);
+          tma_load_2d(sb + 2 * SZ_Y, &maps.xh, kc * TBK, xrow, fb);
+          tma_load_2d(sb + 2 * SZ_Y + SZ_X, &maps.xl, kc * TBK, xrow, fb);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ct = 0; ct < n_ct; ++ct) {
+        const int acc = ct & 1;
+        mbar_wait(bar_tempty + 8 * acc, ((ct >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * TN;
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sb = sbase + stage * STAGE_BYTES;
+          const uint64_t dyh = umma_desc_sw128(sb), dyl = umma_desc_sw128(sb + SZ_Y);
+          const uint64_t dxh = umma_desc_sw128(sb + 2 * SZ_Y), dxl = umma_desc_sw128(sb + 2 * SZ_Y + SZ_X);
+#pragma unroll
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            const uint64_t ko = uint64_t((k * UMMA_K * 2) >> 4);  // 32 bytes per K step inside the swizzle row
+            tc_mma_bf16(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);
+            tc_mma_bf16(tacc, dyh + ko, dxl + ko, kIdesc, 1);
+            tc_mma_bf16(tacc, dyl + ko, dxh + ko, kIdesc, 1);
+          }
+          tc_commit(bar_empty + 8 * stage);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM lanes 32*(warp%4) .. +31
+    const int q = warp & 3;
+    const int trow = 32 * q + lane;  // accumulator row of this thread
+    const int et = threadIdx.x - 64;  // 0..127
+    float* patch = reinterpret_cast<float*>(sgen + OFF_PATCH + q * PATCH_BYTES);
+    Top3* colred = reinterpret_cast<Top3*>(sgen + OFF_COLRED);          // [2][kMaxEpi][4][CCH]
+    float* rowsb = reinterpret_cast<float*>(sgen + OFF_ROWSB);          // [e][0=scale,1=bias][TN]
+    float* colsb = reinterpret_cast<float*>(sgen + OFF_COLSB);          // [e][0=scale,1=bias][TM_ROWS]
+
+    Top3 rowst[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) rowst[r] = top3_init();
+
+    // per-row scale / bias of the column epilogues (fixed for the CTA)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = row0 + et;
+      const bool v = i < nq;
+      colsb[(c * 2 + 0) * TM_ROWS + et] = v ? __ldg(P.col[c].sf + q0 + i) : 0.f;
+      colsb[(c * 2 + 1) * TM_ROWS + et] = v ? __ldg(P.col[c].bf + q0 + i) : -INFINITY;
+    }
+
+    for (int ct = 0; ct < n_ct; ++ct) {
+      const int acc = ct & 1;
+      const int col0 = ct * TN;
+      // per-column scale / bias of the row epilogues for this tile
+      epi_bar_sync();  // everyone is done with the previous tile's arrays
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int h = 0; h < TN / (kEpiWarps * 32); ++h) {
+          const int jj = et + h * kEpiWarps * 32;
+          const int j = col0 + jj;
+          const bool v = j < nd;
+          rowsb[(r * 2 + 0) * TN + jj] = v ? __ldg(P.row[r].sf + d0 + j) : 0.f;
+          rowsb[(r * 2 + 1) * TN + jj] = v ? __ldg(P.row[r].bf + d0 + j) : -INFINITY;
+        }
+      epi_bar_sync();
+
+      mbar_wait(bar_tfull + 8 * acc, (ct >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * TN + (uint32_t(32 * q) << 16);
+      const int n_ch = min(TN, nd - col0 + CCH - 1) / CCH;  // chunks that hold at least one valid column
+      for (int ch = 0; ch < TN / CCH; ++ch) {
+        if (ch >= n_ch) break;  // uniform over the CTA
+        float v[32];
+        tmem_ld32(taddr + ch * CCH, v);
+        if (DEBUG) {
+          const int i = row0 + trow;
+          if (i < nq)
+#pragma unroll
+            for (int c = 0; c < CCH; ++c) {
+              const int j = col0 + ch * CCH + c;
+              if (j < nd) dbg.S[int64_t(i) * dbg.ldS + j] = v[c];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
+          const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+          const int jb = col0 + ch * CCH;
+#pragma unroll
+          for (int c4 = 0; c4 < CCH / 4; ++c4) {
+            const float4 s = s4[c4], b = b4[c4];
+            top3_push(rowst[r], fmaf(v[4 * c4 + 0], s.x, b.x), jb + 4 * c4 + 0);
+            top3_push(rowst[r], fmaf(v[4 * c4 + 1], s.y, b.y), jb + 4 * c4 + 1);
+            top3_push(rowst[r], fmaf(v[4 * c4 + 2], s.z, b.z), jb + 4 * c4 + 2);
+            top3_push(rowst[r], fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4 + 3);
+          }
+        }
+        if (NC > 0) {
+          // transpose the warp's 32x32 block: lane becomes the column, rows are scanned in ascending order
+#pragma unroll
+          for (int c = 0; c < CCH; ++c) patch[lane * 33 + c] = v[c];
+          __syncwarp();
+          Top3 cst[NC > 0 ? NC : 1];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) cst[c] = top3_init();
+          const int ib = row0 + 32 * q;
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            float s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[u] = patch[(4 * r4 + u) * 33 + lane];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const float4 sc = *reinterpret_cast<const float4*>(colsb + (c * 2 + 0) * TM_ROWS + 32 * q + 4 * r4);
+              const float4 bi = *reinterpret_cast<const float4*>(colsb + (c * 2 + 1) * TM_ROWS + 32 * q + 4 * r4);
+              top3_push(cst[c], fmaf(s[0], sc.x, bi.x), ib + 4 * r4 + 0);
+              top3_push(cst[c], fmaf(s[1], sc.y, bi.y), ib + 4 * r4 + 1);
+              top3_push(cst[c], fmaf(s[2], sc.z, bi.z), ib + 4 * r4 + 2);
+              top3_push(cst[c], fmaf(s[3], sc.w, bi.w), ib + 4 * r4 + 3);
+            }
+          }
+          const int par = ch & 1;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) colred[((par * kMaxEpi + c) * kEpiWarps + q) * CCH + lane] = cst[c];
+          epi_bar_sync();  // also orders the patch reuse of the next chunk
+          // warp c merges the four row groups of column epilogue c and writes the partial of this row tile.
+          // The merge order must be ascending in the row index: TMEM quarter q' holds rows 32 q' .. 32 q' + 31.
+          const int slot = (warp - 2);  // 0..3
+          if (slot < NC) {
+            const int j = col0 + ch * CCH + lane;
+            Top3 m = colred[((par * kMaxEpi + slot) * kEpiWarps + 0) * CCH + lane];
+#pragma unroll
+            for (int w = 1; w < kEpiWarps; ++w) top3_merge(m, colred[((par * kMaxEpi + slot) * kEpiWarps + w) * CCH + lane]);
+            if (j < nd) P.col_partial[((int64_t(slot) * P.n_pairs + p) * P.max_rt + rt) * P.max_db + j] = m;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int i = row0 + trow;
+      if (i < nq) emit_result(P, P.row[r], false, r, p, q0 + i, i, P.norm_q[q0 + i], rowst[r]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int kp, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) DM_FAIL(DM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {cuuint64_t(kp), cuuint64_t(rows > 0 ? rows : 1)};
+  const cuuint64_t gstr[1] = {cuuint64_t(kp) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(TBK), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DM_FAIL(DM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return DM_OK;
+}
+
+template <int NR, int NC, bool DEBUG>
+int launch(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    DM_CUDA_OK(cudaFuncSetAttribute(nn_tc_kernel<NR, NC, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+    attr_done = true;
+  }
+  nn_tc_kernel<NR, NC, DEBUG><<<grid, kThreads, SMEM_BYTES, st>>>(maps, P, dbg);
+  return DM_OK;
+}
+
+}  // namespace
+
+int nn_tc_kp(int d) { return (d + TBK - 1) / TBK * TBK; }
+
+int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, float* dbgS,
+                 int64_t ldS, cudaStream_t st) {
+  if (P.n_pairs <= 0 || P.total_q <= 0) return DM_OK;
+  if (P.total_q > 0x7fffffffLL || P.total_db > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
+  TcMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.yh, Yh, P.total_q, P.kp, TM_ROWS))) return rc;
+  if ((rc = make_map(&maps.yl, Yl, P.total_q, P.kp, TM_ROWS))) return rc;
+  if ((rc = make_map(&maps.xh, Xh, P.total_db, P.kp, TN))) return rc;
+  if ((rc = make_map(&maps.xl, Xl, P.total_db, P.kp, TN))) return rc;
+  const int64_t nblk = int64_t(P.n_pairs) * P.max_rt;
+  if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles (%lld)", (long long)nblk);
+  dim3 grid((unsigned)nblk);
+  DebugOut dbg{dbgS, ldS};
+  if (dbgS) {
+    if ((rc = launch<0, 0, true>(maps, P, dbg, grid, st))) return rc;
+  } else {
+    const int key = P.n_row * 10 + P.n_col;
+    switch (key) {
+      case 0 * 10 + 1: rc = launch<0, 1, false>(maps, P, dbg, grid, st); break;
+      case 0 * 10 + 2: rc = launch<0, 2, false>(maps, P, dbg, grid, st); break;
+      case 1 * 10 + 0: rc = launch<1, 0, false>(maps, P, dbg, grid, st); break;
+      case 1 * 10 + 1: rc = launch<1, 1, false>(maps, P, dbg, grid, st); break;
+      case 1 * 10 + 2: rc = launch<1, 2, false>(maps, P, dbg, grid, st); break;
+      case 2 * 10 + 0: rc = launch<2, 0, false>(maps, P, dbg, grid, st); break;
+      case 2 * 10 + 1: rc = launch<2, 1, false>(maps, P, dbg, grid, st); break;
+      case 2 * 10 + 2: rc = launch<2, 2, false>(maps, P, dbg, grid, st); break;
+      default: DM_FAIL(DM_ERR_BADARG, "unsupported epilogue combination %d row / %d col", P.n_row, P.n_col);
+    }
+    if (rc) return rc;
+  }
+  DM_LAUNCH_OK("nn_tc_kernel");
+  return DM_OK;
+}
+
+}  // namespace dm

@@ -148,7 +148,7 @@ def nn_argmax(Y: torch.Tensor, X: torch.Tensor, q_off=None, db_off=None, *, row_
             raise ValueError("empty database: no nearest neighbour exists")
         for t in row_out + col_out:
             t.zero_()
-        return (row_out, col_out, (0, 0)) if return_stats else (row_out, col_out)
+        return (row_out, col_out, (0, 0, 0)) if return_stats else (row_out, col_out)
     keep = []
     RowArr = _lib.NNEpi * max(n_row, 1)
     ColArr = _lib.NNEpi * max(n_col, 1)
@@ -166,14 +166,8 @@ def nn_argmax(Y: torch.Tensor, X: torch.Tensor, q_off=None, db_off=None, *, row_
         _lib.check(rc, "dm_nn_argmax_f64" if f64 else "dm_nn_argmax_f32")
         if return_stats:
             st = (C.c_int64 * 4)()
-            # the f64 entry carves its fp32 copies first; the counters live at the start of the inner workspace
-            off = 0
-            if f64:
-                ldd = (d + 3) // 4 * 4
-                r256 = lambda n: (n + 255) // 256 * 256
-                off = r256(total_q * ldd * 4) + r256(total_db * ldd * 4)
-            _lib.check(lib.dm_nn_read_stats(ws.data_ptr() + off, st, stream), "dm_nn_read_stats")
-            return row_out, col_out, (int(st[0]), int(st[1]))
+            _lib.check(lib.dm_nn_read_stats(ws.data_ptr(), st, stream), "dm_nn_read_stats")
+            return row_out, col_out, (int(st[0]), int(st[1]), int(st[3]))
     return row_out, col_out
 
 
@@ -181,7 +175,7 @@ def debug_scores(Y, X, flags=0):
     """The fp32-grade score matrix exactly as the selected engine accumulates it (testing aid)."""
     lib = _lib.load()
     S = torch.empty(Y.shape[0], X.shape[0], dtype=torch.float32, device=Y.device)
-    ws = default_workspace(Y.device, "dbg").get(1 << 20)
+    ws = default_workspace(Y.device, "dbg").get(max(256, lib.dm_nn_debug_workspace_bytes(Y.shape[0], X.shape[0], Y.shape[1], flags)))
     with torch.cuda.device(Y.device):
         rc = lib.dm_nn_debug_scores_f32(Y.data_ptr(), Y.stride(0), Y.shape[0], X.data_ptr(), X.stride(0), X.shape[0],
                                         Y.shape[1], S.data_ptr(), S.stride(0), flags, ws.data_ptr(), ws.numel(),

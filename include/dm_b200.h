@@ -51,8 +51,8 @@ enum {
 enum {
   DM_I64_OUT = 1 << 0,      /* index outputs are int64 instead of int32 */
   DM_NO_RECHECK = 1 << 1,   /* skip the float64 near-tie re-evaluation (results are then only fp32-grade) */
-  DM_ENGINE_FFMA = 1 << 2,  /* force the CUDA-core fp32 score kernel */
-  DM_ENGINE_TC = 1 << 3,    /* force the tcgen05 split-bf16 tensor-core score kernel */
+  DM_ENGINE_FFMA = 1 << 2,  /* force the CUDA-core fp32 score kernel (default: tcgen05 split-bf16 tensor-core kernel) */
+  DM_ENGINE_TC = 1 << 3,    /* force the tcgen05 split-bf16 tensor-core score kernel (the default) */
   DM_RECHECK_ALL = 1 << 4,  /* testing: send every row through the float64 path */
   DM_SKIP_PREP = 1 << 5,    /* profiling: reuse the operand preparation a previous identical call left in the workspace */
   DM_SKIP_FINISH = 1 << 6   /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
@@ -95,7 +95,8 @@ const char* dm_build_info(void);
  * X: database [total_db, d] (ld = ldX), pair p = rows db_off[p]..db_off[p+1]
  * max_q / max_db: upper bounds of the per-pair row counts (host knowledge; sizes the grid).
  * Up to 2 row and 2 column epilogues share one pass over S.
- * Scores are evaluated in fp32-grade arithmetic; rows whose top-2 gap is below a rigorous
+ * Scores are evaluated in fp32-grade arithmetic (three bf16 tcgen05 passes over a hi/lo split of the
+ * operands, fp32 accumulation in tensor memory); results whose top-2 gap is below a rigorous
  * rounding-error bound are re-evaluated in float64 so that the index equals the float64
  * argmax of the reference.
  * ---------------------------------------------------------------------------------------- */
@@ -111,7 +112,7 @@ int dm_nn_argmax_f32(const float* Y, int64_t ldY, const int64_t* q_off, int64_t 
 
 /* Same for float64 operands (the spectral embeddings of FM_to_p2p are float64 in the reference,
  * convert.py:134-140): the score pass runs on an fp32 copy made in the workspace, the near-tie
- * re-evaluation on the float64 originals. */
+ * re-evaluation on the float64 originals.  (The tensor-core engine splits the float64 values directly.) */
 size_t dm_nn_f64_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d,
                                  int n_row_epi, int n_col_epi, int flags);
 int dm_nn_argmax_f64(const double* Y, int64_t ldY, const int64_t* q_off, int64_t total_q, int max_q,
@@ -122,12 +123,14 @@ int dm_nn_argmax_f64(const double* Y, int64_t ldY, const int64_t* q_off, int64_t
                      int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
 
 /* counters of the last call that used `workspace`: out_h[0] = row results re-evaluated in float64,
- * out_h[1] = column results re-evaluated, out_h[2] = their sum, out_h[3] reserved.
+ * out_h[1] = column results re-evaluated, out_h[2] = their sum, out_h[3] = how many of those needed a scan of
+ * the whole candidate set (the rest were decided between the two leading candidates).
  * Synchronises the stream (diagnostics only). */
 int dm_nn_read_stats(const void* workspace, int64_t* out_h, dm_stream_t stream);
 
 /* Testing aid: materialise the fp32-grade score matrix of ONE pair as the selected engine computes it
  * (S_out [nq, ldS]); used to measure the engine's rounding error against float64. */
+size_t dm_nn_debug_workspace_bytes(int nq, int ndb, int d, int flags);
 int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, int64_t ldX, int ndb, int d,
                            float* S_out, int64_t ldS, int flags, void* workspace, size_t workspace_bytes,
                            dm_stream_t stream);
