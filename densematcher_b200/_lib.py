@@ -21,6 +21,7 @@ DM_ENGINE_TC = 1 << 3
 DM_RECHECK_ALL = 1 << 4
 DM_SKIP_PREP = 1 << 5
 DM_SKIP_FINISH = 1 << 6
+DM_F64_GEMM = 1 << 7
 SCALE_NONE, SCALE_ARRAY, SCALE_INVNORM = 0, 1, 2
 BIAS_NONE, BIAS_ARRAY, BIAS_NEG_HALF_SQNORM = 0, 1, 2
 
@@ -56,6 +57,8 @@ SIGNATURES = {
     "dm_project_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_int, c_int]),
     "dm_project": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp,
                            c_sz, c_vp]),
+    "dm_project_ex": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_int,
+                              c_vp, c_sz, c_vp]),
     "dm_fmap_solve_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_fmap_solve": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_vp, c_vp,
                               c_sz, c_vp]),

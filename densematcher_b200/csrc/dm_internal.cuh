@@ -241,6 +241,14 @@ size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int ma
                           int n_col, int flags);
 int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// tcgen05 projection engine (proj_tc.cu): out[b] = (a_scale A)^T (b_scale B[gather]) over the rows of batch b
+bool proj_tc_supported(int k, int d);
+size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d);
+int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float* Bf, const double* Bd, int64_t ldB,
+                const double* b_scale, const void* b_gather, int b_gather_i64, const int64_t* b_gather_src_off,
+                const int64_t* off, int64_t total_n, int max_n, int n_batch, int k, int d, double* out, void* ws,
+                size_t ws_bytes, cudaStream_t st);
+
 int num_sms();
 int cvt_f64_f32(const double* src, int64_t lds, int64_t rows, int d, float* dst, int ldd, cudaStream_t st);
 

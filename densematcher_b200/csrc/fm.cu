@@ -3,6 +3,7 @@
 // N x N x k score pass runs through the fused NN engine with the float64 near-tie re-evaluation.
 #include "dm_internal.cuh"
 #include "gemm64.cuh"
+#include "linalg64.cuh"
 
 namespace dm {
 namespace {
@@ -21,86 +22,190 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) out[row] = -0.5 * s;
 }
 
-// One CTA per (pair, row i of C): solve (w_d Abar Abar^T + w_l diag(Delta_i)) c = w_d Abar (B_i - c_i0 A_0)^T
-// by an in-shared-memory Cholesky factorisation (float64).
-__global__ void __launch_bounds__(256)
+// Closed-form rows of C: one 128-thread CTA per (pair, row i of C) solves
+//     (w_d Abar Abar^T + w_l diag(Delta_i)) c = w_d Abar (B_i - c_i0 A_0)^T          (n = k1 - 1 unknowns)
+// by a left-looking Cholesky factorisation held in shared memory as a packed lower triangle (40 KB at k = 100, five
+// systems resident per SM).  The right-hand side is carried as an extra matrix row n, so the forward substitution
+// falls out of the factorisation.  The k2 systems of a pair share the Gram matrix and differ only on the diagonal,
+// but there is no factorisation to share.
+// Columns are produced four at a time: each thread owns one matrix row (two beyond 128 rows) and accumulates
+// a[r][j0..j0+3] - sum_{k<j0} L[r][k] L[j0+c][k] in registers, so every L[r][k] read from shared memory feeds four
+// FMAs; the 4x4 diagonal block is then factorised redundantly by every thread (no serial owner, two block barriers
+// per four columns) and each thread finishes its own row.  Row starts r(r+1)/2 put 16 consecutive rows into 16
+// distinct 8-byte banks.  The back substitution runs in warp 0 with the unknowns in registers.
+constexpr int kSolveNB = 4;        // columns per block step
+constexpr int kSolveThreads = 128;
+
+// 1 / sqrt(v) in float64 from the fp32 hardware estimate and two Newton steps (error ~2^-52; the factorisation does
+// not need a correctly rounded square root, and this replaces a ~50-instruction sqrt + divide dependency chain).
+__device__ __forceinline__ double rsqrt64(double v) {
+  if (!(v > 1e-30 && v < 1e30)) return 1.0 / sqrt(v);  // outside the fp32 estimate's comfortable range
+  double y = double(rsqrtf(float(v)));
+  const double h = 0.5 * v;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+template <int RPT>  // rows per thread: (n + 1) <= 128 * RPT
+__global__ void __launch_bounds__(kSolveThreads)
     fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ ev1,
                       const double* __restrict__ ev2, const double* __restrict__ c00, double wd, double wl, int k1,
                       int k2, double* __restrict__ C, int* __restrict__ status) {
   extern __shared__ double sm[];
-  const int n = k1 - 1, ldm = n + 1;
-  double* Mx = sm;             // [n][ldm]
-  double* rhs = sm + n * ldm;  // [n]
-  __shared__ double s_scale;
-  __shared__ int s_bad;
-  const int b = blockIdx.x / k2, i = blockIdx.x % k2;
-  const int t = threadIdx.x;
+  constexpr int RPL = 4 * RPT;  // unknowns per lane in the single-warp back substitution
+  const int n = k1 - 1;
+  const int t = threadIdx.x, lane = t & 31;
+  const int sys = blockIdx.x;
+  double* L = sm;                                        // row r starts at r (r + 1) / 2; row n = right-hand side
+  double* Dbuf = sm + size_t(n + 1) * (n + 2) / 2;       // [2][4][4] accumulated diagonal blocks (double-buffered)
+  double* invd = Dbuf + 32;                              // [n] reciprocals of the diagonal of L
+  __shared__ double s_scale[kSolveThreads / 32];
+  const int b = sys / k2, i = sys % k2;
   const double* aat = AAt + int64_t(b) * k1 * k1;
   const double* bat = BAt + int64_t(b) * k2 * k1;
   const double* l1 = ev1 + int64_t(b) * k1;
   const double* l2 = ev2 + int64_t(b) * k2;
-  if (t == 0) {
-    double m = -INFINITY;
-    for (int j = 0; j < k1; ++j) m = fmax(m, l1[j]);
-    for (int j = 0; j < k2; ++j) m = fmax(m, l2[j]);
-    s_scale = m;
-    s_bad = 0;
-  }
+  double scale = -INFINITY;
+  for (int j = t; j < k1; j += kSolveThreads) scale = fmax(scale, l1[j]);
+  for (int j = t; j < k2; j += kSolveThreads) scale = fmax(scale, l2[j]);
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, sh));
+  if (lane == 0) s_scale[t >> 5] = scale;
   __syncthreads();
-  const double scale = s_scale;
+  scale = fmax(fmax(s_scale[0], s_scale[1]), fmax(s_scale[2], s_scale[3]));
   const double ci0 = (i == 0) ? c00[b] : 0.0;
   const double l2i = l2[i] / scale;
-  for (int e = t; e < n * n; e += blockDim.x) {
-    const int r = e / n, c = e % n;
-    double v = wd * aat[int64_t(r + 1) * k1 + (c + 1)];
-    if (r == c) {
+  const int n_tri = n * (n + 1) / 2;
+  for (int e = t; e < n_tri; e += kSolveThreads) {  // flat index over the packed triangle -> (r, c)
+    int r = int((sqrtf(8.f * float(e) + 1.f) - 1.f) * 0.5f);
+    while (r * (r + 1) / 2 > e) --r;
+    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+    const int c = e - r * (r + 1) / 2;
+    double v = wd * aat[int64_t(r + 1) * k1 + c + 1];
+    if (c == r) {
       const double df = l1[c + 1] / scale - l2i;
       v += wl * (df * df);
     }
-    Mx[r * ldm + c] = v;
+    L[e] = v;
   }
-  for (int r = t; r < n; r += blockDim.x) rhs[r] = wd * (bat[int64_t(i) * k1 + r + 1] - ci0 * aat[r + 1]);
+  for (int c = t; c < n; c += kSolveThreads) L[n_tri + c] = wd * (bat[int64_t(i) * k1 + c + 1] - ci0 * aat[c + 1]);
   __syncthreads();
-  // right-looking Cholesky, lower triangle
-  for (int j = 0; j < n; ++j) {
-    if (t == 0) {
-      const double dj = Mx[j * ldm + j];
-      if (!(dj > 0.0)) s_bad = 1;
-      Mx[j * ldm + j] = sqrt(dj);
+  bool bad = false;
+  int par = 0;
+  for (int j0 = 0; j0 < n; j0 += kSolveNB, par ^= 1) {
+    const int nb = min(kSolveNB, n - j0);
+    // rows of this block step, thread-cyclic from j0: r = j0 + t + 128 q  (row n = right-hand side included)
+    double acc[RPT][kSolveNB];
+    const double* rowr[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int r = j0 + t + kSolveThreads * q;
+      const int rc = min(r, n);
+      rowr[q] = L + size_t(rc) * (rc + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < kSolveNB; ++c) acc[q][c] = (r <= n && c < nb && j0 + c <= min(r, n - 1)) ? rowr[q][j0 + c] : 0.0;
+    }
+    const double* rowc[kSolveNB];
+#pragma unroll
+    for (int c = 0; c < kSolveNB; ++c) {
+      const int jc = min(j0 + c, n - 1);
+      rowc[c] = L + size_t(jc) * (jc + 1) / 2;
+    }
+    if (j0 + (t & ~31) <= n) {  // warps whose rows all lie beyond the matrix skip the bulk (warp-uniform)
+#pragma unroll 4
+      for (int k = 0; k < j0; ++k) {
+        double lc[kSolveNB];
+#pragma unroll
+        for (int c = 0; c < kSolveNB; ++c) lc[c] = rowc[c][k];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          const double lr = rowr[q][k];
+#pragma unroll
+          for (int c = 0; c < kSolveNB; ++c) acc[q][c] = fma(-lr, lc[c], acc[q][c]);
+        }
+      }
+    }
+    // publish the accumulated diagonal block (rows j0 .. j0+3 live in threads 0 .. 3, slot 0)
+    double* D = Dbuf + par * 16;
+    if (t < kSolveNB) {
+#pragma unroll
+      for (int c = 0; c < kSolveNB; ++c) D[t * 4 + c] = acc[0][c];
     }
     __syncthreads();
-    const double inv = 1.0 / Mx[j * ldm + j];
-    for (int r = j + 1 + t; r < n; r += blockDim.x) Mx[r * ldm + j] *= inv;
-    __syncthreads();
-    const int m = n - j - 1;
-    for (int e = t; e < m * m; e += blockDim.x) {
-      const int r = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= r) Mx[r * ldm + c] = fma(-Mx[r * ldm + j], Mx[c * ldm + j], Mx[r * ldm + c]);
+    // every thread factorises the 4x4 block: l[c][c2], c2 < c, and the reciprocal diagonal li[c]
+    double l[kSolveNB][kSolveNB], li[kSolveNB];
+#pragma unroll
+    for (int c = 0; c < kSolveNB; ++c) {
+#pragma unroll
+      for (int c2 = 0; c2 <= c; ++c2) {
+        double v = D[c * 4 + c2];
+#pragma unroll
+        for (int c3 = 0; c3 < c2; ++c3) v = fma(-l[c][c3], l[c2][c3], v);
+        if (c2 == c) {
+          if (c < nb && !(v > 0.0)) bad = true;
+          li[c] = c < nb ? rsqrt64(v) : 1.0;
+          l[c][c] = v * li[c];
+        } else {
+          l[c][c2] = c < nb ? v * li[c2] : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kSolveNB; ++c)
+      if (t == c && c < nb) invd[j0 + c] = li[c];
+    // own rows: forward substitution against the block, then store the four new entries of L
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int r = j0 + t + kSolveThreads * q;
+      if (r <= n) {
+        double* row = L + size_t(r) * (r + 1) / 2;
+        double v[kSolveNB];
+#pragma unroll
+        for (int c = 0; c < kSolveNB; ++c) {
+          double x = acc[q][c];
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) x = fma(-v[c2], l[c][c2], x);
+          v[c] = (r == j0 + c) ? l[c][c] : x * li[c];
+          if (c < nb && j0 + c <= min(r, n - 1)) row[j0 + c] = v[c];
+        }
+      }
     }
     __syncthreads();
   }
-  // forward substitution L y = rhs
-  for (int j = 0; j < n; ++j) {
-    if (t == 0) rhs[j] /= Mx[j * ldm + j];
-    __syncthreads();
-    const double yj = rhs[j];
-    for (int r = j + 1 + t; r < n; r += blockDim.x) rhs[r] = fma(-Mx[r * ldm + j], yj, rhs[r]);
-    __syncthreads();
+  if (t == 0 && bad) atomicExch(status, 1);
+  if (t >= 32) return;
+  // back substitution L^T x = y with y = row n; unknown r lives in lane r % 32, slot r / 32
+  double x[RPL];
+  {
+    const double* y = L + n_tri;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = lane + 32 * q;
+      x[q] = r < n ? y[r] : 0.0;
+    }
   }
-  // back substitution L^T x = y
   for (int j = n - 1; j >= 0; --j) {
-    if (t == 0) rhs[j] /= Mx[j * ldm + j];
-    __syncthreads();
-    const double xj = rhs[j];
-    for (int r = t; r < j; r += blockDim.x) rhs[r] = fma(-Mx[j * ldm + r], xj, rhs[r]);
-    __syncthreads();
+    const double* row = L + size_t(j) * (j + 1) / 2;
+    double xj = 0.0;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q)
+      if ((j >> 5) == q) xj = x[q];
+    xj = __shfl_sync(0xffffffffu, xj, j & 31) * invd[j];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = lane + 32 * q;
+      if (r == j) x[q] = xj;
+      else if (r < j) x[q] = fma(-row[r], xj, x[q]);
+    }
   }
   double* Ci = C + (int64_t(b) * k2 + i) * k1;
-  if (t == 0) {
-    Ci[0] = ci0;
-    if (s_bad) atomicExch(status, 1);
+  if (lane == 0) Ci[0] = ci0;
+#pragma unroll
+  for (int q = 0; q < RPL; ++q) {
+    const int r = lane + 32 * q;
+    if (r < n) Ci[r + 1] = x[q];
   }
-  for (int r = t; r < n; r += blockDim.x) Ci[r + 1] = rhs[r];
 }
 
 int neg_half_sqnorm(const double* M, int64_t ld, int64_t rows, int d, double* out, cudaStream_t st) {
@@ -186,24 +291,37 @@ using namespace dm;
 extern "C" {
 
 // ------------------------------------------------------------------ projection
-size_t dm_project_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int d) {
-  (void)total_n;
+static size_t project_f64_ws(int n_meshes, int max_n, int k, int d) {
   const int ks = (max_n + 255) / 256;
   Carver c(nullptr);
   if (ks > 1) c.take<double>(size_t(ks) * n_meshes * k * d);
   return c.bytes();
 }
 
-int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
-               const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d, double* out,
-               void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+size_t dm_project_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int d) {
+  if (n_meshes < 0 || total_n < 0 || max_n < 0 || k <= 0 || d <= 0) return 0;
+  const size_t a = project_f64_ws(n_meshes, max_n, k, d);
+  const size_t b = proj_tc_supported(k, d) ? proj_tc_workspace_bytes(n_meshes, total_n, max_n, k, d) : 0;
+  return a > b ? a : b;
+}
+
+int dm_project_ex(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
+                  const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d, double* out,
+                  int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream) {
   if (n_meshes < 0 || k <= 0 || d <= 0 || total_n < 0 || max_n < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
   if (n_meshes == 0) return DM_OK;
   if (!Phi || !area || !F || !row_off || !out) DM_FAIL(DM_ERR_BADARG, "null argument");
   if (ldPhi < k || ldF < d) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
-  const size_t need = dm_project_workspace_bytes(n_meshes, total_n, max_n, k, d);
-  if (need > workspace_bytes || (need && !workspace)) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(flags & DM_F64_GEMM) && proj_tc_supported(k, d)) {
+    const size_t need = proj_tc_workspace_bytes(n_meshes, total_n, max_n, k, d);
+    if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+    return proj_tc_run(Phi, ldPhi, area, F, nullptr, ldF, nullptr, nullptr, 0, nullptr, row_off, total_n, max_n,
+                       n_meshes, k, d, out, workspace, workspace_bytes, st);
+  }
+  const size_t need = project_f64_ws(n_meshes, max_n, k, d);
+  if (need > workspace_bytes || (need && !workspace)) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
   const int ks = (max_n + 255) / 256;
   GemmProblem G;
   G.A.d = Phi, G.A.ld = ldPhi, G.A.off = row_off, G.A.trans = 1, G.A.kscale = area;
@@ -220,6 +338,13 @@ int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float
   int rc;
   if ((rc = gemm64_launch(G, st))) return rc;
   return sum_partials_launch(part, ks, G.split_stride, G.split_stride, out, st);
+}
+
+int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
+               const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d, double* out,
+               void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  return dm_project_ex(Phi, ldPhi, area, F, ldF, row_off, total_n, max_n, n_meshes, k, d, out, 0, workspace,
+                       workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------ closed-form C
@@ -241,8 +366,8 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   const size_t need = dm_fmap_solve_workspace_bytes(n_pairs, k1, k2, d);
   if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
   const int n = k1 - 1;
-  const size_t shm = sizeof(double) * (size_t(n) * (n + 1) + n);
-  if (shm > 227 * 1024) DM_FAIL(DM_ERR_UNSUPPORTED, "k1 = %d too large for the in-shared-memory Cholesky (max ~168)", k1);
+  const size_t per = sizeof(double) * (size_t(n + 1) * (n + 2) / 2);
+  if (per > 220 * 1024 || n + 1 > 256) DM_FAIL(DM_ERR_UNSUPPORTED, "k1 = %d too large for the in-shared-memory Cholesky (max 236)", k1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Carver c(workspace);
   double* AAt = c.take<double>(size_t(n_pairs) * k1 * k1);
@@ -259,10 +384,21 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
   G.M = k2, G.maxM = k2, G.C = BAt, G.c_batch_stride = int64_t(k2) * k1;
   if ((rc = gemm64_launch(G, st))) return rc;
-  if (shm > 48 * 1024)
-    DM_CUDA_OK(cudaFuncSetAttribute(fmap_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm)));
-  fmap_solve_kernel<<<unsigned(n_pairs) * k2, 256, shm, st>>>(AAt, BAt, evals1, evals2, c00, w_descr, w_lap, k1, k2, C,
-                                                              status);
+  const size_t shm = per + (2 * 16 + size_t(n)) * sizeof(double);
+  const int64_t n_sys = int64_t(n_pairs) * k2;
+  if (n_sys > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many systems");
+#define DM_SOLVE(RPT)                                                                                              \
+  do {                                                                                                             \
+    if (shm > 48 * 1024)                                                                                           \
+      DM_CUDA_OK(cudaFuncSetAttribute(fmap_solve_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
+    fmap_solve_kernel<RPT><<<unsigned(n_sys), kSolveThreads, shm, st>>>(AAt, BAt, evals1, evals2, c00, w_descr, w_lap, k1, \
+                                                                        k2, C, status);                            \
+  } while (0)
+  if (n + 1 <= kSolveThreads)
+    DM_SOLVE(1);
+  else
+    DM_SOLVE(2);
+#undef DM_SOLVE
   DM_LAUNCH_OK("fmap_solve_kernel");
   return DM_OK;
 }
@@ -458,6 +594,104 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   if (p2p_out) {
     if ((rc = p2p21_run(nit == 0 ? C0 : C_out, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2,
                         total_n2, max_n2, n_pairs, p2p_out, flags, S, st)))
+      return rc;
+  }
+  return DM_OK;
+}
+
+// ------------------------------------------------------------------ spectral ICP
+namespace {
+struct IcpLayout {
+  double *G, *Ginv, *Phi2p, *X, *lin;
+  int* status;
+  P2P21Scratch S;
+  float* Phi2f;
+  void* p2p;
+  void* pf_ws;
+  size_t pf_bytes, bytes;
+};
+IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1, int k2,
+                    int flags) {
+  Carver c(ws);
+  IcpLayout L;
+  L.G = c.take<double>(size_t(n_pairs) * k2 * k2);
+  L.Ginv = c.take<double>(size_t(n_pairs) * k2 * k2);
+  L.Phi2p = c.take<double>(size_t(total_n2) * k2);
+  L.X = c.take<double>(size_t(n_pairs) * k2 * k1);
+  const size_t lin = spd_inverse_scratch_doubles(k2) > polar_scratch_doubles(k2, k1) ? spd_inverse_scratch_doubles(k2)
+                                                                                     : polar_scratch_doubles(k2, k1);
+  L.lin = c.take<double>(lin * n_pairs);
+  L.status = c.take<int>(4);
+  L.S.lde = k2, L.S.ldf = pad4(k2);
+  L.S.emb1 = c.take<double>(size_t(total_n1) * k2);
+  const bool tc = nn_use_tc(flags);
+  L.S.Xf = c.take<float>(tc ? 0 : size_t(total_n1) * L.S.ldf);
+  L.Phi2f = c.take<float>(tc ? 0 : size_t(total_n2) * L.S.ldf);
+  L.p2p = c.take<int64_t>(size_t(total_n2));
+  const int k = k1 > k2 ? k1 : k2;
+  L.pf_bytes = p2p_to_fm_ws(n_pairs, max_n2, k, k2);
+  L.pf_ws = c.take<char>(L.pf_bytes);
+  L.S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2, 1, 0, flags);
+  L.S.nn_ws = c.take<char>(L.S.nn_ws_bytes);
+  L.bytes = c.bytes();
+  return L;
+}
+}  // namespace
+
+size_t dm_icp_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1, int k2,
+                              int flags) {
+  if (n_pairs < 0 || total_n1 < 0 || total_n2 < 0 || k1 <= 0 || k2 <= 0) return 0;
+  return icp_carve(nullptr, n_pairs, total_n1, total_n2, max_n1, max_n2, k1, k2, flags).bytes;
+}
+
+int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_t ld1, const int64_t* off1,
+           int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2,
+           int max_n2, int n_pairs, double* C_out, void* p2p_out, int flags, void* workspace, size_t workspace_bytes,
+           dm_stream_t stream) {
+  if (n_pairs < 0 || k1 <= 0 || k2 <= 0 || nit < 0 || total_n1 < 0 || total_n2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0) return DM_OK;
+  if (!C0 || !Phi1 || !Phi2 || !off1 || !off2 || !C_out) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ld1 < k1 || ld2 < k2) DM_FAIL(DM_ERR_BADARG, "eigenbasis has fewer columns than the functional map");
+  if (!workspace) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  IcpLayout L = icp_carve(workspace, n_pairs, total_n1, total_n2, max_n1, max_n2, k1, k2, flags);
+  if (L.bytes > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", L.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
+  int rc;
+  DM_CUDA_OK(cudaMemsetAsync(L.status, 0, 4 * sizeof(int), st));
+  if (nit > 0) {
+    // lstsq(Phi2, Phi1[p]) = (Phi2 G^-1)^T Phi1[p] with G = Phi2^T Phi2, factorised once   (icp.py:38 -> convert.py:51)
+    if ((rc = p2p_to_fm_run(nullptr, 0, Phi2, ld2, off2, Phi2, ld2, off2, max_n2, nullptr, n_pairs, k2, k2, L.G, L.pf_ws,
+                            st)))
+      return rc;
+    if ((rc = spd_inverse_launch(L.G, L.Ginv, k2, n_pairs, L.lin, L.status, st))) return rc;
+    GemmProblem G;
+    G.A.d = Phi2, G.A.ld = ld2, G.A.off = off2, G.A.trans = 0;
+    G.B.d = L.Ginv, G.B.ld = k2, G.B.batch_stride = int64_t(k2) * k2, G.B.rows = k2, G.B.trans = 0;
+    G.N = k2, G.K = k2, G.maxM = max_n2, G.maxN = k2, G.maxK = k2, G.n_batch = n_pairs;
+    G.C = L.Phi2p, G.ldc = k2, G.c_off = off2;
+    if ((rc = gemm64_launch(G, st))) return rc;
+  }
+  if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2, L.Phi2f, L.S.ldf, st))) return rc;
+  const double* Ccur = C0;
+  for (int it = 0; it < nit; ++it) {
+    // p = p2p_21(C)  (icp.py:37; the other two outputs of FM_to_p2p are discarded there)
+    if ((rc = p2p21_run(Ccur, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, L.Phi2f, L.S.ldf, off2, total_n2,
+                        max_n2, n_pairs, L.p2p, flags, L.S, st)))
+      return rc;
+    if ((rc = p2p_to_fm_run(L.p2p, i64, Phi1, ld1, off1, L.Phi2p, k2, off2, max_n2, nullptr, n_pairs, k1, k2, L.X,
+                            L.pf_ws, st)))
+      return rc;
+    // C <- U I V^T  (icp.py:39-40)
+    if ((rc = polar_factor_launch(L.X, C_out, k2, k1, n_pairs, L.lin, st))) return rc;
+    Ccur = C_out;
+  }
+  if (nit == 0)
+    DM_CUDA_OK(cudaMemcpyAsync(C_out, C0, sizeof(double) * size_t(n_pairs) * k1 * k2, cudaMemcpyDeviceToDevice, st));
+  if (p2p_out) {
+    if ((rc = p2p21_run(nit == 0 ? C0 : C_out, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, L.Phi2f, L.S.ldf,
+                        off2, total_n2, max_n2, n_pairs, p2p_out, flags, L.S, st)))
       return rc;
   }
   return DM_OK;

@@ -1,16 +1,23 @@
+// Batched / ragged float64 GEMM on the CUDA-core FP64 pipe (see gemm64.cuh for the operand model).
+//
+// 128 x 128 output tile per 256-thread CTA, 8 x 8 accumulators per thread (two 4-wide groups per dimension so that the
+// shared-memory reads are 16-byte vectors: the A fragment is a warp broadcast, the B fragment 512 contiguous bytes),
+// K advanced 8 at a time through a double-buffered shared-memory stage with the next stage's global loads issued into
+// registers before the current stage is consumed.  64 FMAs per 8 shared-memory doubles per thread keeps the kernel on
+// the FP64 pipe rather than on shared-memory bandwidth.
 #include "gemm64.cuh"
 
 namespace dm {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 128, TN = 128, TK = 8, NT = 256;
+constexpr int LDT = TM + 2;  // padded row of a stage (keeps 16-byte alignment, spreads the transposing stores)
+static_assert(TM == TN, "loader assumes square tiles");
 
 struct OpView {  // an operand resolved for one batch
   const double* d;
   const float* f;
   int64_t ld;
-  int col0;
-  int trans;
   const void* gather;
   int gather_i64;
   int64_t gbase;
@@ -20,32 +27,16 @@ struct OpView {  // an operand resolved for one batch
 __device__ __forceinline__ OpView resolve(const GemmOperand& o, int b) {
   OpView v;
   const int64_t row0 = o.off ? o.off[b] : 0;
-  const int64_t base = (o.off ? 0 : int64_t(b) * o.batch_stride) + row0 * o.ld;
+  const int64_t base = (o.off ? 0 : int64_t(b) * o.batch_stride) + row0 * o.ld + o.col0;
   v.d = o.d ? o.d + base : nullptr;
   v.f = o.f ? o.f + base : nullptr;
   v.ld = o.ld;
-  v.col0 = o.col0;
-  v.trans = o.trans;
   v.gather = o.gather;
   v.gather_i64 = o.gather_i64;
   v.gbase = o.gather_off ? o.gather_off[b] : 0;
   const int64_t kbase = o.gather_off ? o.gather_off[b] : row0;
   v.kscale = o.kscale ? o.kscale + kbase : nullptr;
   return v;
-}
-
-__device__ __forceinline__ double op_load(const OpView& v, int i, int k) {
-  int64_t r, c;
-  if (v.trans == 0) {
-    r = i;
-    c = v.col0 + k;
-  } else {
-    r = v.gather ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : k;
-    c = v.col0 + i;
-  }
-  double x = v.d ? v.d[r * v.ld + c] : double(v.f[r * v.ld + c]);
-  if (v.trans == 1 && v.kscale) x *= v.kscale[k];
-  return x;
 }
 
 __device__ __forceinline__ int ragged_k(const GemmOperand& o, int b) {
@@ -55,7 +46,69 @@ __device__ __forceinline__ int ragged_k(const GemmOperand& o, int b) {
   return -1;
 }
 
-__global__ void __launch_bounds__(256) gemm64_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
+// The four elements of a TM x TK operand tile one thread moves per stage.
+//   TRANS = false: element(i, k) = Mat[i][k]   -> thread owns k = t % 8 of rows i = t / 8 + 32 e
+//   TRANS = true : element(i, k) = Mat[k][i]   -> thread owns i = t % 128 of contraction rows k = t / 128 + 2 e
+// Raw registers of one stage: nothing here consumes a loaded value, so the loads stay in flight while the previous
+// stage is being multiplied (any arithmetic on them would stall the in-order warp on the memory latency).
+struct Staged {
+  double d[4];
+  float f[4];
+  double s[4];
+};
+
+template <bool TRANS>
+struct Loader {
+  const OpView& v;
+  int i0, lim;  // first output index of the tile, number of valid output indices (M or N)
+  int t;
+  __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {}
+
+  __device__ __forceinline__ void fetch(int k0, int kend, Staged& r) const {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int i, k;
+      if (!TRANS) {
+        k = k0 + (t & 7);
+        i = i0 + (t >> 3) + 32 * e;
+      } else {
+        i = i0 + (t & 127);
+        k = k0 + (t >> 7) + 2 * e;
+      }
+      r.d[e] = 0.0, r.f[e] = 0.f, r.s[e] = 1.0;
+      if (i < lim && k < kend) {
+        int64_t idx;
+        if (!TRANS) {
+          idx = int64_t(i) * v.ld + k;
+        } else {
+          const int64_t row = v.gather ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : k;
+          idx = row * v.ld + i;
+        }
+        if (v.d)
+          r.d[e] = __ldg(v.d + idx);
+        else
+          r.f[e] = __ldg(v.f + idx);
+        if (TRANS && v.kscale) r.s[e] = __ldg(v.kscale + k);
+      }
+    }
+  }
+  __device__ __forceinline__ void stash(double* stage, const Staged& r) const {
+    const bool is_d = v.d != nullptr;
+    const bool scaled = TRANS && v.kscale != nullptr;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double x = is_d ? r.d[e] : double(r.f[e]);
+      if (scaled) x *= r.s[e];
+      if (!TRANS)
+        stage[(t & 7) * LDT + (t >> 3) + 32 * e] = x;
+      else
+        stage[((t >> 7) + 2 * e) * LDT + (t & 127)] = x;
+    }
+  }
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
   int bid = blockIdx.x;
   const int tn = bid % tiles_n;
   bid /= tiles_n;
@@ -64,8 +117,8 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const GemmProblem P, int ti
   const int ks = bid % P.ksplit;
   const int b = bid / P.ksplit;
 
-  const int M = (P.A.trans == 0 && P.A.off) ? int(P.A.off[b + 1] - P.A.off[b]) : P.M;
-  const int N = (P.B.trans == 0 && P.B.off) ? int(P.B.off[b + 1] - P.B.off[b]) : P.N;
+  const int M = (!TA && P.A.off) ? int(P.A.off[b + 1] - P.A.off[b]) : P.M;
+  const int N = (!TB && P.B.off) ? int(P.B.off[b + 1] - P.B.off[b]) : P.N;
   int K = ragged_k(P.A, b);
   if (K < 0) K = ragged_k(P.B, b);
   if (K < 0) K = P.K;
@@ -77,64 +130,71 @@ __global__ void __launch_bounds__(256) gemm64_kernel(const GemmProblem P, int ti
     kend = min(K, kbeg + P.kchunk);
   }
 
-  __shared__ double As[TK][TM + 1];
-  __shared__ double Bs[TK][TN + 1];
+  __shared__ __align__(16) double As[2][TK * LDT];
+  __shared__ __align__(16) double Bs[2][TK * LDT];
   const OpView A = resolve(P.A, b), B = resolve(P.B, b);
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+  const Loader<TA> la(A, m0, M, t);
+  const Loader<TB> lb(B, n0, N, t);
 
-  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+  double acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = t + 256 * i;
-      int mm, kk;
-      if (A.trans == 0) {
-        kk = e % TK;
-        mm = e / TK;
-      } else {
-        mm = e % TM;
-        kk = e / TM;
-      }
-      As[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? op_load(A, m0 + mm, k0 + kk) : 0.0;
-      int nn;
-      if (B.trans == 0) {
-        kk = e % TK;
-        nn = e / TK;
-      } else {
-        nn = e % TN;
-        kk = e / TN;
-      }
-      Bs[kk][nn] = (n0 + nn < N && k0 + kk < kend) ? op_load(B, n0 + nn, k0 + kk) : 0.0;
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0;
+
+  Staged ra, rb;
+  if (kbeg < kend) {
+    la.fetch(kbeg, kend, ra);
+    lb.fetch(kbeg, kend, rb);
+    la.stash(As[0], ra);
+    lb.stash(Bs[0], rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+    const bool more = k0 + TK < kend;
+    if (more) {
+      la.fetch(k0 + TK, kend, ra);
+      lb.fetch(k0 + TK, kend, rb);
     }
-    __syncthreads();
+    const double* as = As[buf];
+    const double* bs = Bs[buf];
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      double av[4], bv[4];
+      double av[8], bv[8];
+      const double2 a0 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4);
+      const double2 a1 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4 + 2);
+      const double2 a2 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4);
+      const double2 a3 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4 + 2);
+      const double2 b0 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4);
+      const double2 b1 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4 + 2);
+      const double2 b2 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4);
+      const double2 b3 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4 + 2);
+      av[0] = a0.x, av[1] = a0.y, av[2] = a1.x, av[3] = a1.y, av[4] = a2.x, av[5] = a2.y, av[6] = a3.x, av[7] = a3.y;
+      bv[0] = b0.x, bv[1] = b0.y, bv[2] = b1.x, bv[3] = b1.y, bv[4] = b2.x, bv[5] = b2.y, bv[6] = b3.x, bv[7] = b3.y;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = Bs[k][tx * 4 + c];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+        for (int c = 0; c < 8; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+    }
+    if (more) {
+      la.stash(As[buf ^ 1], ra);
+      lb.stash(Bs[buf ^ 1], rb);
     }
     __syncthreads();
+    buf ^= 1;
   }
 
   double* C = P.C + int64_t(ks) * P.split_stride + (P.c_off ? P.c_off[b] * P.ldc : int64_t(b) * P.c_batch_stride);
   const double* cs = P.c_colscale ? P.c_colscale + (P.c_colscale_off ? P.c_colscale_off[b] : 0) : nullptr;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int m = m0 + ty * 4 + a;
+  for (int a = 0; a < 8; ++a) {
+    const int m = m0 + (a >> 2) * 64 + ty * 4 + (a & 3);
     if (m >= M) continue;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n = n0 + tx * 4 + c;
+    for (int c = 0; c < 8; ++c) {
+      const int n = n0 + (c >> 2) * 64 + tx * 4 + (c & 3);
       if (n >= N) continue;
       double v = P.alpha * acc[a][c];
       if (cs) v *= cs[n];
@@ -161,7 +221,15 @@ int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
   if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "gemm64: grid too large");
   GemmProblem Q = P;
   if (Q.ksplit < 1) Q.ksplit = 1;
-  gemm64_kernel<<<unsigned(nblk), 256, 0, st>>>(Q, tiles_m, tiles_n);
+  const unsigned grid = unsigned(nblk);
+  if (Q.A.trans && Q.B.trans)
+    gemm64_kernel<true, true><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+  else if (Q.A.trans)
+    gemm64_kernel<true, false><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+  else if (Q.B.trans)
+    gemm64_kernel<false, true><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+  else
+    gemm64_kernel<false, false><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
   DM_LAUNCH_OK("gemm64_kernel");
   return DM_OK;
 }

@@ -1,0 +1,214 @@
+// Batched float64 dense linear algebra of the spectral ICP step, one CTA per mesh pair.
+//
+//   spd_inverse : G^-1 of the Gram matrix Phi2^T Phi2 (Cholesky + two triangular solves per unit vector); it turns the
+//                 least squares of icp.py:38 / convert.py:51, lstsq(Phi2, Phi1[p]), into one contraction
+//                 (Phi2 G^-1)^T Phi1[p] per iteration (differs from LAPACK gelsd by ~3e-15).
+//   polar_factor: U I V^T of the SVD (icp.py:39-40) through a one-sided Jacobi iteration with a round-robin
+//                 ordering: every warp orthogonalises one column pair per step.
+//
+// The matrices live in shared memory when they fit (k up to ~110 for the polar factor) and in an L2-resident
+// global scratch otherwise; the code is the same through generic pointers.
+#include "linalg64.cuh"
+
+namespace dm {
+namespace {
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ SPD inverse
+__global__ void __launch_bounds__(256)
+    spd_inverse_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int n, double* scratch, size_t per,
+                       int use_smem, int* status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int ldl = n + 1;
+  double* L = use_smem ? sm : scratch + size_t(b) * per;  // [n][ldl]
+  double* Z = L + size_t(n) * ldl;                         // [n][n]
+  const double* g = G + size_t(b) * n * n;
+  __shared__ int s_bad;
+  if (t == 0) s_bad = 0;
+  for (int e = t; e < n * n; e += blockDim.x) L[(e / n) * ldl + (e % n)] = g[e];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {  // right-looking Cholesky, lower triangle
+    if (t == 0) {
+      const double dj = L[j * ldl + j];
+      if (!(dj > 0.0)) s_bad = 1;
+      L[j * ldl + j] = sqrt(dj);
+    }
+    __syncthreads();
+    const double inv = 1.0 / L[j * ldl + j];
+    for (int r = j + 1 + t; r < n; r += blockDim.x) L[r * ldl + j] *= inv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int r = j + 1 + (t >> 4); r < n; r += (blockDim.x >> 4)) {
+      const double lr = L[r * ldl + j];
+      for (int c = j + 1 + (t & 15); c <= r; c += 16) L[r * ldl + c] = fma(-lr, L[c * ldl + j], L[r * ldl + c]);
+    }
+    (void)m;
+    __syncthreads();
+  }
+  // column c of the inverse: L y = e_c, L^T x = y   (thread c; reads of L are warp broadcasts)
+  for (int c = t; c < n; c += blockDim.x) {
+    for (int j = 0; j < c; ++j) Z[j * n + c] = 0.0;
+    for (int j = c; j < n; ++j) {
+      double s = (j == c) ? 1.0 : 0.0;
+      for (int i = c; i < j; ++i) s = fma(-L[j * ldl + i], Z[i * n + c], s);
+      Z[j * n + c] = s / L[j * ldl + j];
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      double s = Z[j * n + c];
+      for (int i = j + 1; i < n; ++i) s = fma(-L[i * ldl + j], Z[i * n + c], s);
+      Z[j * n + c] = s / L[j * ldl + j];
+    }
+  }
+  __syncthreads();
+  double* out = Ginv + size_t(b) * n * n;
+  // symmetrise: the two triangles agree to rounding; average them so that Ginv is exactly symmetric
+  for (int e = t; e < n * n; e += blockDim.x) {
+    const int r = e / n, c = e % n;
+    out[e] = 0.5 * (Z[r * n + c] + Z[c * n + r]);
+  }
+  if (t == 0 && s_bad) atomicExch(status, 1);
+}
+
+// ------------------------------------------------------------------------------------------ polar factor
+__global__ void __launch_bounds__(1024)
+    polar_kernel(const double* X, double* C, int rows, int cols, double* scratch, size_t per, int use_smem) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  const bool tr = rows < cols;  // iterate on X^T so that the orthogonalised columns are the long ones
+  const int m = tr ? cols : rows, n = tr ? rows : cols;
+  double* W = use_smem ? sm : scratch + size_t(b) * per;  // [n][m] columns of the working matrix
+  double* J = W + size_t(n) * m;                           // [n][n] columns of the accumulated rotations
+  double* sig = J + size_t(n) * n;                         // [n]
+  const double* x = X + size_t(b) * rows * cols;
+  double* cout = C + size_t(b) * rows * cols;
+  __shared__ int s_rot;
+  for (int e = t; e < n * m; e += blockDim.x) {
+    const int c = e / m, r = e % m;
+    W[e] = tr ? x[size_t(c) * cols + r] : x[size_t(r) * cols + c];
+  }
+  for (int e = t; e < n * n; e += blockDim.x) J[e] = (e / n == e % n) ? 1.0 : 0.0;
+  if (t == 0) s_rot = 0;
+  __syncthreads();
+  const int np = (n + 1) & ~1;
+  const double tol = sqrt(double(m)) * 2.220446049250313e-16;
+  for (int sweep = 0; sweep < 40 && n > 1; ++sweep) {
+    for (int step = 0; step < np - 1; ++step) {
+      for (int pr = warp; pr < np / 2; pr += nwarps) {
+        int p, q;
+        if (pr == 0) {
+          p = np - 1;
+          q = step;
+        } else {
+          p = (step + pr) % (np - 1);
+          q = (step + np - 1 - pr) % (np - 1);
+        }
+        if (p >= n || q >= n) continue;  // the bye of an odd column count
+        if (p > q) {
+          const int s = p;
+          p = q;
+          q = s;
+        }
+        double* wp = W + size_t(p) * m;
+        double* wq = W + size_t(q) * m;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int r = lane; r < m; r += 32) {
+          const double a = wp[r], c = wq[r];
+          al = fma(a, a, al);
+          be = fma(c, c, be);
+          ga = fma(a, c, ga);
+        }
+        al = warp_sum(al), be = warp_sum(be), ga = warp_sum(ga);
+        if (ga != 0.0 && fabs(ga) > tol * sqrt(al * be)) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+          for (int r = lane; r < m; r += 32) {
+            const double a = wp[r], c = wq[r];
+            wp[r] = cs * a - sn * c;
+            wq[r] = sn * a + cs * c;
+          }
+          double* jp = J + size_t(p) * n;
+          double* jq = J + size_t(q) * n;
+          for (int r = lane; r < n; r += 32) {
+            const double a = jp[r], c = jq[r];
+            jp[r] = cs * a - sn * c;
+            jq[r] = sn * a + cs * c;
+          }
+          if (lane == 0) s_rot = 1;
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (!rot) break;
+    if (t == 0) s_rot = 0;
+    __syncthreads();
+  }
+  for (int i = warp; i < n; i += nwarps) {
+    double s = 0.0;
+    for (int r = lane; r < m; r += 32) s = fma(W[size_t(i) * m + r], W[size_t(i) * m + r], s);
+    s = warp_sum(s);
+    if (lane == 0) sig[i] = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+  }
+  __syncthreads();
+  // P = sum_i (w_i / sigma_i) j_i^T  (m x n);  C = P or P^T
+  for (int e = t; e < m * n; e += blockDim.x) {
+    const int r = e % m, c = e / m;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = fma(W[size_t(i) * m + r] * sig[i], J[size_t(i) * n + c], s);
+    if (tr)
+      cout[size_t(c) * cols + r] = s;
+    else
+      cout[size_t(r) * cols + c] = s;
+  }
+}
+
+size_t spd_doubles(int n) { return size_t(n) * (n + 1) + size_t(n) * n; }
+size_t polar_doubles(int rows, int cols) {
+  const int m = rows > cols ? rows : cols, n = rows > cols ? cols : rows;
+  return size_t(n) * m + size_t(n) * n + size_t(n);
+}
+
+}  // namespace
+
+size_t spd_inverse_scratch_doubles(int n) { return spd_doubles(n) * 8 > kSmemBudget ? spd_doubles(n) : 0; }
+size_t polar_scratch_doubles(int rows, int cols) {
+  return polar_doubles(rows, cols) * 8 > kSmemBudget ? polar_doubles(rows, cols) : 0;
+}
+
+int spd_inverse_launch(const double* G, double* Ginv, int n, int n_batch, double* scratch, int* status, cudaStream_t st) {
+  if (n_batch <= 0 || n <= 0) return DM_OK;
+  const size_t per = spd_doubles(n), bytes = per * 8;
+  const int use_smem = bytes <= kSmemBudget;
+  if (!use_smem && !scratch) DM_FAIL(DM_ERR_WORKSPACE, "spd_inverse: scratch missing");
+  if (use_smem && bytes > 48 * 1024)
+    DM_CUDA_OK(cudaFuncSetAttribute(spd_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
+  spd_inverse_kernel<<<n_batch, 256, use_smem ? bytes : 0, st>>>(G, Ginv, n, scratch, per, use_smem, status);
+  DM_LAUNCH_OK("spd_inverse_kernel");
+  return DM_OK;
+}
+
+int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, cudaStream_t st) {
+  if (n_batch <= 0 || rows <= 0 || cols <= 0) return DM_OK;
+  const size_t per = polar_doubles(rows, cols), bytes = per * 8;
+  const int use_smem = bytes <= kSmemBudget;
+  if (!use_smem && !scratch) DM_FAIL(DM_ERR_WORKSPACE, "polar_factor: scratch missing");
+  if (use_smem && bytes > 48 * 1024)
+    DM_CUDA_OK(cudaFuncSetAttribute(polar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
+  const int n = rows < cols ? rows : cols;
+  const int threads = n >= 48 ? 1024 : (n >= 16 ? 256 : 64);
+  polar_kernel<<<n_batch, threads, use_smem ? bytes : 0, st>>>(X, C, rows, cols, scratch, per, use_smem);
+  DM_LAUNCH_OK("polar_kernel");
+  return DM_OK;
+}
+
+}  // namespace dm

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .nn import Workspace, as_offsets, default_workspace
+from .nn import Offsets, Workspace, as_offsets, default_workspace
 
 __all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "PairBatch"]
 
@@ -35,15 +35,20 @@ def _offsets(off, total, dev):
     """-> (device offsets, host offsets, max rows)."""
     if off is None:
         off = [0, total]
+    if isinstance(off, Offsets):
+        if off.host[0] != 0 or off.host[-1] != total:
+            raise ValueError("offsets do not cover the rows")
+        return off.dev, off.host, off.max
     od, oh = as_offsets(off, dev)
     if oh[0] != 0 or oh[-1] != total or np.any(np.diff(oh) < 0):
         raise ValueError("offsets do not cover the rows")
     return od, oh, int(np.diff(oh).max()) if len(oh) > 1 else 0
 
 
-def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = None):
+def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = None, flags: int = 0):
     """out[m] = Phi_m[:, :k]^T diag(area_m) F_m -> [n_meshes, k, d] float64.
-    (optimize/base_functions.py:526-532; TriMesh.project mesh/trimesh.py:533-556)"""
+    (optimize/base_functions.py:526-532; TriMesh.project mesh/trimesh.py:533-556)
+    Default: tcgen05 split-bf16 engine (fp32-grade, rel. error ~1e-6); ``flags=_lib.DM_F64_GEMM`` for float64."""
     lib = _lib.load()
     dev = Phi.device
     Phi, area = _f64(Phi), _f64(area)
@@ -62,9 +67,10 @@ def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = Non
     need = lib.dm_project_workspace_bytes(n_m, total, max_n, k, d)
     ws = (workspace or default_workspace(dev, "fm")).get(max(need, 256))
     with torch.cuda.device(dev):
-        rc = lib.dm_project(Phi.data_ptr(), Phi.stride(0), area.data_ptr(), F.data_ptr(), F.stride(0), od.data_ptr(),
-                            total, max_n, n_m, k, d, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
-    _lib.check(rc, "dm_project")
+        rc = lib.dm_project_ex(Phi.data_ptr(), Phi.stride(0), area.data_ptr(), F.data_ptr(), F.stride(0),
+                               od.data_ptr(), total, max_n, n_m, k, d, out.data_ptr(), int(flags), ws.data_ptr(),
+                               ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_project_ex")
     return out
 
 

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["Epi", "COSINE_UNIT", "COSINE", "EUCLID", "nn_argmax", "debug_scores", "match_dist", "Workspace",
-           "as_offsets"]
+           "as_offsets", "Offsets"]
 
 
 @dataclass
@@ -61,8 +61,22 @@ def default_workspace(device, key="nn"):
     return _default_ws[k]
 
 
+class Offsets:
+    """Row offsets of a ragged batch known on both sides: int64 device tensor + host copy (+ the largest
+    segment).  Passing one avoids a host->device copy of the offsets in every call."""
+
+    def __init__(self, dev: torch.Tensor, host: np.ndarray):
+        self.dev, self.host = dev, np.ascontiguousarray(np.asarray(host, dtype=np.int64))
+        self.max = int(np.diff(self.host).max()) if len(self.host) > 1 else 0
+
+    def __len__(self):
+        return len(self.host)
+
+
 def as_offsets(off, device):
     """-> (int64 device tensor [n+1], host numpy int64 [n+1])."""
+    if isinstance(off, Offsets):
+        return off.dev, off.host
     off_h = np.ascontiguousarray(np.asarray(off, dtype=np.int64))
     return torch.from_numpy(off_h).to(device, non_blocking=True), off_h
 

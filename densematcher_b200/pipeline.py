@@ -76,19 +76,21 @@ class PairBatchHost:
 
 
 class PairBatchDevice:
-    """The same batch in HBM (layout described in DESIGN.md): row-packed matrices + int64 offsets."""
+    """The same batch in HBM (layout described in DESIGN.md): row-packed matrices + int64 offsets.
+    ``off1`` / ``off2`` may be host offset arrays (copied to the device here) or ``nn.Offsets``."""
 
     def __init__(self, F1, F2, off1_h, off2_h, device, Phi1=None, Phi2=None, evals1=None, evals2=None, area1=None,
                  area2=None):
         self.F1, self.F2, self.Phi1, self.Phi2 = F1, F2, Phi1, Phi2
         self.evals1, self.evals2, self.area1, self.area2 = evals1, evals2, area1, area2
-        self.off1_h, self.off2_h = off1_h, off2_h
         self.device = torch.device(device)
-        self.off1 = torch.from_numpy(off1_h).to(device, non_blocking=True)
-        self.off2 = torch.from_numpy(off2_h).to(device, non_blocking=True)
-        self.n_pairs = len(off1_h) - 1
-        self.max1 = int(np.diff(off1_h).max()) if self.n_pairs else 0
-        self.max2 = int(np.diff(off2_h).max()) if self.n_pairs else 0
+        mk = lambda o: o if isinstance(o, _nn.Offsets) else _nn.Offsets(
+            torch.from_numpy(np.ascontiguousarray(o, dtype=np.int64)).to(device, non_blocking=True), o)
+        self.o1, self.o2 = mk(off1_h), mk(off2_h)
+        self.off1, self.off2 = self.o1.dev, self.o2.dev
+        self.off1_h, self.off2_h = self.o1.host, self.o2.host
+        self.n_pairs = len(self.off1_h) - 1
+        self.max1, self.max2 = self.o1.max, self.o2.max
 
 
 def _segment_sum(x, off_dev):
@@ -121,50 +123,118 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
         if batch.Phi1 is None:
             raise ValueError("functional_map=True needs eigenbases")
         k = batch.Phi1.shape[1] if k is None else int(k)
-        A = _fm.project(batch.Phi1, batch.area1, batch.F1, batch.off1_h, k=k)
-        B = _fm.project(batch.Phi2, batch.area2, batch.F2, batch.off2_h, k=k)
+        A = _fm.project(batch.Phi1, batch.area1, batch.F1, batch.o1, k=k)
+        B = _fm.project(batch.Phi2, batch.area2, batch.F2, batch.o2, k=k)
         C = _fm.fmap_solve(A, B, batch.evals1[:, :k], batch.evals2[:, :k], fmap_c00(batch), w_descr, w_lap)
-        res = _fm.fm_to_p2p(C, batch.Phi1[:, :k], batch.Phi2[:, :k], batch.area1, batch.off1_h, batch.off2_h,
+        res = _fm.fm_to_p2p(C, batch.Phi1[:, :k], batch.Phi2[:, :k], batch.area1, batch.o1, batch.o2,
                             flags=flags, out_dtype=out_dtype)
         out.update(C=C, p2p_21=res["dense_21"], p2p_12=res["dense_12"], p2p_21_adjoint=res["p2p_21"],
                    p2p_12_adjoint=res["p2p_12"])
     return out
 
 
-def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 64, **kw):
-    """Host buffers in, host (numpy) results out: H2D copies, the device pipeline, D2H copies.  Pairs are
-    processed in chunks on two alternating streams so that the copies of chunk i+1 overlap the kernels of
-    chunk i (pin the batch first with ``batch.pin()``)."""
+class HostStager:
+    """Staged host-buffer entry: three streams (H2D, compute, D2H), two input slots in HBM and one pinned
+    result buffer per output, all grow-only and reused across calls, so the steady state performs no
+    allocation and no host synchronisation until the final wait.  Chunk i+1 is copied in while chunk i
+    computes and chunk i-1 is copied out (the two DMA directions are independent engines)."""
+
+    N_SLOTS = 2
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.h2d, self.comp, self.d2h = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.slots = [dict(bufs={}, stage=None, in_ev=None, done_ev=None) for _ in range(self.N_SLOTS)]
+        self.out = {}
+
+    def _slot_buf(self, slot, name, rows, like):
+        """device buffer of the slot for field `name` with at least `rows` rows"""
+        b = slot["bufs"].get(name)
+        if b is None or b.shape[0] < rows or b.shape[1:] != like.shape[1:] or b.dtype != like.dtype:
+            b = torch.empty((int(rows * 1.1) + 1,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.device)
+            b.record_stream(self.comp)
+            slot["bufs"][name] = b
+        return b[:rows]
+
+    def _out_buf(self, name, rows, like):
+        b = self.out.get(name)
+        if b is None or b.shape[0] < rows or b.shape[1:] != like.shape[1:] or b.dtype != like.dtype:
+            b = torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype, pin_memory=True)
+            self.out[name] = b
+        return b
+
+    def run(self, batch: "PairBatchHost", chunk_pairs: int, **kw):
+        if not batch._pinned:
+            batch.pin()
+        P = batch.n_pairs
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.h2d, self.comp, self.d2h):
+            s.wait_stream(cur)
+        off1, off2 = np.asarray(batch.off1, np.int64), np.asarray(batch.off2, np.int64)
+        keep, outs = [], {}
+        for ci, lo in enumerate(range(0, P, chunk_pairs)):
+            hi = min(P, lo + chunk_pairs)
+            slot = self.slots[ci % self.N_SLOTS]
+            r1, r2, rp = slice(off1[lo], off1[hi]), slice(off2[lo], off2[hi]), slice(lo, hi)
+            n = hi - lo
+            if slot["in_ev"] is not None:
+                slot["in_ev"].synchronize()       # the pinned offset staging of this slot is free again
+            if slot["stage"] is None or slot["stage"].shape[1] < n + 1:
+                slot["stage"] = torch.empty(2, chunk_pairs + 1, dtype=torch.int64, pin_memory=True)
+            o1h, o2h = off1[lo:hi + 1] - off1[lo], off2[lo:hi + 1] - off2[lo]
+            slot["stage"][0, :n + 1] = torch.from_numpy(o1h)
+            slot["stage"][1, :n + 1] = torch.from_numpy(o2h)
+            with torch.cuda.stream(self.h2d):
+                if slot["done_ev"] is not None:
+                    self.h2d.wait_event(slot["done_ev"])  # compute of the chunk that used this slot has finished
+                dev_t = {}
+                for name in PairBatchHost.FIELDS:
+                    src = batch._pinned.get(name)
+                    if src is None:
+                        dev_t[name] = None
+                        continue
+                    src = src[rp if name.startswith("evals") else (r1 if name.endswith("1") else r2)]
+                    dst = self._slot_buf(slot, name, src.shape[0], src)
+                    dst.copy_(src, non_blocking=True)
+                    dev_t[name] = dst
+                offd = self._slot_buf(slot, "_off", 2, slot["stage"])[:, :n + 1]
+                offd.copy_(slot["stage"][:, :n + 1], non_blocking=True)
+                slot["in_ev"] = torch.cuda.Event()
+                slot["in_ev"].record(self.h2d)
+            with torch.cuda.stream(self.comp):
+                self.comp.wait_event(slot["in_ev"])
+                dev = PairBatchDevice(off1_h=_nn.Offsets(offd[0], o1h), off2_h=_nn.Offsets(offd[1], o2h),
+                                      device=self.device, **dev_t)
+                res = match_pairs_device(dev, **kw)
+                slot["done_ev"] = torch.cuda.Event()
+                slot["done_ev"].record(self.comp)
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(slot["done_ev"])
+                for name, t in res.items():
+                    rows, sl = ((P, rp) if name == "C" else
+                                (int(off2[-1]), r2) if "_21" in name else (int(off1[-1]), r1))
+                    ob = self._out_buf(name, rows, t)
+                    ob[sl].copy_(t, non_blocking=True)
+                    outs[name] = rows
+            keep.append(res)  # results stay alive until the D2H copies have run
+        self.d2h.synchronize()
+        cur.wait_stream(self.comp)
+        return {n: self.out[n][:rows].numpy().copy() for n, rows in outs.items()}
+
+
+_stagers = {}
+
+
+def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 32, **kw):
+    """Host buffers in, host (numpy) results out -- the call a user of the reference would make per batch:
+    pinned H2D copies, the device pipeline, D2H copies, overlapped chunk by chunk (see ``HostStager``)."""
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    P = batch.n_pairs
-    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
-    cur = torch.cuda.current_stream(device)
-    parts, events = [], []
-    pinned = bool(batch._pinned)
-    for ci, lo in enumerate(range(0, P, chunk_pairs)):
-        hi = min(P, lo + chunk_pairs)
-        sub = batch.slice_pairs(lo, hi)
-        if pinned:  # views of the pinned tensors keep the DMA path
-            r1, r2 = slice(batch.off1[lo], batch.off1[hi]), slice(batch.off2[lo], batch.off2[hi])
-            for n in PairBatchHost.FIELDS:
-                if n in batch._pinned:
-                    sub._pinned[n] = batch._pinned[n][slice(lo, hi) if n.startswith("evals") else (r1 if n.endswith("1") else r2)]
-        s = streams[ci % 2]
-        s.wait_stream(cur)
-        with torch.cuda.stream(s):
-            dev = sub.to_device(device)
-            res = match_pairs_device(dev, **kw)
-            host = {n: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True)
-                    for n, t in res.items()}
-            ev = torch.cuda.Event()
-            ev.record(s)
-        parts.append(host)
-        events.append((ev, dev, res))
-    for ev, _, _ in events:
-        ev.synchronize()
-    out = {n: np.concatenate([p[n].numpy() for p in parts]) for n in parts[0]} if parts else {}
-    return out
+    device = torch.device(device)
+    st = _stagers.get(str(device))
+    if st is None:
+        st = _stagers[str(device)] = HostStager(device)
+    return st.run(batch, int(chunk_pairs), **kw)
 
 
 def shard_pairs(n_pairs: int, rank: int, world: int):

@@ -55,7 +55,8 @@ enum {
   DM_ENGINE_TC = 1 << 3,    /* force the tcgen05 split-bf16 tensor-core score kernel (the default) */
   DM_RECHECK_ALL = 1 << 4,  /* testing: send every row through the float64 path */
   DM_SKIP_PREP = 1 << 5,    /* profiling: reuse the operand preparation a previous identical call left in the workspace */
-  DM_SKIP_FINISH = 1 << 6   /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
+  DM_SKIP_FINISH = 1 << 6,  /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
+  DM_F64_GEMM = 1 << 7      /* projection: float64 CUDA-core contraction instead of the tcgen05 split-bf16 engine */
 };
 
 /* how the per-element scale / bias of one argmax epilogue is obtained */
@@ -144,12 +145,20 @@ int dm_match_dist_f32(const float* Y, int64_t ldY, const float* X, int64_t ldX, 
  * Spectral projection  out[m] = Phi_m[:, :k]^T diag(area_m) F_m     (k x d per mesh, float64 out)
  * Replaces: optimize/base_functions.py:526-532, TriMesh.project mesh/trimesh.py:533-556.
  * Phi [total_n, ldPhi] float64, area [total_n] float64, F [total_n, ldF] float32, meshes ragged-packed
- * by row_off.  Products are formed in fp32 split arithmetic with float64 accumulation across row blocks.
+ * by row_off.  Default engine: tcgen05 tensor cores on a three-way bf16 split of both operands (six bf16
+ * products per fp32-grade product, fp32 accumulation in tensor memory, float64 reduction of the split-K
+ * partials): relative error ~1e-6 of |Phi|.|F|, i.e. the reference's own fp32 arithmetic
+ * (base_functions.py:516-532 runs in float32).  flags & DM_F64_GEMM selects the float64 CUDA-core
+ * contraction (error ~1e-15) and is also the fallback when d > 512.
  * ---------------------------------------------------------------------------------------- */
 size_t dm_project_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int d);
 int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
                const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d,
                double* out /* [n_meshes, k, d] */, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+int dm_project_ex(const double* Phi, int64_t ldPhi, const double* area, const float* F, int64_t ldF,
+                  const int64_t* row_off, int64_t total_n, int max_n, int n_meshes, int k, int d,
+                  double* out /* [n_meshes, k, d] */, int flags, void* workspace, size_t workspace_bytes,
+                  dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Functional-map solve: exact minimiser of  w_descr/2 |C A - B|^2 + w_lap/2 sum C^2 Delta  with column 0

@@ -25,18 +25,38 @@ def fm():
 
 
 def test_projection_and_closed_form_solve(fm, golden_fm):
+    from densematcher_b200 import _lib
     g = golden_fm
     k = int(g["k"])
-    A = fm.project(dev(g["Phi1"]), dev(g["area1"]), dev(g["c1"]), k=k)[0].cpu().numpy()
-    B = fm.project(dev(g["Phi2"]), dev(g["area2"]), dev(g["c2"]), k=k)[0].cpu().numpy()
-    assert relF(A, orc.project(g["Phi1"], g["area1"], g["c1"], k)) < 1e-12
-    assert relF(B, orc.project(g["Phi2"], g["area2"], g["c2"], k)) < 1e-12
+    Ao, Bo = orc.project(g["Phi1"], g["area1"], g["c1"], k), orc.project(g["Phi2"], g["area2"], g["c2"], k)
     c00 = orc.fmap_c00(g["Phi1"], g["Phi2"], g["area1"], g["area2"])
-    C = fm.fmap_solve(dev(A)[None], dev(B)[None], dev(g["evals1"][:k])[None], dev(g["evals2"][:k])[None],
-                      dev(np.array([c00])), float(g["w_descr"]), float(g["w_lap"]))[0].cpu().numpy()
-    assert relF(C, g["C_closed_form"]) < 1e-9          # bar: 1e-4 (north star)
-    assert relF(C, g["ref_C_lbfgs"]) < 1e-3            # the reference's own L-BFGS noise
-    assert C[0, 0] == c00 and np.all(C[1:, 0] == 0)
+    # float64 contraction: agrees with numpy to rounding; tcgen05 split-bf16 contraction (default): fp32-grade,
+    # like the reference's own float32 projection (base_functions.py:516-532)
+    for flags, tolA, tolC in ((_lib.DM_F64_GEMM, 1e-12, 1e-9), (0, 5e-6, 1e-4)):
+        A = fm.project(dev(g["Phi1"]), dev(g["area1"]), dev(g["c1"]), k=k, flags=flags)[0].cpu().numpy()
+        B = fm.project(dev(g["Phi2"]), dev(g["area2"]), dev(g["c2"]), k=k, flags=flags)[0].cpu().numpy()
+        assert relF(A, Ao) < tolA and relF(B, Bo) < tolA
+        C = fm.fmap_solve(dev(A)[None], dev(B)[None], dev(g["evals1"][:k])[None], dev(g["evals2"][:k])[None],
+                          dev(np.array([c00])), float(g["w_descr"]), float(g["w_lap"]))[0].cpu().numpy()
+        assert relF(C, g["C_closed_form"]) < tolC          # bar: 1e-4 (north star)
+        assert relF(C, g["ref_C_lbfgs"]) < 1e-3            # the reference's own L-BFGS noise
+        assert C[0, 0] == c00 and np.all(C[1:, 0] == 0)
+
+
+def test_projection_tensor_core_engine_shapes(fm):
+    """tcgen05 projection on ragged batches, k above one 128-row tile, d not a multiple of 64, tiny meshes."""
+    rng = np.random.default_rng(21)
+    for ns, k, d in (((2000, 1963, 1500), 100, 384), ((700, 33), 130, 200), ((17,), 5, 7), ((2500, 80, 64), 64, 512)):
+        bases = [meshgen.synthetic_basis(n, min(k, n), rng) for n in ns]
+        kk = min(k, min(ns))
+        Phi = np.concatenate([b[1][:, :kk] for b in bases]); area = np.concatenate([b[2] for b in bases])
+        F = meshgen.random_unit_features(sum(ns), d, rng)
+        off = np.concatenate([[0], np.cumsum(ns)])
+        out = fm.project(dev(Phi), dev(area), dev(F), off, k=kk).cpu().numpy()
+        for i in range(len(ns)):
+            s = slice(off[i], off[i + 1])
+            ref = orc.project(Phi[s], area[s], F[s], kk)
+            assert np.abs(out[i] - ref).max() < 4e-6 * np.abs(ref).max() + 1e-12, (ns, k, d, i)
 
 
 def test_fm_to_p2p_four_outputs(fm, golden_fm):
@@ -111,7 +131,7 @@ def test_batched_pairs_equal_single_pairs(fm):
         s1, s2 = slice(o1[i], o1[i + 1]), slice(o2[i], o2[i + 1])
         Ao, Bo = orc.project(Phi1[s1], ar1[s1], F1[s1], k), orc.project(Phi2[s2], ar2[s2], F2[s2], k)
         Co = orc.fmap_solve_closed_form(Ao, Bo, ev1[i], ev2[i], c00[i], 1e4, 1e3)
-        assert relF(C[i].cpu().numpy(), Co) < 1e-9
+        assert relF(C[i].cpu().numpy(), Co) < 1e-4
         Cg = C[i].cpu().numpy()
         p21, p12, MI = orc.fm_to_p2p(Cg, Phi1[s1, :k], Phi2[s2, :k], ar1[s1])
         assert np.array_equal(out["p2p_21"][s2].cpu().numpy(), p21)
@@ -122,3 +142,82 @@ def test_batched_pairs_equal_single_pairs(fm):
         Czo, pzo = orc.zoomout_refine(Cg, Phi1[s1], Phi2[s2], nit=8, step=1, A2=ar2[s2], return_p2p=True)
         assert relF(Cz[i].cpu().numpy(), Czo) < 1e-10
         assert np.array_equal(pz[s2].cpu().numpy(), pzo)
+
+
+def test_icp_matches_reference_golden(fm, golden_fm):
+    """Spectral ICP, 10 iterations from the closed-form C: the reference's own icp_refine output
+    (icp.py:43-107 run in the authoring container) is reproduced -- C within 1e-4 (in practice ~1e-12), p2p exact."""
+    from densematcher_b200.pyFM import refine
+    g = golden_fm
+    C, p = refine.icp_refine(g["C_closed_form"], g["Phi1"], g["Phi2"], g["area1"], nit=10, return_p2p=True)
+    assert relF(C, g["ref_cf_C_icp"]) < 1e-9
+    assert np.array_equal(p, g["ref_cf_p2p_icp"])
+    assert np.allclose(C @ C.T, np.eye(C.shape[0]), atol=1e-12)        # U I V^T of a square map is orthogonal
+    # every iteration count agrees with the oracle restatement, also on a rectangular (k2 != k1) map
+    for nit in (1, 3):
+        Co, po = orc.icp_refine(g["C_closed_form"], g["Phi1"], g["Phi2"], nit=nit, return_p2p=True)
+        Cg, pg = fm.icp(dev(g["C_closed_form"]), dev(g["Phi1"]), dev(g["Phi2"]), nit=nit, return_p2p=True)
+        assert relF(Cg[0].cpu().numpy(), Co) < 1e-9 and np.array_equal(pg.cpu().numpy(), po)
+    for shape in ((14, 20), (20, 13)):
+        C0 = g["C_closed_form"][:shape[0], :shape[1]]
+        Co, po = orc.icp_refine(C0, g["Phi1"], g["Phi2"], nit=4, return_p2p=True)
+        Cg, pg = fm.icp(dev(C0), dev(g["Phi1"][:, :shape[1]]), dev(g["Phi2"][:, :shape[0]]), nit=4, return_p2p=True)
+        assert relF(Cg[0].cpu().numpy(), Co) < 1e-9 and np.array_equal(pg.cpu().numpy(), po)
+
+
+def test_icp_tolerance_mode_and_batch(fm, golden_fm, golden_zo):
+    from densematcher_b200.pyFM import refine
+    g = golden_fm
+    Co = orc.icp_refine(g["C_closed_form"], g["Phi1"], g["Phi2"], nit=None, tol=1e-10)
+    C = refine.icp_refine(g["C_closed_form"], g["Phi1"], g["Phi2"], g["area1"], nit=None, tol=1e-10)
+    assert relF(C, Co) < 1e-8
+    # two different pairs in one ragged batch == two single-pair oracle runs
+    z = golden_zo
+    k = 12
+    Phi1 = np.concatenate([g["Phi1"][:, :k], z["Phi1"][:, :k]]); Phi2 = np.concatenate([g["Phi2"][:, :k], z["Phi2"][:, :k]])
+    off = np.array([0, 642, 1284])
+    C0 = np.stack([g["C_closed_form"][:k, :k], z["C0"]])
+    Cg, pg = fm.icp(dev(C0), dev(Phi1), dev(Phi2), nit=5, off1=off, off2=off, return_p2p=True)
+    for i, src in enumerate((g, z)):
+        Co, po = orc.icp_refine(C0[i], src["Phi1"][:, :k], src["Phi2"][:, :k], nit=5, return_p2p=True)
+        assert relF(Cg[i].cpu().numpy(), Co) < 1e-9
+        assert np.array_equal(pg[off[i]:off[i + 1]].cpu().numpy(), po)
+
+
+def test_polar_and_gram_inverse_large_k(fm):
+    """k = 130 exceeds the shared-memory budget of the Jacobi kernel: the L2-scratch variant must agree too."""
+    rng = np.random.default_rng(5)
+    n, k = 900, 130
+    Q1 = np.linalg.qr(rng.standard_normal((n, k)))[0] * (1 + 0.3 * rng.random((n, 1)))
+    Q2 = np.linalg.qr(rng.standard_normal((n, k)))[0] * (1 + 0.3 * rng.random((n, 1)))
+    C0 = np.linalg.qr(rng.standard_normal((k, k)))[0]
+    Co, po = orc.icp_refine(C0, Q1, Q2, nit=2, return_p2p=True)
+    Cg, pg = fm.icp(dev(C0), dev(Q1), dev(Q2), nit=2, return_p2p=True)
+    assert relF(Cg[0].cpu().numpy(), Co) < 1e-9 and np.array_equal(pg.cpu().numpy(), po)
+
+
+def test_host_entry_equals_device_pipeline():
+    """match_pairs_host (pinned H2D -> staged chunks on three streams -> D2H) returns exactly what the
+    device-resident pipeline returns, for a ragged batch and for chunk sizes that do / do not divide it."""
+    from densematcher_b200 import pipeline
+    rng = np.random.default_rng(11)
+    P, d, K = 7, 48, 16
+    n1 = rng.integers(150, 260, size=P); n2 = rng.integers(150, 260, size=P)
+    o1 = np.concatenate([[0], np.cumsum(n1)]).astype(np.int64); o2 = np.concatenate([[0], np.cumsum(n2)]).astype(np.int64)
+    b1 = [meshgen.synthetic_basis(int(n), K, rng) for n in n1]; b2 = [meshgen.synthetic_basis(int(n), K, rng) for n in n2]
+    host = pipeline.PairBatchHost(
+        F1=meshgen.random_unit_features(int(o1[-1]), d, rng), F2=meshgen.random_unit_features(int(o2[-1]), d, rng),
+        off1=o1, off2=o2, Phi1=np.concatenate([b[1] for b in b1]), Phi2=np.concatenate([b[1] for b in b2]),
+        evals1=np.stack([b[0] for b in b1]), evals2=np.stack([b[0] for b in b2]),
+        area1=np.concatenate([b[2] for b in b1]), area2=np.concatenate([b[2] for b in b2])).pin()
+    ref = {n: t.cpu().numpy() for n, t in pipeline.match_pairs_device(host.to_device("cuda:0"), k=12).items()}
+    for chunk in (3, 7, 64):
+        for _ in range(2):  # second call reuses every staging buffer
+            out = pipeline.match_pairs_host(host, "cuda:0", chunk_pairs=chunk, k=12)
+            assert set(out) == set(ref)
+            for n in ref:
+                assert out[n].dtype == ref[n].dtype and np.array_equal(out[n], ref[n]), (n, chunk)
+    # and against the oracle for one pair of the batch
+    s1, s2 = slice(o1[2], o1[3]), slice(o2[2], o2[3])
+    assert np.array_equal(ref["nn_p2p_21"][s2], orc.nn_argmax(host.F2[s2], host.F1[s1]))
+    assert np.array_equal(ref["nn_p2p_12"][s1], orc.nn_argmax(host.F2[s2], host.F1[s1], axis=0))
