@@ -143,7 +143,7 @@ int dm_nn_read_stats(const void* workspace, int64_t* out_h, dm_stream_t stream) 
   DM_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   out_h[0] = c[1];
   out_h[1] = c[2];
-  out_h[2] = c[0];
+  out_h[2] = int64_t(c[0]) + c[3];
   out_h[3] = c[3];  // results that needed the full float64 scan (the others were decided between two candidates)
   return DM_OK;
 }

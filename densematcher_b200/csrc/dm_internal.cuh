@@ -155,8 +155,9 @@ struct NNProblem {
   Top3* col_partial;  // [n_col][n_pairs * max_rt][max_db]
   int max_rt;         // row tiles per pair upper bound
   int rt_rows;        // rows per row tile (engine dependent)
-  FlagEntry* flags;
-  unsigned int* counters;  // [0] = number of flagged entries, [1] rows flagged, [2] cols flagged, [3] full scans
+  FlagEntry* flags;        // two-candidate entries grow from the front, full-scan entries from the back
+  int64_t flag_cap;        // entries allocated
+  unsigned int* counters;  // [0] = two-candidate entries, [1] rows flagged, [2] cols flagged, [3] full-scan entries
 };
 
 // Writes the fp32-grade argmax and, when the top-2 gap is inside the rounding-error bound of the score
@@ -172,7 +173,7 @@ __device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E,
   const bool safe = (s.m1 - s.m2) > thr;  // NaN -> not safe
   if (!safe || P.recheck_all) {
     const bool two = !P.recheck_all && (s.m1 - s.m3) > thr && s.i2 != kNoIdx;
-    const unsigned slot = atomicAdd(&P.counters[0], 1u);
+    const unsigned slot = atomicAdd(&P.counters[two ? 0 : 3], 1u);
     FlagEntry f;
     f.pair = pair;
     f.local = local;
@@ -181,9 +182,8 @@ __device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E,
     f.c1 = s.i1;
     f.c2 = s.i2;
     f.pad0 = f.pad1 = 0;
-    P.flags[slot] = f;
+    P.flags[two ? int64_t(slot) : P.flag_cap - 1 - int64_t(slot)] = f;
     atomicAdd(&P.counters[is_col ? 2 : 1], 1u);
-    if (!two) atomicAdd(&P.counters[3], 1u);
   }
 }
 

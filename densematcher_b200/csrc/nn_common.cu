@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 #include "dm_internal.cuh"
 
 namespace dm {
@@ -124,113 +125,110 @@ __global__ void __launch_bounds__(256) col_finalize_kernel(const NNProblem P) {
 // ---------------------------------------------------------------- float64 re-evaluation
 constexpr int RC_THREADS = 256;
 
-template <typename TM>
-__device__ __forceinline__ double dot64(const double* __restrict__ vec, const TM* __restrict__ r, int d);
+// Full float64 re-evaluation of one flagged result: argmax_j dot(vec, mat[j]) * sc[j] + bi[j] over all n candidate
+// rows, lowest index on ties.  A thread-block CLUSTER of kScanCluster CTAs owns one flagged result: CTA r scans the
+// r-th slice of the candidate rows (one warp per row, four rows in flight per warp, lane-strided partial sums + xor
+// tree -- the same summation order as the two-candidate kernel, so both paths agree bit for bit), the per-CTA
+// winners are combined by rank 0 through distributed shared memory.
+constexpr int kScanCluster = 8;
 
-template <>
-__device__ __forceinline__ double dot64<float>(const double* __restrict__ vec, const float* __restrict__ r, int d) {
-  double s = 0.0;
-  int k = 0;
-  if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
-    for (; k + 4 <= d; k += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(r + k));
-      s = fma(vec[k + 0], double(v.x), s);
-      s = fma(vec[k + 1], double(v.y), s);
-      s = fma(vec[k + 2], double(v.z), s);
-      s = fma(vec[k + 3], double(v.w), s);
-    }
-  }
-  for (; k < d; ++k) s = fma(vec[k], double(__ldg(r + k)), s);
-  return s;
-}
-template <>
-__device__ __forceinline__ double dot64<double>(const double* __restrict__ vec, const double* __restrict__ r, int d) {
-  double s = 0.0;
-  int k = 0;
-  if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
-    for (; k + 2 <= d; k += 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(r + k));
-      s = fma(vec[k + 0], v.x, s);
-      s = fma(vec[k + 1], v.y, s);
-    }
-  }
-  for (; k < d; ++k) s = fma(vec[k], __ldg(r + k), s);
-  return s;
-}
-
-// argmax_j  dot(vec, mat[j]) * sc[j] + bi[j]  over n candidate rows, float64, lowest index on ties.
-// One CTA; each thread walks candidates t, t+256, ... (ascending, so strict '>' keeps the lowest index).
 template <typename TV, typename TM>
-__device__ int scan64(double* vec, double* sbest, int* sidx, const TV* __restrict__ v, const TM* __restrict__ mat,
-                      int64_t ldm, int n, int d, const double* __restrict__ sc, const double* __restrict__ bi) {
-  const int t = threadIdx.x;
+__device__ void scan64_slice(double* vec, double* sbest, int* sidx, const TV* __restrict__ v, const TM* __restrict__ mat,
+                             int64_t ldm, int j_beg, int j_end, int d, const double* __restrict__ sc,
+                             const double* __restrict__ bi) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int k = t; k < d; k += RC_THREADS) vec[k] = double(v[k]);
   __syncthreads();
   double best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int j = t; j < n; j += RC_THREADS) {
-    const double s = dot64<TM>(vec, mat + int64_t(j) * ldm, d);
-    const double val = __dadd_rn(__dmul_rn(s, sc[j]), bi[j]);  // same two roundings as numpy's S *= s; S += b
-    if (val > best) {
-      best = val;
-      besti = j;
-    }
-  }
+  constexpr int NW = RC_THREADS / 32, U = 4;
+  for (int j0 = j_beg + warp; j0 < j_end; j0 += NW * U) {  // a warp walks its rows in ascending order
+    double s[U];
+    const TM* __restrict__ r[U];
 #pragma unroll
-  for (int sh = 16; sh > 0; sh >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, sh);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, sh);
-    if (ob > best || (ob == best && oi < besti)) {
-      best = ob;
-      besti = oi;
+    for (int u = 0; u < U; ++u) {
+      s[u] = 0.0;
+      r[u] = mat + int64_t(min(j0 + u * NW, j_end - 1)) * ldm;
+    }
+#pragma unroll 4
+    for (int k = lane; k < d; k += 32) {
+      const double x = vec[k];
+#pragma unroll
+      for (int u = 0; u < U; ++u) s[u] = fma(x, double(r[u][k]), s[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], sh);
+      const int j = j0 + u * NW;
+      if (j < j_end) {
+        const double val = __dadd_rn(__dmul_rn(s[u], sc[j]), bi[j]);  // same two roundings as numpy's S *= s; S += b
+        if (val > best) {
+          best = val;
+          besti = j;
+        }
+      }
     }
   }
-  if ((t & 31) == 0) {
-    sbest[t >> 5] = best;
-    sidx[t >> 5] = besti;
+  if (lane == 0) {
+    sbest[1 + warp] = best;
+    sidx[1 + warp] = besti;
   }
   __syncthreads();
   if (t == 0) {
-    for (int w = 1; w < RC_THREADS / 32; ++w)
-      if (sbest[w] > best || (sbest[w] == best && sidx[w] < besti)) {
-        best = sbest[w];
-        besti = sidx[w];
+    for (int w = 1; w < NW; ++w)
+      if (sbest[1 + w] > best || (sbest[1 + w] == best && sidx[1 + w] < besti)) {
+        best = sbest[1 + w];
+        besti = sidx[1 + w];
       }
+    sbest[0] = best;  // slot 0 = this CTA's winner, read by rank 0 of the cluster
     sidx[0] = besti;
   }
-  __syncthreads();
-  const int res = sidx[0];
-  __syncthreads();
-  return res;
 }
 
 template <typename TY, typename TX>
-__global__ void __launch_bounds__(RC_THREADS) recheck_kernel(const NNProblem P) {
+__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(RC_THREADS) recheck_kernel(const NNProblem P) {
+  namespace cg = cooperative_groups;
   extern __shared__ double vec[];
-  __shared__ double sbest[RC_THREADS / 32];
-  __shared__ int sidx[RC_THREADS / 32];
-  const unsigned count = P.counters[0];
+  __shared__ double sbest[1 + RC_THREADS / 32];
+  __shared__ int sidx[1 + RC_THREADS / 32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const unsigned cid = blockIdx.x / kScanCluster, ncl = gridDim.x / kScanCluster;
+  const unsigned count = P.counters[3];
   const TY* Y = static_cast<const TY*>(P.Y64);
   const TX* X = static_cast<const TX*>(P.X64);
-  for (unsigned f = blockIdx.x; f < count; f += gridDim.x) {
-    const FlagEntry e = P.flags[f];
-    if (e.mode != kFlagFull) continue;  // block-uniform
+  for (unsigned f = cid; f < count; f += ncl) {  // uniform over the cluster
+    const FlagEntry e = P.flags[P.flag_cap - 1 - int64_t(f)];
     const int p = e.pair, epi = e.epi & 255;
     const bool is_col = (e.epi & 256) != 0;
     const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
     const int nq = int(P.q_off[p + 1] - q0), nd = int(P.db_off[p + 1] - d0);
-    int res;
-    if (!is_col) {
-      const EpiDev& E = P.row[epi];
-      res = scan64<TY, TX>(vec, sbest, sidx, Y + (q0 + e.local) * P.ldY64, X + d0 * P.ldX64, P.ldX64, nd, P.d,
+    const int n = is_col ? nq : nd;
+    const int per = (n + kScanCluster - 1) / kScanCluster;
+    const int j_beg = min(n, int(rank) * per), j_end = min(n, j_beg + per);
+    const EpiDev& E = is_col ? P.col[epi] : P.row[epi];
+    if (!is_col)
+      scan64_slice<TY, TX>(vec, sbest, sidx, Y + (q0 + e.local) * P.ldY64, X + d0 * P.ldX64, P.ldX64, j_beg, j_end, P.d,
                            E.sd + d0, E.bd + d0);
-      if (threadIdx.x == 0) store_index(E.out, q0 + e.local, res == 0x7fffffff ? 0 : res, P.i64_out != 0);
-    } else {
-      const EpiDev& E = P.col[epi];
-      res = scan64<TX, TY>(vec, sbest, sidx, X + (d0 + e.local) * P.ldX64, Y + q0 * P.ldY64, P.ldY64, nq, P.d,
+    else
+      scan64_slice<TX, TY>(vec, sbest, sidx, X + (d0 + e.local) * P.ldX64, Y + q0 * P.ldY64, P.ldY64, j_beg, j_end, P.d,
                            E.sd + q0, E.bd + q0);
-      if (threadIdx.x == 0) store_index(E.out, d0 + e.local, res == 0x7fffffff ? 0 : res, P.i64_out != 0);
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+      double best = sbest[0];
+      int besti = sidx[0];
+      for (unsigned r = 1; r < kScanCluster; ++r) {  // ascending slices: strict '>' keeps the lowest index
+        const double ov = *cluster.map_shared_rank(&sbest[0], r);
+        const int oi = *cluster.map_shared_rank(&sidx[0], r);
+        if (ov > best) {
+          best = ov;
+          besti = oi;
+        }
+      }
+      store_index(E.out, (is_col ? d0 : q0) + e.local, besti == 0x7fffffff ? 0 : besti, P.i64_out != 0);
     }
+    cluster.sync();  // the winners may be overwritten only after rank 0 has read them
   }
 }
 
@@ -254,7 +252,6 @@ __global__ void __launch_bounds__(256) recheck_cand_kernel(const NNProblem P) {
   const TX* X = static_cast<const TX*>(P.X64);
   for (unsigned f = warp; f < count; f += nwarp) {
     const FlagEntry e = P.flags[f];
-    if (e.mode != kFlagCand) continue;  // warp-uniform
     const int p = e.pair, epi = e.epi & 255;
     const bool is_col = (e.epi & 256) != 0;
     const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
@@ -315,7 +312,7 @@ int nn_recheck(const NNProblem& P, cudaStream_t st) {
   if (P.flags == nullptr) return DM_OK;
   const size_t shm = sizeof(double) * size_t(P.d);
   if (shm > 200 * 1024) DM_FAIL(DM_ERR_UNSUPPORTED, "inner dimension %d too large for the float64 re-evaluation", P.d);
-  const int grid = num_sms() * 8;
+  const int grid = num_sms() / kScanCluster * kScanCluster * 2;  // a multiple of the cluster size
 #define DM_RC(TY, TX)                                                                                         \
   do {                                                                                                        \
     if (shm > 48 * 1024)                                                                                      \
@@ -357,6 +354,7 @@ struct NNLayout {
   } row[kMaxEpi], col[kMaxEpi];
   Top3* col_partial;
   FlagEntry* flags;
+  int64_t flag_cap;
   uint16_t *yh, *yl, *xh, *xl;  // bf16 split operands of the tensor-core engine [rows, kp]
   size_t bytes;
 };
@@ -389,7 +387,8 @@ NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max
   const int rt_rows = pick_rt_rows(d, flags);
   const int max_rt = (max_q + rt_rows - 1) / rt_rows;
   L.col_partial = c.take<Top3>(size_t(n_col) * n_pairs * max_rt * max_db);
-  L.flags = c.take<FlagEntry>((flags & DM_NO_RECHECK) ? 0 : size_t(n_row) * total_q + size_t(n_col) * total_db);
+  L.flag_cap = (flags & DM_NO_RECHECK) ? 0 : int64_t(n_row) * total_q + int64_t(n_col) * total_db;
+  L.flags = c.take<FlagEntry>(size_t(L.flag_cap));
   L.yh = L.yl = L.xh = L.xl = nullptr;
   if (nn_use_tc(flags)) {
     const size_t kp = size_t(nn_tc_kp(d));
@@ -453,6 +452,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   P.rt_rows = pick_rt_rows(R.d, R.flags);
   P.max_rt = (R.max_q + P.rt_rows - 1) / P.rt_rows;
   P.flags = (R.flags & DM_NO_RECHECK) ? nullptr : L.flags;
+  P.flag_cap = L.flag_cap;
   P.counters = L.counters;
   P.kp = nn_tc_kp(R.d);
   if (tc)

@@ -44,7 +44,8 @@ constexpr int TN = 256;       // database columns per accumulator tile (UMMA N)
 constexpr int TBK = 64;       // K elements per pipeline stage (one 128-byte swizzle row of bf16)
 constexpr int STAGES = 2;
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 4;
+constexpr int kGroupWarps = 4;              // one warp per TMEM lane quarter
+constexpr int kEpiWarps = 2 * kGroupWarps;  // two epilogue groups (see the kernel)
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int CCH = 32;  // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
 
@@ -52,19 +53,32 @@ constexpr uint32_t SZ_Y = TM_ROWS * TBK * 2;  // 16 KB per half
 constexpr uint32_t SZ_X = TN * TBK * 2;       // 32 KB per half
 constexpr uint32_t STAGE_BYTES = 2 * SZ_Y + 2 * SZ_X;
 constexpr uint32_t OFF_PATCH = STAGES * STAGE_BYTES;
-constexpr uint32_t PATCH_BYTES = 32 * 33 * 4;
-constexpr uint32_t OFF_COLRED = OFF_PATCH + kEpiWarps * PATCH_BYTES;            // [2][kMaxEpi][4 warps][32] Top3
-constexpr uint32_t COLRED_BYTES = 2 * kMaxEpi * kEpiWarps * CCH * sizeof(Top3);
+constexpr int PATCH_LD = 36;  // row pitch (words) of the transposition patch: 16-byte stores, conflict-free both ways
+constexpr uint32_t PATCH_BYTES = 32 * PATCH_LD * 4;
+constexpr uint32_t OFF_COLRED = OFF_PATCH + kGroupWarps * PATCH_BYTES;          // [2][kMaxEpi][4 warps][32] Top3
+constexpr uint32_t COLRED_BYTES = 2 * kMaxEpi * kGroupWarps * CCH * sizeof(Top3);
 constexpr uint32_t OFF_ROWSB = OFF_COLRED + COLRED_BYTES;                       // [kMaxEpi][2][TN] float
 constexpr uint32_t ROWSB_BYTES = kMaxEpi * 2 * TN * 4;
-constexpr uint32_t OFF_COLSB = OFF_ROWSB + ROWSB_BYTES;                         // [kMaxEpi][2][TM_ROWS] float
-constexpr uint32_t COLSB_BYTES = kMaxEpi * 2 * TM_ROWS * 4;
-constexpr uint32_t OFF_BAR = OFF_COLSB + COLSB_BYTES;                           // mbarriers + tmem pointer
+constexpr uint32_t OFF_BAR = OFF_ROWSB + ROWSB_BYTES;                           // mbarriers + tmem pointer
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;                           // + alignment slack
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 using namespace tc;
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+// named barriers of the epilogue: 1 = row group (or both groups when they share the row work), 2 = column group
+__device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// Four candidates at a time into TWO independent running top-3 chains (a: first two, b: last two) so that consecutive
+// updates do not serialise on one dependency chain.  Candidates below the running third-best cannot change a top-3,
+// which is the common case after the first few hundred columns: the update is skipped when no lane of the warp needs
+// it (warp-uniform branch on a vote, no divergence).
+__device__ __forceinline__ void top3_offer4(Top3& a, Top3& b, float w0, float w1, float w2, float w3, int idx0) {
+  const bool need = fmaxf(w0, w1) > a.m3 || fmaxf(w2, w3) > b.m3;
+  if (__any_sync(0xffffffffu, need)) {
+    top3_push(a, w0, idx0);
+    top3_push(b, w2, idx0 + 2);
+    top3_push(a, w1, idx0 + 1);
+    top3_push(b, w3, idx0 + 3);
+  }
+}
 
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -194,51 +208,64 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue warps: TMEM lanes 32*(warp%4) .. +31
+    // ===================== epilogue: two groups of four warps; warp w reads TMEM lanes 32*(w%4) .. +31.
+    // With row AND column epilogues, group 0 does the row epilogues and group 1 the column epilogues of every chunk
+    // (both read the accumulator from TMEM).  With row epilogues only, the groups split the chunks of each tile and
+    // their per-row states are merged at the end.
     const int q = warp & 3;
-    const int trow = 32 * q + lane;  // accumulator row of this thread
-    const int et = threadIdx.x - 64;  // 0..127
+    const int group = (warp - 2) >> 2;         // 0: warps 2..5, 1: warps 6..9
+    const int trow = 32 * q + lane;            // accumulator row of this thread
+    const int gt = (threadIdx.x - 64) & 127;   // thread index inside its group
+    constexpr bool kSplitRoles = (NR > 0 && NC > 0);
+    constexpr bool kShareRows = (NC == 0);     // both groups work on rows (also the DEBUG dump)
+    const bool do_rows = kSplitRoles ? group == 0 : (NC == 0 ? true : false);
+    const bool do_cols = NC > 0 && group == 1;
     float* patch = reinterpret_cast<float*>(sgen + OFF_PATCH + q * PATCH_BYTES);
     Top3* colred = reinterpret_cast<Top3*>(sgen + OFF_COLRED);          // [2][kMaxEpi][4][CCH]
     float* rowsb = reinterpret_cast<float*>(sgen + OFF_ROWSB);          // [e][0=scale,1=bias][TN]
-    float* colsb = reinterpret_cast<float*>(sgen + OFF_COLSB);          // [e][0=scale,1=bias][TM_ROWS]
+    const int row_threads = kShareRows ? 2 * kGroupWarps * 32 : kGroupWarps * 32;
 
-    Top3 rowst[NR > 0 ? NR : 1];
+    Top3 rowst[NR > 0 ? NR : 1], rowsu[NR > 0 ? NR : 1];  // two chains per row epilogue (merged at the end)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) rowst[r] = top3_init();
+    for (int r = 0; r < NR; ++r) rowst[r] = rowsu[r] = top3_init();
 
-    // per-row scale / bias of the column epilogues (fixed for the CTA)
+    // scale / bias of THIS thread's accumulator row for the column epilogues (applied before the transposition)
+    float csc[NC > 0 ? NC : 1], cbi[NC > 0 ? NC : 1];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const int i = row0 + et;
-      const bool v = i < nq;
-      colsb[(c * 2 + 0) * TM_ROWS + et] = v ? __ldg(P.col[c].sf + q0 + i) : 0.f;
-      colsb[(c * 2 + 1) * TM_ROWS + et] = v ? __ldg(P.col[c].bf + q0 + i) : -INFINITY;
+      const int i = row0 + trow;
+      const bool ok = do_cols && i < nq;
+      csc[c] = ok ? __ldg(P.col[c].sf + q0 + i) : 0.f;
+      cbi[c] = ok ? __ldg(P.col[c].bf + q0 + i) : -INFINITY;
     }
 
     for (int ct = 0; ct < n_ct; ++ct) {
       const int acc = ct & 1;
       const int col0 = ct * TN;
-      // per-column scale / bias of the row epilogues for this tile
-      epi_bar_sync();  // everyone is done with the previous tile's arrays
+      if (NR > 0 && do_rows) {
+        // per-column scale / bias of the row epilogues for this tile
+        bar_sync_n(1, row_threads);  // everyone is done with the previous tile's arrays
+        const int rt_idx = kShareRows ? int(threadIdx.x) - 64 : gt;
 #pragma unroll
-      for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int h = 0; h < TN / (kEpiWarps * 32); ++h) {
-          const int jj = et + h * kEpiWarps * 32;
-          const int j = col0 + jj;
-          const bool v = j < nd;
-          rowsb[(r * 2 + 0) * TN + jj] = v ? __ldg(P.row[r].sf + d0 + j) : 0.f;
-          rowsb[(r * 2 + 1) * TN + jj] = v ? __ldg(P.row[r].bf + d0 + j) : -INFINITY;
-        }
-      epi_bar_sync();
+        for (int r = 0; r < NR; ++r)
+          for (int jj = rt_idx; jj < TN; jj += row_threads) {
+            const int j = col0 + jj;
+            const bool v = j < nd;
+            rowsb[(r * 2 + 0) * TN + jj] = v ? __ldg(P.row[r].sf + d0 + j) : 0.f;
+            rowsb[(r * 2 + 1) * TN + jj] = v ? __ldg(P.row[r].bf + d0 + j) : -INFINITY;
+          }
+        bar_sync_n(1, row_threads);
+      }
 
       mbar_wait(bar_tfull + 8 * acc, (ct >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TN + (uint32_t(32 * q) << 16);
       const int n_ch = min(TN, nd - col0 + CCH - 1) / CCH;  // chunks that hold at least one valid column
-      for (int ch = 0; ch < TN / CCH; ++ch) {
-        if (ch >= n_ch) break;  // uniform over the CTA
+      const int ch_beg = kShareRows ? group * (TN / CCH / 2) : 0;
+      const int ch_end = kShareRows ? ch_beg + TN / CCH / 2 : TN / CCH;
+      for (int ch = ch_beg; ch < ch_end; ++ch) {
+        if (ch >= n_ch) break;  // uniform over the group
+        if (!do_rows && !do_cols && !DEBUG) break;
         float v[32];
         tmem_ld32(taddr + ch * CCH, v);
         if (DEBUG) {
@@ -250,56 +277,58 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (j < nd) dbg.S[int64_t(i) * dbg.ldS + j] = v[c];
             }
         }
+        if (NR > 0 && do_rows) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
-          const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
-          const int jb = col0 + ch * CCH;
+          for (int r = 0; r < NR; ++r) {
+            const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
+            const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+            const int jb = col0 + ch * CCH;
 #pragma unroll
-          for (int c4 = 0; c4 < CCH / 4; ++c4) {
-            const float4 s = s4[c4], b = b4[c4];
-            top3_push(rowst[r], fmaf(v[4 * c4 + 0], s.x, b.x), jb + 4 * c4 + 0);
-            top3_push(rowst[r], fmaf(v[4 * c4 + 1], s.y, b.y), jb + 4 * c4 + 1);
-            top3_push(rowst[r], fmaf(v[4 * c4 + 2], s.z, b.z), jb + 4 * c4 + 2);
-            top3_push(rowst[r], fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4 + 3);
+            for (int c4 = 0; c4 < CCH / 4; ++c4) {
+              const float4 s = s4[c4], b = b4[c4];
+              top3_offer4(rowst[r], rowsu[r], fmaf(v[4 * c4 + 0], s.x, b.x), fmaf(v[4 * c4 + 1], s.y, b.y),
+                          fmaf(v[4 * c4 + 2], s.z, b.z), fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4);
+            }
           }
         }
-        if (NC > 0) {
-          // transpose the warp's 32x32 block: lane becomes the column, rows are scanned in ascending order
-#pragma unroll
-          for (int c = 0; c < CCH; ++c) patch[lane * 33 + c] = v[c];
-          __syncwarp();
+        if (NC > 0 && do_cols) {
+          // per column epilogue: scale / bias by the own row, transpose the warp's 32x32 block through the patch
+          // (lane becomes the column), scan the 32 rows in two independent ascending chains (rows 0..15, 16..31)
           Top3 cst[NC > 0 ? NC : 1];
-#pragma unroll
-          for (int c = 0; c < NC; ++c) cst[c] = top3_init();
           const int ib = row0 + 32 * q;
 #pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            float s[4];
+          for (int c = 0; c < NC; ++c) {
+            if (c > 0) __syncwarp();  // the previous epilogue's reads of the patch are done
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s[u] = patch[(4 * r4 + u) * 33 + lane];
+            for (int c4 = 0; c4 < CCH / 4; ++c4)
+              *reinterpret_cast<float4*>(patch + lane * PATCH_LD + 4 * c4) =
+                  make_float4(fmaf(v[4 * c4 + 0], csc[c], cbi[c]), fmaf(v[4 * c4 + 1], csc[c], cbi[c]),
+                              fmaf(v[4 * c4 + 2], csc[c], cbi[c]), fmaf(v[4 * c4 + 3], csc[c], cbi[c]));
+            __syncwarp();
+            float w[32];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-              const float4 sc = *reinterpret_cast<const float4*>(colsb + (c * 2 + 0) * TM_ROWS + 32 * q + 4 * r4);
-              const float4 bi = *reinterpret_cast<const float4*>(colsb + (c * 2 + 1) * TM_ROWS + 32 * q + 4 * r4);
-              top3_push(cst[c], fmaf(s[0], sc.x, bi.x), ib + 4 * r4 + 0);
-              top3_push(cst[c], fmaf(s[1], sc.y, bi.y), ib + 4 * r4 + 1);
-              top3_push(cst[c], fmaf(s[2], sc.z, bi.z), ib + 4 * r4 + 2);
-              top3_push(cst[c], fmaf(s[3], sc.w, bi.w), ib + 4 * r4 + 3);
+            for (int r = 0; r < 32; ++r) w[r] = patch[r * PATCH_LD + lane];
+            Top3 ta = top3_init(), tb = top3_init();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              top3_push(ta, w[r], ib + r);
+              top3_push(tb, w[16 + r], ib + 16 + r);
             }
+            top3_merge(ta, tb);
+            cst[c] = ta;
           }
           const int par = ch & 1;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) colred[((par * kMaxEpi + c) * kEpiWarps + q) * CCH + lane] = cst[c];
-          epi_bar_sync();  // also orders the patch reuse of the next chunk
-          // warp c merges the four row groups of column epilogue c and writes the partial of this row tile.
-          // The merge order must be ascending in the row index: TMEM quarter q' holds rows 32 q' .. 32 q' + 31.
-          const int slot = (warp - 2);  // 0..3
+          for (int c = 0; c < NC; ++c) colred[((par * kMaxEpi + c) * kGroupWarps + q) * CCH + lane] = cst[c];
+          bar_sync_n(2, kGroupWarps * 32);  // also orders the patch reuse of the next chunk
+          // warp c of the group merges the four row quarters of column epilogue c and writes the partial of this row
+          // tile.  The merge order must be ascending in the row index: TMEM quarter q' holds rows 32 q' .. 32 q' + 31.
+          const int slot = (warp - 2) & 3;  // 0..3
           if (slot < NC) {
             const int j = col0 + ch * CCH + lane;
-            Top3 m = colred[((par * kMaxEpi + slot) * kEpiWarps + 0) * CCH + lane];
+            Top3 m = colred[((par * kMaxEpi + slot) * kGroupWarps + 0) * CCH + lane];
 #pragma unroll
-            for (int w = 1; w < kEpiWarps; ++w) top3_merge(m, colred[((par * kMaxEpi + slot) * kEpiWarps + w) * CCH + lane]);
+            for (int w = 1; w < kGroupWarps; ++w) top3_merge(m, colred[((par * kMaxEpi + slot) * kGroupWarps + w) * CCH + lane]);
             if (j < nd) P.col_partial[((int64_t(slot) * P.n_pairs + p) * P.max_rt + rt) * P.max_db + j] = m;
           }
         }
@@ -309,10 +338,29 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
     }
 
+    if (NR > 0) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int i = row0 + trow;
-      if (i < nq) emit_result(P, P.row[r], false, r, p, q0 + i, i, P.norm_q[q0 + i], rowst[r]);
+      for (int r = 0; r < NR; ++r) top3_merge(rowst[r], rowsu[r]);
+      if (kShareRows) {
+        // group 1 hands its per-row states to group 0 through shared memory (the patch area is free: NC == 0)
+        Top3* xch = reinterpret_cast<Top3*>(sgen + OFF_PATCH);  // [NR][128]
+        if (group == 1) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) xch[r * TM_ROWS + trow] = rowst[r];
+        }
+        bar_sync_n(1, row_threads);
+        if (group == 0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) top3_merge(rowst[r], xch[r * TM_ROWS + trow]);
+        }
+      }
+      if (group == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int i = row0 + trow;
+          if (i < nq) emit_result(P, P.row[r], false, r, p, q0 + i, i, P.norm_q[q0 + i], rowst[r]);
+        }
+      }
     }
   }
 

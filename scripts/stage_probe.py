@@ -26,6 +26,11 @@ print(f"feature NN stage        {tm(nnc):8.3f} ms")
 print(f"  score kernel only     {tm(lambda: nnc(_lib.DM_SKIP_PREP | _lib.DM_SKIP_FINISH)):8.3f} ms")
 print(f"  no recheck            {tm(lambda: nnc(_lib.DM_NO_RECHECK)):8.3f} ms")
 print(f"  kernel+finish         {tm(lambda: nnc(_lib.DM_SKIP_PREP)):8.3f} ms")
+rowonly = lambda fl: dnn.nn_argmax(b.F2, b.F1, b.off2, b.off1, row_epi=(dnn.COSINE_UNIT,), max_q=b.max2, max_db=b.max1, flags=fl, out_dtype=torch.int32)
+colonly = lambda fl: dnn.nn_argmax(b.F2, b.F1, b.off2, b.off1, row_epi=(), col_epi=(dnn.COSINE_UNIT,), max_q=b.max2, max_db=b.max1, flags=fl, out_dtype=torch.int32)
+rowonly(0); colonly(0)
+print(f"  score kernel row-only {tm(lambda: rowonly(_lib.DM_SKIP_PREP | _lib.DM_SKIP_FINISH)):8.3f} ms")
+print(f"  score kernel col-only {tm(lambda: colonly(_lib.DM_SKIP_PREP | _lib.DM_SKIP_FINISH)):8.3f} ms")
 A = dfm.project(b.Phi1, b.area1, b.F1, b.o1, k=k); B = dfm.project(b.Phi2, b.area2, b.F2, b.o2, k=k)
 print(f"project (one mesh side) {tm(lambda: dfm.project(b.Phi1, b.area1, b.F1, b.o1, k=k)):8.3f} ms")
 c00 = pipeline.fmap_c00(b)
