@@ -1,0 +1,137 @@
+"""``TriMesh``: the fields of the reference container (densematcher/pyFM/mesh/trimesh.py:16-1246) that the
+correspondence hot path reads: ``vertlist``, ``facelist``, ``eigenvalues (K,)``,
+``eigenvectors (n,K)`` float64, ``A`` (scipy sparse diagonal lumped mass), ``area`` -- plus ``process``,
+``project`` and ``decode`` with the reference's signatures (trimesh.py:498-577).
+
+The Laplace-Beltrami eigendecomposition is a precomputed INPUT of the hot path (north star), so the normal way
+to build a mesh here is ``TriMesh.from_basis(...)`` or assigning ``eigenvalues / eigenvectors / A``.  For drop-in
+use with bare geometry, ``process`` falls back to a HOST computation of the spectrum (cotangent stiffness, lumped
+mass, shift-invert ``eigsh`` with sigma = -0.01 like mesh/laplacian.py:143-182).  The reference calls the
+un-vendored ``robust_laplacian`` wheel there (trimesh.py:474); the plain cotangent operator used here differs from
+it on non-Delaunay meshes.  That fallback is preprocessing, not part of the accelerated path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+def _np(a, dtype):
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a), dtype=dtype)
+
+
+class TriMesh:
+    def __init__(self, vertices=None, faces=None, area_normalize=False, center=False):
+        self.vertlist = None if vertices is None else _np(vertices, np.float64)   # trimesh.py:118
+        self.facelist = None if faces is None else _np(faces, np.int64)           # trimesh.py:129
+        self.eigenvalues = None
+        self.eigenvectors = None
+        self.A = None
+        self.W = None
+        if center and self.vertlist is not None:
+            self.vertlist = self.vertlist - self.vertlist.mean(axis=0, keepdims=True)
+        if area_normalize and self.vertlist is not None and self.facelist is not None:
+            self.vertlist = self.vertlist / np.sqrt(self._face_areas().sum())
+
+    # ------------------------------------------------------------------ construction from precomputed data
+    @classmethod
+    def from_basis(cls, eigenvalues, eigenvectors, vertex_areas, vertices=None, faces=None):
+        """Mesh whose spectrum is already known (the hot path's input contract)."""
+        m = cls(vertices, faces)
+        m.eigenvalues = _np(eigenvalues, np.float64)
+        m.eigenvectors = _np(eigenvectors, np.float64)
+        m.A = sp.diags(_np(vertex_areas, np.float64)).tocsc()
+        return m
+
+    # ------------------------------------------------------------------ geometry
+    @property
+    def n_vertices(self):
+        return (self.eigenvectors if self.vertlist is None else self.vertlist).shape[0]
+
+    def _face_areas(self):
+        V, F = self.vertlist, self.facelist
+        return 0.5 * np.linalg.norm(np.cross(V[F[:, 1]] - V[F[:, 0]], V[F[:, 2]] - V[F[:, 0]]), axis=1)
+
+    @property
+    def vertex_areas(self):
+        """(n,) lumped vertex areas = diagonal of A."""
+        if self.A is not None:
+            return np.asarray(self.A.diagonal()).ravel()
+        a = np.zeros(self.vertlist.shape[0])
+        fa = self._face_areas()
+        for c in range(3):
+            np.add.at(a, self.facelist[:, c], fa / 3.0)
+        return a
+
+    @property
+    def area(self):
+        """Total area (trimesh.py:206-221): sum of the lumped mass."""
+        return float(self.vertex_areas.sum())
+
+    # ------------------------------------------------------------------ spectrum (host fallback)
+    def _cotan_stiffness(self):
+        V, F = self.vertlist, self.facelist
+        n = V.shape[0]
+        I, J, S = [], [], []
+        for a, b, c in ((0, 1, 2), (1, 2, 0), (2, 0, 1)):
+            u, w = V[F[:, a]] - V[F[:, c]], V[F[:, b]] - V[F[:, c]]
+            cot = np.einsum("ij,ij->i", u, w) / np.maximum(np.linalg.norm(np.cross(u, w), axis=1), 1e-300)
+            I.append(F[:, a]); J.append(F[:, b]); S.append(0.5 * cot)
+        I, J, S = np.concatenate(I), np.concatenate(J), np.concatenate(S)
+        return sp.coo_matrix((np.concatenate([-S, -S, S, S]),
+                              (np.concatenate([I, J, I, J]), np.concatenate([J, I, I, J]))), shape=(n, n)).tocsc()
+
+    def laplacian_spectrum(self, k, **_):
+        if self.vertlist is None or self.facelist is None:
+            raise ValueError("no geometry and no precomputed spectrum: supply eigenvalues / eigenvectors / A")
+        self.W = self._cotan_stiffness()
+        self.A = None
+        self.A = sp.diags(self.vertex_areas).tocsc()
+        evals, evects = spla.eigsh(self.W, k=k, M=self.A, sigma=-0.01)   # mesh/laplacian.py:165-168
+        order = np.argsort(evals)
+        self.eigenvalues, self.eigenvectors = evals[order], np.ascontiguousarray(evects[:, order])
+        return self
+
+    def process(self, k=200, skip_normals=True, intrinsic=False, robust=False, verbose=False):
+        """trimesh.py:498-531: slice a spectrum that is already there, else compute it (host)."""
+        if self.eigenvectors is not None and self.eigenvalues is not None and len(self.eigenvalues) >= k:
+            self.eigenvectors = self.eigenvectors[:, :k]
+            self.eigenvalues = self.eigenvalues[:k]
+        else:
+            self.laplacian_spectrum(k)
+        return self
+
+    # ------------------------------------------------------------------ projection (GPU)
+    def project(self, func, k=None):
+        """(k,p) or (k,) coefficients of ``func`` in the basis: eigenvectors[:, :k].T @ A @ func
+        (trimesh.py:533-556), float64 contraction on the GPU."""
+        import torch
+        from ... import fm as _fm, _lib
+        from .._dev import to_dev
+        if k is not None and k > self.eigenvectors.shape[1]:
+            raise ValueError(f"At least {k} eigenvectors should be computed before projecting")
+        f = np.asarray(func)
+        one_d = f.ndim == 1
+        f2 = f[:, None] if one_d else f
+        # float64 functions are contracted in float64 through the p2p->FM kernel (identity gather);
+        # float32 ones through the projection entry point with the float64 GEMM selected
+        Phi = to_dev(self.eigenvectors if k is None else self.eigenvectors[:, :k], torch.float64)
+        a = to_dev(self.vertex_areas, torch.float64)
+        if f2.dtype == np.float32:
+            out = _fm.project(Phi, a, to_dev(f2, torch.float32), flags=_lib.DM_F64_GEMM)[0].cpu().numpy()
+        else:
+            Fd = to_dev(f2.astype(np.float64), torch.float64)
+            ident = torch.arange(Fd.shape[0], device=Fd.device)
+            out = _fm.p2p_to_fm(ident, Fd, Phi, a)[0].cpu().numpy()       # Phi^T (a * F)
+        return out[:, 0] if one_d else out
+
+    def decode(self, projection):
+        """eigenvectors[:, :k] @ projection (trimesh.py:558-577)."""
+        projection = np.asarray(projection)
+        k = projection.shape[0]
+        if k > self.eigenvectors.shape[1]:
+            raise ValueError(f"At least {k} eigenvectors should be computed before decoding")
+        return self.eigenvectors[:, :k] @ projection
