@@ -33,6 +33,7 @@ METRIC = "mesh_pairs_per_sec"
 UNIT = "pairs/s"
 ALG_BYTES_NN = 4 * D_FEAT * 2 * N_VERT + 4 * 2 * N_VERT          # 6.160 MB per pair
 ALG_FLOPS_NN = 2 * N_VERT * N_VERT * D_FEAT                      # 3.072 GFLOP per pair
+NCU_DRAM_BYTES_PER_PAIR = (402.482176e6 + 38.458624e6) / 64      # ncu capture of nn_tc_kernel<1,1> at 64 pairs
 
 
 def workload_config(pairs, n_gpus):
@@ -128,6 +129,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     sample = 2
     batch = make_host_batch(sample, pool=4)
+    pairs_cfg = args.pairs
     for _ in range(min(args.warmup, 1)):
         cpu_pair_time(batch, 1, -1)
     times = [cpu_pair_time(batch, sample, -1) for _ in range(max(1, min(args.steps, 3)))]
@@ -137,7 +139,7 @@ def run_reference_arm(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(sample, args.gpus),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(pairs_cfg, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -252,7 +254,10 @@ def main():
     else:
         ex = 3 * alg_tflops
         roof = {"bound": "tensor", "achieved": ex, "peak": tf_peak, "unit": "TFLOP/s", "frac": ex / tf_peak,
-                "traffic": None, "note": "3 bf16 MMA passes per fp32-grade product (split-bf16); peak " + which}
+                "traffic": NCU_DRAM_BYTES_PER_PAIR * P,
+                "note": "3 bf16 MMA passes per fp32-grade product (split-bf16); peak " + which +
+                        "; traffic = dram read+write bytes of this kernel per launch from the ncu --set full capture "
+                        "profiles/r1_nn_tc_11_full_raw.csv (6.89 MB per pair vs 6.16 MB algorithmic)"}
     roof.update({"kernel": "nn score pass (" + engine + ")", "kernel_ms": kern_ms, "nn_stage_ms": nn_stage_ms,
                  "algorithmic_tflops": alg_tflops, "hbm_gbs": hbm_gbs, "hbm_peak_gbs": hbm_peak,
                  "hbm_frac": hbm_gbs / hbm_peak, "peaks": which})
@@ -288,9 +293,10 @@ def main():
                "sample": f"{sample} pairs of the same batch, oracle port of the reference path "
                          "(sklearn kd-tree n_jobs=-1, numpy/scipy float64)"}
 
-    # launches of OUR kernels per step: NN stage = memset-free count of kernels: 2 prep + score + finalize + recheck = 5;
-    # projection 2 x (gemm + reduce) = 4; solve 2 gemm + 1 = 3; fm_to_p2p = 2 gemm + sqnorm + 2 cvt + 5 = 10
-    launches_per_step = 5 + 4 + 3 + 10
+    # launches of OUR kernels per step (profiles/launches_*): feature NN 8 (2 prep, 2 per-pair maxima, score, column
+    # finalise, 2 re-evaluation) + projection 2 x 4 (2 split, tcgen05 GEMM, reduce) + solve 3 (2 Gram GEMMs, Cholesky)
+    # + FM->p2p 11 (2 embedding GEMMs, norms, 2 prep, 2 per-pair maxima, score, finalise, 2 re-evaluation)
+    launches_per_step = 8 + 8 + 3 + 11
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

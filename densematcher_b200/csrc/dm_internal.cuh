@@ -88,6 +88,34 @@ __device__ __forceinline__ void top3_merge(Top3& a, float bm1, int bi1, float bm
 }
 __device__ __forceinline__ void top3_merge(Top3& a, const Top3& b) { top3_merge(a, b.m1, b.i1, b.m2, b.i2, b.m3); }
 
+// Cheaper tracking for short-lived partial scans (the 32-row column partials of the tensor-core kernel): best value +
+// index and the runner-up VALUE only.  Converted to a Top3 whose runner-up index is unknown (kNoIdx) and whose third
+// value is the conservative bound m2; top3_merge then yields exact (m1, i1, m2), a known i2 whenever the runner-up
+// comes from another partial, and an upper bound m3 -- exactly what emit_result needs (an unknown i2 or a loose m3
+// only turns a two-candidate re-evaluation into a full one).
+struct Top2 {
+  float m1;
+  int i1;
+  float m2;
+};
+__device__ __forceinline__ Top2 top2_init() {
+  Top2 t;
+  t.m1 = t.m2 = -INFINITY;
+  t.i1 = kNoIdx;
+  return t;
+}
+__device__ __forceinline__ void top2_push(Top2& t, float v, int idx) {  // ascending idx: strict '>' keeps the lowest
+  const bool c1 = v > t.m1;
+  t.m2 = fmaxf(t.m2, fminf(t.m1, v));
+  t.i1 = c1 ? idx : t.i1;
+  t.m1 = fmaxf(t.m1, v);
+}
+__device__ __forceinline__ Top3 top3_from(const Top2& t) {
+  Top3 r;
+  r.m1 = t.m1, r.i1 = t.i1, r.m2 = t.m2, r.i2 = kNoIdx, r.m3 = t.m2;
+  return r;
+}
+
 __device__ __forceinline__ void store_index(void* out, int64_t pos, int v, bool i64) {
   if (i64)
     static_cast<int64_t*>(out)[pos] = v;
@@ -96,6 +124,34 @@ __device__ __forceinline__ void store_index(void* out, int64_t pos, int v, bool 
 }
 __device__ __forceinline__ int64_t load_index(const void* in, int64_t pos, bool i64) {
   return i64 ? static_cast<const int64_t*>(in)[pos] : static_cast<const int32_t*>(in)[pos];
+}
+
+// ---------------------------------------------------------------- vectorised row access for the split kernels
+// A lane reads W consecutive elements of a matrix row with one 16-byte load (W = 4 floats / 2 doubles).
+template <typename T>
+struct RowVec;
+template <>
+struct RowVec<float> {
+  static constexpr int W = 4;
+  typedef float4 V;
+  static __device__ __forceinline__ void unpack(const V& v, double (&o)[4]) { o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w; }
+};
+template <>
+struct RowVec<double> {
+  static constexpr int W = 2;
+  typedef double2 V;
+  static __device__ __forceinline__ void unpack(const V& v, double (&o)[2]) { o[0] = v.x, o[1] = v.y; }
+};
+// packs W bf16 values into one 8- or 4-byte store
+template <int W>
+__device__ __forceinline__ void store_bf16_vec(void* dst, const unsigned short (&b)[W]);
+template <>
+__device__ __forceinline__ void store_bf16_vec<4>(void* dst, const unsigned short (&b)[4]) {
+  *reinterpret_cast<uint2*>(dst) = make_uint2(uint32_t(b[0]) | (uint32_t(b[1]) << 16), uint32_t(b[2]) | (uint32_t(b[3]) << 16));
+}
+template <>
+__device__ __forceinline__ void store_bf16_vec<2>(void* dst, const unsigned short (&b)[2]) {
+  *reinterpret_cast<uint32_t*>(dst) = uint32_t(b[0]) | (uint32_t(b[1]) << 16);
 }
 
 // ---------------------------------------------------------------- the NN problem, device view

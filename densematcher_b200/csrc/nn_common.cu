@@ -52,14 +52,66 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     prep_side_kernel(const T* __restrict__ M, int64_t ld, const int64_t* __restrict__ off, int n_pairs, int64_t total,
                      int d, float* __restrict__ norm_out, SpecArr specs, int n_specs, __nv_bfloat16* __restrict__ hi,
-                     __nv_bfloat16* __restrict__ lo, int kp) {
+                     __nv_bfloat16* __restrict__ lo, int kp, int need_sq64) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= total) return;
   const T* r = M + row * ld;
   double s = 0.0;
-  if (hi) {
-    // split representation for the tensor-core engine: v = hi + lo + O(2^-18 |v|), zero-padded to kp columns
+  float s32 = 0.f;
+  typedef RowVec<T> RV;
+  constexpr int W = RV::W, U = 4;
+  const bool vec_ok = (ld % W) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0;
+  if (hi && vec_ok) {
+    // split representation for the tensor-core engine: v = hi + lo + O(2^-18 |v|), zero-padded to kp columns.
+    // 16-byte loads, U of them in flight per lane before the first use; packed bf16 stores.
+    __nv_bfloat16* h = hi + row * kp;
+    __nv_bfloat16* l = lo + row * kp;
+    for (int k0 = lane * W; k0 < kp; k0 += 32 * W * U) {
+      typename RV::V buf[U];
+      bool full[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * 32 * W;
+        full[u] = k + W <= d;
+        if (full[u]) buf[u] = __ldg(reinterpret_cast<const typename RV::V*>(r + k));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * 32 * W;
+        if (k >= kp) continue;
+        double v[W];
+        float vf[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          T e = T(0);
+          if (full[u])
+            e = reinterpret_cast<const T*>(&buf[u])[w];
+          else if (k + w < d)
+            e = r[k + w];
+          vf[w] = float(e);
+          v[w] = (sizeof(T) == 8 || need_sq64) ? double(e) : 0.0;
+        }
+        unsigned short bh[W], bl[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          // fp32 split: hi = bf16(x), lo = bf16(x - hi) (the difference is exact in fp32).  Conversions between fp32
+          // and fp64 are slow-pipe instructions, so the float64 sum of squares is formed only when an epilogue needs
+          // it (cosine scale / Euclidean bias); otherwise an fp32 sum feeds the (rounded-up) error bound.
+          const float x = sizeof(T) == 8 ? float(v[w]) : vf[w];
+          if (sizeof(T) == 8 || need_sq64)
+            s = fma(v[w], v[w], s);
+          else
+            s32 = fmaf(x, x, s32);
+          const __nv_bfloat16 vh = __float2bfloat16_rn(x);
+          const __nv_bfloat16 vl = __float2bfloat16_rn(x - __bfloat162float(vh));
+          bh[w] = __bfloat16_as_ushort(vh), bl[w] = __bfloat16_as_ushort(vl);
+        }
+        store_bf16_vec<W>(h + k, bh);
+        store_bf16_vec<W>(l + k, bl);
+      }
+    }
+  } else if (hi) {
     __nv_bfloat16* h = hi + row * kp;
     __nv_bfloat16* l = lo + row * kp;
     for (int k = lane; k < kp; k += 32) {
@@ -76,12 +128,16 @@ __global__ void __launch_bounds__(256)
     }
   }
 #pragma unroll
-  for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, sh);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, sh);
+  }
   if (lane != 0) return;
+  // the fp32 sum (only used when no epilogue needs the float64 one) carries a relative error <= (d + 32) 2^-24
+  if (s == 0.0 && s32 > 0.f) s = double(s32) * (1.0 + (double(d) + 32.0) * 5.9604644775390625e-08);
   const double nrm = sqrt(s);
   const float nf = __double2float_ru(nrm) * 1.0000005f;
   norm_out[row] = nf;
-  const int p = find_pair(off, n_pairs, row);
   for (int e = 0; e < n_specs; ++e) {
     const SideEpiSpec& S = specs.s[e];
     double sc = 1.0, bi = 0.0;
@@ -98,9 +154,31 @@ __global__ void __launch_bounds__(256)
     const float scf = float(sc), bif = float(bi);
     S.sf[row] = scf;
     S.bf[row] = bif;
-    // non-negative floats order like their bit patterns
-    atomicMax(reinterpret_cast<unsigned int*>(S.G + p), __float_as_uint(nf * fabsf(scf) * 1.0000005f));
-    atomicMax(reinterpret_cast<unsigned int*>(S.Bm + p), __float_as_uint(fabsf(bif)));
+  }
+}
+
+// per pair and epilogue: G = max_j |row_j| |scale_j| and Bm = max_j |bias_j| (the error-bound maxima), one CTA each
+__global__ void __launch_bounds__(256)
+    pair_max_kernel(const int64_t* __restrict__ off, const float* __restrict__ norm, SpecArr specs, int n_pairs) {
+  const int p = blockIdx.x, e = blockIdx.y;
+  const SideEpiSpec& S = specs.s[e];
+  float g = 0.f, b = 0.f;
+  for (int64_t r = off[p] + threadIdx.x; r < off[p + 1]; r += blockDim.x) {
+    g = fmaxf(g, norm[r] * fabsf(S.sf[r]) * 1.0000005f);
+    b = fmaxf(b, fabsf(S.bf[r]));
+  }
+  __shared__ float sg[8], sb[8];
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, sh));
+    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, sh));
+  }
+  if ((threadIdx.x & 31) == 0) sg[threadIdx.x >> 5] = g, sb[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) g = fmaxf(g, sg[w]), b = fmaxf(b, sb[w]);
+    S.G[p] = g;
+    S.Bm[p] = b;
   }
 }
 
@@ -284,19 +362,22 @@ int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, i
   if (total <= 0) return DM_OK;
   SpecArr arr;
   for (int e = 0; e < kMaxEpi; ++e) arr.s[e] = specs && e < n_specs ? specs[e] : SideEpiSpec{};
-  for (int e = 0; e < n_specs; ++e) {
-    DM_CUDA_OK(cudaMemsetAsync(specs[e].G, 0, sizeof(float) * n_pairs, st));
-    DM_CUDA_OK(cudaMemsetAsync(specs[e].Bm, 0, sizeof(float) * n_pairs, st));
-  }
   const int wpb = 8;
   const unsigned grid = unsigned((total + wpb - 1) / wpb);
+  int need_sq64 = hi ? 0 : 1;  // the scalar (CUDA-core engine) path always sums in float64
+  for (int e = 0; e < n_specs; ++e)
+    if (specs[e].scale_mode == DM_SCALE_INVNORM || specs[e].bias_mode == DM_BIAS_NEG_HALF_SQNORM) need_sq64 = 1;
   if (is_double)
     prep_side_kernel<double><<<grid, wpb * 32, 0, st>>>(static_cast<const double*>(M), ld, off, n_pairs, total, d,
-                                                        norm_out, arr, n_specs, hi, lo, kp);
+                                                        norm_out, arr, n_specs, hi, lo, kp, need_sq64);
   else
     prep_side_kernel<float><<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(M), ld, off, n_pairs, total, d,
-                                                       norm_out, arr, n_specs, hi, lo, kp);
+                                                       norm_out, arr, n_specs, hi, lo, kp, need_sq64);
   DM_LAUNCH_OK("prep_side_kernel");
+  if (n_specs > 0 && n_pairs > 0) {
+    pair_max_kernel<<<dim3(unsigned(n_pairs), unsigned(n_specs)), 256, 0, st>>>(off, norm_out, arr, n_pairs);
+    DM_LAUNCH_OK("pair_max_kernel");
+  }
   return DM_OK;
 }
 

@@ -308,13 +308,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             float w[32];
 #pragma unroll
             for (int r = 0; r < 32; ++r) w[r] = patch[r * PATCH_LD + lane];
-            Top3 ta = top3_init(), tb = top3_init();
+            Top2 ua = top2_init(), ub = top2_init();
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-              top3_push(ta, w[r], ib + r);
-              top3_push(tb, w[16 + r], ib + 16 + r);
+              top2_push(ua, w[r], ib + r);
+              top2_push(ub, w[16 + r], ib + 16 + r);
             }
-            top3_merge(ta, tb);
+            Top3 ta = top3_from(ua);
+            top3_merge(ta, top3_from(ub));
             cst[c] = ta;
           }
           const int par = ch & 1;

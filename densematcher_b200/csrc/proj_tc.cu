@@ -23,7 +23,7 @@ using namespace tc;
 constexpr int PM = 128;   // UMMA M: eigen-index rows of one output tile
 constexpr int PKC = 16;   // vertices per pipeline stage (= UMMA K for bf16)
 constexpr int kProjThreads = 192;
-constexpr int kSliceChunks = 32;  // vertex chunks (of PKC) per CTA: 512 vertices
+constexpr int kSliceChunks = 16;  // vertex chunks (of PKC) per CTA: 256 vertices (short fp32 accumulation chains: the TMEM accumulate truncates)
 constexpr uint32_t GROUP_BYTES = PKC * 128;  // one 64-column group of one stage: 16 vertices x 128 B
 constexpr uint32_t A_BYTES = 2 * GROUP_BYTES;  // 128 columns
 
@@ -242,6 +242,52 @@ __global__ void __launch_bounds__(256)
   if (gather) srow = (gather_src_off ? gather_src_off[b] : 0) + load_index(gather, prow, gather_i64 != 0);
   const double sc = rowscale ? rowscale[prow] : 1.0;
   const T* s = src + srow * ld;
+  typedef RowVec<T> RV;
+  constexpr int W = RV::W, U = 4;
+  if ((ld % W) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads, U in flight per lane; packed bf16 stores
+    for (int k0 = lane * W; k0 < kp; k0 += 32 * W * U) {
+      typename RV::V buf[U];
+      bool full[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * 32 * W;
+        full[u] = k + W <= cols;
+        if (full[u]) buf[u] = __ldg(reinterpret_cast<const typename RV::V*>(s + k));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * 32 * W;
+        if (k >= kp) continue;
+        T v[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          v[w] = T(0);
+          if (full[u])
+            v[w] = reinterpret_cast<const T*>(&buf[u])[w];
+          else if (k + w < cols)
+            v[w] = s[k + w];
+        }
+        unsigned short bh[W], bm[W], bl[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          // one rounding to fp32 (2^-24, the precision of the whole engine), then an exact three-way split in fp32:
+          // conversions between fp32 and fp64 are slow-pipe instructions and are kept to one per element
+          const float x = (rowscale || sizeof(T) == 8) ? float(sc * v[w]) : float(v[w]);
+          const __nv_bfloat16 vh = __float2bfloat16_rn(x);
+          const float r1 = x - __bfloat162float(vh);
+          const __nv_bfloat16 vm = __float2bfloat16_rn(r1);
+          const float r2 = r1 - __bfloat162float(vm);
+          bh[w] = __bfloat16_as_ushort(vh), bm[w] = __bfloat16_as_ushort(vm);
+          bl[w] = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+        }
+        store_bf16_vec<W>(ph + k, bh);
+        store_bf16_vec<W>(pm + k, bm);
+        store_bf16_vec<W>(pl + k, bl);
+      }
+    }
+    return;
+  }
   for (int c = lane; c < kp; c += 32) {
     const double v = c < cols ? sc * double(s[c]) : 0.0;
     const __nv_bfloat16 vh = __float2bfloat16_rn(float(v));

@@ -26,3 +26,14 @@ for (n, k, d, nb) in [(64, 8, 64, 1), (300, 20, 32, 1), (2000, 100, 384, 1), (20
         print("   BAD entries", len(bad), "rows", np.unique(bad[:, 0])[:20], "cols", np.unique(bad[:, 1])[:20], flush=True)
         print("   out[0,:4,:6]\n", out[0, :4, :6], "\n   ref\n", ref[0, :4, :6], flush=True)
 print("probe done")
+# effect on C (N=2000, k=100, d=384, notebook weights)
+n, k, d = 2000, 100, 384
+b1, b2 = meshgen.synthetic_basis(n, k, rng), meshgen.synthetic_basis(n, k, rng)
+F1, F2 = meshgen.random_unit_features(n, d, rng), meshgen.random_unit_features(n, d, rng)
+c00 = orc.fmap_c00(b1[1], b2[1], b1[2], b2[2])
+Cs = {}
+for name, fl in (("f64", _lib.DM_F64_GEMM), ("tc", 0)):
+    A = fm.project(dev(b1[1]), dev(b1[2]), dev(F1), k=k, flags=fl); B = fm.project(dev(b2[1]), dev(b2[2]), dev(F2), k=k, flags=fl)
+    Cs[name] = fm.fmap_solve(A, B, dev(b1[0])[None], dev(b2[0])[None], dev(np.array([c00])), 1e4, 1e3)[0].cpu().numpy()
+Co = orc.fmap_solve_closed_form(orc.project(b1[1], b1[2], F1, k), orc.project(b2[1], b2[2], F2, k), b1[0], b2[0], c00, 1e4, 1e3)
+print(f"C relF vs oracle closed form: f64 projection {relF(Cs['f64'], Co):.2e}, tc projection {relF(Cs['tc'], Co):.2e}")
