@@ -4,6 +4,7 @@
 #include "dm_internal.cuh"
 #include "gemm64.cuh"
 #include "linalg64.cuh"
+#include "tc_ptx.cuh"
 
 namespace dm {
 namespace {
@@ -39,57 +40,102 @@ constexpr int kSolveThreads = 128;
 // 1 / sqrt(v) in float64 from the fp32 hardware estimate and two Newton steps (error ~2^-52; the factorisation does
 // not need a correctly rounded square root, and this replaces a ~50-instruction sqrt + divide dependency chain).
 __device__ __forceinline__ double rsqrt64(double v) {
-  if (!(v > 1e-30 && v < 1e30)) return 1.0 / sqrt(v);  // outside the fp32 estimate's comfortable range
+  // fp32 hardware estimate (2^-22) + two Newton steps in float64.  Pivots outside the fp32 range (never the case
+  // for sensibly scaled energies) are rescaled by an exact power of four first.
+  double sc = 1.0;
+  if (!(v > 1e-30 && v < 1e30)) {
+    if (!(v > 0.0) || !(v < INFINITY)) return 1.0 / sqrt(v);
+    int e;
+    frexp(v, &e);
+    e &= ~1;
+    v = ldexp(v, -e);
+    sc = ldexp(1.0, -e / 2);
+  }
   double y = double(rsqrtf(float(v)));
   const double h = 0.5 * v;
-  y = y * fma(-h * y, y, 1.5);
-  y = y * fma(-h * y, y, 1.5);
-  return y;
+  y = y * fma(-h * y, y, 1.5);  // 2^-22 -> 2^-43
+  y = y * fma(-h * y, y, 1.5);  // -> rounding level
+  return y * sc;
+}
+
+// w_d * (A A^T)[1:, 1:] of every pair as a packed lower triangle (row r starts at r (r + 1) / 2), the form in which the
+// k2 systems of the pair bulk-copy it into shared memory.  stride = packed length rounded up to an even count.
+__global__ void __launch_bounds__(256)
+    solve_pack_kernel(const double* __restrict__ AAt, double wd, int k1, int64_t stride, double* __restrict__ Lp) {
+  const int n = k1 - 1, n_tri = n * (n + 1) / 2;
+  const double* aat = AAt + int64_t(blockIdx.x) * k1 * k1;
+  double* out = Lp + int64_t(blockIdx.x) * stride;
+  for (int e = threadIdx.x; e < n_tri; e += blockDim.x) {
+    int r = int((sqrtf(8.f * float(e) + 1.f) - 1.f) * 0.5f);
+    while (r * (r + 1) / 2 > e) --r;
+    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+    const int c = e - r * (r + 1) / 2;
+    out[e] = wd * aat[int64_t(r + 1) * k1 + c + 1];
+  }
+  if (threadIdx.x == 0 && stride > n_tri) out[n_tri] = 0.0;
 }
 
 template <int RPT>  // rows per thread: (n + 1) <= 128 * RPT
 __global__ void __launch_bounds__(kSolveThreads)
-    fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ ev1,
-                      const double* __restrict__ ev2, const double* __restrict__ c00, double wd, double wl, int k1,
-                      int k2, double* __restrict__ C, int* __restrict__ status) {
-  extern __shared__ double sm[];
+    fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ Lp,
+                      int64_t lp_stride, const double* __restrict__ ev1, const double* __restrict__ ev2,
+                      const double* __restrict__ c00, double wd, double wl, int k1, int k2, double* __restrict__ C,
+                      int* __restrict__ status) {
+  extern __shared__ __align__(16) double sm[];
   constexpr int RPL = 4 * RPT;  // unknowns per lane in the single-warp back substitution
   const int n = k1 - 1;
   const int t = threadIdx.x, lane = t & 31;
   const int sys = blockIdx.x;
+  const int n_tri = n * (n + 1) / 2;
   double* L = sm;                                        // row r starts at r (r + 1) / 2; row n = right-hand side
-  double* Dbuf = sm + size_t(n + 1) * (n + 2) / 2;       // [2][4][4] accumulated diagonal blocks (double-buffered)
+  double* Dbuf = sm + size_t(n + 1) * (n + 2) / 2 + 1;   // [2][4][4] accumulated diagonal blocks (double-buffered)
   double* invd = Dbuf + 32;                              // [n] reciprocals of the diagonal of L
   __shared__ double s_scale[kSolveThreads / 32];
+  __shared__ __align__(8) unsigned long long s_bar;
   const int b = sys / k2, i = sys % k2;
   const double* aat = AAt + int64_t(b) * k1 * k1;
   const double* bat = BAt + int64_t(b) * k2 * k1;
   const double* l1 = ev1 + int64_t(b) * k1;
   const double* l2 = ev2 + int64_t(b) * k2;
+  // the shared part of the matrix arrives by one bulk copy while the threads prepare the system-specific part
+  const uint32_t bar = tc::smem_u32(&s_bar);
+  if (t == 0) {
+    tc::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = uint32_t(lp_stride * sizeof(double));
+    tc::mbar_expect_tx(bar, bytes);
+    tc::tma_load_1d(tc::smem_u32(L), Lp + int64_t(b) * lp_stride, bytes, bar);
+  }
   double scale = -INFINITY;
   for (int j = t; j < k1; j += kSolveThreads) scale = fmax(scale, l1[j]);
   for (int j = t; j < k2; j += kSolveThreads) scale = fmax(scale, l2[j]);
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, sh));
   if (lane == 0) s_scale[t >> 5] = scale;
-  __syncthreads();
+  __syncthreads();  // also publishes the barrier initialisation to the waiting threads
   scale = fmax(fmax(s_scale[0], s_scale[1]), fmax(s_scale[2], s_scale[3]));
   const double ci0 = (i == 0) ? c00[b] : 0.0;
   const double l2i = l2[i] / scale;
-  const int n_tri = n * (n + 1) / 2;
-  for (int e = t; e < n_tri; e += kSolveThreads) {  // flat index over the packed triangle -> (r, c)
-    int r = int((sqrtf(8.f * float(e) + 1.f) - 1.f) * 0.5f);
-    while (r * (r + 1) / 2 > e) --r;
-    while ((r + 1) * (r + 2) / 2 <= e) ++r;
-    const int c = e - r * (r + 1) / 2;
-    double v = wd * aat[int64_t(r + 1) * k1 + c + 1];
-    if (c == r) {
+  double dg[RPT], rh[RPT];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int c = t + kSolveThreads * q;
+    dg[q] = rh[q] = 0.0;
+    if (c < n) {
       const double df = l1[c + 1] / scale - l2i;
-      v += wl * (df * df);
+      dg[q] = wl * (df * df);
+      rh[q] = wd * (bat[int64_t(i) * k1 + c + 1] - ci0 * aat[c + 1]);
     }
-    L[e] = v;
   }
-  for (int c = t; c < n; c += kSolveThreads) L[n_tri + c] = wd * (bat[int64_t(i) * k1 + c + 1] - ci0 * aat[c + 1]);
+  tc::mbar_wait(bar, 0);
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int c = t + kSolveThreads * q;
+    if (c < n) {
+      L[size_t(c) * (c + 1) / 2 + c] += dg[q];
+      L[n_tri + c] = rh[q];
+    }
+  }
   __syncthreads();
   bool bad = false;
   int par = 0;
@@ -185,18 +231,21 @@ __global__ void __launch_bounds__(kSolveThreads)
       x[q] = r < n ? y[r] : 0.0;
     }
   }
-  for (int j = n - 1; j >= 0; --j) {
-    const double* row = L + size_t(j) * (j + 1) / 2;
-    double xj = 0.0;
+  // slots from the top; inside a slot the 32 unknowns are finished from lane 31 down (static register indexing)
 #pragma unroll
-    for (int q = 0; q < RPL; ++q)
-      if ((j >> 5) == q) xj = x[q];
-    xj = __shfl_sync(0xffffffffu, xj, j & 31) * invd[j];
+  for (int qj = RPL - 1; qj >= 0; --qj) {
+    if (32 * qj >= n) continue;
+    for (int lj = min(31, n - 1 - 32 * qj); lj >= 0; --lj) {
+      const int j = 32 * qj + lj;
+      const double* row = L + size_t(j) * (j + 1) / 2;
+      const double xj = __shfl_sync(0xffffffffu, x[qj], lj) * invd[j];
 #pragma unroll
-    for (int q = 0; q < RPL; ++q) {
-      const int r = lane + 32 * q;
-      if (r == j) x[q] = xj;
-      else if (r < j) x[q] = fma(-row[r], xj, x[q]);
+      for (int q = 0; q < RPL; ++q) {
+        if (q > qj) continue;
+        const int r = lane + 32 * q;
+        if (r == j) x[q] = xj;
+        else if (r < j) x[q] = fma(-row[r], xj, x[q]);
+      }
     }
   }
   double* Ci = C + (int64_t(b) * k2 + i) * k1;
@@ -206,6 +255,11 @@ __global__ void __launch_bounds__(kSolveThreads)
     const int r = lane + 32 * q;
     if (r < n) Ci[r + 1] = x[q];
   }
+}
+
+int64_t solve_lp_stride(int k1) {  // packed lower triangle of the (k1 - 1)^2 system, rounded up to an even count
+  const int64_t n = k1 - 1, n_tri = n * (n + 1) / 2;
+  return (n_tri + 1) & ~int64_t(1);
 }
 
 int neg_half_sqnorm(const double* M, int64_t ld, int64_t rows, int d, double* out, cudaStream_t st) {
@@ -354,6 +408,7 @@ size_t dm_fmap_solve_workspace_bytes(int n_pairs, int k1, int k2, int d) {
   c.take<double>(size_t(n_pairs) * k1 * k1);
   c.take<double>(size_t(n_pairs) * k2 * k1);
   c.take<int>(4);
+  c.take<double>(size_t(n_pairs) * solve_lp_stride(k1));
   return c.bytes();
 }
 
@@ -373,6 +428,8 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   double* AAt = c.take<double>(size_t(n_pairs) * k1 * k1);
   double* BAt = c.take<double>(size_t(n_pairs) * k2 * k1);
   int* status = c.take<int>(4);
+  const int64_t lp_stride = solve_lp_stride(k1);
+  double* Lp = c.take<double>(size_t(n_pairs) * lp_stride);
   DM_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
   int rc;
   GemmProblem G;
@@ -384,15 +441,17 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
   G.M = k2, G.maxM = k2, G.C = BAt, G.c_batch_stride = int64_t(k2) * k1;
   if ((rc = gemm64_launch(G, st))) return rc;
-  const size_t shm = per + (2 * 16 + size_t(n)) * sizeof(double);
+  const size_t shm = per + (1 + 2 * 16 + size_t(n)) * sizeof(double);
   const int64_t n_sys = int64_t(n_pairs) * k2;
   if (n_sys > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many systems");
+  solve_pack_kernel<<<unsigned(n_pairs), 256, 0, st>>>(AAt, w_descr, k1, lp_stride, Lp);
+  DM_LAUNCH_OK("solve_pack_kernel");
 #define DM_SOLVE(RPT)                                                                                              \
   do {                                                                                                             \
     if (shm > 48 * 1024)                                                                                           \
       DM_CUDA_OK(cudaFuncSetAttribute(fmap_solve_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
-    fmap_solve_kernel<RPT><<<unsigned(n_sys), kSolveThreads, shm, st>>>(AAt, BAt, evals1, evals2, c00, w_descr, w_lap, k1, \
-                                                                        k2, C, status);                            \
+    fmap_solve_kernel<RPT><<<unsigned(n_sys), kSolveThreads, shm, st>>>(AAt, BAt, Lp, lp_stride, evals1, evals2, c00,  \
+                                                                        w_descr, w_lap, k1, k2, C, status);        \
   } while (0)
   if (n + 1 <= kSolveThreads)
     DM_SOLVE(1);

@@ -12,7 +12,6 @@ namespace {
 
 constexpr int TM = 128, TN = 128, TK = 8, NT = 256;
 constexpr int LDT = TM + 2;  // padded row of a stage (keeps 16-byte alignment, spreads the transposing stores)
-static_assert(TM == TN, "loader assumes square tiles");
 
 struct OpView {  // an operand resolved for one batch
   const double* d;
@@ -51,29 +50,32 @@ __device__ __forceinline__ int ragged_k(const GemmOperand& o, int b) {
 //   TRANS = true : element(i, k) = Mat[k][i]   -> thread owns i = t % 128 of contraction rows k = t / 128 + 2 e
 // Raw registers of one stage: nothing here consumes a loaded value, so the loads stay in flight while the previous
 // stage is being multiplied (any arithmetic on them would stall the in-order warp on the memory latency).
+template <int NE>
 struct Staged {
-  double d[4];
-  float f[4];
-  double s[4];
+  double d[NE];
+  float f[NE];
+  double s[NE];
 };
 
-template <bool TRANS>
+// TW = tile width along the output index (128 or 64); a thread moves NE = TW * TK / NT elements per stage
+template <bool TRANS, int TW>
 struct Loader {
+  static constexpr int NE = TW * TK / NT;
   const OpView& v;
   int i0, lim;  // first output index of the tile, number of valid output indices (M or N)
   int t;
   __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {}
 
-  __device__ __forceinline__ void fetch(int k0, int kend, Staged& r) const {
+  __device__ __forceinline__ void fetch(int k0, int kend, Staged<NE>& r) const {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       int i, k;
       if (!TRANS) {
         k = k0 + (t & 7);
         i = i0 + (t >> 3) + 32 * e;
       } else {
-        i = i0 + (t & 127);
-        k = k0 + (t >> 7) + 2 * e;
+        i = i0 + (t % TW);
+        k = k0 + (t / TW) + (NT / TW) * e;
       }
       r.d[e] = 0.0, r.f[e] = 0.f, r.s[e] = 1.0;
       if (i < lim && k < kend) {
@@ -92,23 +94,27 @@ struct Loader {
       }
     }
   }
-  __device__ __forceinline__ void stash(double* stage, const Staged& r) const {
+  __device__ __forceinline__ void stash(double* stage, const Staged<NE>& r) const {
     const bool is_d = v.d != nullptr;
     const bool scaled = TRANS && v.kscale != nullptr;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       double x = is_d ? r.d[e] : double(r.f[e]);
       if (scaled) x *= r.s[e];
       if (!TRANS)
         stage[(t & 7) * LDT + (t >> 3) + 32 * e] = x;
       else
-        stage[((t >> 7) + 2 * e) * LDT + (t & 127)] = x;
+        stage[((t / TW) + (NT / TW) * e) * LDT + (t % TW)] = x;
     }
   }
 };
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
+// NB = accumulator columns per thread: 8 -> 128 x 128 tile, one CTA per SM (long contractions);
+//                                      4 -> 128 x 64 tile, two CTAs per SM (short contractions are latency-bound:
+//                                           the second CTA covers the other one's prologue and epilogue)
+template <bool TA, bool TB, int NB>
+__global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
+  constexpr int TNW = 16 * NB;  // tile width in N
   int bid = blockIdx.x;
   const int tn = bid % tiles_n;
   bid /= tiles_n;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int 
   int K = ragged_k(P.A, b);
   if (K < 0) K = ragged_k(P.B, b);
   if (K < 0) K = P.K;
-  const int m0 = tm * TM, n0 = tn * TN;
+  const int m0 = tm * TM, n0 = tn * TNW;
   if (m0 >= M || n0 >= N) return;
   int kbeg = 0, kend = K;
   if (P.ksplit > 1) {
@@ -134,16 +140,17 @@ __global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int 
   __shared__ __align__(16) double Bs[2][TK * LDT];
   const OpView A = resolve(P.A, b), B = resolve(P.B, b);
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const Loader<TA> la(A, m0, M, t);
-  const Loader<TB> lb(B, n0, N, t);
+  const Loader<TA, TM> la(A, m0, M, t);
+  const Loader<TB, TNW> lb(B, n0, N, t);
 
-  double acc[8][8];
+  double acc[8][NB];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0;
+    for (int c = 0; c < NB; ++c) acc[a][c] = 0.0;
 
-  Staged ra, rb;
+  Staged<Loader<TA, TM>::NE> ra;
+  Staged<Loader<TB, TNW>::NE> rb;
   if (kbeg < kend) {
     la.fetch(kbeg, kend, ra);
     lb.fetch(kbeg, kend, rb);
@@ -162,21 +169,24 @@ __global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int 
     const double* bs = Bs[buf];
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      double av[8], bv[8];
+      double av[8], bv[NB];
       const double2 a0 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4);
       const double2 a1 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4 + 2);
       const double2 a2 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4);
       const double2 a3 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4 + 2);
       const double2 b0 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4);
       const double2 b1 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4 + 2);
-      const double2 b2 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4);
-      const double2 b3 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4 + 2);
       av[0] = a0.x, av[1] = a0.y, av[2] = a1.x, av[3] = a1.y, av[4] = a2.x, av[5] = a2.y, av[6] = a3.x, av[7] = a3.y;
-      bv[0] = b0.x, bv[1] = b0.y, bv[2] = b1.x, bv[3] = b1.y, bv[4] = b2.x, bv[5] = b2.y, bv[6] = b3.x, bv[7] = b3.y;
+      bv[0] = b0.x, bv[1] = b0.y, bv[2] = b1.x, bv[3] = b1.y;
+      if (NB == 8) {
+        const double2 b2 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4);
+        const double2 b3 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4 + 2);
+        bv[NB - 4] = b2.x, bv[NB - 3] = b2.y, bv[NB - 2] = b3.x, bv[NB - 1] = b3.y;
+      }
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+        for (int c = 0; c < NB; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
     }
     if (more) {
       la.stash(As[buf ^ 1], ra);
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(NT, 1) gemm64_kernel(const GemmProblem P, int 
     const int m = m0 + (a >> 2) * 64 + ty * 4 + (a & 3);
     if (m >= M) continue;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < NB; ++c) {
       const int n = n0 + (c >> 2) * 64 + tx * 4 + (c & 3);
       if (n >= N) continue;
       double v = P.alpha * acc[a][c];
@@ -216,20 +226,33 @@ __global__ void __launch_bounds__(256)
 
 int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
   if (P.n_batch <= 0 || P.maxM <= 0 || P.maxN <= 0) return DM_OK;
-  const int tiles_m = (P.maxM + TM - 1) / TM, tiles_n = (P.maxN + TN - 1) / TN;
+  // narrow tiles when the contraction is short (latency-bound) or when they waste less of the N range
+  const int waste128 = (P.maxN + 127) / 128 * 128 - P.maxN, waste64 = (P.maxN + 63) / 64 * 64 - P.maxN;
+  const int kper = P.ksplit > 1 ? P.kchunk : P.maxK;
+  const bool narrow = kper <= 512 || waste64 < waste128;
+  const int tnw = narrow ? 64 : 128;
+  const int tiles_m = (P.maxM + TM - 1) / TM, tiles_n = (P.maxN + tnw - 1) / tnw;
   const int64_t nblk = int64_t(P.n_batch) * (P.ksplit > 0 ? P.ksplit : 1) * tiles_m * tiles_n;
   if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "gemm64: grid too large");
   GemmProblem Q = P;
   if (Q.ksplit < 1) Q.ksplit = 1;
   const unsigned grid = unsigned(nblk);
+#define DM_GEMM(TA_, TB_)                                                          \
+  do {                                                                             \
+    if (narrow)                                                                    \
+      gemm64_kernel<TA_, TB_, 4><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);        \
+    else                                                                           \
+      gemm64_kernel<TA_, TB_, 8><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);        \
+  } while (0)
   if (Q.A.trans && Q.B.trans)
-    gemm64_kernel<true, true><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+    DM_GEMM(true, true);
   else if (Q.A.trans)
-    gemm64_kernel<true, false><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+    DM_GEMM(true, false);
   else if (Q.B.trans)
-    gemm64_kernel<false, true><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+    DM_GEMM(false, true);
   else
-    gemm64_kernel<false, false><<<grid, NT, 0, st>>>(Q, tiles_m, tiles_n);
+    DM_GEMM(false, false);
+#undef DM_GEMM
   DM_LAUNCH_OK("gemm64_kernel");
   return DM_OK;
 }
