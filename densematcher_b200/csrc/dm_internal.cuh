@@ -167,6 +167,7 @@ struct EpiDev {
   const float* G;    // per pair: max_j |v_j| * |scale_j|
   const float* Bm;   // per pair: max_j |bias_j|
   void* out;
+  int identity;      // scale == 1 and bias == 0 everywhere (plain dot-product argmax)
 };
 
 struct FlagEntry {  // one result that must be re-evaluated in float64

@@ -547,12 +547,14 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   for (int e = 0; e < R.n_row; ++e) {
     rs[e] = SideEpiSpec{R.row[e].scale_mode, R.row[e].bias_mode, R.row[e].scale, R.row[e].bias, L.row[e].sf,
                         L.row[e].bf,         L.row[e].sd,        L.row[e].bd,    L.row[e].G,    L.row[e].Bm};
-    P.row[e] = EpiDev{L.row[e].sf, L.row[e].bf, L.row[e].sd, L.row[e].bd, L.row[e].G, L.row[e].Bm, R.row[e].out};
+    P.row[e] = EpiDev{L.row[e].sf, L.row[e].bf, L.row[e].sd, L.row[e].bd, L.row[e].G, L.row[e].Bm, R.row[e].out,
+                      R.row[e].scale_mode == DM_SCALE_NONE && R.row[e].bias_mode == DM_BIAS_NONE};
   }
   for (int e = 0; e < R.n_col; ++e) {
     cs[e] = SideEpiSpec{R.col[e].scale_mode, R.col[e].bias_mode, R.col[e].scale, R.col[e].bias, L.col[e].sf,
                         L.col[e].bf,         L.col[e].sd,        L.col[e].bd,    L.col[e].G,    L.col[e].Bm};
-    P.col[e] = EpiDev{L.col[e].sf, L.col[e].bf, L.col[e].sd, L.col[e].bd, L.col[e].G, L.col[e].Bm, R.col[e].out};
+    P.col[e] = EpiDev{L.col[e].sf, L.col[e].bf, L.col[e].sd, L.col[e].bd, L.col[e].G, L.col[e].Bm, R.col[e].out,
+                      R.col[e].scale_mode == DM_SCALE_NONE && R.col[e].bias_mode == DM_BIAS_NONE};
   }
   int rc;
   if (!(R.flags & DM_SKIP_PREP)) {

@@ -278,16 +278,23 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
         if (NR > 0 && do_rows) {
+          const bool full_tile = col0 + TN <= nd;  // no masked tail columns in this tile
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
-            const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
-            const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
             const int jb = col0 + ch * CCH;
+            if (P.row[r].identity && full_tile) {  // plain dot-product argmax: no scale / bias traffic
 #pragma unroll
-            for (int c4 = 0; c4 < CCH / 4; ++c4) {
-              const float4 s = s4[c4], b = b4[c4];
-              top3_offer4(rowst[r], rowsu[r], fmaf(v[4 * c4 + 0], s.x, b.x), fmaf(v[4 * c4 + 1], s.y, b.y),
-                          fmaf(v[4 * c4 + 2], s.z, b.z), fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4);
+              for (int c4 = 0; c4 < CCH / 4; ++c4)
+                top3_offer4(rowst[r], rowsu[r], v[4 * c4 + 0], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3], jb + 4 * c4);
+            } else {
+              const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
+              const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+#pragma unroll
+              for (int c4 = 0; c4 < CCH / 4; ++c4) {
+                const float4 s = s4[c4], b = b4[c4];
+                top3_offer4(rowst[r], rowsu[r], fmaf(v[4 * c4 + 0], s.x, b.x), fmaf(v[4 * c4 + 1], s.y, b.y),
+                            fmaf(v[4 * c4 + 2], s.z, b.z), fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4);
+              }
             }
           }
         }
@@ -299,11 +306,18 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             if (c > 0) __syncwarp();  // the previous epilogue's reads of the patch are done
+            if (P.col[c].identity && row0 + TM_ROWS <= nq) {  // plain dot products, no masked tail rows
 #pragma unroll
-            for (int c4 = 0; c4 < CCH / 4; ++c4)
-              *reinterpret_cast<float4*>(patch + lane * PATCH_LD + 4 * c4) =
-                  make_float4(fmaf(v[4 * c4 + 0], csc[c], cbi[c]), fmaf(v[4 * c4 + 1], csc[c], cbi[c]),
-                              fmaf(v[4 * c4 + 2], csc[c], cbi[c]), fmaf(v[4 * c4 + 3], csc[c], cbi[c]));
+              for (int c4 = 0; c4 < CCH / 4; ++c4)
+                *reinterpret_cast<float4*>(patch + lane * PATCH_LD + 4 * c4) =
+                    make_float4(v[4 * c4 + 0], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            } else {
+#pragma unroll
+              for (int c4 = 0; c4 < CCH / 4; ++c4)
+                *reinterpret_cast<float4*>(patch + lane * PATCH_LD + 4 * c4) =
+                    make_float4(fmaf(v[4 * c4 + 0], csc[c], cbi[c]), fmaf(v[4 * c4 + 1], csc[c], cbi[c]),
+                                fmaf(v[4 * c4 + 2], csc[c], cbi[c]), fmaf(v[4 * c4 + 3], csc[c], cbi[c]));
+            }
             __syncwarp();
             float w[32];
 #pragma unroll
@@ -324,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           bar_sync_n(2, kGroupWarps * 32);  // also orders the patch reuse of the next chunk
           // warp c of the group merges the four row quarters of column epilogue c and writes the partial of this row
           // tile.  The merge order must be ascending in the row index: TMEM quarter q' holds rows 32 q' .. 32 q' + 31.
-          const int slot = (warp - 2) & 3;  // 0..3
+          // the merging warp rotates with the chunk so that the extra work is spread over the four warps
+          const int slot = ((warp - 2) - ch) & 3;  // 0..3
           if (slot < NC) {
             const int j = col0 + ch * CCH + lane;
             Top3 m = colred[((par * kMaxEpi + slot) * kGroupWarps + 0) * CCH + lane];

@@ -221,3 +221,25 @@ def test_host_entry_equals_device_pipeline():
     s1, s2 = slice(o1[2], o1[3]), slice(o2[2], o2[3])
     assert np.array_equal(ref["nn_p2p_21"][s2], orc.nn_argmax(host.F2[s2], host.F1[s1]))
     assert np.array_equal(ref["nn_p2p_12"][s1], orc.nn_argmax(host.F2[s2], host.F1[s1], axis=0))
+
+
+def test_zoomout_ladder_full_size_30_to_200():
+    """BASELINE config 4 shape for one pair: N = 2000, ladder k = 30 -> 200 step 1 (170 iterations).  Every
+    intermediate p2p must match for the final C to match: C within 1e-4 (in practice ~1e-10) and
+    the final map bit-exact against the float64 oracle."""
+    rng = np.random.default_rng(4000)
+    n, K = 2000, 200
+    e1, P1, a1 = meshgen.synthetic_basis(n, K, rng)
+    e2, P2, a2 = meshgen.synthetic_basis(n, K, rng)
+    # a smooth-ish ground-truth relation between the bases so that the ladder is not pure noise
+    C0 = np.linalg.qr(rng.standard_normal((30, 30)))[0]
+    Cz, pz = fm_mod().zoomout(dev(C0), dev(P1), dev(P2), dev(a2), nit=170, step=1, return_p2p=True)
+    Co, po = orc.zoomout_refine(C0, P1, P2, nit=170, step=1, A2=a2, return_p2p=True)
+    assert Cz.shape == (1, 200, 200)
+    assert relF(Cz[0].cpu().numpy(), Co) < 1e-4
+    assert np.array_equal(pz.cpu().numpy(), po)
+
+
+def fm_mod():
+    from densematcher_b200 import fm as _fm
+    return _fm

@@ -207,3 +207,24 @@ def test_full_size_properties_cfg3(nn):
     perm = torch.randperm(int(nd[p]), device="cuda")
     (rp,), _ = nn.nn_argmax(Y[qo[p]:qo[p + 1]], X[do[p]:do[p + 1]][perm])
     assert torch.equal(perm[rp], r[qo[p]:qo[p + 1]])
+
+
+def test_cfg3_full_size_1024_ragged_pairs(nn):
+    """BASELINE config 3 at full size: 1024 pairs, N ~ U(1500, 2500), d = 384, one launch sequence (4 M query rows).
+    The batch is generated on the device (torch is plumbing); a sample of pairs is checked against the float64
+    argmax, and every returned index is checked to lie inside its own pair."""
+    g = torch.Generator(device="cuda").manual_seed(3001)
+    rng = np.random.default_rng(3001)
+    P = 1024
+    nq, nd = rng.integers(1500, 2501, size=P), rng.integers(1500, 2501, size=P)
+    qo, do = np.concatenate([[0], np.cumsum(nq)]), np.concatenate([[0], np.cumsum(nd)])
+    Y = torch.nn.functional.normalize(torch.randn(int(qo[-1]), 384, device="cuda", generator=g), dim=1)
+    X = torch.nn.functional.normalize(torch.randn(int(do[-1]), 384, device="cuda", generator=g), dim=1)
+    (r,), (c,), stats = nn.nn_argmax(Y, X, qo, do, col_epi=(nn.COSINE_UNIT,), out_dtype=torch.int32, return_stats=True)
+    nd_of_row = torch.repeat_interleave(torch.from_numpy(nd).cuda(), torch.from_numpy(nq).cuda())
+    nq_of_col = torch.repeat_interleave(torch.from_numpy(nq).cuda(), torch.from_numpy(nd).cuda())
+    assert bool((r >= 0).all()) and bool((r < nd_of_row).all()) and bool((c >= 0).all()) and bool((c < nq_of_col).all())
+    assert stats[0] + stats[1] < 0.02 * (qo[-1] + do[-1])
+    for p in (0, 1, 317, 511, 777, 1023):
+        S = Y[qo[p]:qo[p + 1]].double() @ X[do[p]:do[p + 1]].double().T
+        assert torch.equal(S.argmax(1).int(), r[qo[p]:qo[p + 1]]) and torch.equal(S.argmax(0).int(), c[do[p]:do[p + 1]])
