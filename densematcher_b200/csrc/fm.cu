@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
 // FMAs; the 4x4 diagonal block is then factorised redundantly by every thread (no serial owner, two block barriers
 // per four columns) and each thread finishes its own row.  Row starts r(r+1)/2 put 16 consecutive rows into 16
 // distinct 8-byte banks.  The back substitution runs in warp 0 with the unknowns in registers.
-constexpr int kSolveNB = 4;        // columns per block step
+constexpr int kSolveNB = 4;        // columns per block step (8 was measured slower: registers cut the resident systems per SM)
 constexpr int kSolveThreads = 128;
 
 // 1 / sqrt(v) in float64 from the fp32 hardware estimate and two Newton steps (error ~2^-52; the factorisation does
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256)
 }
 
 template <int RPT>  // rows per thread: (n + 1) <= 128 * RPT
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, RPT == 1 ? 5 : 1)
     fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ Lp,
                       int64_t lp_stride, const double* __restrict__ ev1, const double* __restrict__ ev2,
                       const double* __restrict__ c00, double wd, double wl, int k1, int k2, double* __restrict__ C,
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kSolveThreads)
   const int n_tri = n * (n + 1) / 2;
   double* L = sm;                                        // row r starts at r (r + 1) / 2; row n = right-hand side
   double* Dbuf = sm + size_t(n + 1) * (n + 2) / 2 + 1;   // [2][4][4] accumulated diagonal blocks (double-buffered)
-  double* invd = Dbuf + 32;                              // [n] reciprocals of the diagonal of L
+  double* invd = Dbuf + 2 * kSolveNB * kSolveNB;                           // [n] reciprocals of the diagonal of L
   __shared__ double s_scale[kSolveThreads / 32];
   __shared__ __align__(8) unsigned long long s_bar;
   const int b = sys / k2, i = sys % k2;
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(kSolveThreads)
       }
     }
     // publish the accumulated diagonal block (rows j0 .. j0+3 live in threads 0 .. 3, slot 0)
-    double* D = Dbuf + par * 16;
+    double* D = Dbuf + par * kSolveNB * kSolveNB;
     if (t < kSolveNB) {
 #pragma unroll
-      for (int c = 0; c < kSolveNB; ++c) D[t * 4 + c] = acc[0][c];
+      for (int c = 0; c < kSolveNB; ++c) D[t * kSolveNB + c] = acc[0][c];
     }
     __syncthreads();
     // every thread factorises the 4x4 block: l[c][c2], c2 < c, and the reciprocal diagonal li[c]
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kSolveThreads)
     for (int c = 0; c < kSolveNB; ++c) {
 #pragma unroll
       for (int c2 = 0; c2 <= c; ++c2) {
-        double v = D[c * 4 + c2];
+        double v = D[c * kSolveNB + c2];
 #pragma unroll
         for (int c3 = 0; c3 < c2; ++c3) v = fma(-l[c][c3], l[c2][c3], v);
         if (c2 == c) {
@@ -441,7 +441,7 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
   G.M = k2, G.maxM = k2, G.C = BAt, G.c_batch_stride = int64_t(k2) * k1;
   if ((rc = gemm64_launch(G, st))) return rc;
-  const size_t shm = per + (1 + 2 * 16 + size_t(n)) * sizeof(double);
+  const size_t shm = per + (1 + 2 * kSolveNB * kSolveNB + size_t(n)) * sizeof(double);
   const int64_t n_sys = int64_t(n_pairs) * k2;
   if (n_sys > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many systems");
   solve_pack_kernel<<<unsigned(n_pairs), 256, 0, st>>>(AAt, w_descr, k1, lp_stride, Lp);

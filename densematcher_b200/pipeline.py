@@ -145,7 +145,9 @@ class HostStager:
         self.device = torch.device(device)
         self.h2d, self.comp, self.d2h = (torch.cuda.Stream(self.device) for _ in range(3))
         self.slots = [dict(bufs={}, stage=None, in_ev=None, done_ev=None) for _ in range(self.N_SLOTS)]
-        self.out = {}
+        self.out_sets = [{}, {}]   # two sets of pinned result buffers, used alternately (see ``run(copy=False)``)
+        self.out = self.out_sets[0]
+        self.calls = 0
 
     def _slot_buf(self, slot, name, rows, like):
         """device buffer of the slot for field `name` with at least `rows` rows"""
@@ -163,9 +165,13 @@ class HostStager:
             self.out[name] = b
         return b
 
-    def run(self, batch: "PairBatchHost", chunk_pairs: int, **kw):
+    def run(self, batch: "PairBatchHost", chunk_pairs: int, copy: bool = True, **kw):
+        """``copy=False`` returns numpy VIEWS of the pinned result buffers: no extra host pass over the results, valid
+        until the call after the next one on this stager (the two buffer sets alternate)."""
         if not batch._pinned:
             batch.pin()
+        self.calls += 1
+        self.out = self.out_sets[self.calls & 1]
         P = batch.n_pairs
         cur = torch.cuda.current_stream(self.device)
         for s in (self.h2d, self.comp, self.d2h):
@@ -219,22 +225,25 @@ class HostStager:
             keep.append(res)  # results stay alive until the D2H copies have run
         self.d2h.synchronize()
         cur.wait_stream(self.comp)
-        return {n: self.out[n][:rows].numpy().copy() for n, rows in outs.items()}
+        if copy:
+            return {n: self.out[n][:rows].numpy().copy() for n, rows in outs.items()}
+        return {n: self.out[n][:rows].numpy() for n, rows in outs.items()}
 
 
 _stagers = {}
 
 
-def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 32, **kw):
+def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 16, copy: bool = True, **kw):
     """Host buffers in, host (numpy) results out -- the call a user of the reference would make per batch:
-    pinned H2D copies, the device pipeline, D2H copies, overlapped chunk by chunk (see ``HostStager``)."""
+    pinned H2D copies, the device pipeline, D2H copies, overlapped chunk by chunk (see ``HostStager``).
+    ``copy=False``: results are views of pinned buffers that stay valid until the call after the next one."""
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
     st = _stagers.get(str(device))
     if st is None:
         st = _stagers[str(device)] = HostStager(device)
-    return st.run(batch, int(chunk_pairs), **kw)
+    return st.run(batch, int(chunk_pairs), copy=copy, **kw)
 
 
 def shard_pairs(n_pairs: int, rank: int, world: int):

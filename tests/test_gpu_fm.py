@@ -213,7 +213,7 @@ def test_host_entry_equals_device_pipeline():
     ref = {n: t.cpu().numpy() for n, t in pipeline.match_pairs_device(host.to_device("cuda:0"), k=12).items()}
     for chunk in (3, 7, 64):
         for _ in range(2):  # second call reuses every staging buffer
-            out = pipeline.match_pairs_host(host, "cuda:0", chunk_pairs=chunk, k=12)
+            out = pipeline.match_pairs_host(host, "cuda:0", chunk_pairs=chunk, k=12, copy=(chunk != 7))
             assert set(out) == set(ref)
             for n in ref:
                 assert out[n].dtype == ref[n].dtype and np.array_equal(out[n], ref[n]), (n, chunk)
