@@ -22,6 +22,7 @@ DM_RECHECK_ALL = 1 << 4
 DM_SKIP_PREP = 1 << 5
 DM_SKIP_FINISH = 1 << 6
 DM_F64_GEMM = 1 << 7
+DM_FAST_FM = 1 << 8
 SCALE_NONE, SCALE_ARRAY, SCALE_INVNORM = 0, 1, 2
 BIAS_NONE, BIAS_ARRAY, BIAS_NEG_HALF_SQNORM = 0, 1, 2
 

@@ -279,6 +279,13 @@ size_t p2p_to_fm_ws(int n_pairs, int max_n2, int k1, int k2) {
   if (ks > 1) c.take<double>(size_t(ks) * n_pairs * k1 * k2);
   return c.bytes();
 }
+size_t zoomout_pf_ws(int n_pairs, int64_t total_n2, int max_n2, int k1m, int k2m, int flags) {
+  const size_t a = p2p_to_fm_ws(n_pairs, max_n2, k1m, k2m);
+  const size_t b = ((flags & DM_FAST_FM) && proj_tc_supported(k2m, k1m))
+                       ? proj_tc_workspace_bytes(n_pairs, total_n2, max_n2, k2m, k1m) : 0;
+  return a > b ? a : b;
+}
+
 int p2p_to_fm_run(const void* p2p, int p2p_i64, const double* Phi1, int64_t ld1, const int64_t* off1,
                   const double* Phi2, int64_t ld2, const int64_t* off2, int max_n2, const double* area2, int n_pairs,
                   int k1, int k2, double* C, void* ws, cudaStream_t st) {
@@ -598,7 +605,7 @@ size_t dm_zoomout_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n
   c.take<float>(size_t(total_n1) * pad4(k2m));  // fp32 emb1
   c.take<float>(size_t(total_n2) * pad4(k2m));  // fp32 Phi2
   c.take<int32_t>(size_t(total_n2) * 2);        // p2p (int32 or int64)
-  c.take<char>(p2p_to_fm_ws(n_pairs, max_n2, k1m, k2m));
+  c.take<char>(zoomout_pf_ws(n_pairs, total_n2, max_n2, k1m, k2m, flags));
   c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags));
   return c.bytes();
 }
@@ -627,8 +634,9 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   S.Xf = c.take<float>(size_t(total_n1) * S.ldf);
   float* Phi2f = c.take<float>(size_t(total_n2) * S.ldf);
   void* p2p = c.take<int32_t>(size_t(total_n2) * 2);
-  const size_t pf_bytes = p2p_to_fm_ws(n_pairs, max_n2, k1m, k2m);
+  const size_t pf_bytes = zoomout_pf_ws(n_pairs, total_n2, max_n2, k1m, k2m, flags);
   void* pf_ws = c.take<char>(pf_bytes);
+  const bool fast_fm = (flags & DM_FAST_FM) && proj_tc_supported(k2m, k1m);
   S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags);
   S.nn_ws = c.take<char>(S.nn_ws_bytes);
   const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
@@ -642,8 +650,13 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
                         max_n2, n_pairs, p2p, flags, S, st)))
       return rc;
     double* Cnext = (it == nit - 1) ? C_out : Cbuf[it & 1];
-    if ((rc = p2p_to_fm_run(p2p, i64, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs, k1 + step1, k2 + step2,
-                            Cnext, pf_ws, st)))
+    if (fast_fm) {
+      // C = Phi2[:, :k2+s]^T (a2 * Phi1[p, :k1+s]) on the tensor cores: A operand = Phi2, B operand = gathered, scaled Phi1
+      if ((rc = proj_tc_run(Phi2, ld2, nullptr, nullptr, Phi1, ld1, area2, p2p, i64, off1, off2, total_n2, max_n2, n_pairs,
+                            k2 + step2, k1 + step1, Cnext, pf_ws, pf_bytes, st)))
+        return rc;
+    } else if ((rc = p2p_to_fm_run(p2p, i64, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs, k1 + step1,
+                                   k2 + step2, Cnext, pf_ws, st)))
       return rc;
     Ccur = Cnext;
     k1 += step1, k2 += step2;

@@ -56,7 +56,9 @@ enum {
   DM_RECHECK_ALL = 1 << 4,  /* testing: send every row through the float64 path */
   DM_SKIP_PREP = 1 << 5,    /* profiling: reuse the operand preparation a previous identical call left in the workspace */
   DM_SKIP_FINISH = 1 << 6,  /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
-  DM_F64_GEMM = 1 << 7      /* projection: float64 CUDA-core contraction instead of the tcgen05 split-bf16 engine */
+  DM_F64_GEMM = 1 << 7,     /* projection: float64 CUDA-core contraction instead of the tcgen05 split-bf16 engine */
+  DM_FAST_FM = 1 << 8       /* ZoomOut: form C = Phi2^T A2 Phi1[p] on the tcgen05 split-bf16 engine (fp32-grade, ~2e-6)
+                               instead of float64; p2p near ties may then resolve differently from the float64 reference */
 };
 
 /* how the per-element scale / bias of one argmax epilogue is obtained */

@@ -243,3 +243,14 @@ def test_zoomout_ladder_full_size_30_to_200():
 def fm_mod():
     from densematcher_b200 import fm as _fm
     return _fm
+
+
+def test_zoomout_fast_mode_stays_close(golden_zo):
+    """DM_FAST_FM (tensor-core accumulation of C, fp32-grade) is an opt-in: C within 1e-3 of the float64 ladder and
+    the final map equal on all but a handful of near-tie vertices."""
+    from densematcher_b200 import _lib
+    g = golden_zo
+    C, p = fm_mod().zoomout(dev(g["C0"]), dev(g["Phi1"]), dev(g["Phi2"]), dev(g["area2"]), nit=14, step=1,
+                            return_p2p=True, flags=_lib.DM_FAST_FM)
+    assert relF(C[0].cpu().numpy(), g["ref_C_zo"]) < 1e-3
+    assert np.mean(p.cpu().numpy() != g["ref_p2p_zo"]) < 0.01
