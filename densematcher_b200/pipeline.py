@@ -20,8 +20,8 @@ import torch
 from . import fm as _fm
 from . import nn as _nn
 
-__all__ = ["PairBatchHost", "PairBatchDevice", "match_pairs_device", "match_pairs_host", "shard_pairs",
-           "gather_results"]
+__all__ = ["PairBatchHost", "PairBatchDevice", "MeshBankDevice", "match_pairs_device", "match_pairs_host",
+           "match_bank_pairs", "intra_category_pairs", "shard_pairs", "gather_results"]
 
 
 @dataclass
@@ -244,6 +244,80 @@ def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 16, c
     if st is None:
         st = _stagers[str(device)] = HostStager(device)
     return st.run(batch, int(chunk_pairs), copy=copy, **kw)
+
+
+class MeshBankDevice:
+    """A dataset of meshes resident in HBM once (features, eigenbasis, eigenvalues, vertex areas, ragged-packed by
+    ``off``), from which batches of (source, target) pairs are assembled ON THE DEVICE.  This is the layout for
+    dataset-shaped workloads (BASELINE config 5: 599 meshes, every intra-category pair): each mesh is uploaded once
+    (~4.7 MB at N = 2000, d = 384, K = 100) instead of once per pair it takes part in; assembling a pair costs one
+    gather of its rows (~19 MB of HBM traffic, ~3 us) against ~55 us of matching."""
+
+    def __init__(self, F, off, Phi=None, evals=None, area=None, device=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        to = lambda a, dt: None if a is None else torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a,
+                                                                   dtype=dt).to(device)
+        self.device = device
+        self.F, self.Phi, self.area = to(F, torch.float32), to(Phi, torch.float64), to(area, torch.float64)
+        self.evals = to(evals, torch.float64)                     # [n_meshes, K]
+        self.off_h = np.ascontiguousarray(np.asarray(off, dtype=np.int64))
+        self.off = torch.from_numpy(self.off_h).to(device)
+        self.n_meshes = len(self.off_h) - 1
+        self.sizes_h = np.diff(self.off_h)
+
+    def _rows(self, mesh_ids_h):
+        """global row indices of the listed meshes, concatenated (device int64) + packed offsets (host)."""
+        sizes = self.sizes_h[mesh_ids_h]
+        o = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        ids = torch.from_numpy(np.ascontiguousarray(mesh_ids_h, dtype=np.int64)).to(self.device)
+        start = self.off[ids]                                                    # [P]
+        od = torch.from_numpy(o).to(self.device)
+        seg = torch.repeat_interleave(torch.arange(len(sizes), device=self.device), torch.from_numpy(sizes).to(self.device))
+        rows = start[seg] + (torch.arange(int(o[-1]), device=self.device) - od[:-1][seg])
+        return rows, o, od
+
+    def assemble(self, src_ids, dst_ids):
+        """PairBatchDevice of the pairs (src_ids[p] -> mesh 1, dst_ids[p] -> mesh 2), gathered on the device."""
+        src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
+        r1, o1h, o1d = self._rows(src_ids)
+        r2, o2h, o2d = self._rows(dst_ids)
+        g = lambda t, r: None if t is None else t.index_select(0, r)
+        i1 = torch.from_numpy(src_ids).to(self.device)
+        i2 = torch.from_numpy(dst_ids).to(self.device)
+        return PairBatchDevice(F1=g(self.F, r1), F2=g(self.F, r2), off1_h=_nn.Offsets(o1d, o1h), off2_h=_nn.Offsets(o2d, o2h),
+                               device=self.device, Phi1=g(self.Phi, r1), Phi2=g(self.Phi, r2),
+                               evals1=g(self.evals, i1), evals2=g(self.evals, i2), area1=g(self.area, r1),
+                               area2=g(self.area, r2))
+
+
+def intra_category_pairs(categories):
+    """All ordered pairs (i, j), i != j, of meshes that share a category label (BASELINE config 5), grouped by
+    category so that consecutive pairs reuse the same meshes (L2 locality).  Returns two int64 arrays."""
+    categories = np.asarray(categories)
+    src, dst = [], []
+    for c in np.unique(categories):
+        idx = np.nonzero(categories == c)[0]
+        ii, jj = np.meshgrid(idx, idx, indexing="ij")
+        keep = ii != jj
+        src.append(ii[keep]); dst.append(jj[keep])
+    cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.zeros(0, np.int64)
+    return cat(src), cat(dst)
+
+
+def match_bank_pairs(bank: MeshBankDevice, src_ids, dst_ids, chunk_pairs: int = 128, rank: int = 0, world: int = 1,
+                     to_host: bool = True, **kw):
+    """Runs the hot path over a list of pairs drawn from a device-resident mesh bank, ``chunk_pairs`` at a time.
+    With ``world > 1`` only this rank's contiguous block of the pair list (``shard_pairs``) is processed.
+    Returns (list of per-chunk result dicts, (lo, hi) of the processed block); index maps are local to each pair
+    and packed in pair order."""
+    src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
+    lo, hi = shard_pairs(len(src_ids), rank, world)
+    out = []
+    for a in range(lo, hi, chunk_pairs):
+        b = min(hi, a + chunk_pairs)
+        res = match_pairs_device(bank.assemble(src_ids[a:b], dst_ids[a:b]), **kw)
+        out.append({n: (t.cpu().numpy() if to_host else t) for n, t in res.items()})
+    return out, (lo, hi)
 
 
 def shard_pairs(n_pairs: int, rank: int, world: int):

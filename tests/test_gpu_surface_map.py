@@ -118,3 +118,43 @@ def test_trimesh_host_spectrum_fallback():
     r21, r12, MI = orc.fm_to_p2p(model._FM_base, m1.eigenvectors, m2.eigenvectors, m1.vertex_areas)
     assert np.array_equal(out[10], r21) and np.array_equal(out[11], r12)
     assert np.array_equal(out[0], MI.argmax(1)) and np.array_equal(out[1], MI.argmax(0))
+
+
+def test_mesh_bank_intra_category_pairs_cfg5_shape():
+    """BASELINE config 5 stand-in at reduced scale: a bank of meshes in a few categories, every ordered
+    intra-category pair matched from the device-resident bank; equals the packed-batch pipeline and the oracle."""
+    import torch
+    from oracle import meshgen
+    from densematcher_b200 import pipeline
+    rng = np.random.default_rng(5000)
+    cats = np.array([0, 0, 0, 1, 1, 2, 2, 2, 2])
+    sizes = rng.integers(180, 260, size=len(cats))
+    K, d, k = 16, 48, 12
+    bases = [meshgen.synthetic_basis(int(n), K, rng) for n in sizes]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    F = meshgen.random_unit_features(int(off[-1]), d, rng)
+    bank = pipeline.MeshBankDevice(F, off, Phi=np.concatenate([b[1] for b in bases]), evals=np.stack([b[0] for b in bases]),
+                                   area=np.concatenate([b[2] for b in bases]))
+    src, dst = pipeline.intra_category_pairs(cats)
+    assert len(src) == 3 * 2 + 2 * 1 + 4 * 3 and np.all(cats[src] == cats[dst]) and np.all(src != dst)
+    chunks, (lo, hi) = pipeline.match_bank_pairs(bank, src, dst, chunk_pairs=7, k=k)
+    assert (lo, hi) == (0, len(src)) and len(chunks) == 3
+    # the same pairs as one packed host batch
+    sl = lambda a, i: a[off[i]:off[i + 1]]
+    host = pipeline.PairBatchHost(
+        F1=np.concatenate([sl(F, i) for i in src]), F2=np.concatenate([sl(F, j) for j in dst]),
+        off1=np.concatenate([[0], np.cumsum(sizes[src])]), off2=np.concatenate([[0], np.cumsum(sizes[dst])]),
+        Phi1=np.concatenate([bases[i][1] for i in src]), Phi2=np.concatenate([bases[j][1] for j in dst]),
+        evals1=np.stack([bases[i][0] for i in src]), evals2=np.stack([bases[j][0] for j in dst]),
+        area1=np.concatenate([bases[i][2] for i in src]), area2=np.concatenate([bases[j][2] for j in dst]))
+    ref = {n: t.cpu().numpy() for n, t in pipeline.match_pairs_device(host.to_device("cuda:0"), k=k).items()}
+    for n in ref:
+        got = np.concatenate([c[n] for c in chunks])
+        assert np.array_equal(got, ref[n]), n
+    # oracle on the first pair
+    i, j = int(src[0]), int(dst[0])
+    assert np.array_equal(chunks[0]["nn_p2p_21"][:sizes[j]], orc.nn_argmax(sl(F, j), sl(F, i)))
+    # two ranks cover the list without overlap
+    blocks = [pipeline.match_bank_pairs(bank, src, dst, chunk_pairs=64, rank=r, world=2, feature_nn=True,
+                                        functional_map=False)[1] for r in range(2)]
+    assert blocks[0][0] == 0 and blocks[0][1] == blocks[1][0] and blocks[1][1] == len(src)
