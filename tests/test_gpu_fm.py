@@ -254,3 +254,19 @@ def test_zoomout_fast_mode_stays_close(golden_zo):
                             return_p2p=True, flags=_lib.DM_FAST_FM)
     assert relF(C[0].cpu().numpy(), g["ref_C_zo"]) < 1e-3
     assert np.mean(p.cpu().numpy() != g["ref_p2p_zo"]) < 0.01
+
+
+def test_diffusionnet_to_basis_matches_torch():
+    """to_basis (diffusion_net/geometry.py:572-583) on the tcgen05 projection engine vs the plain float64 product."""
+    import torch
+    from densematcher_b200.spectral_ops import to_basis, from_basis
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, V, K, D = 3, 700, 64, 96
+    vals = torch.randn(B, V, D, device="cuda", generator=g)
+    basis = torch.linalg.qr(torch.randn(B, V, K, device="cuda", generator=g, dtype=torch.float64))[0]
+    mass = torch.rand(B, V, device="cuda", generator=g, dtype=torch.float64) + 0.5
+    ref = basis.transpose(1, 2) @ (vals.double() * mass[..., None])
+    out = to_basis(vals, basis, mass)
+    assert out.shape == (B, K, D) and float((out.double() - ref).norm() / ref.norm()) < 5e-6
+    back = from_basis(out[0].double(), basis[0])
+    assert back.shape == (V, D)
