@@ -270,3 +270,53 @@ def test_diffusionnet_to_basis_matches_torch():
     assert out.shape == (B, K, D) and float((out.double() - ref).norm() / ref.norm()) < 5e-6
     back = from_basis(out[0].double(), basis[0])
     assert back.shape == (V, D)
+
+
+@pytest.mark.parametrize("k1,k2", [(2, 2), (3, 5), (33, 20), (64, 64), (129, 100), (160, 170), (236, 30)])
+def test_fmap_solve_sizes(k1, k2):
+    """Closed-form solve across system sizes: tiny, non-square, one row per thread (k1 <= 128) and two (k1 > 128),
+    up to the shared-memory limit (k1 = 236)."""
+    rng = np.random.default_rng(k1 * 1000 + k2)
+    d, P = 48, 2
+    A = rng.standard_normal((P, k1, d)); B = rng.standard_normal((P, k2, d))
+    ev1 = np.sort(rng.random((P, k1)) * 50, axis=1); ev2 = np.sort(rng.random((P, k2)) * 50, axis=1)
+    ev1[:, 0] = ev2[:, 0] = 0.0
+    c00 = rng.standard_normal(P)
+    C = fm_mod().fmap_solve(dev(A), dev(B), dev(ev1), dev(ev2), dev(c00), 3.0, 0.7).cpu().numpy()
+    for p in range(P):
+        Co = orc.fmap_solve_closed_form(A[p], B[p], ev1[p], ev2[p], c00[p], 3.0, 0.7)
+        assert relF(C[p], Co) < 1e-9, (k1, k2, p)
+    if k1 == 236:
+        with pytest.raises(Exception):
+            fm_mod().fmap_solve(dev(rng.standard_normal((1, 260, 8))), dev(B[:1, :, :8]), dev(np.zeros((1, 260))),
+                                dev(ev2[:1]), dev(c00[:1]), 1.0, 1.0)
+
+
+def test_random_shape_sweep_projection_p2p_to_fm_fm_to_p2p():
+    """Randomised shapes through the tensor-core projection, the float64 GEMM paths and the fused FM->p2p pass."""
+    rng = np.random.default_rng(99)
+    f = fm_mod()
+    for trial in range(12):
+        P = int(rng.integers(1, 4))
+        n1, n2 = rng.integers(3, 400, size=P), rng.integers(3, 400, size=P)
+        k1, k2 = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        k1, k2 = min(k1, int(n1.min())), min(k2, int(n2.min()))
+        d = int(rng.integers(1, 90))
+        o1 = np.concatenate([[0], np.cumsum(n1)]); o2 = np.concatenate([[0], np.cumsum(n2)])
+        Phi1 = rng.standard_normal((o1[-1], k1)); Phi2 = rng.standard_normal((o2[-1], k2))
+        a1 = rng.random(o1[-1]) + 0.1; a2 = rng.random(o2[-1]) + 0.1
+        F1 = rng.standard_normal((o1[-1], d)).astype(np.float32)
+        A = f.project(dev(Phi1), dev(a1), dev(F1), o1).cpu().numpy()
+        C = rng.standard_normal((P, k2, k1))
+        out = f.fm_to_p2p(dev(C), dev(Phi1), dev(Phi2), dev(a1), o1, o2)
+        p21 = out["p2p_21"].cpu().numpy()
+        Cn = f.p2p_to_fm(dev(p21), dev(Phi1), dev(Phi2), dev(a2), o1, o2).cpu().numpy()
+        for p in range(P):
+            s1, s2 = slice(o1[p], o1[p + 1]), slice(o2[p], o2[p + 1])
+            ref = orc.project(Phi1[s1], a1[s1], F1[s1])
+            assert np.abs(A[p] - ref).max() < 5e-6 * np.abs(ref).max() + 1e-9, (trial, "project")
+            r21, r12, MI = orc.fm_to_p2p(C[p], Phi1[s1], Phi2[s2], a1[s1])
+            assert np.array_equal(p21[s2], r21) and np.array_equal(out["p2p_12"][s1].cpu().numpy(), r12), (trial, "p2p")
+            assert np.array_equal(out["dense_21"][s2].cpu().numpy(), MI.argmax(1)), (trial, "dense_21")
+            assert np.array_equal(out["dense_12"][s1].cpu().numpy(), MI.argmax(0)), (trial, "dense_12")
+            assert relF(Cn[p], orc.p2p_to_fm(r21, Phi1[s1], Phi2[s2], a2[s2])) < 1e-11, (trial, "p2p_to_fm")

@@ -228,3 +228,32 @@ def test_cfg3_full_size_1024_ragged_pairs(nn):
     for p in (0, 1, 317, 511, 777, 1023):
         S = Y[qo[p]:qo[p + 1]].double() @ X[do[p]:do[p + 1]].double().T
         assert torch.equal(S.argmax(1).int(), r[qo[p]:qo[p + 1]]) and torch.equal(S.argmax(0).int(), c[do[p]:do[p + 1]])
+
+
+def test_random_shape_sweep_against_float64(nn):
+    """Randomised ragged batches (tiny pairs, d from 1 to 530, non-unit rows, every epilogue kind) against the
+    float64 argmax; the boundaries of the 128-row / 256-column / 64-K tiling are all crossed."""
+    rng = np.random.default_rng(2024)
+    for trial in range(25):
+        P = int(rng.integers(1, 6))
+        nq = rng.integers(1, 700, size=P); nd = rng.integers(1, 700, size=P)
+        if trial % 5 == 0:
+            nq[0], nd[0] = (128, 256) if trial % 10 == 0 else (129, 257)
+        d = int(rng.choice([2, 3, 31, 64, 65, 100, 128, 200, 384, 530]))
+        qo, do = np.concatenate([[0], np.cumsum(nq)]), np.concatenate([[0], np.cumsum(nd)])
+        Y = (rng.standard_normal((qo[-1], d)) * rng.uniform(0.1, 3)).astype(np.float32)
+        X = (rng.standard_normal((do[-1], d)) * rng.uniform(0.1, 3)).astype(np.float32)
+        sc = rng.random(do[-1]) + 0.2
+        rows = (nn.EUCLID, nn.Epi(scale=dev(sc)))
+        cols = (nn.COSINE, nn.COSINE_UNIT)
+        (e, w), (cc, cu) = nn.nn_argmax(dev(Y), dev(X), qo, do, row_epi=rows, col_epi=cols)
+        for p in range(P):
+            y, x = Y[qo[p]:qo[p + 1]].astype(np.float64), X[do[p]:do[p + 1]].astype(np.float64)
+            S = y @ x.T
+            tag = (trial, p, int(nq[p]), int(nd[p]), d)
+            assert np.array_equal(e[qo[p]:qo[p + 1]].cpu().numpy(), (S - 0.5 * (x * x).sum(1)[None]).argmax(1)), tag
+            assert np.array_equal(w[qo[p]:qo[p + 1]].cpu().numpy(), (S * sc[do[p]:do[p + 1]][None]).argmax(1)), tag
+            if d >= 3:  # in 1-2 dimensions cosines tie exactly up to rounding: the float64 winner is rounding noise
+                assert np.array_equal(cc[do[p]:do[p + 1]].cpu().numpy(),
+                                      (S * (1.0 / np.linalg.norm(y, axis=1))[:, None]).argmax(0)), tag
+            assert np.array_equal(cu[do[p]:do[p + 1]].cpu().numpy(), S.argmax(0)), tag
