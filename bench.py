@@ -293,10 +293,11 @@ def main():
                "sample": f"{sample} pairs of the same batch, oracle port of the reference path "
                          "(sklearn kd-tree n_jobs=-1, numpy/scipy float64)"}
 
-    # launches of OUR kernels per step (profiles/launches_*): feature NN 8 (2 prep, 2 per-pair maxima, score, column
-    # finalise, 2 re-evaluation) + projection 2 x 4 (2 split, tcgen05 GEMM, reduce) + solve 4 (2 Gram GEMMs, pack, Cholesky)
-    # + FM->p2p 11 (2 embedding GEMMs, norms, 2 prep, 2 per-pair maxima, score, finalise, 2 re-evaluation)
-    launches_per_step = 8 + 8 + 4 + 11
+    # launches of OUR kernels per step (profiles/launches_*; one dm_match_pairs call): feature NN 8 (2 prep, 2 per-pair
+    # maxima, score, column finalise, 2 re-evaluation) + projection 2 x 3 (split of Phi, tcgen05 GEMM, reduce; the
+    # feature splits come from the NN stage) + pinned entry 1 + solve 4 (2 Gram GEMMs, pack, Cholesky) + FM->p2p 11
+    # (2 embedding GEMMs, norms, 2 prep, 2 per-pair maxima, score, finalise, 2 re-evaluation)
+    launches_per_step = 8 + 6 + 1 + 4 + 11
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

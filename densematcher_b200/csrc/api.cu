@@ -187,8 +187,8 @@ int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, 
   set_single_pair_offsets<<<1, 1, 0, st>>>(off, nq, off + 2, ndb);
   DM_LAUNCH_OK("set_single_pair_offsets");
   int rc;
-  if ((rc = nn_prep_side(Y, 0, ldY, off, 1, nq, d, nqv, nullptr, 0, yh, yl, kp, st))) return rc;
-  if ((rc = nn_prep_side(X, 0, ldX, off + 2, 1, ndb, d, ndv, nullptr, 0, xh, xl, kp, st))) return rc;
+  if ((rc = nn_prep_side(Y, 0, ldY, off, 1, nq, d, nqv, nullptr, 0, yh, yl, nullptr, kp, st))) return rc;
+  if ((rc = nn_prep_side(X, 0, ldX, off + 2, 1, ndb, d, ndv, nullptr, 0, xh, xl, nullptr, kp, st))) return rc;
   NNProblem P{};
   P.q_off = off, P.db_off = off + 2, P.total_q = nq, P.total_db = ndb, P.max_q = nq, P.max_db = ndb;
   P.n_pairs = 1, P.d = d, P.kp = kp, P.rt_rows = kFfmaRowTile, P.max_rt = (nq + kFfmaRowTile - 1) / kFfmaRowTile;

@@ -269,7 +269,8 @@ struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of
 };
 // norms + derived scale/bias + per-pair maxima for one side; M is float or double
 int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
-                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi, void* lo, int kp, cudaStream_t st);
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi, void* lo, void* lo2, int kp,
+                 cudaStream_t st);
 int nn_col_finalize(const NNProblem& P, cudaStream_t st);
 int nn_recheck(const NNProblem& P, cudaStream_t st);
 
@@ -296,15 +297,23 @@ struct NNRequest {
 };
 size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                           int n_col, int flags);
-int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st);
+// internal flag: also keep the third bf16 split (v = hi + lo + lo2) of both operands in the workspace, so that the
+// projection engine can reuse the feature splits of the nearest-neighbour stage (dm_match_pairs)
+constexpr int kFlagSplit3 = 1 << 30;
+struct NNSplits {  // where nn_run left the split operands ([rows, kp] bf16 each)
+  const void *yh, *yl, *yl2, *xh, *xl, *xl2;
+  int kp;
+};
+int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSplits* splits = nullptr);
 
 // tcgen05 projection engine (proj_tc.cu): out[b] = (a_scale A)^T (b_scale B[gather]) over the rows of batch b
 bool proj_tc_supported(int k, int d);
 size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d);
+// b_presplit (optional): three [total_n, pad64(d)] bf16 arrays (hi, mid, lo) of the B operand prepared elsewhere
 int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float* Bf, const double* Bd, int64_t ldB,
                 const double* b_scale, const void* b_gather, int b_gather_i64, const int64_t* b_gather_src_off,
                 const int64_t* off, int64_t total_n, int max_n, int n_batch, int k, int d, double* out, void* ws,
-                size_t ws_bytes, cudaStream_t st);
+                size_t ws_bytes, cudaStream_t st, const void* const* b_presplit = nullptr);
 
 int num_sms();
 int cvt_f64_f32(const double* src, int64_t lds, int64_t rows, int d, float* dst, int ldd, cudaStream_t st);

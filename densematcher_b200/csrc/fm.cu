@@ -674,7 +674,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
 // ------------------------------------------------------------------ spectral ICP
 namespace {
 struct IcpLayout {
-  double *G, *Ginv, *Phi2p, *X, *lin;
+  double *G, *Ginv, *Phi2p, *X, *lin, *ns;
   int* status;
   P2P21Scratch S;
   float* Phi2f;
@@ -693,6 +693,7 @@ IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, i
   const size_t lin = spd_inverse_scratch_doubles(k2) > polar_scratch_doubles(k2, k1) ? spd_inverse_scratch_doubles(k2)
                                                                                      : polar_scratch_doubles(k2, k1);
   L.lin = c.take<double>(lin * n_pairs);
+  L.ns = c.take<double>(polar_ns_scratch_doubles(k2, k1, n_pairs));
   L.status = c.take<int>(4);
   L.S.lde = k2, L.S.ldf = pad4(k2);
   L.S.emb1 = c.take<double>(size_t(total_n1) * k2);
@@ -756,7 +757,7 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
                             L.pf_ws, st)))
       return rc;
     // C <- U I V^T  (icp.py:39-40)
-    if ((rc = polar_factor_launch(L.X, C_out, k2, k1, n_pairs, L.lin, st))) return rc;
+    if ((rc = polar_factor_launch(L.X, C_out, k2, k1, n_pairs, L.lin, L.ns, st))) return rc;
     Ccur = C_out;
   }
   if (nit == 0)
@@ -767,6 +768,153 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
       return rc;
   }
   return DM_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ the whole per-pair path in one call
+namespace dm {
+namespace {
+// c00[p] = sign(Phi1[first row of p][0] * Phi2[first row][0]) * sqrt(sum area2 / sum area1)   (functional.py:654-658)
+__global__ void __launch_bounds__(256)
+    c00_kernel(const double* __restrict__ Phi1, int64_t ld1, const int64_t* __restrict__ off1,
+               const double* __restrict__ Phi2, int64_t ld2, const int64_t* __restrict__ off2,
+               const double* __restrict__ area1, const double* __restrict__ area2, double* __restrict__ c00) {
+  const int p = blockIdx.x, t = threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t r = off1[p] + t; r < off1[p + 1]; r += 256) s1 += area1[r];
+  for (int64_t r = off2[p] + t; r < off2[p + 1]; r += 256) s2 += area2[r];
+  __shared__ double r1[8], r2[8];
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+  }
+  if ((t & 31) == 0) r1[t >> 5] = s1, r2[t >> 5] = s2;
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < 8; ++w) s1 += r1[w], s2 += r2[w];
+    const double pr = Phi1[off1[p] * ld1] * Phi2[off2[p] * ld2];
+    const double sg = pr > 0.0 ? 1.0 : (pr < 0.0 ? -1.0 : 0.0);
+    c00[p] = sg * sqrt(s2 / s1);
+  }
+}
+
+struct MatchLayout {
+  void* nn_ws;
+  size_t nn_bytes;
+  double *A, *B, *c00;
+  void* proj_ws;
+  size_t proj_bytes;
+  void* solve_ws;
+  size_t solve_bytes;
+  void* p2p_ws;
+  size_t p2p_bytes, bytes;
+};
+MatchLayout match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d, int k,
+                        int flags) {
+  Carver c(ws);
+  MatchLayout L;
+  L.nn_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, d, 1, 1, flags | kFlagSplit3);
+  L.nn_ws = c.take<char>(L.nn_bytes);
+  L.A = c.take<double>(size_t(n_pairs) * k * d);
+  L.B = c.take<double>(size_t(n_pairs) * k * d);
+  L.c00 = c.take<double>(size_t(n_pairs));
+  const size_t p1 = proj_tc_workspace_bytes(n_pairs, total_n1, max_n1, k, d);
+  const size_t p2 = proj_tc_workspace_bytes(n_pairs, total_n2, max_n2, k, d);
+  L.proj_bytes = p1 > p2 ? p1 : p2;
+  L.proj_ws = c.take<char>(L.proj_bytes);
+  L.solve_bytes = dm_fmap_solve_workspace_bytes(n_pairs, k, k, d);
+  L.solve_ws = c.take<char>(L.solve_bytes);
+  L.p2p_bytes = dm_fm_to_p2p_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k, k, flags);
+  L.p2p_ws = c.take<char>(L.p2p_bytes);
+  L.bytes = c.bytes();
+  return L;
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" {
+
+size_t dm_match_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d,
+                                      int k, int flags) {
+  if (n_pairs < 0 || total_n1 < 0 || total_n2 < 0 || d <= 0 || k < 2) return 0;
+  return match_carve(nullptr, n_pairs, total_n1, total_n2, max_n1, max_n2, d, k, flags).bytes;
+}
+
+int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2, const double* Phi1, int64_t ld1,
+                   const double* Phi2, int64_t ld2, const double* area1, const double* area2, const double* evals1,
+                   const double* evals2, const int64_t* off1, int64_t total_n1, int max_n1, const int64_t* off2,
+                   int64_t total_n2, int max_n2, int n_pairs, int d, int k, double w_descr, double w_lap,
+                   void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12, void* dense_21,
+                   void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_pairs < 0 || d <= 0 || k < 2 || total_n1 < 0 || total_n2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size (need k >= 2)");
+  if (n_pairs == 0) return DM_OK;
+  if (!F1 || !F2 || !Phi1 || !Phi2 || !area1 || !area2 || !evals1 || !evals2 || !off1 || !off2 || !C || !nn_p2p_21 ||
+      !nn_p2p_12)
+    DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ldF1 < d || ldF2 < d || ld1 < k || ld2 < k) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
+  if (total_n1 == 0 || total_n2 == 0) DM_FAIL(DM_ERR_BADARG, "empty meshes");
+  if (!nn_use_tc(flags) || !proj_tc_supported(k, d)) DM_FAIL(DM_ERR_UNSUPPORTED, "dm_match_pairs needs the tensor-core engines (d <= 512)");
+  if (!workspace) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  MatchLayout L = match_carve(workspace, n_pairs, total_n1, total_n2, max_n1, max_n2, d, k, flags);
+  if (L.bytes > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", L.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  // 1. feature NN: queries = mesh 2, database = mesh 1 (rows -> p2p_21, columns -> p2p_12); keeps the three-way splits
+  NNRequest R{};
+  R.Y = F2, R.ldY = ldF2, R.X = F1, R.ldX = ldF1;
+  R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
+  R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = d;
+  R.n_row = 1, R.n_col = 1;
+  R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_21};
+  R.col[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_12};
+  R.flags = flags | kFlagSplit3;
+  NNSplits sp{};
+  if ((rc = nn_run(R, L.nn_ws, L.nn_bytes, st, &sp))) return rc;
+  // 2. projections, reusing the feature splits (mesh 1 = database side, mesh 2 = query side)
+  const void* s1[3] = {sp.xh, sp.xl, sp.xl2};
+  const void* s2[3] = {sp.yh, sp.yl, sp.yl2};
+  if ((rc = proj_tc_run(Phi1, ld1, area1, F1, nullptr, ldF1, nullptr, nullptr, 0, nullptr, off1, total_n1, max_n1, n_pairs,
+                        k, d, L.A, L.proj_ws, L.proj_bytes, st, s1)))
+    return rc;
+  if ((rc = proj_tc_run(Phi2, ld2, area2, F2, nullptr, ldF2, nullptr, nullptr, 0, nullptr, off2, total_n2, max_n2, n_pairs,
+                        k, d, L.B, L.proj_ws, L.proj_bytes, st, s2)))
+    return rc;
+  // 3. pinned entry, closed-form C
+  c00_kernel<<<unsigned(n_pairs), 256, 0, st>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, L.c00);
+  DM_LAUNCH_OK("c00_kernel");
+  if ((rc = dm_fmap_solve(L.A, L.B, evals1, evals2, L.c00, w_descr, w_lap, n_pairs, k, k, d, C, L.solve_ws, L.solve_bytes,
+                          stream)))
+    return rc;
+  // 4. the four index maps
+  if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) return DM_OK;
+  return dm_fm_to_p2p(C, k, k, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs, p2p_21,
+                      p2p_12, dense_21, dense_12, flags, L.p2p_ws, L.p2p_bytes, stream);
+}
+
+// ------------------------------------------------------------------ polar factor (the SVD step of ICP, exposed)
+size_t dm_polar_factor_workspace_bytes(int n_batch, int rows, int cols) {
+  if (n_batch < 0 || rows <= 0 || cols <= 0) return 0;
+  Carver c(nullptr);
+  c.take<double>(polar_scratch_doubles(rows, cols) * size_t(n_batch));
+  c.take<double>(polar_ns_scratch_doubles(rows, cols, n_batch));
+  return c.bytes();
+}
+
+int dm_polar_factor(const double* X, int rows, int cols, int n_batch, double* C, int flags, void* workspace,
+                    size_t workspace_bytes, dm_stream_t stream) {
+  if (n_batch < 0 || rows <= 0 || cols <= 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_batch == 0) return DM_OK;
+  if (!X || !C || X == C) DM_FAIL(DM_ERR_BADARG, "null or aliased argument");
+  const size_t need = dm_polar_factor_workspace_bytes(n_batch, rows, cols);
+  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
+  Carver c(workspace);
+  double* jac = c.take<double>(polar_scratch_doubles(rows, cols) * size_t(n_batch));
+  double* ns = c.take<double>(polar_ns_scratch_doubles(rows, cols, n_batch));
+  return polar_factor_launch(X, C, rows, cols, n_batch, jac, (flags & DM_POLAR_JACOBI) ? nullptr : ns,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 // The matrices live in shared memory when they fit (k up to ~110 for the polar factor) and in an L2-resident
 // global scratch otherwise; the code is the same through generic pointers.
 #include "linalg64.cuh"
+#include "gemm64.cuh"
 
 namespace dm {
 namespace {
@@ -79,9 +80,11 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------ polar factor
 __global__ void __launch_bounds__(1024)
-    polar_kernel(const double* X, double* C, int rows, int cols, double* scratch, size_t per, int use_smem) {
+    polar_kernel(const double* X, double* C, int rows, int cols, double* scratch, size_t per, int use_smem,
+                 const int* __restrict__ need) {
   extern __shared__ double sm[];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  if (need && need[b] == 0) return;  // the Newton-Schulz iteration already delivered this one
   const bool tr = rows < cols;  // iterate on X^T so that the orthogonalised columns are the long ones
   const int m = tr ? cols : rows, n = tr ? rows : cols;
   double* W = use_smem ? sm : scratch + size_t(b) * per;  // [n][m] columns of the working matrix
@@ -172,6 +175,84 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ------------------------------------------------------------------------------------------ Newton-Schulz polar
+// X0 = X / s with s = sqrt(|X|_1 |X|_inf) >= sigma_max, so that every singular value starts in (0, 1]
+__global__ void __launch_bounds__(256)
+    ns_scale_kernel(const double* __restrict__ X, double* __restrict__ A, int rows, int cols) {
+  const double* x = X + size_t(blockIdx.x) * rows * cols;
+  double* a = A + size_t(blockIdx.x) * rows * cols;
+  __shared__ double red[256];
+  __shared__ double s_scale;
+  const int t = threadIdx.x;
+  double m1 = 0.0, mi = 0.0;
+  for (int c = t; c < cols; c += 256) {  // column sums
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += fabs(x[size_t(r) * cols + c]);
+    m1 = fmax(m1, s);
+  }
+  for (int r = t; r < rows; r += 256) {  // row sums
+    double s = 0.0;
+    for (int c = 0; c < cols; ++c) s += fabs(x[size_t(r) * cols + c]);
+    mi = fmax(mi, s);
+  }
+  red[t] = m1;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (t < h) red[t] = fmax(red[t], red[t + h]);
+    __syncthreads();
+  }
+  m1 = red[0];
+  __syncthreads();
+  red[t] = mi;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (t < h) red[t] = fmax(red[t], red[t + h]);
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double s = sqrt(m1 * red[0]);
+    s_scale = s > 0.0 ? 1.0 / s : 0.0;
+  }
+  __syncthreads();
+  for (int e = t; e < rows * cols; e += 256) a[e] = x[e] * s_scale;
+}
+
+// W = 1.5 I - 0.5 Z  (n x n per batch), in place
+__global__ void __launch_bounds__(256) ns_w_kernel(double* __restrict__ Z, int n, int64_t total) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = int(i % (int64_t(n) * n));
+  Z[i] = ((e / n == e % n) ? 1.5 : 0.0) - 0.5 * Z[i];
+}
+
+// need[b] = 1 if the Gram matrix of the iterate is not the identity to 1e-12 (not converged: singular values of the
+// input too small for the fixed iteration count); otherwise the iterate is copied to the output
+__global__ void __launch_bounds__(256)
+    ns_check_kernel(const double* __restrict__ Z, const double* __restrict__ A, double* __restrict__ C, int n, int rows,
+                    int cols, int* __restrict__ need) {
+  const double* z = Z + size_t(blockIdx.x) * n * n;
+  __shared__ double red[256];
+  const int t = threadIdx.x;
+  double m = 0.0;
+  for (int e = t; e < n * n; e += 256) {
+    const double v = fabs(z[e] - ((e / n == e % n) ? 1.0 : 0.0));
+    m = (v == v) ? fmax(m, v) : INFINITY;  // NaN -> not converged
+  }
+  red[t] = m;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (t < h) red[t] = fmax(red[t], red[t + h]);
+    __syncthreads();
+  }
+  const bool ok = red[0] < 1e-12;
+  if (t == 0) need[blockIdx.x] = ok ? 0 : 1;
+  if (ok) {
+    const double* a = A + size_t(blockIdx.x) * rows * cols;
+    double* c = C + size_t(blockIdx.x) * rows * cols;
+    for (int e = t; e < rows * cols; e += 256) c[e] = a[e];
+  }
+}
+
 size_t spd_doubles(int n) { return size_t(n) * (n + 1) + size_t(n) * n; }
 size_t polar_doubles(int rows, int cols) {
   const int m = rows > cols ? rows : cols, n = rows > cols ? cols : rows;
@@ -197,7 +278,8 @@ int spd_inverse_launch(const double* G, double* Ginv, int n, int n_batch, double
   return DM_OK;
 }
 
-int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, cudaStream_t st) {
+int polar_jacobi_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, const int* need,
+                        cudaStream_t st) {
   if (n_batch <= 0 || rows <= 0 || cols <= 0) return DM_OK;
   const size_t per = polar_doubles(rows, cols), bytes = per * 8;
   const int use_smem = bytes <= kSmemBudget;
@@ -206,9 +288,73 @@ int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_ba
     DM_CUDA_OK(cudaFuncSetAttribute(polar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
   const int n = rows < cols ? rows : cols;
   const int threads = n >= 48 ? 1024 : (n >= 16 ? 256 : 64);
-  polar_kernel<<<n_batch, threads, use_smem ? bytes : 0, st>>>(X, C, rows, cols, scratch, per, use_smem);
+  polar_kernel<<<n_batch, threads, use_smem ? bytes : 0, st>>>(X, C, rows, cols, scratch, per, use_smem, need);
   DM_LAUNCH_OK("polar_kernel");
   return DM_OK;
+}
+
+// Scratch of the Newton-Schulz stage in doubles: two iterates + the Gram matrix + the fallback flags
+size_t polar_ns_scratch_doubles(int rows, int cols, int n_batch) {
+  const int n = rows < cols ? rows : cols;
+  return size_t(n_batch) * (2 * size_t(rows) * cols + size_t(n) * n) + size_t(n_batch) / 2 + 8;
+}
+
+// U I V^T of X = U S V^T.  Fast path: Newton-Schulz  A <- A (1.5 I - 0.5 A^T A)  on batched float64 GEMMs (quadratic
+// convergence; kNsIters steps cover singular values down to ~2 % of the 1-norm/inf-norm scale).  Every matrix whose
+// iterate is not orthonormal to 1e-12 afterwards (ill-conditioned or rank-deficient input) is redone by the one-sided
+// Jacobi SVD, which needs no conditioning assumption.
+constexpr int kNsIters = 16;
+
+int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, double* ns_scratch,
+                        cudaStream_t st) {
+  if (n_batch <= 0 || rows <= 0 || cols <= 0) return DM_OK;
+  if (!ns_scratch) return polar_jacobi_launch(X, C, rows, cols, n_batch, scratch, nullptr, st);
+  const bool wide = rows < cols;
+  const int n = wide ? rows : cols;
+  const size_t mat = size_t(rows) * cols;
+  double* A0 = ns_scratch;
+  double* A1 = A0 + size_t(n_batch) * mat;
+  double* Z = A1 + size_t(n_batch) * mat;
+  int* need = reinterpret_cast<int*>(Z + size_t(n_batch) * n * n);
+  ns_scale_kernel<<<n_batch, 256, 0, st>>>(X, A0, rows, cols);
+  DM_LAUNCH_OK("ns_scale_kernel");
+  int rc;
+  auto gram = [&](const double* A) {  // Z = A^T A (tall) or A A^T (wide), n x n
+    GemmProblem G;
+    G.A.d = A, G.A.ld = cols, G.A.batch_stride = int64_t(mat), G.A.rows = rows, G.A.trans = wide ? 0 : 1;
+    G.B = G.A;
+    G.M = n, G.N = n, G.K = wide ? cols : rows, G.maxM = n, G.maxN = n, G.maxK = G.K, G.n_batch = n_batch;
+    G.C = Z, G.ldc = n, G.c_batch_stride = int64_t(n) * n;
+    return gemm64_launch(G, st);
+  };
+  double* cur = A0;
+  double* nxt = A1;
+  for (int it = 0; it < kNsIters; ++it) {
+    if ((rc = gram(cur))) return rc;
+    const int64_t total = int64_t(n_batch) * n * n;
+    ns_w_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(Z, n, total);
+    DM_LAUNCH_OK("ns_w_kernel");
+    GemmProblem G;
+    if (!wide) {  // A <- A W            (rows x n) (n x n), W symmetric
+      G.A.d = cur, G.A.ld = cols, G.A.batch_stride = int64_t(mat), G.A.rows = rows, G.A.trans = 0;
+      G.B.d = Z, G.B.ld = n, G.B.batch_stride = int64_t(n) * n, G.B.rows = n, G.B.trans = 0;
+      G.M = rows, G.N = cols, G.K = n;
+    } else {      // A <- W A            (n x n) (n x cols)
+      G.A.d = Z, G.A.ld = n, G.A.batch_stride = int64_t(n) * n, G.A.rows = n, G.A.trans = 0;
+      G.B.d = cur, G.B.ld = cols, G.B.batch_stride = int64_t(mat), G.B.rows = rows, G.B.trans = 1;
+      G.M = rows, G.N = cols, G.K = n;
+    }
+    G.maxM = G.M, G.maxN = G.N, G.maxK = G.K, G.n_batch = n_batch;
+    G.C = nxt, G.ldc = cols, G.c_batch_stride = int64_t(mat);
+    if ((rc = gemm64_launch(G, st))) return rc;
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  if ((rc = gram(cur))) return rc;
+  ns_check_kernel<<<n_batch, 256, 0, st>>>(Z, cur, C, n, rows, cols, need);
+  DM_LAUNCH_OK("ns_check_kernel");
+  return polar_jacobi_launch(X, C, rows, cols, n_batch, scratch, need, st);
 }
 
 }  // namespace dm

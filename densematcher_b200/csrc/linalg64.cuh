@@ -16,8 +16,10 @@ int spd_inverse_launch(const double* G, double* Ginv, int n, int n_batch, double
                        cudaStream_t st);
 
 // C[b] = U I V^T where X[b] = U S V^T (rows x cols, row-major, contiguous): the nearest (partial) isometry.
-// scratch: n_batch * polar_scratch_doubles(rows, cols).  X and C may alias.
-int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch,
+// scratch: n_batch * polar_scratch_doubles(rows, cols) (Jacobi);  ns_scratch: polar_ns_scratch_doubles(...) doubles
+// for the Newton-Schulz fast path (nullptr = Jacobi only).  X and C must not alias when ns_scratch is given.
+size_t polar_ns_scratch_doubles(int rows, int cols, int n_batch);
+int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, double* ns_scratch,
                         cudaStream_t st);
 
 }  // namespace dm

@@ -52,7 +52,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     prep_side_kernel(const T* __restrict__ M, int64_t ld, const int64_t* __restrict__ off, int n_pairs, int64_t total,
                      int d, float* __restrict__ norm_out, SpecArr specs, int n_specs, __nv_bfloat16* __restrict__ hi,
-                     __nv_bfloat16* __restrict__ lo, int kp, int need_sq64) {
+                     __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2, int kp, int need_sq64) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= total) return;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256)
           vf[w] = float(e);
           v[w] = (sizeof(T) == 8 || need_sq64) ? double(e) : 0.0;
         }
-        unsigned short bh[W], bl[W];
+        unsigned short bh[W], bl[W], bl2[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) {
           // fp32 split: hi = bf16(x), lo = bf16(x - hi) (the difference is exact in fp32).  Conversions between fp32
@@ -104,11 +104,14 @@ __global__ void __launch_bounds__(256)
           else
             s32 = fmaf(x, x, s32);
           const __nv_bfloat16 vh = __float2bfloat16_rn(x);
-          const __nv_bfloat16 vl = __float2bfloat16_rn(x - __bfloat162float(vh));
+          const float r1 = x - __bfloat162float(vh);
+          const __nv_bfloat16 vl = __float2bfloat16_rn(r1);
           bh[w] = __bfloat16_as_ushort(vh), bl[w] = __bfloat16_as_ushort(vl);
+          bl2[w] = __bfloat16_as_ushort(__float2bfloat16_rn(r1 - __bfloat162float(vl)));
         }
         store_bf16_vec<W>(h + k, bh);
         store_bf16_vec<W>(l + k, bl);
+        if (lo2) store_bf16_vec<W>(lo2 + row * kp + k, bl2);
       }
     }
   } else if (hi) {
@@ -119,7 +122,10 @@ __global__ void __launch_bounds__(256)
       s = fma(v, v, s);
       const __nv_bfloat16 vh = __float2bfloat16_rn(float(v));
       h[k] = vh;
-      l[k] = __float2bfloat16_rn(float(v - double(__bfloat162float(vh))));
+      const double r1 = v - double(__bfloat162float(vh));
+      const __nv_bfloat16 vl = __float2bfloat16_rn(float(r1));
+      l[k] = vl;
+      if (lo2) lo2[row * kp + k] = __float2bfloat16_rn(float(r1 - double(__bfloat162float(vl))));
     }
   } else {
     for (int k = lane; k < d; k += 32) {
@@ -356,9 +362,11 @@ __global__ void __launch_bounds__(256) recheck_cand_kernel(const NNProblem P) {
 }  // namespace
 
 int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
-                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi_v, void* lo_v, int kp, cudaStream_t st) {
+                 float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi_v, void* lo_v, void* lo2_v, int kp,
+                 cudaStream_t st) {
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(hi_v);
   __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(lo_v);
+  __nv_bfloat16* lo2 = static_cast<__nv_bfloat16*>(lo2_v);
   if (total <= 0) return DM_OK;
   SpecArr arr;
   for (int e = 0; e < kMaxEpi; ++e) arr.s[e] = specs && e < n_specs ? specs[e] : SideEpiSpec{};
@@ -369,10 +377,10 @@ int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, i
     if (specs[e].scale_mode == DM_SCALE_INVNORM || specs[e].bias_mode == DM_BIAS_NEG_HALF_SQNORM) need_sq64 = 1;
   if (is_double)
     prep_side_kernel<double><<<grid, wpb * 32, 0, st>>>(static_cast<const double*>(M), ld, off, n_pairs, total, d,
-                                                        norm_out, arr, n_specs, hi, lo, kp, need_sq64);
+                                                        norm_out, arr, n_specs, hi, lo, lo2, kp, need_sq64);
   else
     prep_side_kernel<float><<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(M), ld, off, n_pairs, total, d,
-                                                       norm_out, arr, n_specs, hi, lo, kp, need_sq64);
+                                                       norm_out, arr, n_specs, hi, lo, lo2, kp, need_sq64);
   DM_LAUNCH_OK("prep_side_kernel");
   if (n_specs > 0 && n_pairs > 0) {
     pair_max_kernel<<<dim3(unsigned(n_pairs), unsigned(n_specs)), 256, 0, st>>>(off, norm_out, arr, n_pairs);
@@ -437,6 +445,7 @@ struct NNLayout {
   FlagEntry* flags;
   int64_t flag_cap;
   uint16_t *yh, *yl, *xh, *xl;  // bf16 split operands of the tensor-core engine [rows, kp]
+  uint16_t *yl2, *xl2;          // third split (kFlagSplit3 only)
   size_t bytes;
 };
 
@@ -470,13 +479,17 @@ NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max
   L.col_partial = c.take<Top3>(size_t(n_col) * n_pairs * max_rt * max_db);
   L.flag_cap = (flags & DM_NO_RECHECK) ? 0 : int64_t(n_row) * total_q + int64_t(n_col) * total_db;
   L.flags = c.take<FlagEntry>(size_t(L.flag_cap));
-  L.yh = L.yl = L.xh = L.xl = nullptr;
+  L.yh = L.yl = L.xh = L.xl = L.yl2 = L.xl2 = nullptr;
   if (nn_use_tc(flags)) {
     const size_t kp = size_t(nn_tc_kp(d));
     L.yh = c.take<uint16_t>(size_t(total_q) * kp);
     L.yl = c.take<uint16_t>(size_t(total_q) * kp);
     L.xh = c.take<uint16_t>(size_t(total_db) * kp);
     L.xl = c.take<uint16_t>(size_t(total_db) * kp);
+    if (flags & kFlagSplit3) {
+      L.yl2 = c.take<uint16_t>(size_t(total_q) * kp);
+      L.xl2 = c.take<uint16_t>(size_t(total_db) * kp);
+    }
   }
   L.bytes = c.bytes();
   return L;
@@ -488,7 +501,7 @@ size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int ma
   return carve(nullptr, n_pairs, total_q, total_db, max_q, max_db, d, n_row, n_col, flags).bytes;
 }
 
-int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
+int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSplits* splits) {
   if (R.n_pairs < 0 || R.d <= 0 || R.total_q < 0 || R.total_db < 0 || R.max_q < 0 || R.max_db < 0)
     DM_FAIL(DM_ERR_BADARG, "negative size");
   if (R.n_row < 0 || R.n_row > kMaxEpi || R.n_col < 0 || R.n_col > kMaxEpi || R.n_row + R.n_col == 0)
@@ -560,12 +573,13 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!(R.flags & DM_SKIP_PREP)) {
     // database side carries the row epilogues' scale/bias, query side the column epilogues'
     if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row,
-                           L.xh, L.xl, P.kp, st)))
+                           L.xh, L.xl, L.xl2, P.kp, st)))
       return rc;
     if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col,
-                           L.yh, L.yl, P.kp, st)))
+                           L.yh, L.yl, L.yl2, P.kp, st)))
       return rc;
   }
+  if (splits) *splits = NNSplits{L.yh, L.yl, L.yl2, L.xh, L.xl, L.xl2, P.kp};
   if (tc) {
     if ((rc = nn_tc_launch(P, L.yh, L.yl, L.xh, L.xl, nullptr, 0, st))) return rc;
   } else {

@@ -342,7 +342,7 @@ size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, i
 int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float* Bf, const double* Bd, int64_t ldB,
                 const double* b_scale, const void* b_gather, int b_gather_i64, const int64_t* b_gather_src_off,
                 const int64_t* off, int64_t total_n, int max_n, int n_batch, int k, int d, double* out, void* ws,
-                size_t ws_bytes, cudaStream_t st) {
+                size_t ws_bytes, cudaStream_t st, const void* const* b_presplit) {
   if (n_batch <= 0) return DM_OK;
   if (total_n > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
   const int kpA = pad_to(k, 128), kpB = pad_to(d, 64);
@@ -363,7 +363,9 @@ int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float
   split3_kernel<double><<<unsigned((a_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
       A, ldA, off, n_batch, k, a_scale, nullptr, 0, nullptr, a3[0], a3[1], a3[2], kpA, a_stride, a_rows);
   DM_LAUNCH_OK("split3_kernel(A)");
-  if (total_n > 0) {
+  if (b_presplit) {
+    for (int i = 0; i < 3; ++i) b3[i] = static_cast<__nv_bfloat16*>(const_cast<void*>(b_presplit[i]));
+  } else if (total_n > 0) {
     if (Bf)
       split3_kernel<float><<<unsigned((total_n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
           Bf, ldB, off, n_batch, d, b_scale, b_gather, b_gather_i64, b_gather_src_off, b3[0], b3[1], b3[2], kpB, 0, total_n);

@@ -14,7 +14,8 @@ import torch
 from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
-__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "PairBatch"]
+__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "polar_factor",
+           "match_pairs", "PairBatch"]
 
 
 def _stream(dev):
@@ -258,6 +259,61 @@ def icp(C0, Phi1, Phi2, nit=10, off1=None, off2=None, return_p2p=False, flags=0,
                         p2p.data_ptr() if p2p is not None else None, flags, ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "dm_icp")
     return (C, p2p) if return_p2p else C
+
+
+def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k, w_descr, w_lap, flags=0,
+                out_dtype=torch.int32, workspace: Optional[Workspace] = None):
+    """The whole per-pair hot path in ONE library call (``dm_match_pairs``): feature NN both directions, both
+    projections (reusing the feature splits of the NN stage), closed-form C, the four FM->p2p index maps.
+    Returns a dict like ``pipeline.match_pairs_device``."""
+    lib = _lib.load()
+    dev = F1.device
+    F1 = F1 if (F1.dtype == torch.float32 and F1.stride(1) == 1) else F1.float().contiguous()
+    F2 = F2 if (F2.dtype == torch.float32 and F2.stride(1) == 1) else F2.float().contiguous()
+    Phi1, Phi2, area1, area2 = _f64(Phi1), _f64(Phi2), _f64(area1).contiguous(), _f64(area2).contiguous()
+    k = int(k)
+    if k > Phi1.shape[1] or k > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    evals1, evals2 = _f64(evals1)[:, :k].contiguous(), _f64(evals2)[:, :k].contiguous()
+    n1, n2, d = F1.shape[0], F2.shape[0], F1.shape[1]
+    o1, o1h, max1 = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    P = len(o1h) - 1
+    if out_dtype == torch.int64:
+        flags |= _lib.DM_I64_OUT
+    mk = lambda n: torch.empty(n, dtype=out_dtype, device=dev)
+    out = dict(nn_p2p_21=mk(n2), nn_p2p_12=mk(n1), C=torch.empty(P, k, k, dtype=torch.float64, device=dev),
+               p2p_21=mk(n2), p2p_12=mk(n1), p2p_21_adjoint=mk(n2), p2p_12_adjoint=mk(n1))
+    need = lib.dm_match_pairs_workspace_bytes(P, n1, n2, max1, max2, d, k, flags)
+    ws = (workspace or default_workspace(dev, "match")).get(need)
+    with torch.cuda.device(dev):
+        rc = lib.dm_match_pairs(F1.data_ptr(), F1.stride(0), F2.data_ptr(), F2.stride(0), Phi1.data_ptr(), Phi1.stride(0),
+                                Phi2.data_ptr(), Phi2.stride(0), area1.data_ptr(), area2.data_ptr(), evals1.data_ptr(),
+                                evals2.data_ptr(), o1.data_ptr(), n1, max1, o2.data_ptr(), n2, max2, P, d, k,
+                                float(w_descr), float(w_lap), out["nn_p2p_21"].data_ptr(), out["nn_p2p_12"].data_ptr(),
+                                out["C"].data_ptr(), out["p2p_21_adjoint"].data_ptr(), out["p2p_12_adjoint"].data_ptr(),
+                                out["p2p_21"].data_ptr(), out["p2p_12"].data_ptr(), flags, ws.data_ptr(), ws.numel(),
+                                _stream(dev))
+    _lib.check(rc, "dm_match_pairs")
+    return out
+
+
+def polar_factor(X, flags=0):
+    """U I V^T of every matrix of X [P, rows, cols] (float64): the SVD step of ICP (icp.py:39-40)."""
+    lib = _lib.load()
+    X = _f64(X)
+    if X.dim() == 2:
+        X = X[None]
+    X = X.contiguous()
+    P, rows, cols = X.shape
+    C = torch.empty_like(X)
+    need = lib.dm_polar_factor_workspace_bytes(P, rows, cols)
+    ws = default_workspace(X.device, "fm").get(max(need, 256))
+    with torch.cuda.device(X.device):
+        rc = lib.dm_polar_factor(X.data_ptr(), rows, cols, P, C.data_ptr(), int(flags), ws.data_ptr(), ws.numel(),
+                                 _stream(X.device))
+    _lib.check(rc, "dm_polar_factor")
+    return C
 
 
 class PairBatch:

@@ -17,6 +17,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+from . import _lib
 from . import fm as _fm
 from . import nn as _nn
 
@@ -107,12 +108,19 @@ def fmap_c00(batch: PairBatchDevice):
 
 
 def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr: float = 1e4, w_lap: float = 1e3,
-                       feature_nn: bool = True, functional_map: bool = True, out_dtype=torch.int32, flags: int = 0):
+                       feature_nn: bool = True, functional_map: bool = True, out_dtype=torch.int32, flags: int = 0,
+                       fused: bool = True):
     """Runs the hot path on a device-resident batch.  Returns a dict of device tensors:
     ``nn_p2p_21`` / ``nn_p2p_12`` (feature NN), ``C`` [P,k,k], ``p2p_21`` / ``p2p_12`` (dense-argmax override,
     what compute_surface_map returns in slots 0/1) and ``p2p_21_adjoint`` / ``p2p_12_adjoint`` (kd-tree-equivalent
     searches, slots 10/11).  Indices are local to each pair."""
     out = {}
+    if (feature_nn and functional_map and fused and batch.Phi1 is not None and batch.F1.shape[1] <= 512
+            and not (flags & _lib.DM_ENGINE_FFMA) and batch.n_pairs > 0):
+        # one library call for the whole path; the projections reuse the feature splits of the NN stage
+        k = batch.Phi1.shape[1] if k is None else int(k)
+        return _fm.match_pairs(batch.F1, batch.F2, batch.Phi1, batch.Phi2, batch.area1, batch.area2, batch.evals1,
+                               batch.evals2, batch.o1, batch.o2, k, w_descr, w_lap, flags=flags, out_dtype=out_dtype)
     if feature_nn:
         # for each vertex of mesh 2 its nearest feature on mesh 1 (rows), and the reverse (columns)
         (r,), (c,) = _nn.nn_argmax(batch.F2, batch.F1, batch.off2, batch.off1, row_epi=(_nn.COSINE_UNIT,),

@@ -242,6 +242,35 @@ int dm_icp(const double* C0, int k1, int k2, int nit,
            int n_pairs, double* C_out, void* p2p_out,
            int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The whole per-pair hot path of compute_surface_map (functional_map.py:44-50) for a ragged batch, in one call:
+ *   feature NN both directions (knn_query on the unit features)          -> nn_p2p_21 [total_n2], nn_p2p_12 [total_n1]
+ *   A = Phi1^T A1 F1, B = Phi2^T A2 F2 (tensor cores; the bf16 splits of F prepared for the NN pass are reused)
+ *   C = closed-form minimiser, column 0 pinned to sign(Phi1[0,0] Phi2[0,0]) sqrt(area2/area1)  -> C [n_pairs, k, k]
+ *   FM -> p2p: p2p_21, p2p_12 (kd-tree equivalent) and dense_21, dense_12 (argmax override); any may be NULL
+ * F1 [total_n1, ldF1] / F2 float32; Phi [.., ld >= k] float64; evals1 / evals2 [n_pairs, k] contiguous float64.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_match_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d,
+                                      int k, int flags);
+int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
+                   const double* Phi1, int64_t ld1, const double* Phi2, int64_t ld2,
+                   const double* area1, const double* area2, const double* evals1, const double* evals2,
+                   const int64_t* off1, int64_t total_n1, int max_n1, const int64_t* off2, int64_t total_n2, int max_n2,
+                   int n_pairs, int d, int k, double w_descr, double w_lap,
+                   void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12, void* dense_21,
+                   void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Nearest (partial) isometry  C[b] = U I V^T  of  X[b] = U S V^T  (the SVD step of icp.py:39-40), float64,
+ * X / C [n_batch, rows, cols] contiguous, X != C.  Newton-Schulz iteration on batched GEMMs; matrices it cannot
+ * orthonormalise to 1e-12 in its fixed step count (ill-conditioned or rank-deficient) are redone by a one-sided
+ * Jacobi SVD.  flags & DM_POLAR_JACOBI forces the Jacobi path for all.
+ * ---------------------------------------------------------------------------------------- */
+enum { DM_POLAR_JACOBI = 1 << 9 };
+size_t dm_polar_factor_workspace_bytes(int n_batch, int rows, int cols);
+int dm_polar_factor(const double* X, int rows, int cols, int n_batch, double* C, int flags, void* workspace,
+                    size_t workspace_bytes, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

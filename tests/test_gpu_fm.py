@@ -211,6 +211,11 @@ def test_host_entry_equals_device_pipeline():
         evals1=np.stack([b[0] for b in b1]), evals2=np.stack([b[0] for b in b2]),
         area1=np.concatenate([b[2] for b in b1]), area2=np.concatenate([b[2] for b in b2])).pin()
     ref = {n: t.cpu().numpy() for n, t in pipeline.match_pairs_device(host.to_device("cuda:0"), k=12).items()}
+    # the single-call path (dm_match_pairs, shared feature splits) and the stage-by-stage path agree bit for bit
+    staged = pipeline.match_pairs_device(host.to_device("cuda:0"), k=12, fused=False)
+    assert set(staged) == set(ref)
+    for n in ref:
+        assert np.array_equal(staged[n].cpu().numpy(), ref[n]), n
     for chunk in (3, 7, 64):
         for _ in range(2):  # second call reuses every staging buffer
             out = pipeline.match_pairs_host(host, "cuda:0", chunk_pairs=chunk, k=12, copy=(chunk != 7))
@@ -320,3 +325,31 @@ def test_random_shape_sweep_projection_p2p_to_fm_fm_to_p2p():
             assert np.array_equal(out["dense_21"][s2].cpu().numpy(), MI.argmax(1)), (trial, "dense_21")
             assert np.array_equal(out["dense_12"][s1].cpu().numpy(), MI.argmax(0)), (trial, "dense_12")
             assert relF(Cn[p], orc.p2p_to_fm(r21, Phi1[s1], Phi2[s2], a2[s2])) < 1e-11, (trial, "p2p_to_fm")
+
+
+def test_polar_factor_newton_schulz_and_jacobi_fallback():
+    """U I V^T against scipy's SVD: well-conditioned matrices (Newton-Schulz path), an ill-conditioned and a
+    rank-deficient one in the same batch (Jacobi fallback), tall and wide shapes, and the forced Jacobi path."""
+    import scipy.linalg
+    from densematcher_b200 import _lib
+    rng = np.random.default_rng(17)
+
+    def ref(X):
+        U, _, Vt = scipy.linalg.svd(X)
+        return U @ np.eye(*X.shape) @ Vt
+
+    for rows, cols in ((40, 40), (100, 100), (30, 22), (22, 30), (130, 130)):
+        k = min(rows, cols)
+        Xs = []
+        for cond in (1.5, 5.0, 1e6):
+            U = np.linalg.qr(rng.standard_normal((rows, rows)))[0][:, :k]
+            V = np.linalg.qr(rng.standard_normal((cols, cols)))[0][:, :k]
+            Xs.append(U @ np.diag(np.geomspace(1.0, 1.0 / cond, k)) @ V.T * rng.uniform(0.2, 5))
+        X = np.stack(Xs)
+        for flags in (0, _lib.DM_POLAR_JACOBI):
+            C = fm_mod().polar_factor(dev(X), flags=flags).cpu().numpy()
+            for b in range(3):
+                tol = 1e-11 if b < 2 else 1e-7      # cond 1e6: the polar factor itself is that sensitive
+                assert np.abs(C[b] - ref(X[b])).max() < tol, (rows, cols, b, flags)
+                G = C[b].T @ C[b] if rows >= cols else C[b] @ C[b].T
+                assert np.abs(G - np.eye(k)).max() < 1e-11, (rows, cols, b, flags)
