@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   bid /= tiles_m;
   const int ks = bid % P.ksplit;
   const int b = bid / P.ksplit;
+  if (P.skip && P.skip[b]) return;
 
   const int M = (!TA && P.A.off) ? int(P.A.off[b + 1] - P.A.off[b]) : P.M;
   const int N = (!TB && P.B.off) ? int(P.B.off[b + 1] - P.B.off[b]) : P.N;

@@ -29,6 +29,7 @@ struct GemmProblem {
   int M = 0, N = 0, K = 0;  // fixed sizes; a ragged dimension is taken from the operand offsets instead
   int maxM = 0, maxN = 0, maxK = 0;
   int n_batch = 0;
+  const int* skip = nullptr;  // optional per-batch flag (device): batches with skip[b] != 0 are left untouched
   double* C = nullptr;
   int64_t ldc = 0;
   int64_t c_batch_stride = 0;      // used when the output rows are not ragged

@@ -176,67 +176,22 @@ __global__ void __launch_bounds__(1024)
 }
 
 // ------------------------------------------------------------------------------------------ Newton-Schulz polar
-// X0 = X / s with s = sqrt(|X|_1 |X|_inf) >= sigma_max, so that every singular value starts in (0, 1]
+// Scaling from the first Gram matrix Z = X^T X (or X X^T): sigma_max^2 <= |Z|_inf, so A0 = X / sqrt(|Z|_inf) has all
+// singular values in (0, 1] -- and for the near-isometries ICP produces the bound is tight (|Z|_inf ~ 1), which is
+// what keeps the iteration count small.  Z is rescaled in place to the Gram matrix of A0.
 __global__ void __launch_bounds__(256)
-    ns_scale_kernel(const double* __restrict__ X, double* __restrict__ A, int rows, int cols) {
+    ns_scale_kernel(const double* __restrict__ X, double* __restrict__ Z, double* __restrict__ A, int n, int rows, int cols) {
   const double* x = X + size_t(blockIdx.x) * rows * cols;
   double* a = A + size_t(blockIdx.x) * rows * cols;
+  double* z = Z + size_t(blockIdx.x) * n * n;
   __shared__ double red[256];
-  __shared__ double s_scale;
-  const int t = threadIdx.x;
-  double m1 = 0.0, mi = 0.0;
-  for (int c = t; c < cols; c += 256) {  // column sums
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += fabs(x[size_t(r) * cols + c]);
-    m1 = fmax(m1, s);
-  }
-  for (int r = t; r < rows; r += 256) {  // row sums
-    double s = 0.0;
-    for (int c = 0; c < cols; ++c) s += fabs(x[size_t(r) * cols + c]);
-    mi = fmax(mi, s);
-  }
-  red[t] = m1;
-  __syncthreads();
-  for (int h = 128; h > 0; h >>= 1) {
-    if (t < h) red[t] = fmax(red[t], red[t + h]);
-    __syncthreads();
-  }
-  m1 = red[0];
-  __syncthreads();
-  red[t] = mi;
-  __syncthreads();
-  for (int h = 128; h > 0; h >>= 1) {
-    if (t < h) red[t] = fmax(red[t], red[t + h]);
-    __syncthreads();
-  }
-  if (t == 0) {
-    const double s = sqrt(m1 * red[0]);
-    s_scale = s > 0.0 ? 1.0 / s : 0.0;
-  }
-  __syncthreads();
-  for (int e = t; e < rows * cols; e += 256) a[e] = x[e] * s_scale;
-}
-
-// W = 1.5 I - 0.5 Z  (n x n per batch), in place
-__global__ void __launch_bounds__(256) ns_w_kernel(double* __restrict__ Z, int n, int64_t total) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int e = int(i % (int64_t(n) * n));
-  Z[i] = ((e / n == e % n) ? 1.5 : 0.0) - 0.5 * Z[i];
-}
-
-// need[b] = 1 if the Gram matrix of the iterate is not the identity to 1e-12 (not converged: singular values of the
-// input too small for the fixed iteration count); otherwise the iterate is copied to the output
-__global__ void __launch_bounds__(256)
-    ns_check_kernel(const double* __restrict__ Z, const double* __restrict__ A, double* __restrict__ C, int n, int rows,
-                    int cols, int* __restrict__ need) {
-  const double* z = Z + size_t(blockIdx.x) * n * n;
-  __shared__ double red[256];
+  __shared__ double s_inv2;
   const int t = threadIdx.x;
   double m = 0.0;
-  for (int e = t; e < n * n; e += 256) {
-    const double v = fabs(z[e] - ((e / n == e % n) ? 1.0 : 0.0));
-    m = (v == v) ? fmax(m, v) : INFINITY;  // NaN -> not converged
+  for (int r = t; r < n; r += 256) {
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) s += fabs(z[size_t(r) * n + c]);
+    m = fmax(m, s);
   }
   red[t] = m;
   __syncthreads();
@@ -244,13 +199,47 @@ __global__ void __launch_bounds__(256)
     if (t < h) red[t] = fmax(red[t], red[t + h]);
     __syncthreads();
   }
-  const bool ok = red[0] < 1e-12;
-  if (t == 0) need[blockIdx.x] = ok ? 0 : 1;
-  if (ok) {
+  if (t == 0) s_inv2 = red[0] > 0.0 ? 1.0 / red[0] : 0.0;
+  __syncthreads();
+  const double inv2 = s_inv2, inv = sqrt(inv2);
+  for (int e = t; e < rows * cols; e += 256) a[e] = x[e] * inv;
+  for (int e = t; e < n * n; e += 256) z[e] *= inv2;
+}
+
+// One Newton-Schulz bookkeeping step per batch entry (one CTA each): if the Gram matrix Z of the current iterate is
+// the identity to 1e-13 the iterate is final -- it is copied to the output and the entry is marked done, so that every
+// later kernel skips it; otherwise Z is replaced by W = 1.5 I - 0.5 Z for the update A <- A W.
+__global__ void __launch_bounds__(256)
+    ns_step_kernel(double* __restrict__ Z, const double* __restrict__ A, double* __restrict__ C, int n, int rows, int cols,
+                   int* __restrict__ done) {
+  if (done[blockIdx.x]) return;
+  double* z = Z + size_t(blockIdx.x) * n * n;
+  __shared__ double red[256];
+  const int t = threadIdx.x;
+  double m = 0.0;
+  for (int e = t; e < n * n; e += 256) {
+    const double v = fabs(z[e] - ((e / n == e % n) ? 1.0 : 0.0));
+    m = (v == v) ? fmax(m, v) : INFINITY;  // NaN -> never converged
+  }
+  red[t] = m;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (t < h) red[t] = fmax(red[t], red[t + h]);
+    __syncthreads();
+  }
+  if (red[0] < 1e-13) {
     const double* a = A + size_t(blockIdx.x) * rows * cols;
     double* c = C + size_t(blockIdx.x) * rows * cols;
     for (int e = t; e < rows * cols; e += 256) c[e] = a[e];
+    if (t == 0) done[blockIdx.x] = 1;
+  } else {
+    for (int e = t; e < n * n; e += 256) z[e] = ((e / n == e % n) ? 1.5 : 0.0) - 0.5 * z[e];
   }
+}
+
+__global__ void ns_need_kernel(const int* __restrict__ done, int* __restrict__ need, int n_batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_batch) need[i] = done[i] ? 0 : 1;
 }
 
 size_t spd_doubles(int n) { return size_t(n) * (n + 1) + size_t(n) * n; }
@@ -296,14 +285,14 @@ int polar_jacobi_launch(const double* X, double* C, int rows, int cols, int n_ba
 // Scratch of the Newton-Schulz stage in doubles: two iterates + the Gram matrix + the fallback flags
 size_t polar_ns_scratch_doubles(int rows, int cols, int n_batch) {
   const int n = rows < cols ? rows : cols;
-  return size_t(n_batch) * (2 * size_t(rows) * cols + size_t(n) * n) + size_t(n_batch) / 2 + 8;
+  return size_t(n_batch) * (2 * size_t(rows) * cols + size_t(n) * n) + size_t(n_batch) + 8;
 }
 
 // U I V^T of X = U S V^T.  Fast path: Newton-Schulz  A <- A (1.5 I - 0.5 A^T A)  on batched float64 GEMMs (quadratic
-// convergence; kNsIters steps cover singular values down to ~2 % of the 1-norm/inf-norm scale).  Every matrix whose
+// convergence; entries leave the iteration as soon as they are orthonormal to 1e-13, up to kNsIters steps).  Every matrix whose
 // iterate is not orthonormal to 1e-12 afterwards (ill-conditioned or rank-deficient input) is redone by the one-sided
 // Jacobi SVD, which needs no conditioning assumption.
-constexpr int kNsIters = 16;
+constexpr int kNsIters = 24;
 
 int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_batch, double* scratch, double* ns_scratch,
                         cudaStream_t st) {
@@ -316,24 +305,25 @@ int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_ba
   double* A1 = A0 + size_t(n_batch) * mat;
   double* Z = A1 + size_t(n_batch) * mat;
   int* need = reinterpret_cast<int*>(Z + size_t(n_batch) * n * n);
-  ns_scale_kernel<<<n_batch, 256, 0, st>>>(X, A0, rows, cols);
-  DM_LAUNCH_OK("ns_scale_kernel");
   int rc;
-  auto gram = [&](const double* A) {  // Z = A^T A (tall) or A A^T (wide), n x n
+  auto gram = [&](const double* A, const int* skip) {  // Z = A^T A (tall) or A A^T (wide), n x n
     GemmProblem G;
     G.A.d = A, G.A.ld = cols, G.A.batch_stride = int64_t(mat), G.A.rows = rows, G.A.trans = wide ? 0 : 1;
     G.B = G.A;
     G.M = n, G.N = n, G.K = wide ? cols : rows, G.maxM = n, G.maxN = n, G.maxK = G.K, G.n_batch = n_batch;
-    G.C = Z, G.ldc = n, G.c_batch_stride = int64_t(n) * n;
+    G.C = Z, G.ldc = n, G.c_batch_stride = int64_t(n) * n, G.skip = skip;
     return gemm64_launch(G, st);
   };
+  int* done = need + n_batch;
+  DM_CUDA_OK(cudaMemsetAsync(done, 0, sizeof(int) * n_batch, st));
+  if ((rc = gram(X, nullptr))) return rc;
+  ns_scale_kernel<<<n_batch, 256, 0, st>>>(X, Z, A0, n, rows, cols);
+  DM_LAUNCH_OK("ns_scale_kernel");
   double* cur = A0;
   double* nxt = A1;
   for (int it = 0; it < kNsIters; ++it) {
-    if ((rc = gram(cur))) return rc;
-    const int64_t total = int64_t(n_batch) * n * n;
-    ns_w_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(Z, n, total);
-    DM_LAUNCH_OK("ns_w_kernel");
+    ns_step_kernel<<<n_batch, 256, 0, st>>>(Z, cur, C, n, rows, cols, done);
+    DM_LAUNCH_OK("ns_step_kernel");
     GemmProblem G;
     if (!wide) {  // A <- A W            (rows x n) (n x n), W symmetric
       G.A.d = cur, G.A.ld = cols, G.A.batch_stride = int64_t(mat), G.A.rows = rows, G.A.trans = 0;
@@ -345,15 +335,17 @@ int polar_factor_launch(const double* X, double* C, int rows, int cols, int n_ba
       G.M = rows, G.N = cols, G.K = n;
     }
     G.maxM = G.M, G.maxN = G.N, G.maxK = G.K, G.n_batch = n_batch;
-    G.C = nxt, G.ldc = cols, G.c_batch_stride = int64_t(mat);
+    G.C = nxt, G.ldc = cols, G.c_batch_stride = int64_t(mat), G.skip = done;
     if ((rc = gemm64_launch(G, st))) return rc;
     double* tmp = cur;
     cur = nxt;
     nxt = tmp;
+    if ((rc = gram(cur, done))) return rc;
   }
-  if ((rc = gram(cur))) return rc;
-  ns_check_kernel<<<n_batch, 256, 0, st>>>(Z, cur, C, n, rows, cols, need);
-  DM_LAUNCH_OK("ns_check_kernel");
+  ns_step_kernel<<<n_batch, 256, 0, st>>>(Z, cur, C, n, rows, cols, done);  // catches convergence in the last step
+  DM_LAUNCH_OK("ns_step_kernel");
+  ns_need_kernel<<<(n_batch + 255) / 256, 256, 0, st>>>(done, need, n_batch);
+  DM_LAUNCH_OK("ns_need_kernel");
   return polar_jacobi_launch(X, C, rows, cols, n_batch, scratch, need, st);
 }
 
