@@ -77,6 +77,9 @@ SIGNATURES = {
                                           c_int]),
     "dm_zoomout": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64,
                            c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "dm_dense_energy_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int]),
+    "dm_dense_energy": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
+                                c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "dm_match_pairs_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
     "dm_match_pairs": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_dbl, c_dbl,

@@ -15,7 +15,7 @@ from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
 __all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "polar_factor",
-           "match_pairs", "PairBatch"]
+           "match_pairs", "dense_energy", "DENSE_TERMS", "PairBatch"]
 
 
 def _stream(dev):
@@ -296,6 +296,38 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
                                 _stream(dev))
     _lib.check(rc, "dm_match_pairs")
     return out
+
+
+DENSE_TERMS = ("p2p", "stochastic", "ent", "range01", "sumto1")
+
+
+def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace: Optional[Workspace] = None):
+    """Dense-map energy terms and their gradient (``dm_dense_energy``).  ``weights``: dict over ``DENSE_TERMS``.
+    Returns (energies [P, 5] unweighted, in ``DENSE_TERMS`` order; grad [P, k2, k1] of the weighted sum)."""
+    lib = _lib.load()
+    dev = C.device
+    C = _f64(C)
+    if C.dim() == 2:
+        C = C[None]
+    C = C.contiguous()
+    Phi1, Phi2, area1 = _f64(Phi1), _f64(Phi2), _f64(area1).contiguous()
+    P, k2, k1 = C.shape
+    if k1 > Phi1.shape[1] or k2 > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    n1, n2 = Phi1.shape[0], Phi2.shape[0]
+    o1, o1h, max1 = _offsets(off1, n1, dev)
+    o2, o2h, max2 = _offsets(off2, n2, dev)
+    w = [float(weights.get(t, 0.0)) for t in DENSE_TERMS]
+    energy = torch.zeros(P, 5, dtype=torch.float64, device=dev)
+    grad = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
+    need = lib.dm_dense_energy_workspace_bytes(P, n1, n2, max1, max2, k1, k2)
+    ws = (workspace or default_workspace(dev, "energy")).get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_dense_energy(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1, max1,
+                                 Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, area1.data_ptr(), P, *w,
+                                 energy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_dense_energy")
+    return energy, grad
 
 
 def polar_factor(X, flags=0):

@@ -6,7 +6,9 @@ project / decode / transport / transfer and the ``FM`` / ``FM_type`` / ``k1`` / 
 What differs, deliberately:
 * ``fit`` returns the float64 closed-form minimiser of the descriptor + Laplacian energy instead of running
   L-BFGS-B on a float32 energy (functional.py:381,477): same optimum, without the optimiser noise.  Energy terms
-  outside that pair (w_dcomm, w_orient, w_ent, w_sumto1, ...) are SURVEY.md 8f "next" rows and raise
+  With any of the dense-map terms (w_p2p, w_stochastic, w_ent, w_range01, w_sumto1 -- the notebook's default
+  ``fit_params`` use w_ent and w_sumto1) the reference's L-BFGS-B loop is kept and the energy is evaluated on the
+  GPU (``dm_dense_energy``).  The remaining terms (w_dcomm, w_orient, w_area, w_conformal, ...) raise
   ``NotImplementedError`` when given a non-zero weight -- never silently ignored.
 * ``mapped_indicator`` (n2 x n1 float64, 32 MB at N = 2000) is materialised lazily, only if somebody reads it;
   ``get_p2p(dense=True)`` returns the dense-argmax override of functional_map.py:49-50 straight from the fused
@@ -23,8 +25,10 @@ from .. import fm as _fm
 from ._dev import to_dev
 from . import refine as _refine
 
-_UNSUPPORTED_WEIGHTS = ("w_dcomm", "w_orient", "w_area", "w_conformal", "w_p2p", "w_stochastic", "w_ent", "w_range01",
-                        "w_sumto1", "w_area_difference", "w_mumford_shah", "w_eta_entropy")
+_UNSUPPORTED_WEIGHTS = ("w_dcomm", "w_orient", "w_area", "w_conformal", "w_area_difference", "w_mumford_shah",
+                        "w_eta_entropy")
+_DENSE_WEIGHTS = {"w_p2p": "p2p", "w_stochastic": "stochastic", "w_ent": "ent", "w_range01": "range01",
+                  "w_sumto1": "sumto1"}
 
 
 class FunctionalMapping:
@@ -144,8 +148,9 @@ class FunctionalMapping:
                      w_area_difference=w_area_difference, w_mumford_shah=w_mumford_shah, w_eta_entropy=w_eta_entropy)
         bad = [n for n in _UNSUPPORTED_WEIGHTS if given[n] != 0]
         if bad:
-            raise NotImplementedError(f"energy terms {bad} are not on the accelerated path (SURVEY.md 8f); only "
-                                      "w_descr and w_lap may be non-zero")
+            raise NotImplementedError(f"energy terms {bad} are not implemented (SURVEY.md 8f); supported: w_descr, "
+                                      "w_lap and the dense-map terms w_p2p, w_stochastic, w_ent, w_range01, w_sumto1")
+        dense = {t: float(given[n]) for n, t in _DENSE_WEIGHTS.items() if given[n] != 0}
         if self.partial:
             raise NotImplementedError()                                   # functional.py:479-480
         if not self.preprocessed:
@@ -159,11 +164,44 @@ class FunctionalMapping:
         c00 = float(self.get_x0(optinit)[0, 0])
         ev1 = to_dev(self.mesh1.eigenvalues[:k1], torch.float64)[None]
         ev2 = to_dev(self.mesh2.eigenvalues[:k2], torch.float64)[None]
-        C = _fm.fmap_solve(A, B, ev1, ev2, torch.tensor([c00], dtype=torch.float64, device=A.device), w_descr, w_lap)
-        self.FM = C[0].cpu().numpy()
+        if not dense:
+            C = _fm.fmap_solve(A, B, ev1, ev2, torch.tensor([c00], dtype=torch.float64, device=A.device), w_descr, w_lap)
+            self.FM = C[0].cpu().numpy()
+        else:
+            self.FM = self._fit_lbfgs(A[0], B[0], c00, P1, P2, a1, w_descr, w_lap, dense, maxiter)
         self.eta = np.ones(self.mesh2.eigenvectors.shape[0])              # functional.py:483
         self._mi = None
         return self
+
+    def _fit_lbfgs(self, A, B, c00, P1, P2, a1, w_descr, w_lap, dense, maxiter):
+        """The reference's optimiser loop (functional.py:477: scipy L-BFGS-B, x0 = c00 e_00, gradient of column 0
+        zeroed, base_functions.py:759) with the energy evaluated on the GPU in float64: descriptor and Laplacian
+        terms as two small products, the dense-map terms by ``dm_dense_energy`` (M is never materialised)."""
+        import scipy.optimize
+        k1, k2 = self._k1, self._k2
+        l1, l2 = np.asarray(self.mesh1.eigenvalues[:k1], np.float64), np.asarray(self.mesh2.eigenvalues[:k2], np.float64)
+        scale = max(l1.max(), l2.max())
+        Delta = torch.from_numpy(np.square(l1[None, :] / scale - l2[:, None] / scale)).to(A.device)
+        At = A.T.contiguous()
+
+        def fun(x):
+            C = torch.from_numpy(np.ascontiguousarray(x.reshape(k2, k1))).to(A.device)
+            R = C @ A - B
+            e = 0.5 * w_descr * (R * R).sum() + 0.5 * w_lap * (C * C * Delta).sum()
+            g = w_descr * (R @ At) + w_lap * (C * Delta)
+            ed, gd = _fm.dense_energy(C, P1, P2, a1, dense)
+            wvec = torch.tensor([dense.get(t, 0.0) for t in _fm.DENSE_TERMS], dtype=torch.float64, device=A.device)
+            e = e + (ed[0] * wvec).sum()
+            g = g + gd[0]
+            g[:, 0] = 0.0
+            return float(e), g.reshape(-1).cpu().numpy()
+
+        x0 = np.zeros((k2, k1))
+        x0[0, 0] = c00
+        method = "L-BFGS-B" if self.optimizer in ("fmin_l_bfgs_b", "L-BFGS-B") else self.optimizer
+        res = scipy.optimize.minimize(fun, x0.ravel(), jac=True, method=method, options={"maxiter": int(maxiter)})
+        self.fit_result = res
+        return res.x.reshape(k2, k1)
 
     def _dev_bases(self):
         k2, k1 = self.FM.shape

@@ -243,6 +243,23 @@ int dm_icp(const double* C0, int k1, int k2, int nit,
            int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense-map energy terms of the fit and their gradient with respect to C, without materialising the n2 x n1 map
+ * M = Phi2 C Phi1^T A1 (pyFM/optimize/base_functions.py: p2p :296-325, doubly_stochastic :327-361, entropy :363-372,
+ * range01 :374-385, sumto1 :387-428; evaluated per L-BFGS callback by energy_func_std :480-639).
+ *   energy [n_pairs, 5]      UNWEIGHTED terms in the order p2p, stochastic, ent, range01, sumto1 (0 where the weight is 0)
+ *   grad   [n_pairs, k2, k1] d/dC of  sum_t w_t * term_t
+ * float64 throughout; k1 <= 128.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_dense_energy_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int k1,
+                                       int k2);
+int dm_dense_energy(const double* C, int k1, int k2,
+                    const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1,
+                    const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                    const double* area1, int n_pairs,
+                    double w_p2p, double w_stochastic, double w_ent, double w_range01, double w_sumto1,
+                    double* energy, double* grad, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * The whole per-pair hot path of compute_surface_map (functional_map.py:44-50) for a ragged batch, in one call:
  *   feature NN both directions (knn_query on the unit features)          -> nn_p2p_21 [total_n2], nn_p2p_12 [total_n1]
  *   A = Phi1^T A1 F1, B = Phi2^T A2 F2 (tensor cores; the bf16 splits of F prepared for the NN pass are reused)

@@ -32,7 +32,7 @@ import scipy.linalg
 __all__ = [
     "knn_query", "nn_argmax", "knn_bruteforce", "project", "fmap_c00", "ev_sqdiff",
     "fmap_solve_closed_form", "fmap_energy", "fm_to_p2p", "dense_argmax_override",
-    "p2p_to_fm", "zoomout_refine", "icp_refine", "surface_map_arrays",
+    "p2p_to_fm", "zoomout_refine", "icp_refine", "surface_map_arrays", "dense_map_energy", "fmap_fit_lbfgs",
 ]
 
 
@@ -300,6 +300,87 @@ def icp_refine(FM_12, Phi1, Phi2, nit=10, tol=1e-10, return_p2p=False, nn="brute
     if return_p2p:
         return C, np.asarray(find(P1 @ C.T, P2), dtype=np.int64)
     return C
+
+
+# --------------------------------------------------------------------------------------
+# dense-map energy terms and the L-BFGS-B fit
+# --------------------------------------------------------------------------------------
+DENSE_TERMS = ("p2p", "stochastic", "ent", "range01", "sumto1")
+
+
+def dense_map_energy(C, Phi1, Phi2, a1, weights):
+    """Energy and gradient (w.r.t. ``C``) of the terms defined on the dense map
+    ``M = Phi2 @ C @ Phi1.T @ diag(a1)`` (n2, n1), float64, analytic gradients.
+
+    optimize/base_functions.py: ``p2p`` :296-325 sum (M^2 - M)^2; ``doubly_stochastic`` :327-361
+    sum_j (sum_i M^2 - n2/n1)^2 + sum_i (sum_j M^2 - 1)^2; ``entropy`` :363-372
+    sum -clamp(M,0,1) log(clamp(M,0,1) + 1e-10); ``range01`` :374-385 sum relu(-M)^2 + relu(M-1)^2;
+    ``sumto1`` :387-428 (v is None branch) sum_j (colsum - mean)^2 + sum_i (rowsum - mean)^2.
+    ``weights``: dict with keys from ``DENSE_TERMS`` (missing = 0).  Returns (energy, grad (k2, k1), per-term dict).
+    """
+    C = np.asarray(C, dtype=np.float64)
+    k2, k1 = C.shape
+    P1, P2 = np.asarray(Phi1, np.float64)[:, :k1], np.asarray(Phi2, np.float64)[:, :k2]
+    a1 = np.asarray(a1, np.float64)
+    n1, n2 = P1.shape[0], P2.shape[0]
+    M = (P2 @ C @ P1.T) * a1[None, :]
+    G = np.zeros_like(M)                      # dE/dM
+    E, parts = 0.0, {}
+
+    def add(name, e, g):
+        nonlocal E, G
+        w = float(weights.get(name, 0.0))
+        parts[name] = e
+        if w != 0.0:
+            E += w * e
+            G += w * g
+
+    if weights.get("p2p", 0):
+        q = M * M - M
+        add("p2p", float(np.sum(q * q)), 2.0 * q * (2.0 * M - 1.0))
+    if weights.get("stochastic", 0):
+        M2 = M * M
+        cs, rs = M2.sum(0) - n2 / n1, M2.sum(1) - 1.0
+        add("stochastic", float(np.sum(cs * cs) + np.sum(rs * rs)), 2.0 * M * (2.0 * cs[None, :] + 2.0 * rs[:, None]))
+    if weights.get("ent", 0):
+        Mc = np.clip(M, 0.0, 1.0)
+        inside = (M >= 0.0) & (M <= 1.0)
+        e = float(np.sum(-Mc * np.log(Mc + 1e-10)))
+        add("ent", e, np.where(inside, -np.log(Mc + 1e-10) - Mc / (Mc + 1e-10), 0.0))
+    if weights.get("range01", 0):
+        lo, hi = np.maximum(-M, 0.0), np.maximum(M - 1.0, 0.0)
+        add("range01", float(np.sum(lo * lo) + np.sum(hi * hi)), -2.0 * lo + 2.0 * hi)
+    if weights.get("sumto1", 0):
+        c, r = M.sum(0), M.sum(1)
+        dc, dr = c - c.mean(), r - r.mean()
+        add("sumto1", float(np.sum(dc * dc) + np.sum(dr * dr)), 2.0 * dc[None, :] + 2.0 * dr[:, None])
+    grad = P2.T @ (G * a1[None, :]) @ P1
+    return E, grad, parts
+
+
+def fmap_fit_lbfgs(A, B, evals1, evals2, c00, Phi1, Phi2, a1, w_descr, w_lap, dense_weights, maxiter=5000):
+    """``FunctionalMapping.fit`` with dense-map terms: scipy L-BFGS-B from x0 = c00 * e_00 with the gradient of
+    column 0 zeroed (functional.py:441,477; base_functions.py:759), float64 energy (the reference evaluates it in
+    float32)."""
+    import scipy.optimize
+    A, B = np.asarray(A, np.float64), np.asarray(B, np.float64)
+    k1, k2 = A.shape[0], B.shape[0]
+    Delta = ev_sqdiff(np.asarray(evals1)[:k1], np.asarray(evals2)[:k2])
+
+    def fun(x):
+        C = x.reshape(k2, k1)
+        R = C @ A - B
+        e = 0.5 * w_descr * np.sum(R * R) + 0.5 * w_lap * np.sum(C * C * Delta)
+        g = w_descr * (R @ A.T) + w_lap * (C * Delta)
+        ed, gd, _ = dense_map_energy(C, Phi1, Phi2, a1, dense_weights)
+        g = g + gd
+        g[:, 0] = 0.0
+        return e + ed, g.ravel()
+
+    x0 = np.zeros((k2, k1))
+    x0[0, 0] = c00
+    res = scipy.optimize.minimize(fun, x0.ravel(), jac=True, method="L-BFGS-B", options={"maxiter": maxiter})
+    return res.x.reshape(k2, k1), res
 
 
 # --------------------------------------------------------------------------------------

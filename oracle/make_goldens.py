@@ -163,11 +163,65 @@ def golden_fm(ref):
     print(f"zoomout: shipped reference zoomout_refine broken = {broken}")
 
 
+def golden_energy(ref):
+    """Dense-map energy terms: the reference's own torch implementations
+    (optimize/base_functions.py:296-428) evaluated in float64 at a fixed C, and the reference's full
+    ``FunctionalMapping.fit`` with the notebook's default weights (example.ipynb cell 11: w_ent = 0.1,
+    w_sumto1 = 10, n_ev = 15, L-BFGS-B on the float32 energy)."""
+    import torch
+    from densematcher.pyFM.optimize import base_functions as bf
+    g = dict(np.load(os.path.join(OUT, "fm_pair_ico3.npz")))
+    k = 15
+    P1, P2, a1, a2 = g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"], g["area2"]
+    rng = np.random.default_rng(2011)
+    C = g["C_closed_form"][:k, :k] + 0.05 * rng.standard_normal((k, k))
+    Ct = torch.tensor(C, dtype=torch.float64, requires_grad=True)
+    e1, e2, A1 = torch.tensor(P1), torch.tensor(P2), torch.diag(torch.tensor(a1))
+    out = {}
+    for name, fn, key in (("p2p", bf.p2p, "p2p_grad"), ("stochastic", bf.doubly_stochastic, "doubly_stochastic_grad"),
+                          ("ent", bf.entropy, "entropy_grad"), ("range01", bf.range01, "range01_grad"),
+                          ("sumto1", bf.sumto1, "sumto1_grad")):
+        ctx = {}
+        val = fn(Ct, None, e1, e2, A1, ctx)
+        out["ref_E_" + name] = float(val.detach())
+        out["ref_G_" + name] = ctx[key].detach().numpy().copy()
+    # full fit through the reference driver objects with the notebook weights
+    m1 = ref.TriMesh(np.zeros((642, 3)), np.zeros((1, 3), dtype=int))
+    m2 = ref.TriMesh(np.zeros((642, 3)), np.zeros((1, 3), dtype=int))
+    for m, P, ev, a in ((m1, g["Phi1"], g["evals1"], a1), (m2, g["Phi2"], g["evals2"], a2)):
+        m.eigenvectors, m.eigenvalues = P.copy(), ev.copy()
+        m.A = sp.diags(a).tocsc()
+        m.W = sp.identity(642, format="csc")
+        m.L = sp.identity(642, format="csc")
+    fit_params = dict(w_descr=1e4, w_lap=1e3, w_dcomm=0, w_orient=0, w_area=0, w_conformal=0, w_p2p=0,
+                      w_stochastic=0, w_ent=1e-1, w_range01=0, w_sumto1=1e1, optinit="zeros", maxiter=5000)
+    C_nb, secs = None, 0.0
+    try:
+        model = ref.FunctionalMapping(m1, m2, partial=False, optimizer="L-BFGS-B")
+        model.preprocess(n_ev=(k, k), descr1=g["c1"], descr2=g["c2"], subsample_step=1)
+        t = time.perf_counter()
+        model.fit(**fit_params, device=torch.device("cpu"))
+        secs = time.perf_counter() - t
+        C_nb = np.array(model.FM)
+    except Exception as e:  # the duck meshes may miss geometry the fit touches
+        print("reference notebook fit not available:", repr(e)[:200])
+    np.savez_compressed(os.path.join(OUT, "energy_ico3.npz"), k=k, C=C, **out,
+                        ref_C_notebook=(C_nb if C_nb is not None else np.zeros((0, 0))), ref_fit_seconds=secs,
+                        w_descr=1e4, w_lap=1e3, w_ent=1e-1, w_sumto1=1e1)
+    print("energy golden:", {n: out["ref_E_" + n] for n in ("p2p", "stochastic", "ent", "range01", "sumto1")},
+          "notebook fit", None if C_nb is None else C_nb.shape, f"{secs:.1f}s")
+
+
 def main():
+    only = sys.argv[1:]
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
-    golden_nn(ref)
-    golden_fm(ref)
+    if not only or "nn" in only:
+        golden_nn(ref)
+    if not only or "fm" in only:
+        golden_fm(ref)
+    if not only or "energy" in only:
+        golden_energy(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

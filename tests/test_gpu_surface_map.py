@@ -77,7 +77,7 @@ def test_functional_mapping_surface_and_errors(golden_fm, golden_zo):
     model.preprocess(n_ev=(k, k), descr1=g["c1"], descr2=g["c2"])
     assert model.preprocessed and not model.fitted and (model.k1, model.k2) == (k, k)
     with pytest.raises(NotImplementedError):
-        model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=0, w_ent=1.0)        # dense-map energy term: 8f, never ignored
+        model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=0, w_orient=1.0)     # unimplemented energy term: never ignored
     with pytest.raises(ValueError):
         model.get_p2p()
     model.fit(w_descr=float(g["w_descr"]), w_lap=float(g["w_lap"]), w_dcomm=0)
@@ -158,3 +158,66 @@ def test_mesh_bank_intra_category_pairs_cfg5_shape():
     blocks = [pipeline.match_bank_pairs(bank, src, dst, chunk_pairs=64, rank=r, world=2, feature_nn=True,
                                         functional_map=False)[1] for r in range(2)]
     assert blocks[0][0] == 0 and blocks[0][1] == blocks[1][0] and blocks[1][1] == len(src)
+
+
+def test_dense_energy_kernel_matches_oracle(golden_fm):
+    """dm_dense_energy (fused tile -> loss -> contraction, M never stored) against the float64 oracle whose values are
+    pinned to the reference's torch terms: every term alone, all together, a ragged two-pair batch, k1 != k2."""
+    import torch
+    from conftest import load_golden
+    from densematcher_b200 import fm
+    e = load_golden("energy_ico3.npz")
+    g = golden_fm
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    k = int(e["k"])
+    P1, P2, a1 = g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"]
+    for name in orc.DENSE_TERMS + ("all",):
+        w = {t: 0.3 + 0.1 * i for i, t in enumerate(orc.DENSE_TERMS)} if name == "all" else {name: 1.0}
+        en, gr = fm.dense_energy(dev(e["C"]), dev(P1), dev(P2), dev(a1), w)
+        Eo, Go, parts = orc.dense_map_energy(e["C"], P1, P2, a1, w)
+        for i, t in enumerate(orc.DENSE_TERMS):
+            if t in w:
+                assert np.isclose(float(en[0, i]), parts[t], rtol=1e-11), (name, t)
+                if name != "all":
+                    assert np.isclose(float(en[0, i]), float(e["ref_E_" + t]), rtol=1e-11), t   # the reference's value
+        assert np.abs(gr[0].cpu().numpy() - Go).max() < 1e-10 * np.abs(Go).max(), name
+    # ragged batch of two pairs, rectangular map
+    rng = np.random.default_rng(1)
+    k1, k2 = 9, 13
+    n1a, n2a = 400, 350
+    Phi1 = np.concatenate([g["Phi1"][:n1a, :k1], g["Phi1"][:, :k1]]); Phi2 = np.concatenate([g["Phi2"][:n2a, :k2], g["Phi2"][:, :k2]])
+    ar1 = np.concatenate([a1[:n1a], a1])
+    o1, o2 = np.array([0, n1a, n1a + 642]), np.array([0, n2a, n2a + 642])
+    C = 0.3 * rng.standard_normal((2, k2, k1))
+    w = dict(ent=0.1, sumto1=10.0, stochastic=0.05, p2p=0.2, range01=1.0)
+    en, gr = fm.dense_energy(dev(C), dev(Phi1), dev(Phi2), dev(ar1), w, o1, o2)
+    for p in range(2):
+        s1, s2 = slice(o1[p], o1[p + 1]), slice(o2[p], o2[p + 1])
+        Eo, Go, parts = orc.dense_map_energy(C[p], Phi1[s1], Phi2[s2], ar1[s1], w)
+        assert np.allclose(en[p].cpu().numpy(), [parts[t] for t in orc.DENSE_TERMS], rtol=1e-10)
+        assert np.abs(gr[p].cpu().numpy() - Go).max() < 1e-10 * np.abs(Go).max()
+
+
+def test_fit_with_notebook_default_weights(golden_fm):
+    """example.ipynb cell 11 verbatim: w_ent = 0.1, w_sumto1 = 10 next to w_descr / w_lap, n_ev = 15, L-BFGS-B.  The
+    fit lands on the reference's own result (its float32 energy leaves ~1e-4 of noise) and yields the same p2p."""
+    from conftest import load_golden
+    from densematcher_b200 import _lib
+    from densematcher_b200.pyFM import FunctionalMapping
+    e = load_golden("energy_ico3.npz")
+    g = golden_fm
+    k = int(e["k"])
+    m1, m2 = _meshes(g)
+    fit_params = {'w_descr': 1e4, 'w_lap': 1e3, 'w_dcomm': 0e0, 'w_orient': 0, 'w_area': 0, 'w_conformal': 0e1, 'w_p2p': 0,
+                  'w_stochastic': 0, 'w_ent': 1e-1, 'w_range01': 0, 'w_sumto1': 1e1, 'optinit': 'zeros', 'maxiter': 5000}
+    model = FunctionalMapping(m1, m2, partial=False, optimizer="L-BFGS-B")
+    model.projection_flags = _lib.DM_F64_GEMM
+    model.preprocess(n_ev=(k, k), descr1=g["c1"], descr2=g["c2"])
+    model.fit(**fit_params)
+    Cr = e["ref_C_notebook"]
+    assert relF(model.FM, Cr) < 1e-3 and model.fit_result.nit > 5
+    p21, p12 = model.get_p2p()
+    r21, r12, _ = orc.fm_to_p2p(Cr, g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"])
+    assert np.mean(p21 != r21) < 0.01 and np.mean(p12 != r12) < 0.01
+    with pytest.raises(NotImplementedError):
+        model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=1.0)

@@ -156,3 +156,25 @@ def test_meshgen_basis_is_area_orthonormal():
     ev, Phi, a = meshgen.synthetic_basis(500, 30, np.random.default_rng(0))
     assert np.allclose(Phi.T @ (a[:, None] * Phi), np.eye(30), atol=1e-9)
     assert np.allclose(Phi[:, 0], Phi[0, 0])
+
+
+def test_dense_map_energy_terms_match_reference_torch():
+    """The reference's own torch implementations of the dense-map terms (base_functions.py:296-428), evaluated in
+    float64 at a fixed C in the authoring container, pin the oracle's values and analytic gradients; the oracle's
+    L-BFGS fit with the notebook's weights lands on the reference's fit (within the reference's float32 noise)."""
+    from conftest import load_golden
+    from oracle import dm_oracle as orc
+    g, e = load_golden("fm_pair_ico3.npz"), load_golden("energy_ico3.npz")
+    k = int(e["k"])
+    P1, P2, a1, a2 = g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"], g["area2"]
+    for name in orc.DENSE_TERMS:
+        E, G, parts = orc.dense_map_energy(e["C"], P1, P2, a1, {name: 1.0})
+        assert np.isclose(parts[name], float(e["ref_E_" + name]), rtol=1e-12), name
+        assert np.abs(G - e["ref_G_" + name]).max() < 1e-10 * np.abs(e["ref_G_" + name]).max(), name
+    A, B = orc.project(P1, a1, g["c1"]), orc.project(P2, a2, g["c2"])
+    w = dict(ent=float(e["w_ent"]), sumto1=float(e["w_sumto1"]))
+    C, res = orc.fmap_fit_lbfgs(A, B, g["evals1"], g["evals2"], orc.fmap_c00(P1, P2, a1, a2), P1, P2, a1,
+                                float(e["w_descr"]), float(e["w_lap"]), w)
+    Cr = e["ref_C_notebook"]
+    assert Cr.shape == (k, k) and np.linalg.norm(C - Cr) / np.linalg.norm(Cr) < 1e-3
+    assert np.array_equal(orc.fm_to_p2p(C, P1, P2, a1)[0], orc.fm_to_p2p(Cr, P1, P2, a1)[0])
