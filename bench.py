@@ -145,6 +145,32 @@ def run_reference_arm(args):
         "gpu_launches": 0}))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore its pinned-memory allocations, first-touch) to the CPUs of the NUMA node its
+    GPU hangs off: with one rank per GPU the host->device copies of 8 ranks otherwise cross the socket interconnect.
+    Best effort: returns a description or None when the topology cannot be read."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} cpus"
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -170,6 +196,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
@@ -303,7 +330,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 scores + f64 re-evaluation / f64 functional map", "data": "synthetic",
                 "config": workload_config(P, world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "engine": engine, "lib": info}
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "engine": engine, "lib": info, "numa_binding": numa}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -316,6 +316,18 @@ int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float
                 size_t ws_bytes, cudaStream_t st, const void* const* b_presplit = nullptr);
 
 int num_sms();
+// true exactly once per (call site, device): function attributes such as the dynamic shared-memory limit are
+// per-device state, and one process may drive several devices
+struct OncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const bool f = !done[dev];
+    done[dev] = true;
+    return f;
+  }
+};
 int cvt_f64_f32(const double* src, int64_t lds, int64_t rows, int d, float* dst, int ldd, cudaStream_t st);
 
 }  // namespace dm

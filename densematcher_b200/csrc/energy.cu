@@ -354,11 +354,10 @@ int dm_dense_energy(const double* C, int k1, int k2, const double* Phi1, int64_t
     P.rs = L.rs, P.cs = L.cs, P.means = L.means;
   }
   const size_t shm = sizeof(double) * (2 * size_t(ET) * (k1 + 1) + size_t(ET) * (ET + 1));
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_once;
+  if (attr_once.first()) {
     DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
   }
   const unsigned grid = unsigned(n_pairs) * L.max_rt;
   if (w_stochastic != 0.0) {

@@ -405,10 +405,9 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int kp, int box_row
 
 template <int NR, int NC, bool DEBUG>
 int launch(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, dim3 grid, cudaStream_t st) {
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static OncePerDevice attr_once;
+  if (attr_once.first()) {
     DM_CUDA_OK(cudaFuncSetAttribute(nn_tc_kernel<NR, NC, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-    attr_done = true;
   }
   nn_tc_kernel<NR, NC, DEBUG><<<grid, kThreads, SMEM_BYTES, st>>>(maps, P, dbg);
   return DM_OK;

@@ -387,10 +387,9 @@ int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float
   int stages = int((200 * 1024) / stage_bytes);
   P.stages = stages > 6 ? 6 : (stages < 2 ? 2 : stages);
   const size_t shm = size_t(P.stages) * stage_bytes + 8 * (2 * P.stages + 1) + 16 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_once;
+  if (attr_once.first()) {
     DM_CUDA_OK(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
   }
   const int64_t nblk = int64_t(n_batch) * m_tiles * ksplit;
   if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "projection grid too large");
