@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int ct = 0; ct < n_ct; ++ct) {
         const int xrow = int(d0 + int64_t(ct) * TN);
         for (int kc = 0; kc < n_kc; ++kc) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = sbase + stage * STAGE_BYTES, fb = bar_full + 8 * stage;
           mbar_expect_tx(fb, STAGE_BYTES);
           tma_load_2d(sb, &maps.yh, kc * TBK, yrow, fb);
@@ -182,11 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       for (int ct = 0; ct < n_ct; ++ct) {
         const int acc = ct & 1;
-        mbar_wait(bar_tempty + 8 * acc, ((ct >> 1) & 1) ^ 1);
+        mbar_wait_backoff(bar_tempty + 8 * acc, ((ct >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * TN;
         for (int kc = 0; kc < n_kc; ++kc) {
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait_backoff(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sb = sbase + stage * STAGE_BYTES;
           const uint64_t dyh = umma_desc_sw128(sb), dyl = umma_desc_sw128(sb + SZ_Y);
