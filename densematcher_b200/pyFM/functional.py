@@ -254,6 +254,18 @@ class FunctionalMapping:
         if overwrite:
             self.FM_type = "zoomout"
 
+    def compute_SD(self):
+        """functional.py:619-627."""
+        from .spectral import area_SD, conformal_SD
+        if not self.fitted:
+            raise ValueError("The Functional map must be fit before computing the shape difference")
+        self.D_a = area_SD(self.FM)
+        self.D_c = conformal_SD(self.FM, self.mesh1.eigenvalues, self.mesh2.eigenvalues)
+
+    def get_precise_map(self, *args, **kwargs):
+        """functional.py:221-262: not implemented (barycentric precise map)."""
+        raise NotImplementedError("the barycentric precise map is not implemented")
+
     # ------------------------------------------------------------------ function transfer
     def project(self, func, k=None, mesh_ind=1):
         """functional.py:730-752."""

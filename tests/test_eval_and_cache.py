@@ -34,3 +34,14 @@ def test_operator_cache_roundtrip(tmp_path):
     assert m.eigenvectors.shape == (V.shape[0], 6) and m.eigenvectors.dtype == np.float64
     assert np.allclose(m.eigenvalues, evals[:6], atol=1e-5) and np.allclose(m.vertex_areas, area, rtol=1e-6)
     assert m.process(4).eigenvectors.shape[1] == 4          # slicing an existing spectrum needs no GPU and no geometry
+
+
+def test_shape_difference_operators():
+    from densematcher_b200.pyFM import spectral
+    rng = np.random.default_rng(1)
+    C, l1, l2 = rng.standard_normal((6, 5)), np.array([0.0, 1.0, 2.5, 4.0, 7.0]), np.arange(6.0)
+    assert np.allclose(spectral.area_SD(C), C.T @ C)
+    assert np.allclose(spectral.conformal_SD(C, l1, l2), np.linalg.pinv(np.diag(l1)) @ C.T @ np.diag(l2) @ C)
+    import pytest
+    with pytest.raises(NotImplementedError):
+        spectral.mesh_FM_to_p2p_precise(C, None, None)
