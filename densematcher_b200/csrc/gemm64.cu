@@ -1,17 +1,19 @@
-// Batched / ragged float64 GEMM on the CUDA-core FP64 pipe (see gemm64.cuh for the operand model).
+// Batched / ragged float64 GEMM on the FP64 tensor cores (see gemm64.cuh for the operand model).
 //
-// 128 x 128 output tile per 256-thread CTA, 8 x 8 accumulators per thread (two 4-wide groups per dimension so that the
-// shared-memory reads are 16-byte vectors: the A fragment is a warp broadcast, the B fragment 512 contiguous bytes),
-// K advanced 8 at a time through a double-buffered shared-memory stage with the next stage's global loads issued into
-// registers before the current stage is consumed.  64 FMAs per 8 shared-memory doubles per thread keeps the kernel on
-// the FP64 pipe rather than on shared-memory bandwidth.
+// 128 x 128 (or 128 x 64) output tile per 256-thread CTA; the eight warps form a 4 x 2 grid and each warp accumulates
+// its 32 x 64 (32 x 32) sub-tile with mma.sync.m8n8k4.f64 (DMMA): 256 fused multiply-adds per instruction, so the
+// kernel is bound by the FP64 pipe rather than by instruction issue or shared-memory bandwidth (the FFMA-style inner
+// loop it replaces needed 64 DFMA + 8 LDS.128 per thread and k, and reached 25-40 % of the pipe).  K advances 8 at a
+// time through a double-buffered shared-memory stage ([k][m] layout, row pitch 132 doubles); the next stage's global
+// loads are issued into registers before the current stage is consumed and are not touched until after it.
 #include "gemm64.cuh"
 
 namespace dm {
 namespace {
 
 constexpr int TM = 128, TN = 128, TK = 8, NT = 256;
-constexpr int LDT = TM + 2;  // padded row of a stage (keeps 16-byte alignment, spreads the transposing stores)
+constexpr int LDT = TM + 4;  // padded row of a stage: row pitch = 4 (mod 16) doubles makes the 8x4 / 4x8 fragment loads
+                             // of the FP64 MMA conflict-free (16 lanes -> 16 distinct 8-byte banks)
 
 struct OpView {  // an operand resolved for one batch
   const double* d;
@@ -140,15 +142,20 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   __shared__ __align__(16) double As[2][TK * LDT];
   __shared__ __align__(16) double Bs[2][TK * LDT];
   const OpView A = resolve(P.A, b), B = resolve(P.B, b);
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int t = threadIdx.x;
   const Loader<TA, TM> la(A, m0, M, t);
   const Loader<TB, TNW> lb(B, n0, N, t);
+  // warp grid 4 (M) x 2 (N): warp tile 32 x WN, as 4 x NT8 MMA tiles of 8 x 8
+  constexpr int WN = TNW / 2, NT8 = WN / 8;
+  const int lane = t & 31, warp = t >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
+  const int g = lane >> 2, t4 = lane & 3;  // fragment coordinates: A[row g][k t4], B[k t4][col g], C[row g][col 2 t4 + {0,1}]
 
-  double acc[8][NB];
+  double acc[4][NT8][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < NB; ++c) acc[a][c] = 0.0;
+    for (int c = 0; c < NT8; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
 
   Staged<Loader<TA, TM>::NE> ra;
   Staged<Loader<TB, TNW>::NE> rb;
@@ -166,28 +173,22 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
       la.fetch(k0 + TK, kend, ra);
       lb.fetch(k0 + TK, kend, rb);
     }
-    const double* as = As[buf];
-    const double* bs = Bs[buf];
+    const double* as = As[buf] + wm + g;
+    const double* bs = Bs[buf] + wn + g;
 #pragma unroll
-    for (int k = 0; k < TK; ++k) {
-      double av[8], bv[NB];
-      const double2 a0 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4);
-      const double2 a1 = *reinterpret_cast<const double2*>(as + k * LDT + ty * 4 + 2);
-      const double2 a2 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4);
-      const double2 a3 = *reinterpret_cast<const double2*>(as + k * LDT + 64 + ty * 4 + 2);
-      const double2 b0 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4);
-      const double2 b1 = *reinterpret_cast<const double2*>(bs + k * LDT + tx * 4 + 2);
-      av[0] = a0.x, av[1] = a0.y, av[2] = a1.x, av[3] = a1.y, av[4] = a2.x, av[5] = a2.y, av[6] = a3.x, av[7] = a3.y;
-      bv[0] = b0.x, bv[1] = b0.y, bv[2] = b1.x, bv[3] = b1.y;
-      if (NB == 8) {
-        const double2 b2 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4);
-        const double2 b3 = *reinterpret_cast<const double2*>(bs + k * LDT + 64 + tx * 4 + 2);
-        bv[NB - 4] = b2.x, bv[NB - 3] = b2.y, bv[NB - 2] = b3.x, bv[NB - 1] = b3.y;
-      }
+    for (int k4 = 0; k4 < TK; k4 += 4) {
+      double av[4], bv[NT8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+      for (int a = 0; a < 4; ++a) av[a] = as[(k4 + t4) * LDT + 8 * a];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+      for (int c = 0; c < NT8; ++c) bv[c] = bs[(k4 + t4) * LDT + 8 * c];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < NT8; ++c)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
+                       : "d"(av[a]), "d"(bv[c]));
     }
     if (more) {
       la.stash(As[buf ^ 1], ra);
@@ -200,16 +201,19 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   double* C = P.C + int64_t(ks) * P.split_stride + (P.c_off ? P.c_off[b] * P.ldc : int64_t(b) * P.c_batch_stride);
   const double* cs = P.c_colscale ? P.c_colscale + (P.c_colscale_off ? P.c_colscale_off[b] : 0) : nullptr;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int m = m0 + (a >> 2) * 64 + ty * 4 + (a & 3);
+  for (int a = 0; a < 4; ++a) {
+    const int m = m0 + wm + 8 * a + g;
     if (m >= M) continue;
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      const int n = n0 + (c >> 2) * 64 + tx * 4 + (c & 3);
-      if (n >= N) continue;
-      double v = P.alpha * acc[a][c];
-      if (cs) v *= cs[n];
-      C[int64_t(m) * P.ldc + n] = v;
+    for (int c = 0; c < NT8; ++c) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = n0 + wn + 8 * c + 2 * t4 + h;
+        if (n >= N) continue;
+        double v = P.alpha * acc[a][c][h];
+        if (cs) v *= cs[n];
+        C[int64_t(m) * P.ldc + n] = v;
+      }
     }
   }
 }
