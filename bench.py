@@ -293,7 +293,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         kw = dict(k=K_EIG, w_descr=W_DESCR, w_lap=W_LAP, chunk_pairs=max(8, P // 8), copy=False)
-        out = pipeline.match_pairs_host(host, device, **kw)
+        for _ in range(2):  # both alternating sets of pinned result buffers exist before the timed region
+            out = pipeline.match_pairs_host(host, device, **kw)
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
