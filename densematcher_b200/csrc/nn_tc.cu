@@ -80,6 +80,23 @@ __device__ __forceinline__ void top3_offer4(Top3& a, Top3& b, float w0, float w1
   }
 }
 
+// Two row epilogues at once: one vote for both, four independent chains in the update
+__device__ __forceinline__ void top3_offer4x2(Top3& a0, Top3& b0, Top3& a1, Top3& b1, const float (&w)[4], const float (&u)[4],
+                                              int idx0) {
+  const bool need = fmaxf(w[0], w[1]) > a0.m3 || fmaxf(w[2], w[3]) > b0.m3 || fmaxf(u[0], u[1]) > a1.m3 ||
+                    fmaxf(u[2], u[3]) > b1.m3;
+  if (__any_sync(0xffffffffu, need)) {
+    top3_push(a0, w[0], idx0);
+    top3_push(a1, u[0], idx0);
+    top3_push(b0, w[2], idx0 + 2);
+    top3_push(b1, u[2], idx0 + 2);
+    top3_push(a0, w[1], idx0 + 1);
+    top3_push(a1, u[1], idx0 + 1);
+    top3_push(b0, w[3], idx0 + 3);
+    top3_push(b1, u[3], idx0 + 3);
+  }
+}
+
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -279,21 +296,38 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if (NR > 0 && do_rows) {
           const bool full_tile = col0 + TN <= nd;  // no masked tail columns in this tile
+          const int jb = col0 + ch * CCH;
+          if (NR == 2 && !(full_tile && (P.row[0].identity || P.row[1].identity))) {
+            // both epilogues carry scale / bias: interleave them (one vote, four independent chains)
+            const float4* s40 = reinterpret_cast<const float4*>(rowsb + 0 * TN + ch * CCH);
+            const float4* b40 = reinterpret_cast<const float4*>(rowsb + 1 * TN + ch * CCH);
+            const float4* s41 = reinterpret_cast<const float4*>(rowsb + 2 * TN + ch * CCH);
+            const float4* b41 = reinterpret_cast<const float4*>(rowsb + 3 * TN + ch * CCH);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const int jb = col0 + ch * CCH;
-            if (P.row[r].identity && full_tile) {  // plain dot-product argmax: no scale / bias traffic
+            for (int c4 = 0; c4 < CCH / 4; ++c4) {
+              const float4 s0 = s40[c4], b0 = b40[c4], s1 = s41[c4], b1 = b41[c4];
+              const float w[4] = {fmaf(v[4 * c4 + 0], s0.x, b0.x), fmaf(v[4 * c4 + 1], s0.y, b0.y),
+                                  fmaf(v[4 * c4 + 2], s0.z, b0.z), fmaf(v[4 * c4 + 3], s0.w, b0.w)};
+              const float u[4] = {fmaf(v[4 * c4 + 0], s1.x, b1.x), fmaf(v[4 * c4 + 1], s1.y, b1.y),
+                                  fmaf(v[4 * c4 + 2], s1.z, b1.z), fmaf(v[4 * c4 + 3], s1.w, b1.w)};
+              top3_offer4x2(rowst[0], rowsu[0], rowst[NR - 1], rowsu[NR - 1], w, u, jb + 4 * c4);
+            }
+          } else {
 #pragma unroll
-              for (int c4 = 0; c4 < CCH / 4; ++c4)
-                top3_offer4(rowst[r], rowsu[r], v[4 * c4 + 0], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3], jb + 4 * c4);
-            } else {
-              const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
-              const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+            for (int r = 0; r < NR; ++r) {
+              if (P.row[r].identity && full_tile) {  // plain dot-product argmax: no scale / bias traffic
 #pragma unroll
-              for (int c4 = 0; c4 < CCH / 4; ++c4) {
-                const float4 s = s4[c4], b = b4[c4];
-                top3_offer4(rowst[r], rowsu[r], fmaf(v[4 * c4 + 0], s.x, b.x), fmaf(v[4 * c4 + 1], s.y, b.y),
-                            fmaf(v[4 * c4 + 2], s.z, b.z), fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4);
+                for (int c4 = 0; c4 < CCH / 4; ++c4)
+                  top3_offer4(rowst[r], rowsu[r], v[4 * c4 + 0], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3], jb + 4 * c4);
+              } else {
+                const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
+                const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+#pragma unroll
+                for (int c4 = 0; c4 < CCH / 4; ++c4) {
+                  const float4 s = s4[c4], b = b4[c4];
+                  top3_offer4(rowst[r], rowsu[r], fmaf(v[4 * c4 + 0], s.x, b.x), fmaf(v[4 * c4 + 1], s.y, b.y),
+                              fmaf(v[4 * c4 + 2], s.z, b.z), fmaf(v[4 * c4 + 3], s.w, b.w), jb + 4 * c4);
+                }
               }
             }
           }
@@ -303,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           // (lane becomes the column), scan the 32 rows in two independent ascending chains (rows 0..15, 16..31)
           Top3 cst[NC > 0 ? NC : 1];
           const int ib = row0 + 32 * q;
+          float w[NC > 0 ? NC : 1][32];
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             if (c > 0) __syncwarp();  // the previous epilogue's reads of the patch are done
@@ -319,17 +354,25 @@ __global__ void __launch_bounds__(kThreads, 1)
                                 fmaf(v[4 * c4 + 2], csc[c], cbi[c]), fmaf(v[4 * c4 + 3], csc[c], cbi[c]));
             }
             __syncwarp();
-            float w[32];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) w[r] = patch[r * PATCH_LD + lane];
-            Top2 ua = top2_init(), ub = top2_init();
+            for (int r = 0; r < 32; ++r) w[c][r] = patch[r * PATCH_LD + lane];
+          }
+          // all epilogues' chains advance together: 2 NC independent dependency chains
+          Top2 ua[NC > 0 ? NC : 1], ub[NC > 0 ? NC : 1];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              top2_push(ua, w[r], ib + r);
-              top2_push(ub, w[16 + r], ib + 16 + r);
+          for (int c = 0; c < NC; ++c) ua[c] = ub[c] = top2_init();
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              top2_push(ua[c], w[c][r], ib + r);
+              top2_push(ub[c], w[c][16 + r], ib + 16 + r);
             }
-            Top3 ta = top3_from(ua);
-            top3_merge(ta, top3_from(ub));
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            Top3 ta = top3_from(ua[c]);
+            top3_merge(ta, top3_from(ub[c]));
             cst[c] = ta;
           }
           const int par = ch & 1;
