@@ -221,3 +221,27 @@ def test_fit_with_notebook_default_weights(golden_fm):
     assert np.mean(p21 != r21) < 0.01 and np.mean(p12 != r12) < 0.01
     with pytest.raises(NotImplementedError):
         model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=1.0)
+
+
+def test_cfg2_full_size_pipeline_against_oracle():
+    """BASELINE config 2 at full size (N = M = 2000, d = 384, k = 100, notebook weights) for a small batch through the
+    single-call pipeline: feature NN bit-exact, C within 1e-4 of the float64 closed form, and -- given that C -- all
+    four FM->p2p index maps bit-exact against the float64 oracle."""
+    import torch
+    import bench
+    from densematcher_b200 import pipeline
+    P = 3
+    host = bench.make_host_batch(P, seed=2222, pool=4)
+    out = pipeline.match_pairs_device(host.to_device("cuda:0"), k=100, w_descr=1e4, w_lap=1e3, out_dtype=torch.int64)
+    out = {n: t.cpu().numpy() for n, t in out.items()}
+    for p in range(P):
+        s1, s2 = slice(host.off1[p], host.off1[p + 1]), slice(host.off2[p], host.off2[p + 1])
+        F1, F2, P1, P2, a1, a2 = host.F1[s1], host.F2[s2], host.Phi1[s1], host.Phi2[s2], host.area1[s1], host.area2[s2]
+        assert np.array_equal(out["nn_p2p_21"][s2], orc.nn_argmax(F2, F1))
+        assert np.array_equal(out["nn_p2p_12"][s1], orc.nn_argmax(F2, F1, axis=0))
+        Co = orc.fmap_solve_closed_form(orc.project(P1, a1, F1), orc.project(P2, a2, F2), host.evals1[p], host.evals2[p],
+                                        orc.fmap_c00(P1, P2, a1, a2), 1e4, 1e3)
+        assert relF(out["C"][p], Co) < 1e-4
+        r21, r12, MI = orc.fm_to_p2p(out["C"][p], P1, P2, a1)
+        assert np.array_equal(out["p2p_21_adjoint"][s2], r21) and np.array_equal(out["p2p_12_adjoint"][s1], r12)
+        assert np.array_equal(out["p2p_21"][s2], MI.argmax(1)) and np.array_equal(out["p2p_12"][s1], MI.argmax(0))
