@@ -41,6 +41,8 @@ f2p = lambda fl=0, want=("p2p_21", "p2p_12", "dense_21", "dense_12"): dfm.fm_to_
 print(f"fm_to_p2p (4 outputs)   {tm(f2p):8.3f} ms")
 print(f"fm_to_p2p no recheck    {tm(lambda: f2p(_lib.DM_NO_RECHECK)):8.3f} ms")
 print(f"fm_to_p2p p2p_21 only   {tm(lambda: f2p(0, ('p2p_21',))):8.3f} ms")
+for want in (("p2p_21", "dense_21"), ("p2p_12", "dense_12"), ("p2p_12",), ("dense_12",), ("p2p_21", "p2p_12")):
+    print(f"fm_to_p2p {'+'.join(want):22s} {tm(lambda: f2p(0, want)):8.3f} ms")
 print(f"whole step              {tm(lambda: pipeline.match_pairs_device(b, k=k, w_descr=bench.W_DESCR, w_lap=bench.W_LAP)):8.3f} ms")
 if "--icp" in sys.argv:
     print(f"icp nit=10              {tm(lambda: dfm.icp(C, b.Phi1[:, :k], b.Phi2[:, :k], 10, b.o1, b.o2), 2):8.3f} ms")
