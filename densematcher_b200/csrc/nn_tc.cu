@@ -45,8 +45,10 @@ constexpr int TBK = 64;       // K elements per pipeline stage (one 128-byte swi
 constexpr int STAGES = 2;
 constexpr int UMMA_K = 16;
 constexpr int kGroupWarps = 4;              // one warp per TMEM lane quarter
-constexpr int kEpiWarps = 2 * kGroupWarps;  // two epilogue groups (see the kernel)
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+// Two epilogue groups, or three when there are two row epilogues AND column epilogues (see the kernel)
+__host__ __device__ constexpr bool three_groups(int nr, int nc, bool debug) { return nr == 2 && nc > 0 && !debug; }
+__host__ __device__ constexpr int epi_warps(int nr, int nc, bool debug) { return (three_groups(nr, nc, debug) ? 3 : 2) * kGroupWarps; }
+__host__ __device__ constexpr int n_threads(int nr, int nc, bool debug) { return 32 * (2 + epi_warps(nr, nc, debug)); }
 constexpr int CCH = 32;  // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
 
 constexpr uint32_t SZ_Y = TM_ROWS * TBK * 2;  // 16 KB per half
@@ -64,7 +66,8 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;                           
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 using namespace tc;
-// named barriers of the epilogue: 1 = row group (or both groups when they share the row work), 2 = column group
+// named barriers of the epilogue: 1 = row group (or both groups when they share the row work), 2 = column group,
+// 3 = second row group
 __device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // Four candidates at a time into TWO independent running top-3 chains (a: first two, b: last two) so that consecutive
 // updates do not serialise on one dependency chain.  Candidates below the running third-best cannot change a top-3,
@@ -121,7 +124,7 @@ struct DebugOut {
 
 // ------------------------------------------------------------------ the kernel
 template <int NR, int NC, bool DEBUG>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
     nn_tc_kernel(const __grid_constant__ TcMaps maps, const NNProblem P, const DebugOut dbg) {
   const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
   const int64_t q0 = P.q_off[p];
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, kEpiWarps);
+      mbar_init(bar_tempty + 8 * a, epi_warps(NR, NC, DEBUG));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -225,26 +228,41 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue: two groups of four warps; warp w reads TMEM lanes 32*(w%4) .. +31.
+    // ===================== epilogue: groups of four warps; warp w reads TMEM lanes 32*(w%4) .. +31.
     // With row AND column epilogues, group 0 does the row epilogues and group 1 the column epilogues of every chunk
-    // (both read the accumulator from TMEM).  With row epilogues only, the groups split the chunks of each tile and
-    // their per-row states are merged at the end.
+    // (both read the accumulator from TMEM); with TWO row epilogues a third group takes the second one (kG3).
+    // With row epilogues only, two groups split the chunks of each tile and their per-row states are merged at the end.
+    constexpr bool kG3 = three_groups(NR, NC, DEBUG);
+    constexpr int NRS = kG3 ? 1 : NR;          // row epilogues handled by one thread
     const int q = warp & 3;
-    const int group = (warp - 2) >> 2;         // 0: warps 2..5, 1: warps 6..9
+    const int group = (warp - 2) >> 2;         // 0: warps 2..5, 1: warps 6..9, 2: warps 10..13 (kG3)
     const int trow = 32 * q + lane;            // accumulator row of this thread
     const int gt = (threadIdx.x - 64) & 127;   // thread index inside its group
     constexpr bool kSplitRoles = (NR > 0 && NC > 0);
     constexpr bool kShareRows = (NC == 0);     // both groups work on rows (also the DEBUG dump)
-    const bool do_rows = kSplitRoles ? group == 0 : (NC == 0 ? true : false);
+    const bool do_rows = kSplitRoles ? group != 1 : (NC == 0 ? true : false);
     const bool do_cols = NC > 0 && group == 1;
+    const int r_base = kG3 && group == 2 ? 1 : 0;  // first row epilogue of this thread
+    const int row_bar = kG3 && group == 2 ? 3 : 1;
     float* patch = reinterpret_cast<float*>(sgen + OFF_PATCH + q * PATCH_BYTES);
     Top3* colred = reinterpret_cast<Top3*>(sgen + OFF_COLRED);          // [2][kMaxEpi][4][CCH]
     float* rowsb = reinterpret_cast<float*>(sgen + OFF_ROWSB);          // [e][0=scale,1=bias][TN]
     const int row_threads = kShareRows ? 2 * kGroupWarps * 32 : kGroupWarps * 32;
 
-    Top3 rowst[NR > 0 ? NR : 1], rowsu[NR > 0 ? NR : 1];  // two chains per row epilogue (merged at the end)
+    Top3 rowst[NRS > 0 ? NRS : 1], rowsu[NRS > 0 ? NRS : 1];  // two chains per row epilogue (merged at the end)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) rowst[r] = rowsu[r] = top3_init();
+    for (int r = 0; r < NRS; ++r) rowst[r] = rowsu[r] = top3_init();
+    // row epilogue descriptors of this thread (kG3: the group's own one)
+    const float* rsf[NRS > 0 ? NRS : 1];
+    const float* rbf[NRS > 0 ? NRS : 1];
+    bool rident[NRS > 0 ? NRS : 1];
+#pragma unroll
+    for (int r = 0; r < NRS; ++r) {
+      const bool second = kG3 ? r_base == 1 : r == 1;
+      rsf[r] = second ? P.row[NR > 1 ? 1 : 0].sf : P.row[0].sf;
+      rbf[r] = second ? P.row[NR > 1 ? 1 : 0].bf : P.row[0].bf;
+      rident[r] = second ? P.row[NR > 1 ? 1 : 0].identity : P.row[0].identity;
+    }
 
     // scale / bias of THIS thread's accumulator row for the column epilogues (applied before the transposition)
     float csc[NC > 0 ? NC : 1], cbi[NC > 0 ? NC : 1];
@@ -261,17 +279,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int col0 = ct * TN;
       if (NR > 0 && do_rows) {
         // per-column scale / bias of the row epilogues for this tile
-        bar_sync_n(1, row_threads);  // everyone is done with the previous tile's arrays
+        bar_sync_n(row_bar, row_threads);  // everyone is done with the previous tile's arrays
         const int rt_idx = kShareRows ? int(threadIdx.x) - 64 : gt;
 #pragma unroll
-        for (int r = 0; r < NR; ++r)
+        for (int r = 0; r < NRS; ++r)
           for (int jj = rt_idx; jj < TN; jj += row_threads) {
             const int j = col0 + jj;
             const bool v = j < nd;
-            rowsb[(r * 2 + 0) * TN + jj] = v ? __ldg(P.row[r].sf + d0 + j) : 0.f;
-            rowsb[(r * 2 + 1) * TN + jj] = v ? __ldg(P.row[r].bf + d0 + j) : -INFINITY;
+            rowsb[((r_base + r) * 2 + 0) * TN + jj] = v ? __ldg(rsf[r] + d0 + j) : 0.f;
+            rowsb[((r_base + r) * 2 + 1) * TN + jj] = v ? __ldg(rbf[r] + d0 + j) : -INFINITY;
           }
-        bar_sync_n(1, row_threads);
+        bar_sync_n(row_bar, row_threads);
       }
 
       mbar_wait(bar_tfull + 8 * acc, (ct >> 1) & 1);
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (NR > 0 && do_rows) {
           const bool full_tile = col0 + TN <= nd;  // no masked tail columns in this tile
           const int jb = col0 + ch * CCH;
-          if (NR == 2 && !(full_tile && (P.row[0].identity || P.row[1].identity))) {
+          if (NRS == 2 && !(full_tile && (rident[0] || rident[NRS - 1]))) {
             // both epilogues carry scale / bias: interleave them (one vote, four independent chains)
             const float4* s40 = reinterpret_cast<const float4*>(rowsb + 0 * TN + ch * CCH);
             const float4* b40 = reinterpret_cast<const float4*>(rowsb + 1 * TN + ch * CCH);
@@ -310,18 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                                   fmaf(v[4 * c4 + 2], s0.z, b0.z), fmaf(v[4 * c4 + 3], s0.w, b0.w)};
               const float u[4] = {fmaf(v[4 * c4 + 0], s1.x, b1.x), fmaf(v[4 * c4 + 1], s1.y, b1.y),
                                   fmaf(v[4 * c4 + 2], s1.z, b1.z), fmaf(v[4 * c4 + 3], s1.w, b1.w)};
-              top3_offer4x2(rowst[0], rowsu[0], rowst[NR - 1], rowsu[NR - 1], w, u, jb + 4 * c4);
+              top3_offer4x2(rowst[0], rowsu[0], rowst[NRS - 1], rowsu[NRS - 1], w, u, jb + 4 * c4);
             }
           } else {
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              if (P.row[r].identity && full_tile) {  // plain dot-product argmax: no scale / bias traffic
+            for (int r = 0; r < NRS; ++r) {
+              if (rident[r] && full_tile) {  // plain dot-product argmax: no scale / bias traffic
 #pragma unroll
                 for (int c4 = 0; c4 < CCH / 4; ++c4)
                   top3_offer4(rowst[r], rowsu[r], v[4 * c4 + 0], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3], jb + 4 * c4);
               } else {
-                const float4* s4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 0) * TN + ch * CCH);
-                const float4* b4 = reinterpret_cast<const float4*>(rowsb + (r * 2 + 1) * TN + ch * CCH);
+                const float4* s4 = reinterpret_cast<const float4*>(rowsb + ((r_base + r) * 2 + 0) * TN + ch * CCH);
+                const float4* b4 = reinterpret_cast<const float4*>(rowsb + ((r_base + r) * 2 + 1) * TN + ch * CCH);
 #pragma unroll
                 for (int c4 = 0; c4 < CCH / 4; ++c4) {
                   const float4 s = s4[c4], b = b4[c4];
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     if (NR > 0) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) top3_merge(rowst[r], rowsu[r]);
+      for (int r = 0; r < NRS; ++r) top3_merge(rowst[r], rowsu[r]);
       if (kShareRows) {
         // group 1 hands its per-row states to group 0 through shared memory (the patch area is free: NC == 0)
         Top3* xch = reinterpret_cast<Top3*>(sgen + OFF_PATCH);  // [NR][128]
@@ -413,12 +431,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int r = 0; r < NR; ++r) top3_merge(rowst[r], xch[r * TM_ROWS + trow]);
         }
       }
-      if (group == 0) {
+      const int i = row0 + trow;
+      if (kG3) {
+        if (i < nq && group == 0) emit_result(P, P.row[0], false, 0, p, q0 + i, i, P.norm_q[q0 + i], rowst[0]);
+        if (i < nq && group == 2) emit_result(P, P.row[NR > 1 ? 1 : 0], false, 1, p, q0 + i, i, P.norm_q[q0 + i], rowst[0]);
+      } else if (group == 0) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const int i = row0 + trow;
+        for (int r = 0; r < NR; ++r)
           if (i < nq) emit_result(P, P.row[r], false, r, p, q0 + i, i, P.norm_q[q0 + i], rowst[r]);
-        }
       }
     }
   }
@@ -452,7 +472,7 @@ int launch(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, dim3 gri
   if (attr_once.first()) {
     DM_CUDA_OK(cudaFuncSetAttribute(nn_tc_kernel<NR, NC, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   }
-  nn_tc_kernel<NR, NC, DEBUG><<<grid, kThreads, SMEM_BYTES, st>>>(maps, P, dbg);
+  nn_tc_kernel<NR, NC, DEBUG><<<grid, n_threads(NR, NC, DEBUG), SMEM_BYTES, st>>>(maps, P, dbg);
   return DM_OK;
 }
 
