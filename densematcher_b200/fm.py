@@ -348,6 +348,58 @@ def polar_factor(X, flags=0):
     return C
 
 
+def lap_solve(costs, maximize=False, return_status=False):
+    """``scipy.optimize.linear_sum_assignment`` for a batch of dense float64 matrices resident in HBM (the Hungarian
+    slots of ``compute_surface_map``, functional_map.py:57,66,78).  ``costs``: one 2-D CUDA tensor or a list of them
+    (shapes may differ).  Returns a list of ``(row_ind, col_ind)`` int64 numpy pairs, identical to scipy's (same
+    assignment, same tie-breaking); raises ``ValueError`` with scipy's messages on invalid / infeasible input."""
+    lib = _lib.load()
+    single = torch.is_tensor(costs)
+    mats = [costs] if single else list(costs)
+    if not mats:
+        return []
+    dev = mats[0].device
+    mats = [m if (m.dtype == torch.float64 and m.is_contiguous()) else m.to(torch.float64).contiguous() for m in mats]
+    for m in mats:
+        if m.dim() != 2:
+            raise ValueError("expected a matrix (2-D array), got a %d array" % m.dim())
+    nr = np.array([m.shape[0] for m in mats], dtype=np.int64)
+    nc = np.array([m.shape[1] for m in mats], dtype=np.int64)
+    ptr = np.array([m.data_ptr() for m in mats], dtype=np.int64)
+    nonempty = nr * nc > 0
+    base = int(ptr[nonempty].min()) if nonempty.any() else 0
+    n = len(mats)
+    meta_h = np.concatenate([np.where(nonempty, (ptr - base) // 8, 0), np.concatenate([[0], np.cumsum(nr)]), np.concatenate([[0], np.cumsum(nc)])])
+    meta = torch.from_numpy(meta_h).to(dev)
+    cost_off, row_off, col_off = meta[:n], meta[n:2 * n + 1], meta[2 * n + 1:]
+    tall = int((nr * nc)[nc < nr].sum())
+    out = torch.empty(int(nr.sum()), dtype=torch.int64, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    max_nr, max_nc = int(nr.max()), int(nc.max())
+    need = lib.dm_lap_workspace_bytes(n, max_nr, max_nc, tall)
+    ws = default_workspace(dev, "lap").get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_lap_solve(base, cost_off.data_ptr(), row_off.data_ptr(), col_off.data_ptr(), n, max_nr, max_nc, tall,
+                              int(bool(maximize)), out.data_ptr(), status.data_ptr(), _lib.DM_I64_OUT, ws.data_ptr(),
+                              ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_lap_solve")
+    out_h, st_h = out.cpu().numpy(), status.cpu().numpy()
+    if not return_status:
+        if (st_h == 1).any():
+            raise ValueError("matrix contains invalid numeric entries")
+        if (st_h == 2).any():
+            raise ValueError("cost matrix is infeasible")
+    res = []
+    ro = meta_h[n:2 * n + 1]
+    for b in range(n):
+        col = out_h[ro[b]:ro[b + 1]]
+        rows = np.nonzero(col >= 0)[0].astype(np.int64)
+        res.append((rows, col[rows].copy()))
+    if return_status:
+        return res, st_h
+    return res[0] if single else res
+
+
 class PairBatch:
     """A ragged batch of mesh pairs resident in HBM: packed features, eigenbases and offsets.
 

@@ -288,6 +288,25 @@ size_t dm_polar_factor_workspace_bytes(int n_batch, int rows, int cols);
 int dm_polar_factor(const double* X, int rows, int cols, int n_batch, double* C, int flags, void* workspace,
                     size_t workspace_bytes, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rectangular linear sum assignment, float64, batched: the `linear_sum_assignment(MI * eta - 1000 (1 - eta),
+ * maximize=True)` calls of compute_surface_map (densematcher/functional_map.py:57,66,78; the solver itself is
+ * scipy.optimize's shortest-augmenting-path implementation, a third-party dependency of the reference).
+ * Problem b is the dense row-major matrix cost + cost_off[b] with row_off[b+1]-row_off[b] rows and
+ * col_off[b+1]-col_off[b] columns (leading dimension = its column count); cost_off / row_off / col_off are device
+ * int64 arrays of n_batch(+1) entries.  tall_elems = total element count of the problems with more rows than
+ * columns (they are solved on a transposed copy in the workspace; 0 if there are none).
+ * Output: col_of_row[row_off[b] + i] = column assigned to row i, or -1 (only possible when rows > columns);
+ * (rows with an assignment, their columns) is exactly scipy's (row_ind, col_ind) -- the same assignment, including
+ * scipy's tie-breaking, not merely one of equal cost.  status[b] (device int32): 0 = solved, 1 = the matrix holds
+ * NaN / -inf (+inf when maximising), 2 = infeasible; scipy raises ValueError for both.  One CTA per problem:
+ * at most 8192 columns / rows, n_batch <= 65535.  flags: DM_I64_OUT.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_lap_workspace_bytes(int n_batch, int max_nr, int max_nc, int64_t tall_elems);
+int dm_lap_solve(const double* cost, const int64_t* cost_off, const int64_t* row_off, const int64_t* col_off, int n_batch,
+                 int max_nr, int max_nc, int64_t tall_elems, int maximize, void* col_of_row, int* status, int flags,
+                 void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
