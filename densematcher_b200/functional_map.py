@@ -50,8 +50,10 @@ def compute_surface_map(mesh1_t, mesh2_t, c1, c2, n_ev=50, compute_extra=False, 
     model.fit(**(fit_params or {}))
 
     def assign():
-        mi = model.mapped_indicator * model.eta[..., None] - 1000 * (1 - model.eta[..., None])
-        return linear_sum_assignment(mi, maximize=True)
+        if hungarian == "scipy":                              # host solver on the materialised indicator
+            mi = model.mapped_indicator * model.eta[..., None] - 1000 * (1 - model.eta[..., None])
+            return linear_sum_assignment(mi, maximize=True)
+        return model.hungarian()                              # dm_lap_solve: identical assignment, in HBM
 
     p2p_21_adjoint, p2p_12_adjoint, p2p_21, p2p_12 = model.get_p2p(n_jobs=1, dense=True)
     hung = assign() if (compute_extra and hungarian) else None

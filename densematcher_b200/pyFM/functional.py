@@ -234,6 +234,21 @@ class FunctionalMapping:
             self._mi_for = key
         return self._mi
 
+    def hungarian(self, indicator=None):
+        """``linear_sum_assignment(MI * eta - 1000 (1 - eta), maximize=True)`` (functional_map.py:57,66,78) solved in
+        HBM by ``dm_lap_solve``: the same (row_ind, col_ind) as scipy.  ``indicator``: a dense (n2, n1) map to use
+        instead of the current ``mapped_indicator`` (the precise map, functional_map.py:62-66)."""
+        if not self.fitted:
+            raise ValueError("Model should be fit first")
+        if indicator is None:
+            P1, P2, a1 = self._dev_bases()
+            mi = _fm.mapped_indicator(to_dev(self.FM, torch.float64), P1, P2, a1)
+        else:
+            mi = to_dev(indicator, torch.float64)
+        eta = to_dev(self.eta, torch.float64)[:, None]
+        cost = mi * eta - 1000 * (1 - eta)
+        return _fm.lap_solve(cost, maximize=True)
+
     def icp_refine(self, nit=10, tol=None, use_adj=False, overwrite=True, verbose=False, n_jobs=1):
         """functional.py:564-586."""
         if not self.fitted:

@@ -33,6 +33,7 @@ __all__ = [
     "knn_query", "nn_argmax", "knn_bruteforce", "project", "fmap_c00", "ev_sqdiff",
     "fmap_solve_closed_form", "fmap_energy", "fm_to_p2p", "dense_argmax_override",
     "p2p_to_fm", "zoomout_refine", "icp_refine", "surface_map_arrays", "dense_map_energy", "fmap_fit_lbfgs",
+    "hungarian", "tri_closest_point", "project_points_to_triangles", "fm_to_precise_map",
 ]
 
 
@@ -413,3 +414,155 @@ def surface_map_arrays(Phi1, evals1, a1, Phi2, evals2, a2, c1, c2, n_ev, w_descr
     out["p2p_21_icp_adjoint"], out["p2p_12_icp_adjoint"] = p21_adj, p12_adj
     out["p2p_21_icp"], out["p2p_12_icp"] = dense_argmax_override(MI)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Hungarian assignment and the barycentric "precise map"
+# --------------------------------------------------------------------------------------
+def hungarian(MI, eta=None):
+    """``linear_sum_assignment(MI * eta - 1000 (1 - eta), maximize=True)``, densematcher/functional_map.py:57,66,78.
+    Same third-party call as the reference (scipy.optimize, 1.18.1 here)."""
+    from scipy.optimize import linear_sum_assignment
+    MI = np.asarray(MI, np.float64)
+    eta = np.ones(MI.shape[0]) if eta is None else np.asarray(eta, np.float64)
+    return linear_sum_assignment(MI * eta[..., None] - 1000 * (1 - eta[..., None]), maximize=True)
+
+
+def tri_closest_point(a, b, c, d, e, f, many=False):
+    """Closest point of a triangle B + s E0 + t E1 to a point P, from the six inner products
+    a = E0.E0, b = E0.E1, c = E1.E1, d = E0.(B-P), e = E1.(B-P), f = (B-P).(B-P): the seven-region case analysis of
+    Eberly's "Distance between point and triangle" as written in ``pointTriangleDistance``
+    (pyFM/spectral/projection_utils.py:820-976).  Returns (squared distance, s, t).
+
+    ``many=True`` reproduces the vectorised ``point_to_triangles_projection`` (:483-757), which is what the reference
+    runs whenever a point has more than one candidate triangle.  It differs from the scalar routine in two region-4
+    branches, where the squared distance is formed with the UN-normalised s / t of the region test (:543-544
+    ``d * s + f`` and :563-564 ``e * t + f``) -- the barycentric coordinates are the same, but that (wrong) distance
+    takes part in the argmin over the candidates, so it is restated as is."""
+    det = a * c - b * b
+    s = b * e - c * d
+    t = b * d - a * e
+
+    def full(s, t):
+        return s * (a * s + b * t + 2.0 * d) + t * (b * s + c * t + 2.0 * e) + f
+
+    if s + t <= det:
+        if s < 0:
+            if t < 0:                                   # region 4
+                if d < 0:
+                    if -d >= a:
+                        return a + 2.0 * d + f, 1.0, 0.0
+                    return (d * s + f if many else d * (-d / a) + f), -d / a, 0.0
+                if e >= 0:
+                    return f, 0.0, 0.0
+                if -e >= c:
+                    return c + 2.0 * e + f, 0.0, 1.0
+                return (e * t + f if many else e * (-e / c) + f), 0.0, -e / c
+            if e >= 0:                                  # region 3
+                return f, 0.0, 0.0
+            if -e >= c:
+                return c + 2.0 * e + f, 0.0, 1.0
+            return e * (-e / c) + f, 0.0, -e / c
+        if t < 0:                                       # region 5
+            if d >= 0:
+                return f, 0.0, 0.0
+            if -d >= a:
+                return a + 2.0 * d + f, 1.0, 0.0
+            return d * (-d / a) + f, -d / a, 0.0
+        inv = 1.0 / det                                 # region 0
+        s, t = s * inv, t * inv
+        return full(s, t), s, t
+    if s < 0:                                           # region 2
+        tmp0, tmp1 = b + d, c + e
+        if tmp1 > tmp0:
+            numer, denom = tmp1 - tmp0, a - 2.0 * b + c
+            if numer >= denom:
+                return a + 2.0 * d + f, 1.0, 0.0
+            s = numer / denom
+            return full(s, 1 - s), s, 1 - s
+        if tmp1 <= 0:
+            return c + 2.0 * e + f, 0.0, 1.0
+        if e >= 0:
+            return f, 0.0, 0.0
+        return e * (-e / c) + f, 0.0, -e / c
+    if t < 0:                                           # region 6
+        tmp0, tmp1 = b + e, a + d
+        if tmp1 > tmp0:
+            numer, denom = tmp1 - tmp0, a - 2.0 * b + c
+            if numer >= denom:
+                return c + 2.0 * e + f, 0.0, 1.0
+            t = numer / denom
+            return full(1 - t, t), 1 - t, t
+        if tmp1 <= 0:
+            return a + 2.0 * d + f, 1.0, 0.0
+        if d >= 0:
+            return f, 0.0, 0.0
+        return d * (-d / a) + f, -d / a, 0.0
+    numer = c + e - b - d                               # region 1
+    if numer <= 0:
+        return c + 2.0 * e + f, 0.0, 1.0
+    denom = a - 2.0 * b + c
+    if numer >= denom:
+        return a + 2.0 * d + f, 1.0, 0.0
+    s = numer / denom
+    return full(s, 1 - s), s, 1 - s
+
+
+def project_points_to_triangles(vert_emb, faces, points_emb, nn="kdtree"):
+    """For every point the triangle of the p-dimensional mesh (vert_emb, faces) it projects onto and the barycentric
+    coordinates of the projection: ``project_pc_to_triangles`` with ``precompute_dmin=True``
+    (pyFM/spectral/projection_utils.py:16-115).  Per point (``project_to_mesh`` :329-377): candidate faces are those
+    with  delta_min - l_max < Delta_min  (delta_min: distance to the nearest of the face's three vertices through
+    the |x|^2 - 2 x.y + |y|^2 expansion, :294-326 / :191-238; l_max: longest edge, :118-146; Delta_min: distance to
+    the nearest vertex, :149-186), each candidate is projected (``tri_closest_point``) and the first minimum of the
+    distances wins.  Returns (face_match (n2,) int64, bary (n2, 3) float64)."""
+    X, Y, faces = np.asarray(vert_emb, np.float64), np.asarray(points_emb, np.float64), np.asarray(faces)
+    e0, e1, e2 = X[faces[:, 0]], X[faces[:, 1]], X[faces[:, 2]]
+    lmax = np.maximum(np.maximum(np.linalg.norm(e1 - e0, axis=1), np.linalg.norm(e2 - e1, axis=1)),
+                      np.linalg.norm(e0 - e2, axis=1))
+    if nn == "kdtree":
+        Deltamin = knn_query(X, Y, return_distance=True)[0].reshape(-1)
+    else:
+        Deltamin = np.linalg.norm(Y - X[knn_bruteforce(X, Y)], axis=1)
+    sqX, sqY = np.linalg.norm(X, axis=1) ** 2, np.linalg.norm(Y, axis=1) ** 2
+    face_match = np.zeros(Y.shape[0], dtype=np.int64)
+    bary = np.zeros((Y.shape[0], 3))
+    for i in range(Y.shape[0]):
+        d2 = X @ Y[i]
+        d2 *= -2
+        d2 += sqX
+        d2 += sqY[i]
+        np.maximum(d2, 0, out=d2)
+        dmin = np.sqrt(np.minimum(np.minimum(d2[faces[:, 0]], d2[faces[:, 1]]), d2[faces[:, 2]]))
+        cand = np.nonzero(dmin - lmax < Deltamin[i])[0]
+        best = (np.inf, -1, 0.0, 0.0)
+        for fi in cand:
+            B = X[faces[fi, 0]]
+            E0, E1, D = X[faces[fi, 1]] - B, X[faces[fi, 2]] - B, B - Y[i]
+            sq, s, t = tri_closest_point(E0 @ E0, E0 @ E1, E1 @ E1, E0 @ D, E1 @ D, D @ D, many=len(cand) > 1)
+            dist = np.sqrt(max(sq, 0.0))
+            if dist < best[0]:
+                best = (dist, fi, s, t)
+        face_match[i] = best[1]
+        bary[i] = (1 - best[2] - best[3], best[2], best[3])
+    return face_match, bary
+
+
+def fm_to_precise_map(C, Phi1, Phi2, faces1, use_adj=True, nn="kdtree"):
+    """``mesh_FM_to_p2p_precise`` (pyFM/spectral/convert.py:186-231) + ``barycentric_to_precise``
+    (projection_utils.py:380-417): the (n2, n1) sparse map whose row i holds the barycentric coordinates of the image
+    of vertex i of mesh 2 on a triangle of mesh 1.  Returns (csr matrix, face_match, bary)."""
+    import scipy.sparse as sp
+    C = np.asarray(C, np.float64)
+    k2, k1 = C.shape
+    if use_adj:
+        emb1, emb2 = Phi1[:, :k1], Phi2[:, :k2] @ C
+    else:
+        emb1, emb2 = Phi1[:, :k1] @ C.T, Phi2[:, :k2]
+    fm, bary = project_points_to_triangles(emb1, faces1, emb2, nn=nn)
+    faces1 = np.asarray(faces1)
+    n2, n1 = emb2.shape[0], emb1.shape[0]
+    I = np.tile(np.arange(n2), 3)
+    J = np.concatenate([faces1[fm, 0], faces1[fm, 1], faces1[fm, 2]])
+    S = np.concatenate([bary[:, 0], bary[:, 1], bary[:, 2]])
+    return sp.csr_matrix((S, (I, J)), shape=(n2, n1)), fm, bary

@@ -212,6 +212,47 @@ def golden_energy(ref):
           "notebook fit", None if C_nb is None else C_nb.shape, f"{secs:.1f}s")
 
 
+def golden_extras(ref):
+    """the barycentric precise map (pyFM/spectral/projection_utils.py, run through the
+    reference's ``project_pc_to_triangles``) and the Hungarian assignments of functional_map.py:57,66 on the
+    reference's own mapped indicator / precise map, all from the closed-form C of fm_pair_ico3."""
+    from densematcher.pyFM.spectral import projection_utils as pju
+    from scipy.optimize import linear_sum_assignment
+    g = dict(np.load(os.path.join(OUT, "fm_pair_ico3.npz")))
+    _, F = meshgen.icosphere(3)
+    k = int(g["k"])
+    C = g["C_closed_form"]
+    emb1, emb2 = g["Phi1"][:, :k], g["Phi2"][:, :k] @ C              # convert.py:219-221 (use_adj=True)
+    t = time.perf_counter()
+    P = pju.project_pc_to_triangles(emb1, F, emb2, precompute_dmin=True, n_jobs=1)
+    dt = time.perf_counter() - t
+    P.sum_duplicates()
+    P.sort_indices()
+    _, _, MI = ref.FM_to_p2p(C, g["Phi1"][:, :k], g["Phi2"][:, :k], sp.diags(g["area1"]).tocsc())
+    eta = np.ones(MI.shape[0])
+    hung = linear_sum_assignment(MI * eta[..., None] - 1000 * (1 - eta[..., None]), maximize=True)
+    Pd = P.toarray()
+    hung_p = linear_sum_assignment(Pd * eta[..., None] - 1000 * (1 - eta[..., None]), maximize=True)
+    # a small random 5-dimensional "mesh" with far-away points: exercises all seven regions of the projection and
+    # the single-candidate path
+    rng = np.random.default_rng(77)
+    X = rng.standard_normal((40, 5))
+    Fr = np.stack([rng.choice(40, 3, replace=False) for _ in range(70)])
+    Y = np.concatenate([rng.standard_normal((150, 5)), 3.0 * rng.standard_normal((60, 5)),
+                        X[:20] + 1e-3 * rng.standard_normal((20, 5))])
+    Pr = pju.project_pc_to_triangles(X, Fr, Y, precompute_dmin=True, n_jobs=1)
+    Pr.sum_duplicates()
+    Pr.sort_indices()
+    np.savez_compressed(
+        os.path.join(OUT, "extras_ico3.npz"), faces=F.astype(np.int32),
+        ref_precise_data=P.data, ref_precise_indices=P.indices.astype(np.int32), ref_precise_indptr=P.indptr.astype(np.int32),
+        ref_hungarian_rows=hung[0], ref_hungarian_cols=hung[1],
+        ref_hungarian_precise_rows=hung_p[0], ref_hungarian_precise_cols=hung_p[1],
+        rnd_X=X, rnd_F=Fr.astype(np.int32), rnd_Y=Y, ref_rnd_data=Pr.data, ref_rnd_indices=Pr.indices.astype(np.int32),
+        ref_rnd_indptr=Pr.indptr.astype(np.int32), ref_seconds=dt)
+    print(f"extras: reference precise map {dt:.1f}s, nnz {P.nnz}; random mesh nnz {Pr.nnz}")
+
+
 def main():
     only = sys.argv[1:]
     os.makedirs(OUT, exist_ok=True)
@@ -222,6 +263,8 @@ def main():
         golden_fm(ref)
     if not only or "energy" in only:
         golden_energy(ref)
+    if not only or "extras" in only:
+        golden_extras(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

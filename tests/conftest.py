@@ -51,3 +51,8 @@ def golden_fm():
 @pytest.fixture(scope="session")
 def golden_zo():
     return load_golden("zoomout_ico3.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_extras():
+    return load_golden("extras_ico3.npz")

@@ -178,3 +178,40 @@ def test_dense_map_energy_terms_match_reference_torch():
     Cr = e["ref_C_notebook"]
     assert Cr.shape == (k, k) and np.linalg.norm(C - Cr) / np.linalg.norm(Cr) < 1e-3
     assert np.array_equal(orc.fm_to_p2p(C, P1, P2, a1)[0], orc.fm_to_p2p(Cr, P1, P2, a1)[0])
+
+
+def _csr(g, prefix, shape):
+    import scipy.sparse as sp
+    return sp.csr_matrix((g[prefix + "_data"], g[prefix + "_indices"], g[prefix + "_indptr"]), shape=shape)
+
+
+def test_precise_map_matches_reference(golden_fm, golden_extras):
+    """8f rank 2: the oracle's barycentric precise map against the reference's project_pc_to_triangles."""
+    g, x = golden_fm, golden_extras
+    k = int(g["k"])
+    P, fm_, bary = orc.fm_to_precise_map(g["C_closed_form"], g["Phi1"][:, :k], g["Phi2"][:, :k], x["faces"])
+    ref = _csr(x, "ref_precise", (642, 642))
+    assert abs(P - ref).max() < 1e-12
+    assert np.allclose(bary.sum(1), 1.0) and bary.min() > -1e-12
+    # every region of the case analysis incl. the two branches where the vectorised routine differs
+    Pr = orc.project_points_to_triangles(x["rnd_X"], x["rnd_F"], x["rnd_Y"])
+    F = x["rnd_F"]
+    import scipy.sparse as sp
+    n = len(x["rnd_Y"])
+    got = sp.csr_matrix((Pr[1].T.ravel(), (np.tile(np.arange(n), 3), F[Pr[0]].T.ravel())), shape=(n, 40))
+    assert abs(got - _csr(x, "ref_rnd", (n, 40))).max() < 1e-12
+    # brute-force nearest vertex instead of the kd-tree gives the same map
+    Pb = orc.project_points_to_triangles(x["rnd_X"], x["rnd_F"], x["rnd_Y"], nn="brute")
+    assert np.array_equal(Pb[0], Pr[0]) and np.array_equal(Pb[1], Pr[1])
+
+
+def test_hungarian_matches_reference(golden_fm, golden_extras):
+    g, x = golden_fm, golden_extras
+    k = int(g["k"])
+    _, _, MI = orc.fm_to_p2p(g["C_closed_form"], g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"])
+    r, c = orc.hungarian(MI)
+    assert np.array_equal(r, x["ref_hungarian_rows"])
+    # the indicator is reproduced to rounding, so the optimal assignment (unique here) must agree
+    assert np.array_equal(c, x["ref_hungarian_cols"])
+    rp, cp = orc.hungarian(_csr(x, "ref_precise", (642, 642)).toarray())
+    assert np.array_equal(cp, x["ref_hungarian_precise_cols"])
