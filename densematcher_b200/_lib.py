@@ -88,6 +88,9 @@ SIGNATURES = {
     "dm_polar_factor": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
     "dm_lap_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_i64]),
     "dm_lap_solve": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "dm_precise_map_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_i64, c_i64]),
+    "dm_precise_map": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int,
+                               c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     "dm_icp_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
     "dm_icp": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
                        c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

@@ -47,7 +47,10 @@ def _compile(src, force, verbose):
     if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src)
             and os.path.getmtime(obj) >= _deps_mtime()):
         return obj, ""
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+    with open(src) as f:                      # per-file flags: a first line "// dm-nvcc-flags: ..."
+        first = f.readline()
+    extra = first.split("dm-nvcc-flags:", 1)[1].split() if "dm-nvcc-flags:" in first else []
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

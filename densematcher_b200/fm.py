@@ -348,6 +348,39 @@ def polar_factor(X, flags=0):
     return C
 
 
+def precise_map(emb1, faces, emb2, off1=None, face_off=None, off2=None, out_dtype=torch.int64):
+    """Barycentric precise map (projection_utils.py:16-115): for every row of ``emb2`` the face of the mesh
+    (``emb1``, ``faces``) it projects onto and the barycentric coordinates of the projection.  Ragged batches: packed
+    rows with ``off1`` / ``face_off`` / ``off2``; face vertex ids are local to their mesh.
+    Returns (face_match [n2] (local face index), bary [n2, 3] float64), both on the device."""
+    lib = _lib.load()
+    emb1, emb2 = _f64(emb1).contiguous(), _f64(emb2).contiguous()
+    dev = emb1.device
+    faces = torch.as_tensor(faces, device=dev).to(torch.int32).contiguous()
+    n1, p = emb1.shape
+    n2 = emb2.shape[0]
+    if emb2.shape[1] != p:
+        raise ValueError("embedding dimensions differ")
+    off1_d, off1_h, max_n1 = _offsets(off1, n1, dev)
+    off2_d, off2_h, max_n2 = _offsets(off2, n2, dev)
+    foff_d, foff_h, _ = _offsets(face_off, faces.shape[0], dev)
+    n_pairs = len(off1_h) - 1
+    if len(off2_h) - 1 != n_pairs or len(foff_h) - 1 != n_pairs:
+        raise ValueError("offset arrays describe different numbers of pairs")
+    face_match = torch.empty(n2, dtype=out_dtype, device=dev)
+    bary = torch.empty((n2, 3), dtype=torch.float64, device=dev)
+    need = lib.dm_precise_map_workspace_bytes(n_pairs, n1, max_n1, n2, faces.shape[0])
+    ws = default_workspace(dev, "fm").get(max(need, 256))
+    flags = _lib.DM_I64_OUT if out_dtype == torch.int64 else 0
+    with torch.cuda.device(dev):
+        rc = lib.dm_precise_map(emb1.data_ptr(), emb1.stride(0), off1_d.data_ptr(), n1, max_n1, faces.data_ptr(),
+                                foff_d.data_ptr(), faces.shape[0], emb2.data_ptr(), emb2.stride(0), off2_d.data_ptr(), n2,
+                                max_n2, n_pairs, p, face_match.data_ptr(), bary.data_ptr(), flags, ws.data_ptr(),
+                                ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_precise_map")
+    return face_match, bary
+
+
 def lap_solve(costs, maximize=False, return_status=False):
     """``scipy.optimize.linear_sum_assignment`` for a batch of dense float64 matrices resident in HBM (the Hungarian
     slots of ``compute_surface_map``, functional_map.py:57,66,78).  ``costs``: one 2-D CUDA tensor or a list of them

@@ -5,9 +5,10 @@
 
 Slots 0/1 and 4/5 are the dense-argmax maps (functional_map.py:49-50, :76-77), the ``*_adjoint`` slots the
 kd-tree-equivalent searches of FM_to_p2p (:48, :75) -- all four come out of one fused GPU pass per map.
-The Hungarian assignments (:57, :66, :78) are a SURVEY.md 8f "next" row: they are computed on the HOST with scipy
-from the lazily materialised ``mapped_indicator`` (``hungarian_icp`` always, like the reference; pass
-``hungarian=False`` to skip it); the barycentric precise map (:62) is not implemented and its slot is ``None``.
+The Hungarian assignments (:57, :66, :78) are solved in HBM by ``dm_lap_solve`` -- the same assignment scipy returns,
+tie-breaking included (``hungarian_icp`` always, like the reference; ``hungarian=False`` skips them,
+``hungarian="scipy"`` runs scipy on the host instead); with ``compute_extra`` the barycentric precise map (:62,
+``dm_precise_map``) feeds ``hungarian_precise``.
 
 ``mesh1_t`` / ``mesh2_t`` may be pytorch3d-like objects (only ``verts_list()[0]`` / ``faces_list()[0]`` are read,
 :17-18) or ``densematcher_b200.pyFM.mesh.TriMesh`` instances that already carry a spectrum (the accelerated
@@ -57,7 +58,14 @@ def compute_surface_map(mesh1_t, mesh2_t, c1, c2, n_ev=50, compute_extra=False, 
 
     p2p_21_adjoint, p2p_12_adjoint, p2p_21, p2p_12 = model.get_p2p(n_jobs=1, dense=True)
     hung = assign() if (compute_extra and hungarian) else None
-    hung_precise = None                                       # precise map: not implemented (8f)
+    hung_precise = None
+    if compute_extra and hungarian:                           # functional_map.py:60-66
+        precise = model.get_precise_map().toarray()
+        if hungarian == "scipy":
+            eta = model.eta[..., None]
+            hung_precise = linear_sum_assignment(precise * eta - 1000 * (1 - eta), maximize=True)
+        else:
+            hung_precise = model.hungarian(indicator=precise)
     model.icp_refine()
     p2p_21_icp_adjoint, p2p_12_icp_adjoint, p2p_21_icp, p2p_12_icp = model.get_p2p(n_jobs=1, dense=True)
     hung_icp = assign() if hungarian else None

@@ -24,6 +24,7 @@ import torch
 from .. import fm as _fm
 from ._dev import to_dev
 from . import refine as _refine
+from . import spectral as _spectral
 
 _UNSUPPORTED_WEIGHTS = ("w_dcomm", "w_orient", "w_area", "w_conformal", "w_area_difference", "w_mumford_shah",
                         "w_eta_entropy")
@@ -277,9 +278,12 @@ class FunctionalMapping:
         self.D_a = area_SD(self.FM)
         self.D_c = conformal_SD(self.FM, self.mesh1.eigenvalues, self.mesh2.eigenvalues)
 
-    def get_precise_map(self, *args, **kwargs):
-        """functional.py:221-262: not implemented (barycentric precise map)."""
-        raise NotImplementedError("the barycentric precise map is not implemented")
+    def get_precise_map(self, precompute_dmin=True, use_adj=True, batch_size=None, n_jobs=1, verbose=False):
+        """functional.py:221-251: (n2, n1) sparse barycentric map of mesh 2 onto mesh 1."""
+        if not self.fitted:
+            raise ValueError("Model should be fit and fit to obtain p2p map")
+        return _spectral.mesh_FM_to_p2p_precise(self.FM, self.mesh1, self.mesh2, precompute_dmin=precompute_dmin,
+                                                use_adj=use_adj, batch_size=batch_size, n_jobs=n_jobs, verbose=verbose)
 
     # ------------------------------------------------------------------ function transfer
     def project(self, func, k=None, mesh_ind=1):

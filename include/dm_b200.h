@@ -307,6 +307,23 @@ int dm_lap_solve(const double* cost, const int64_t* cost_off, const int64_t* row
                  int max_nr, int max_nc, int64_t tall_elems, int maximize, void* col_of_row, int* status, int flags,
                  void* workspace, size_t workspace_bytes, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Barycentric precise map (Ezuz & Ben-Chen): project_pc_to_triangles with precompute_dmin=True
+ * (densematcher/pyFM/spectral/projection_utils.py:16-115; callers convert.py:186-231, functional.py:221-251,
+ * functional_map.py:62).  For every point of emb2 [total_n2, p] (pair b: rows off2[b] .. off2[b+1]-1) the triangle
+ * of the p-dimensional mesh (emb1 [total_n1, p] rows off1[b].., faces [total_faces, 3] int32 vertex ids LOCAL to the
+ * pair's mesh, rows face_off[b] .. face_off[b+1]-1) it projects onto:
+ *   face_match[i]  face index local to the pair (int32, int64 with DM_I64_OUT)
+ *   bary[i, 0..2]  barycentric coordinates of the projection on that face (float64)
+ * Row i of the reference's sparse (n2, n1) map holds bary[i] in the columns faces[face_match[i]]
+ * (barycentric_to_precise, projection_utils.py:380-417).
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_precise_map_workspace_bytes(int n_pairs, int64_t total_n1, int max_n1, int64_t total_n2, int64_t total_faces);
+int dm_precise_map(const double* emb1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1, const int32_t* faces,
+                   const int64_t* face_off, int64_t total_faces, const double* emb2, int64_t ld2, const int64_t* off2,
+                   int64_t total_n2, int max_n2, int n_pairs, int p, void* face_match, double* bary, int flags,
+                   void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,102 @@
+"""GPU barycentric precise map (dm_precise_map) against the reference-minted golden and the oracle, and the
+compute_extra slots of compute_surface_map (Hungarian on the mapped indicator and on the precise map)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import dm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _csr(g, prefix, shape):
+    return sp.csr_matrix((g[prefix + "_data"], g[prefix + "_indices"], g[prefix + "_indptr"]), shape=shape)
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def test_random_mesh_all_regions_match_reference(golden_extras):
+    from densematcher_b200.pyFM.spectral import projection_utils as pju
+    x = golden_extras
+    P, face, bary = pju.project_pc_to_triangles(x["rnd_X"], x["rnd_F"], x["rnd_Y"], return_bary=True)
+    n = len(x["rnd_Y"])
+    assert abs(P - _csr(x, "ref_rnd", (n, 40))).max() < 1e-12
+    # Face ids are compared through the map they define: a point whose projection is a mesh vertex or lies on an edge
+    # is equidistant (to rounding) from every face sharing it (and this random soup repeats triangles), and which of
+    # them the argmin reports is decided by the last bit of six inner products -- in the reference as much as here.
+    fo, bo = orc.project_points_to_triangles(x["rnd_X"], x["rnd_F"], x["rnd_Y"])
+    assert abs(P - pju.barycentric_to_precise(x["rnd_F"], fo, bo, 40)).max() < 1e-12
+    assert np.abs(bary.sum(1) - 1).max() < 1e-12
+    assert face.dtype == np.int64 and sp.isspmatrix_csr(P)
+
+
+def test_spectral_precise_map_matches_reference(golden_fm, golden_extras):
+    from densematcher_b200.pyFM import spectral
+    from densematcher_b200.pyFM.mesh import TriMesh
+    g, x = golden_fm, golden_extras
+    k = int(g["k"])
+    m1 = TriMesh.from_basis(g["evals1"], g["Phi1"], g["area1"], faces=x["faces"])
+    m2 = TriMesh.from_basis(g["evals2"], g["Phi2"], g["area2"], faces=x["faces"])
+    P = spectral.mesh_FM_to_p2p_precise(g["C_closed_form"], m1, m2)
+    ref = _csr(x, "ref_precise", (642, 642))
+    assert P.shape == (642, 642) and abs(P - ref).max() < 1e-11
+    # on a manifold mesh, points projecting strictly inside a triangle have a well-defined face id
+    _, face, bary = spectral.projection_utils.project_pc_to_triangles(g["Phi1"][:, :k], x["faces"],
+                                                                      g["Phi2"][:, :k] @ g["C_closed_form"], return_bary=True)
+    _, fo, bo = orc.fm_to_precise_map(g["C_closed_form"], g["Phi1"][:, :k], g["Phi2"][:, :k], x["faces"])
+    interior = bo.min(1) > 1e-9
+    assert interior.sum() > 100 and np.array_equal(face[interior], fo[interior])
+    assert np.abs(bary[interior] - bo[interior]).max() < 1e-11
+    # the other branch (use_adj=False) against the oracle
+    P2 = spectral.mesh_FM_to_p2p_precise(g["C_closed_form"], m1, m2, use_adj=False)
+    Po, _, _ = orc.fm_to_precise_map(g["C_closed_form"], g["Phi1"][:, :k], g["Phi2"][:, :k], x["faces"], use_adj=False)
+    assert abs(P2 - Po).max() < 1e-11
+
+
+def test_ragged_batch_equals_single_calls(golden_extras):
+    from densematcher_b200 import fm
+    x = golden_extras
+    X, F, Y = x["rnd_X"], x["rnd_F"], x["rnd_Y"]
+    rng = np.random.default_rng(5)
+    X2 = rng.standard_normal((33, 5))
+    F2 = np.stack([rng.choice(33, 3, replace=False) for _ in range(50)]).astype(np.int32)
+    Y2 = 1.5 * rng.standard_normal((77, 5))
+    face, bary = fm.precise_map(dev(np.concatenate([X, X2])), dev(np.concatenate([F, F2])), dev(np.concatenate([Y, Y2])),
+                                off1=[0, 40, 73], face_off=[0, len(F), len(F) + 50], off2=[0, len(Y), len(Y) + 77],
+                                out_dtype=torch.int32)
+    face, bary = face.cpu().numpy(), bary.cpu().numpy()
+    assert face.dtype == np.int32
+    from densematcher_b200.pyFM.spectral.projection_utils import barycentric_to_precise as b2p
+    for (Xi, Fi, Yi, sl) in ((X, F, Y, slice(0, len(Y))), (X2, F2, Y2, slice(len(Y), len(Y) + 77))):
+        fo, bo = orc.project_points_to_triangles(Xi, Fi, Yi, nn="brute")
+        assert abs(b2p(Fi, face[sl], bary[sl], len(Xi)) - b2p(Fi, fo, bo, len(Xi))).max() < 1e-12
+
+
+def test_compute_extra_slots_match_reference(golden_fm, golden_extras):
+    """compute_surface_map(compute_extra=True): Hungarian on the mapped indicator and on the precise map
+    (functional_map.py:57-66), both solved on the GPU, against scipy run on the reference's own matrices."""
+    from densematcher_b200 import _lib
+    from densematcher_b200.functional_map import compute_surface_map
+    from densematcher_b200.pyFM import FunctionalMapping
+    from densematcher_b200.pyFM.mesh import TriMesh
+    g, x = golden_fm, golden_extras
+    k = int(g["k"])
+    meshes = [TriMesh.from_basis(g["evals1"], g["Phi1"], g["area1"], faces=x["faces"]),
+              TriMesh.from_basis(g["evals2"], g["Phi2"], g["area2"], faces=x["faces"])]
+    FunctionalMapping.projection_flags = _lib.DM_F64_GEMM
+    try:
+        out = compute_surface_map(meshes[0], meshes[1], g["c1"], g["c2"], n_ev=k, compute_extra=True,
+                                  fit_params=dict(w_descr=float(g["w_descr"]), w_lap=float(g["w_lap"]), w_dcomm=0))
+    finally:
+        FunctionalMapping.projection_flags = 0
+    assert np.array_equal(out[2][0], x["ref_hungarian_rows"]) and np.array_equal(out[2][1], x["ref_hungarian_cols"])
+    assert np.array_equal(out[3][0], x["ref_hungarian_precise_rows"])
+    assert np.array_equal(out[3][1], x["ref_hungarian_precise_cols"])
+    # hungarian_icp: identical to scipy on the materialised indicator
+    from scipy.optimize import linear_sum_assignment
+    r, c = linear_sum_assignment(out[7].mapped_indicator, maximize=True)
+    assert np.array_equal(out[6][0], r) and np.array_equal(out[6][1], c)
