@@ -206,6 +206,7 @@ struct NNProblem {
   const float* norm_q;   // |y_i| (fp32, rounded up)
   const float* norm_db;  // |x_j|
   float eps;             // relative error bound of one score: |S~ - S| <= eps |y| |x|
+  float col_trunc;       // extra relative error of the column scores (tcgen05 engine: 5 low mantissa bits carry the row)
   int i64_out;
   int recheck_all;
   // scratch
@@ -227,9 +228,10 @@ __device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E,
   store_index(E.out, gpos, idx, P.i64_out != 0);
   if (P.flags == nullptr) return;
   const float thr = 2.f * P.eps * own_norm * E.G[pair] + 9.6e-7f * (fabsf(s.m1) + E.Bm[pair]);
-  const bool safe = (s.m1 - s.m2) > thr;  // NaN -> not safe
+  const float tr = is_col ? P.col_trunc : 0.f;  // per-value truncation error of the column partials
+  const bool safe = (s.m1 - s.m2) > thr + tr * (fabsf(s.m1) + fabsf(s.m2));  // NaN -> not safe
   if (!safe || P.recheck_all) {
-    const bool two = !P.recheck_all && (s.m1 - s.m3) > thr && s.i2 != kNoIdx;
+    const bool two = !P.recheck_all && (s.m1 - s.m3) > thr + tr * (fabsf(s.m1) + fabsf(s.m3)) && s.i2 != kNoIdx;
     const unsigned slot = atomicAdd(&P.counters[two ? 0 : 3], 1u);
     FlagEntry f;
     f.pair = pair;

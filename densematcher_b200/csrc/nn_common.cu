@@ -549,10 +549,12 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   P.flag_cap = L.flag_cap;
   P.counters = L.counters;
   P.kp = nn_tc_kp(R.d);
-  if (tc)
+  P.col_trunc = 0.f;
+  if (tc) {
     // split-bf16 truncation 3 * 2^-18 (+5%) plus one fp32 rounding (with 2x slack) per accumulated MMA
     P.eps = float(1.2e-5 + (3.0 * (P.kp / 16) + 2.0) * 2.384185791015625e-07);
-  else
+    P.col_trunc = 3.9e-6f;  // 2^-18 (+2%): the column partials keep the row in the 5 low mantissa bits (nn_tc.cu)
+  } else
     // fp32 FMA chain of length d (+ the fp32 rounding of float64 originals): gamma_d = d u / (1 - d u)
     P.eps = float((double(R.d) + 4.0) * 5.9604644775390625e-08 * 1.01);
 

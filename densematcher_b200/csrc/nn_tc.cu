@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       const int i = row0 + trow;
       const bool ok = do_cols && i < nq;
       csc[c] = ok ? __ldg(P.col[c].sf + q0 + i) : 0.f;
-      cbi[c] = ok ? __ldg(P.col[c].bf + q0 + i) : -INFINITY;
+      cbi[c] = ok ? __ldg(P.col[c].bf + q0 + i) : -3.0e38f;  // finite: the packed keys below must not become NaN
     }
 
     for (int ct = 0; ct < n_ct; ++ct) {
@@ -375,23 +375,34 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
 #pragma unroll
             for (int r = 0; r < 32; ++r) w[c][r] = patch[r * PATCH_LD + lane];
           }
-          // all epilogues' chains advance together: 2 NC independent dependency chains
-          Top2 ua[NC > 0 ? NC : 1], ub[NC > 0 ? NC : 1];
+          // Running top-2 of the 32 rows on PACKED keys: the 5 low mantissa bits of the score are replaced by the row
+          // (r = 0..31), so that best and runner-up with their rows cost three FMNMX per element instead of
+          // compares and selects.  The relative error 2^-18 this adds to the column scores is part of the re-evaluation
+          // threshold (NNProblem::col_trunc).  All epilogues' chains advance together: 2 NC independent chains.
+          float k1a[NC > 0 ? NC : 1], k2a[NC > 0 ? NC : 1], k1b[NC > 0 ? NC : 1], k2b[NC > 0 ? NC : 1];
 #pragma unroll
-          for (int c = 0; c < NC; ++c) ua[c] = ub[c] = top2_init();
+          for (int c = 0; c < NC; ++c) k1a[c] = k2a[c] = k1b[c] = k2b[c] = -INFINITY;
 #pragma unroll
           for (int r = 0; r < 16; ++r) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-              top2_push(ua[c], w[c][r], ib + r);
-              top2_push(ub[c], w[c][16 + r], ib + 16 + r);
+              const float ka = __int_as_float((__float_as_int(w[c][r]) & ~31) | r);
+              const float kb = __int_as_float((__float_as_int(w[c][16 + r]) & ~31) | (16 + r));
+              k2a[c] = fmaxf(k2a[c], fminf(k1a[c], ka));
+              k1a[c] = fmaxf(k1a[c], ka);
+              k2b[c] = fmaxf(k2b[c], fminf(k1b[c], kb));
+              k1b[c] = fmaxf(k1b[c], kb);
             }
           }
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            Top3 ta = top3_from(ua[c]);
-            top3_merge(ta, top3_from(ub[c]));
-            cst[c] = ta;
+            const float k1 = fmaxf(k1a[c], k1b[c]);
+            const float k2 = fmaxf(fminf(k1a[c], k1b[c]), fmaxf(k2a[c], k2b[c]));
+            Top3 t;
+            t.m1 = __int_as_float(__float_as_int(k1) & ~31), t.i1 = ib + (__float_as_int(k1) & 31);
+            t.m2 = __int_as_float(__float_as_int(k2) & ~31), t.i2 = ib + (__float_as_int(k2) & 31);
+            t.m3 = t.m2;  // conservative: the third-best of the 32 rows is not tracked
+            cst[c] = t;
           }
           const int par = ch & 1;
 #pragma unroll
