@@ -206,6 +206,7 @@ struct NNProblem {
   const float* norm_q;   // |y_i| (fp32, rounded up)
   const float* norm_db;  // |x_j|
   float eps;             // relative error bound of one score: |S~ - S| <= eps |y| |x|
+  int probe_skip_epilogue;  // profiling (DM_NN_PROBE=1): tcgen05 kernel runs TMA + MMA only; results are garbage
   float col_trunc;       // extra relative error of the column scores (tcgen05 engine: 5 low mantissa bits carry the row)
   int i64_out;
   int recheck_all;

@@ -550,6 +550,10 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   P.counters = L.counters;
   P.kp = nn_tc_kp(R.d);
   P.col_trunc = 0.f;
+  {
+    static const bool probe = [] { const char* e = getenv("DM_NN_PROBE"); return e && e[0] == '1'; }();
+    P.probe_skip_epilogue = probe ? 1 : 0;
+  }
   if (tc) {
     // split-bf16 truncation 3 * 2^-18 (+5%) plus one fp32 rounding (with 2x slack) per accumulated MMA
     P.eps = float(1.2e-5 + (3.0 * (P.kp / 16) + 2.0) * 2.384185791015625e-07);

@@ -42,7 +42,11 @@ namespace {
 constexpr int TM_ROWS = 128;  // query rows per CTA (UMMA M)
 constexpr int TN = 256;       // database columns per accumulator tile (UMMA N)
 constexpr int TBK = 64;       // K elements per pipeline stage (one 128-byte swizzle row of bf16)
-constexpr int STAGES = 2;
+// Pipeline depth and X tile per CTA.  In PAIR mode two CTAs (a cluster of 2 = one TPC) compute a 256 x 256 tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of Y and only HALF of the X tile, so a stage is 64 KB
+// instead of 96 KB -- the L2 -> SM traffic per flop (the measured limiter of the single-CTA kernel) drops by a third,
+// the shared-memory operand reads per SM drop too, and a third stage fits.
+__host__ __device__ constexpr int n_stages(bool pair) { return pair ? 3 : 2; }
 constexpr int UMMA_K = 16;
 constexpr int kGroupWarps = 4;              // one warp per TMEM lane quarter
 // Two epilogue groups, or three when there are two row epilogues AND column epilogues (see the kernel)
@@ -52,9 +56,10 @@ __host__ __device__ constexpr int n_threads(int nr, int nc, bool debug) { return
 constexpr int CCH = 32;  // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
 
 constexpr uint32_t SZ_Y = TM_ROWS * TBK * 2;  // 16 KB per half
-constexpr uint32_t SZ_X = TN * TBK * 2;       // 32 KB per half
-constexpr uint32_t STAGE_BYTES = 2 * SZ_Y + 2 * SZ_X;
-constexpr uint32_t OFF_PATCH = STAGES * STAGE_BYTES;
+__host__ __device__ constexpr uint32_t sz_x(bool pair) { return (pair ? TN / 2 : TN) * TBK * 2; }  // 32 KB / 16 KB per half
+__host__ __device__ constexpr uint32_t stage_bytes(bool pair) { return 2 * SZ_Y + 2 * sz_x(pair); }
+constexpr uint32_t OFF_PATCH = n_stages(false) * stage_bytes(false);
+static_assert(n_stages(true) * stage_bytes(true) == OFF_PATCH, "both modes use the same staging area");
 constexpr int PATCH_LD = 36;  // row pitch (words) of the transposition patch: 16-byte stores, conflict-free both ways
 constexpr uint32_t PATCH_BYTES = 32 * PATCH_LD * 4;
 constexpr uint32_t OFF_COLRED = OFF_PATCH + kGroupWarps * PATCH_BYTES;          // [2][kMaxEpi][4 warps][32] Top3
@@ -111,7 +116,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 // kind::f16, A = B = bf16 (K-major), D = fp32, M = 128, N = TN
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM_ROWS >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc(bool pair) {  // PAIR: M = 256 over the two CTAs
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t((pair ? 2 * TM_ROWS : TM_ROWS) >> 4) << 24);
+}
 
 struct TcMaps {
   CUtensorMap yh, yl, xh, xl;
@@ -123,14 +130,21 @@ struct DebugOut {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int NR, int NC, bool DEBUG>
+template <int NR, int NC, bool DEBUG, bool PAIR>
 __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
     nn_tc_kernel(const __grid_constant__ TcMaps maps, const NNProblem P, const DebugOut dbg) {
-  const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
+  constexpr int STAGES = n_stages(PAIR);
+  constexpr uint32_t SZ_X = sz_x(PAIR), STAGE_BYTES = stage_bytes(PAIR);
+  constexpr uint32_t kIdesc = idesc(PAIR);
+  // PAIR: the grid has an even number of row tiles per pair of meshes; CTAs 2m / 2m+1 of a cluster own row tiles 2m / 2m+1
+  const int mrt = PAIR ? (P.max_rt + 1) & ~1 : P.max_rt;
+  const int p = blockIdx.x / mrt, rt = blockIdx.x % mrt;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
   const int64_t q0 = P.q_off[p];
   const int nq = int(P.q_off[p + 1] - q0);
   const int row0 = rt * TM_ROWS;
-  if (row0 >= nq) return;
+  if ((PAIR ? (rt & ~1) * TM_ROWS : row0) >= nq) return;  // uniform over the cluster
+  const bool active = row0 < nq;  // PAIR: a CTA past the last row still stages its half of X and takes part in the MMA
   const int64_t d0 = P.db_off[p];
   const int nd = int(P.db_off[p + 1] - d0);
   const int n_ct = (nd + TN - 1) / TN;
@@ -154,17 +168,24 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, epi_warps(NR, NC, DEBUG));
+      mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * epi_warps(NR, NC, DEBUG));  // PAIR: both CTAs' warps, on the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its tensor memory allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -179,15 +200,25 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       uint32_t phase = 0;
       const int yrow = int(q0 + row0);
       for (int ct = 0; ct < n_ct; ++ct) {
-        const int xrow = int(d0 + int64_t(ct) * TN);
+        const int xrow = int(d0 + int64_t(ct) * TN) + (PAIR ? int(rank) * (TN / 2) : 0);
         for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = sbase + stage * STAGE_BYTES, fb = bar_full + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);
-          tma_load_2d(sb, &maps.yh, kc * TBK, yrow, fb);
-          tma_load_2d(sb + SZ_Y, &maps.yl, kc * TBK, yrow, fb);
-          tma_load_2d(sb + 2 * SZ_Y, &maps.xh, kc * TBK, xrow, fb);
-          tma_load_2d(sb + 2 * SZ_Y + SZ_X, &maps.xl, kc * TBK, xrow, fb);
+          if (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's barrier (its MMA thread is the only consumer)
+            const uint32_t fbl = mapa_shared(fb, 0);
+            if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sb, &maps.yh, kc * TBK, yrow, fbl);
+            tma_load_2d_pair(sb + SZ_Y, &maps.yl, kc * TBK, yrow, fbl);
+            tma_load_2d_pair(sb + 2 * SZ_Y, &maps.xh, kc * TBK, xrow, fbl);
+            tma_load_2d_pair(sb + 2 * SZ_Y + SZ_X, &maps.xl, kc * TBK, xrow, fbl);
+          } else {
+            mbar_expect_tx(fb, STAGE_BYTES);
+            tma_load_2d(sb, &maps.yh, kc * TBK, yrow, fb);
+            tma_load_2d(sb + SZ_Y, &maps.yl, kc * TBK, yrow, fb);
+            tma_load_2d(sb + 2 * SZ_Y, &maps.xh, kc * TBK, xrow, fb);
+            tma_load_2d(sb + 2 * SZ_Y + SZ_X, &maps.xl, kc * TBK, xrow, fb);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -196,8 +227,8 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================== MMA issuer (one thread; PAIR: of the leader CTA, for both SMs)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ct = 0; ct < n_ct; ++ct) {
@@ -214,17 +245,25 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
             const uint64_t ko = uint64_t((k * UMMA_K * 2) >> 4);  // 32 bytes per K step inside the swizzle row
-            tc_mma_bf16(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);
-            tc_mma_bf16(tacc, dyh + ko, dxl + ko, kIdesc, 1);
-            tc_mma_bf16(tacc, dyl + ko, dxh + ko, kIdesc, 1);
+            if (PAIR) {
+              tc_mma_bf16_pair(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);
+              tc_mma_bf16_pair(tacc, dyh + ko, dxl + ko, kIdesc, 1);
+              tc_mma_bf16_pair(tacc, dyl + ko, dxh + ko, kIdesc, 1);
+            } else {
+              tc_mma_bf16(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);
+              tc_mma_bf16(tacc, dyh + ko, dxl + ko, kIdesc, 1);
+              tc_mma_bf16(tacc, dyl + ko, dxh + ko, kIdesc, 1);
+            }
           }
-          tc_commit(bar_empty + 8 * stage);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (PAIR: in both CTAs)
+          if (PAIR) tc_commit_pair(bar_empty + 8 * stage); else tc_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+        // accumulator complete (PAIR: each CTA's epilogue reads its own 128 rows from its own tensor memory)
+        if (PAIR) tc_commit_pair(bar_tfull + 8 * acc); else tc_commit(bar_tfull + 8 * acc);
       }
     }
   } else {
@@ -300,7 +339,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       const int ch_end = kShareRows ? ch_beg + TN / CCH / 2 : TN / CCH;
       for (int ch = ch_beg; ch < ch_end; ++ch) {
         if (ch >= n_ch) break;  // uniform over the group
-        if (!do_rows && !do_cols && !DEBUG) break;
+        if ((!do_rows && !do_cols && !DEBUG) || P.probe_skip_epilogue) break;
         float v[32];
         tmem_ld32(taddr + ch * CCH, v);
         if (DEBUG) {
@@ -417,13 +456,18 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
             Top3 m = colred[((par * kMaxEpi + slot) * kGroupWarps + 0) * CCH + lane];
 #pragma unroll
             for (int w = 1; w < kGroupWarps; ++w) top3_merge(m, colred[((par * kMaxEpi + slot) * kGroupWarps + w) * CCH + lane]);
-            if (j < nd) P.col_partial[((int64_t(slot) * P.n_pairs + p) * P.max_rt + rt) * P.max_db + j] = m;
+            if (j < nd && active) P.col_partial[((int64_t(slot) * P.n_pairs + p) * P.max_rt + rt) * P.max_db + j] = m;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (PAIR && rank != 0)
+          mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));
+        else
+          mbar_arrive(bar_tempty + 8 * acc);
+      }
     }
 
     if (NR > 0) {
@@ -456,9 +500,13 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs wrote the peer's tensor memory; remote arrivals are all delivered
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -477,14 +525,46 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int kp, int box_row
   return DM_OK;
 }
 
-template <int NR, int NC, bool DEBUG>
-int launch(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, dim3 grid, cudaStream_t st) {
+template <int NR, int NC, bool DEBUG, bool PAIR>
+int launch_mode(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, cudaStream_t st) {
   static OncePerDevice attr_once;
   if (attr_once.first()) {
-    DM_CUDA_OK(cudaFuncSetAttribute(nn_tc_kernel<NR, NC, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+    DM_CUDA_OK(cudaFuncSetAttribute(nn_tc_kernel<NR, NC, DEBUG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(SMEM_BYTES)));
   }
-  nn_tc_kernel<NR, NC, DEBUG><<<grid, n_threads(NR, NC, DEBUG), SMEM_BYTES, st>>>(maps, P, dbg);
+  const int mrt = PAIR ? (P.max_rt + 1) & ~1 : P.max_rt;
+  const int64_t nblk = int64_t(P.n_pairs) * mrt;
+  if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles (%lld)", (long long)nblk);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nblk);
+  cfg.blockDim = dim3(n_threads(NR, NC, DEBUG));
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = PAIR ? 1 : 0;
+  DM_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_tc_kernel<NR, NC, DEBUG, PAIR>, maps, P, dbg));
   return DM_OK;
+}
+
+// DM_NN_SINGLE_CTA=1 in the environment selects the single-CTA (cta_group::1) kernel, for A/B measurements
+bool use_pair_mode() {
+  static const bool single = [] {
+    const char* e = getenv("DM_NN_SINGLE_CTA");
+    return e && e[0] == '1';
+  }();
+  return !single;
+}
+
+// The pair kernel pays off when the MMA pipeline is the limiter (long contractions: the d = 384 feature search, the
+// upper rungs of the ZoomOut ladder).  With a short contraction the epilogues bound the tile time, and coupling two
+// CTAs' accumulator hand-offs only adds lock-step stalls (FM -> p2p at k = 100: 2.39 ms single vs 2.44 ms pair).
+template <int NR, int NC, bool DEBUG>
+int launch(const TcMaps& maps, const TcMaps& maps_pair, const NNProblem& P, const DebugOut& dbg, cudaStream_t st) {
+  if (!DEBUG && use_pair_mode() && P.kp >= 4 * TBK) return launch_mode<NR, NC, false, true>(maps_pair, P, dbg, st);
+  return launch_mode<NR, NC, DEBUG, false>(maps, P, dbg, st);
 }
 
 }  // namespace
@@ -501,23 +581,23 @@ int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void*
   if ((rc = make_map(&maps.yl, Yl, P.total_q, P.kp, TM_ROWS))) return rc;
   if ((rc = make_map(&maps.xh, Xh, P.total_db, P.kp, TN))) return rc;
   if ((rc = make_map(&maps.xl, Xl, P.total_db, P.kp, TN))) return rc;
-  const int64_t nblk = int64_t(P.n_pairs) * P.max_rt;
-  if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles (%lld)", (long long)nblk);
-  dim3 grid((unsigned)nblk);
+  TcMaps maps_pair = maps;  // CTA-pair mode: each CTA stages half of the X tile
+  if ((rc = make_map(&maps_pair.xh, Xh, P.total_db, P.kp, TN / 2))) return rc;
+  if ((rc = make_map(&maps_pair.xl, Xl, P.total_db, P.kp, TN / 2))) return rc;
   DebugOut dbg{dbgS, ldS};
   if (dbgS) {
-    if ((rc = launch<0, 0, true>(maps, P, dbg, grid, st))) return rc;
+    if ((rc = launch<0, 0, true>(maps, maps_pair, P, dbg, st))) return rc;
   } else {
     const int key = P.n_row * 10 + P.n_col;
     switch (key) {
-      case 0 * 10 + 1: rc = launch<0, 1, false>(maps, P, dbg, grid, st); break;
-      case 0 * 10 + 2: rc = launch<0, 2, false>(maps, P, dbg, grid, st); break;
-      case 1 * 10 + 0: rc = launch<1, 0, false>(maps, P, dbg, grid, st); break;
-      case 1 * 10 + 1: rc = launch<1, 1, false>(maps, P, dbg, grid, st); break;
-      case 1 * 10 + 2: rc = launch<1, 2, false>(maps, P, dbg, grid, st); break;
-      case 2 * 10 + 0: rc = launch<2, 0, false>(maps, P, dbg, grid, st); break;
-      case 2 * 10 + 1: rc = launch<2, 1, false>(maps, P, dbg, grid, st); break;
-      case 2 * 10 + 2: rc = launch<2, 2, false>(maps, P, dbg, grid, st); break;
+      case 0 * 10 + 1: rc = launch<0, 1, false>(maps, maps_pair, P, dbg, st); break;
+      case 0 * 10 + 2: rc = launch<0, 2, false>(maps, maps_pair, P, dbg, st); break;
+      case 1 * 10 + 0: rc = launch<1, 0, false>(maps, maps_pair, P, dbg, st); break;
+      case 1 * 10 + 1: rc = launch<1, 1, false>(maps, maps_pair, P, dbg, st); break;
+      case 1 * 10 + 2: rc = launch<1, 2, false>(maps, maps_pair, P, dbg, st); break;
+      case 2 * 10 + 0: rc = launch<2, 0, false>(maps, maps_pair, P, dbg, st); break;
+      case 2 * 10 + 1: rc = launch<2, 1, false>(maps, maps_pair, P, dbg, st); break;
+      case 2 * 10 + 2: rc = launch<2, 2, false>(maps, maps_pair, P, dbg, st); break;
       default: DM_FAIL(DM_ERR_BADARG, "unsupported epilogue combination %d row / %d col", P.n_row, P.n_col);
     }
     if (rc) return rc;
