@@ -37,25 +37,18 @@ __global__ void __launch_bounds__(256)
 constexpr int kSolveNB = 4;        // columns per block step (8 was measured slower: registers cut the resident systems per SM)
 constexpr int kSolveThreads = 128;
 
-// 1 / sqrt(v) in float64 from the fp32 hardware estimate and two Newton steps (error ~2^-52; the factorisation does
-// not need a correctly rounded square root, and this replaces a ~50-instruction sqrt + divide dependency chain).
+// 1 / sqrt(v) in float64 from the FP64 reciprocal-square-root estimate (MUFU.RSQ64H, ~2^-22) and two Newton steps
+// (error at rounding level; the factorisation does not need a correctly rounded square root).  On the critical path
+// of every column: 64 cycles of dependent latency, against 123 through an fp32 estimate with its two conversions
+// and 173 for 1 / sqrt() (scripts/micro/fp64_latency.cu).
 __device__ __forceinline__ double rsqrt64(double v) {
-  // fp32 hardware estimate (2^-22) + two Newton steps in float64.  Pivots outside the fp32 range (never the case
-  // for sensibly scaled energies) are rescaled by an exact power of four first.
-  double sc = 1.0;
-  if (!(v > 1e-30 && v < 1e30)) {
-    if (!(v > 0.0) || !(v < INFINITY)) return 1.0 / sqrt(v);
-    int e;
-    frexp(v, &e);
-    e &= ~1;
-    v = ldexp(v, -e);
-    sc = ldexp(1.0, -e / 2);
-  }
-  double y = double(rsqrtf(float(v)));
+  if (!(v > 1e-300 && v < 1e300)) return 1.0 / sqrt(v);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
   const double h = 0.5 * v;
   y = y * fma(-h * y, y, 1.5);  // 2^-22 -> 2^-43
   y = y * fma(-h * y, y, 1.5);  // -> rounding level
-  return y * sc;
+  return y;
 }
 
 // w_d * (A A^T)[1:, 1:] of every pair as a packed lower triangle (row r starts at r (r + 1) / 2), the form in which the
