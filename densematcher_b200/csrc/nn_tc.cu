@@ -549,13 +549,19 @@ int launch_mode(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, cud
   return DM_OK;
 }
 
-// DM_NN_SINGLE_CTA=1 in the environment selects the single-CTA (cta_group::1) kernel, for A/B measurements
+// DM_NN_SINGLE_CTA=1 in the environment selects the single-CTA (cta_group::1) kernel for A/B measurements;
+// DM_NN_FORCE_PAIR=1 the CTA-pair kernel for every non-debug launch (tests of its ragged / odd-tile handling)
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
 bool use_pair_mode() {
-  static const bool single = [] {
-    const char* e = getenv("DM_NN_SINGLE_CTA");
-    return e && e[0] == '1';
-  }();
+  static const bool single = env_flag("DM_NN_SINGLE_CTA");
   return !single;
+}
+bool force_pair_mode() {
+  static const bool force = env_flag("DM_NN_FORCE_PAIR");
+  return force;
 }
 
 // The pair kernel pays off when the MMA pipeline is the limiter (long contractions: the d = 384 feature search, the
@@ -563,7 +569,11 @@ bool use_pair_mode() {
 // CTAs' accumulator hand-offs only adds lock-step stalls (FM -> p2p at k = 100: 2.39 ms single vs 2.44 ms pair).
 template <int NR, int NC, bool DEBUG>
 int launch(const TcMaps& maps, const TcMaps& maps_pair, const NNProblem& P, const DebugOut& dbg, cudaStream_t st) {
-  if (!DEBUG && use_pair_mode() && P.kp >= 4 * TBK) return launch_mode<NR, NC, false, true>(maps_pair, P, dbg, st);
+  // ... and when no CTA of a pair would idle: all query sets of one size with an even number of row tiles (a ragged
+  // batch pairs the last odd tile of a mesh with an empty one: 94.7 k vs 97.7 k pairs/s on the 1024-pair ragged config)
+  const bool even_tiles = P.max_rt % 2 == 0 && P.total_q == int64_t(P.n_pairs) * P.max_q;
+  if (!DEBUG && ((use_pair_mode() && P.kp >= 4 * TBK && even_tiles) || force_pair_mode()))
+    return launch_mode<NR, NC, false, true>(maps_pair, P, dbg, st);
   return launch_mode<NR, NC, DEBUG, false>(maps, P, dbg, st);
 }
 

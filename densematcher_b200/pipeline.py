@@ -141,6 +141,36 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
     return out
 
 
+def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: int = 32):
+    """Hungarian assignment of every pair's mapped indicator  Phi2 C Phi1^T A1  (functional_map.py:57,78), maximised,
+    for a device-resident batch: the float64 (n2, n1) matrices of ``chunk_pairs`` pairs are materialised at a time
+    (32 MB each at N = 2000) and solved together by ``dm_lap_solve``, one CTA per pair.  Returns a list of
+    ``(row_ind, col_ind)`` numpy pairs identical to scipy's."""
+    k2, k1 = C.shape[1], C.shape[2]
+    res = []
+    for lo in range(0, batch.n_pairs, chunk_pairs):
+        mats = []
+        for p in range(lo, min(lo + chunk_pairs, batch.n_pairs)):
+            a, b = int(batch.off1_h[p]), int(batch.off1_h[p + 1])
+            c, d = int(batch.off2_h[p]), int(batch.off2_h[p + 1])
+            mats.append(_fm.mapped_indicator(C[p], batch.Phi1[a:b, :k1], batch.Phi2[c:d, :k2], batch.area1[a:b]))
+        res.extend(_fm.lap_solve(mats, maximize=True))
+    return res
+
+
+def precise_maps(batch: PairBatchDevice, C: torch.Tensor, faces1, face_off):
+    """Barycentric precise map (convert.py:186-231, use_adj=True) of every pair in one ``dm_precise_map`` call:
+    ``faces1`` are the packed faces of the meshes 1 (vertex ids local to each mesh), ``face_off`` their offsets.
+    Returns (face_match [total_n2], bary [total_n2, 3]) on the device."""
+    k2, k1 = C.shape[1], C.shape[2]
+    emb2 = torch.empty((batch.Phi2.shape[0], k1), dtype=torch.float64, device=C.device)
+    for p in range(batch.n_pairs):
+        c, d = int(batch.off2_h[p]), int(batch.off2_h[p + 1])
+        torch.matmul(batch.Phi2[c:d, :k2], C[p], out=emb2[c:d])
+    emb1 = batch.Phi1[:, :k1].contiguous()
+    return _fm.precise_map(emb1, faces1, emb2, batch.off1_h, face_off, batch.off2_h)
+
+
 class HostStager:
     """Staged host-buffer entry: three streams (H2D, compute, D2H), two input slots in HBM and one pinned
     result buffer per output, all grow-only and reused across calls, so the steady state performs no

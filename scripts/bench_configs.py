@@ -109,9 +109,36 @@ def cfg5():
          "full hot path (NN + projection + solve + FM->p2p)", len(src), ms, {"scaling": "strong"})
 
 
+def extras():
+    """SURVEY 8f rank 2 on a batch of 64 copies of a real mesh pair (two deformations of icosphere(4): 2562 vertices,
+    5120 faces, cotangent LBO basis, k = 50): Hungarian assignment of every pair's mapped indicator and the barycentric
+    precise map."""
+    n_pairs, k = 64, 50
+    V, F = meshgen.icosphere(4)
+    V1 = meshgen.deform(V, (1.0, 0.9, 1.1), 0.1, (0.3, 0.2))
+    V2 = meshgen.deform(V, (1.1, 1.0, 0.85), 0.15, (1.0, 0.5))
+    _, P1, a1 = meshgen.lbo_basis(V1, F, k)
+    _, P2, a2 = meshgen.lbo_basis(V2, F, k)
+    n, nf = len(V), len(F)
+    C1 = P2.T @ (a2[:, None] * P1)                                     # functional map of the identity vertex map
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+    off = np.arange(n_pairs + 1, dtype=np.int64) * n
+    batch = pipeline.PairBatchDevice(None, None, off, off, dev, Phi1=t(P1).repeat(n_pairs, 1), Phi2=t(P2).repeat(n_pairs, 1),
+                                     area1=t(a1).repeat(n_pairs), area2=t(a2).repeat(n_pairs))
+    rng = np.random.default_rng(3)
+    C = torch.stack([t(C1 + 1e-3 * rng.standard_normal(C1.shape)) for _ in range(n_pairs)]).contiguous()
+    ms = timed(lambda: pipeline.hungarian_pairs(batch, C, chunk_pairs=64), steps=1, warm=1)
+    emit(f"extras: Hungarian assignment (dm_lap_solve) of the {n} x {n} mapped indicator, icosphere(4) pair, k = {k}, "
+         f"{n_pairs} pairs (scipy: ~0.3 s per pair and core)", n_pairs, ms, {})
+    faces = t(F, torch.int32).repeat(n_pairs, 1)
+    foff = np.arange(n_pairs + 1, dtype=np.int64) * nf
+    ms = timed(lambda: pipeline.precise_maps(batch, C, faces, foff), steps=3, warm=1)
+    emit(f"extras: barycentric precise map (dm_precise_map), {n} points on {nf} faces, p = {k}, {n_pairs} pairs", n_pairs, ms, {})
+
+
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["cfg3", "cfg4", "cfg4fast", "cfg5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["cfg3", "cfg4", "cfg4fast", "cfg5", "extras"]
     for w in which:
-        {"cfg3": cfg3, "cfg4": lambda: cfg4(False), "cfg4fast": lambda: cfg4(True), "cfg5": cfg5}[w]()
+        {"cfg3": cfg3, "cfg4": lambda: cfg4(False), "cfg4fast": lambda: cfg4(True), "cfg5": cfg5, "extras": extras}[w]()
     if world > 1:
         dist.destroy_process_group()

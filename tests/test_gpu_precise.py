@@ -100,3 +100,27 @@ def test_compute_extra_slots_match_reference(golden_fm, golden_extras):
     from scipy.optimize import linear_sum_assignment
     r, c = linear_sum_assignment(out[7].mapped_indicator, maximize=True)
     assert np.array_equal(out[6][0], r) and np.array_equal(out[6][1], c)
+
+
+def test_batched_hungarian_and_precise_maps(golden_fm, golden_extras):
+    """pipeline.hungarian_pairs / precise_maps on a two-pair batch: every pair equals the reference-minted golden."""
+    from densematcher_b200 import pipeline
+    from densematcher_b200.pyFM.spectral.projection_utils import barycentric_to_precise
+    g, x = golden_fm, golden_extras
+    k = int(g["k"])
+    two = lambda a: np.concatenate([a, a])
+    off = np.array([0, 642, 1284])
+    batch = pipeline.PairBatchDevice(
+        dev(two(g["c1"])), dev(two(g["c2"])), off, off, torch.device("cuda"),
+        Phi1=dev(two(g["Phi1"][:, :k])), Phi2=dev(two(g["Phi2"][:, :k])), evals1=dev(two(g["evals1"][None, :k])),
+        evals2=dev(two(g["evals2"][None, :k])), area1=dev(two(g["area1"])), area2=dev(two(g["area2"])))
+    C = dev(np.stack([g["C_closed_form"]] * 2))
+    for r, c in pipeline.hungarian_pairs(batch, C):
+        assert np.array_equal(r, x["ref_hungarian_rows"]) and np.array_equal(c, x["ref_hungarian_cols"])
+    faces = x["faces"].astype(np.int32)
+    face, bary = pipeline.precise_maps(batch, C, np.concatenate([faces, faces]), [0, len(faces), 2 * len(faces)])
+    face, bary = face.cpu().numpy(), bary.cpu().numpy()
+    ref = _csr(x, "ref_precise", (642, 642))
+    for p in range(2):
+        P = barycentric_to_precise(faces, face[642 * p:642 * (p + 1)], bary[642 * p:642 * (p + 1)], 642)
+        assert abs(P - ref).max() < 1e-11
