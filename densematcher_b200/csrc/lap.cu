@@ -95,15 +95,20 @@ __global__ void lap_transpose_kernel(LapArgs A) {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// (value, key) lexicographic minimum over a warp; returns the winning lane
+// (value, key) lexicographic minimum over a warp; returns the winning lane.  The float64 value is mapped to an
+// order-preserving 64-bit unsigned key and reduced as two 32-bit halves with redux.sync (three REDUX instead of five
+// rounds of 64-bit shuffles + compares: this sits on the critical path of every Dijkstra step, twice).
 __device__ __forceinline__ int warp_argmin(double val, unsigned key, double& vmin, unsigned& kmin) {
-  double w = val;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) w = fmin(w, __shfl_xor_sync(kFull, w, o));
-  const unsigned k = (val == w) ? key : 0xffffffffu;
-  kmin = __reduce_min_sync(kFull, k);
-  vmin = w;
-  return __ffs(__ballot_sync(kFull, k == kmin && val == w)) - 1;
+  const long long b = __double_as_longlong(val);
+  const unsigned long long o = static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
+  const unsigned hi = unsigned(o >> 32), lo = unsigned(o);
+  const unsigned mh = __reduce_min_sync(kFull, hi);
+  const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+  const bool is_min = hi == mh && lo == ml;
+  kmin = __reduce_min_sync(kFull, is_min ? key : 0xffffffffu);
+  const int src = __ffs(__ballot_sync(kFull, is_min && key == kmin)) - 1;
+  vmin = __shfl_sync(kFull, val, src);
+  return src;
 }
 
 template <int CPT>
