@@ -143,18 +143,25 @@ __global__ void __launch_bounds__(kLapThreads, 1) lap_kernel(LapArgs A) {
     row4col[j] = -1;
   }
   double v[CPT], spc[CPT];
-  int pos[CPT];  // position in scipy's `remaining` list; -1: scanned in this search; -2: not a column
 #pragma unroll
   for (int m = 0; m < CPT; ++m) v[m] = 0.0;
   __syncthreads();
 
   int par = 0;
+  constexpr unsigned kGone = 0xffffffffu;  // key of a column that is not in the `remaining` list (scanned, or j >= nc)
   for (int cur = 0; cur < nr; ++cur) {
+    // key[m]: the column's rank in the tie-breaking order, kept up to date instead of being rebuilt in every step.
+    // scipy scans `remaining` by ascending position and lets an unassigned column replace an equal candidate, so among
+    // equal values the LAST unassigned position wins, else the FIRST assigned one:
+    //   unassigned column at position q -> nc - 1 - q,   assigned column -> 0x80000000 | q      (minimum wins)
+    // `remaining` starts as nc-1, nc-2, ..., 0, i.e. column j at position nc - 1 - j.
+    unsigned key[CPT];
+    unsigned scanned = 0;  // bit m: own column m was scanned in this search
 #pragma unroll
     for (int m = 0; m < CPT; ++m) {
       const int j = tid + m * kLapThreads;
       spc[m] = INFINITY;
-      pos[m] = j < nc ? nc - 1 - j : -2;
+      key[m] = j < nc ? (row4col[j] < 0 ? unsigned(j) : (0x80000000u | unsigned(nc - 1 - j))) : kGone;
     }
     int nrem = nc, i = cur, sink = -1;
     double minVal = 0.0;
@@ -163,62 +170,66 @@ __global__ void __launch_bounds__(kLapThreads, 1) lap_kernel(LapArgs A) {
       const double* crow = cost + int64_t(i) * nc;
       double c[CPT];
 #pragma unroll
-      for (int m = 0; m < CPT; ++m) c[m] = pos[m] >= 0 ? __ldg(crow + tid + m * kLapThreads) : 0.0;
+      for (int m = 0; m < CPT; ++m) c[m] = key[m] != kGone ? __ldg(crow + tid + m * kLapThreads) : 0.0;
       double bval = INFINITY;
-      unsigned bkey = 0xffffffffu;
-      int bj = -1, brow = -1;
+      unsigned bkey = kGone;
+      int bm = 0;
 #pragma unroll
       for (int m = 0; m < CPT; ++m)
-        if (pos[m] >= 0) {
-          const int j = tid + m * kLapThreads;
+        if (key[m] != kGone) {
           const double cc = neg ? -c[m] : c[m];
           const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, cc), ui), v[m]);
           if (r < spc[m]) {
             spc[m] = r;
-            path[j] = i;
+            path[tid + m * kLapThreads] = i;
           }
-          const int rj = row4col[j];
-          // scan order = ascending position; an unassigned column replaces an equal candidate (the LAST such wins)
-          const unsigned key = rj < 0 ? unsigned(nc - 1 - pos[m]) : (0x80000000u | unsigned(pos[m]));
-          if (spc[m] < bval || (spc[m] == bval && key < bkey)) {
+          if (spc[m] < bval || (spc[m] == bval && key[m] < bkey)) {
             bval = spc[m];
-            bkey = key;
-            bj = j;
-            brow = rj;
+            bkey = key[m];
+            bm = m;
           }
         }
       double wv;
       unsigned wk;
       int src = warp_argmin(bval, bkey, wv, wk);
-      const int wj = __shfl_sync(kFull, bj, src), wrow = __shfl_sync(kFull, brow, src);
+      const int wj = __shfl_sync(kFull, tid + bm * kLapThreads, src);
       if (lane == 0) {
         red_val[par * kLapWarps + warp] = wv;
         red_key[par * kLapWarps + warp] = wk;
         red_j[par * kLapWarps + warp] = wj;
-        red_row[par * kLapWarps + warp] = wrow;
       }
       __syncthreads();
       const bool has = lane < kLapWarps;
       const double ev = has ? red_val[par * kLapWarps + lane] : INFINITY;
-      const unsigned ek = has ? red_key[par * kLapWarps + lane] : 0xffffffffu;
-      const int ej = has ? red_j[par * kLapWarps + lane] : -1, erow = has ? red_row[par * kLapWarps + lane] : -1;
+      const unsigned ek = has ? red_key[par * kLapWarps + lane] : kGone;
+      const int ej = has ? red_j[par * kLapWarps + lane] : 0;
       double lowest;
       unsigned kmin;
       src = warp_argmin(ev, ek, lowest, kmin);
-      const int jstar = __shfl_sync(kFull, ej, src), rowstar = __shfl_sync(kFull, erow, src);
+      const int jstar = __shfl_sync(kFull, ej, src);
       par ^= 1;
       if (lowest == INFINITY) {  // infeasible cost matrix
         if (tid == 0) A.status[b] = 2;
         return;
       }
       minVal = lowest;
-      const int index = (kmin & 0x80000000u) ? int(kmin & 0x7fffffffu) : nc - 1 - int(kmin);
-      // remaining[index] = remaining[--num_remaining]; the chosen column leaves the list
+      const int rowstar = row4col[jstar];
+      const unsigned index = (kmin & 0x80000000u) ? (kmin & 0x7fffffffu) : unsigned(nc - 1) - kmin;
+      // remaining[index] = remaining[--num_remaining]: the column at the last position moves to `index`; the chosen
+      // column leaves the list
+      const unsigned last_u = unsigned(nc - nrem), last_a = 0x80000000u | unsigned(nrem - 1);
+#pragma unroll
+      const unsigned moved_u = unsigned(nc - 1) - index, moved_a = 0x80000000u | index;
+      const int mstar = (jstar - tid) / kLapThreads;  // own slot of the chosen column, if it is one of this thread's
+      const bool mine = jstar - tid == mstar * kLapThreads;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
-        if (pos[m] == nrem - 1) pos[m] = index;
-        if (tid + m * kLapThreads == jstar) pos[m] = -1;
+        unsigned k = key[m];
+        k = k == last_u ? moved_u : k;
+        k = k == last_a ? moved_a : k;
+        key[m] = (mine && m == mstar) ? kGone : k;
       }
+      if (mine) scanned |= 1u << mstar;
       --nrem;
       if (rowstar < 0) {
         sink = jstar;
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kLapThreads, 1) lap_kernel(LapArgs A) {
     // dual variables: rows reached in this search are exactly the rows of the scanned, assigned columns
 #pragma unroll
     for (int m = 0; m < CPT; ++m)
-      if (pos[m] == -1) {
+      if (scanned & (1u << m)) {
         const double d = __dsub_rn(minVal, spc[m]);
         v[m] = __dsub_rn(v[m], d);
         const int rj = row4col[tid + m * kLapThreads];
@@ -333,12 +344,19 @@ int dm_lap_solve(const double* cost, const int64_t* cost_off, const int64_t* row
       DM_LAUNCH_OK("lap_transpose_kernel");
     }
   }
-  const int cpt = (max_big + kLapThreads - 1) / kLapThreads;
-  if (cpt <= 1) return lap_launch<1>(A, n_batch, smem, st);
-  if (cpt <= 2) return lap_launch<2>(A, n_batch, smem, st);
-  if (cpt <= 4) return lap_launch<4>(A, n_batch, smem, st);
-  if (cpt <= 8) return lap_launch<8>(A, n_batch, smem, st);
-  return lap_launch<16>(A, n_batch, smem, st);
+  const int cpt = (max_big + kLapThreads - 1) / kLapThreads;  // columns per thread
+  switch (cpt) {
+    case 0: case 1: return lap_launch<1>(A, n_batch, smem, st);
+    case 2: return lap_launch<2>(A, n_batch, smem, st);
+    case 3: return lap_launch<3>(A, n_batch, smem, st);
+    case 4: return lap_launch<4>(A, n_batch, smem, st);
+    case 5: return lap_launch<5>(A, n_batch, smem, st);
+    case 6: return lap_launch<6>(A, n_batch, smem, st);
+    case 7: case 8: return lap_launch<8>(A, n_batch, smem, st);
+    case 9: case 10: return lap_launch<10>(A, n_batch, smem, st);
+    case 11: case 12: return lap_launch<12>(A, n_batch, smem, st);
+    default: return lap_launch<16>(A, n_batch, smem, st);
+  }
 }
 
 }  // extern "C"
