@@ -218,6 +218,127 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// "Embedding" shape: out[b] (M x N) = A[b] (M x K, rows contiguous in k) . B[b], with a SMALL B (K, N <= 104: the
+// functional map C or its transpose) and a tall A (a mesh's eigenbasis).  The generic kernel above restarts its
+// k pipeline for every 128 x 64 output tile and runs this shape at ~13 TFLOP/s; here B stays resident in shared
+// memory, a CTA walks over several 64-row tiles of A (cp.async double buffer: the next tile streams in while the
+// current one is multiplied) and every warp owns 8 rows x all columns, so one A fragment feeds up to 13 DMMAs.
+constexpr int ET = 64;          // rows of A per tile
+constexpr int EKP = 104;        // padded K and N
+constexpr int ELD = EKP + 4;    // pitch == 12 (mod 16): conflict-free 8 x 4 / 4 x 8 fragment loads
+constexpr int ETPC = 4;         // tiles per CTA
+constexpr int ENC8 = EKP / 8;   // 8-column accumulator tiles per warp
+constexpr size_t kEmbedSmem = size_t(EKP + 2 * ET) * ELD * sizeof(double);
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+
+template <bool TB, int NC8>  // NC8: 8-column accumulator tiles per warp (N <= 8 NC8)
+__global__ void __launch_bounds__(NT, 1) embed64_kernel(const GemmProblem P, int chunks) {
+  extern __shared__ __align__(16) double esm[];
+  double* Bs = esm;                 // [EKP][ELD]  B[k][n]
+  double* As = esm + EKP * ELD;     // [2][ET][ELD]
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  if (P.skip && P.skip[b]) return;
+  const int M = P.A.off ? int(P.A.off[b + 1] - P.A.off[b]) : P.M;
+  const int N = P.N, K = P.K;
+  const int row_begin = chunk * ET * ETPC;
+  if (row_begin >= M) return;
+  const int n_tiles = min(ETPC, (M - row_begin + ET - 1) / ET);
+  const OpView A = resolve(P.A, b), B = resolve(P.B, b);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int kp = (K + 3) & ~3;
+  constexpr int nc8 = NC8;
+
+  // four threads per row of the tile, each copying every fourth element (no index arithmetic beyond an add)
+  auto prefetch = [&](int tile, int buf) {
+    const int r = t >> 2, row = row_begin + tile * ET + r;
+    double* dst = As + buf * ET * ELD + r * ELD;
+    const double* src = A.d + int64_t(row) * A.ld;
+    const bool row_ok = row < M;
+    for (int k = t & 3; k < kp; k += 4) {
+      if (row_ok && k < K)
+        cp_async8(dst + k, src + k);
+      else
+        dst[k] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
+  // B[k][n]: TB: element(n, k) = Mat[k][n]; else element(n, k) = Mat[n][k]   (zero padding up to kp x 8 nc8)
+  for (int e = t; e < kp * 8 * nc8; e += NT) {
+    int k, n;
+    if (TB) {
+      k = e / (8 * nc8), n = e - k * (8 * nc8);
+    } else {
+      n = e / kp, k = e - n * kp;
+    }
+    double v = 0.0;
+    if (k < K && n < N) v = TB ? B.d[int64_t(k) * B.ld + n] : B.d[int64_t(n) * B.ld + k];
+    Bs[k * ELD + n] = v;
+  }
+  double* C = P.C + (P.c_off ? P.c_off[b] * P.ldc : int64_t(b) * P.c_batch_stride);
+  const double* cs = P.c_colscale ? P.c_colscale + (P.c_colscale_off ? P.c_colscale_off[b] : 0) : nullptr;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // this tile has landed, and every warp is done with the other buffer (the previous tile)
+    if (tile + 1 < n_tiles) prefetch(tile + 1, buf ^ 1);  // streams in during the multiplication below
+    const double* as = As + buf * ET * ELD + (8 * warp + g) * ELD + t4;
+    const double* bs = Bs + t4 * ELD + g;
+    double acc[NC8][2];
+#pragma unroll
+    for (int c = 0; c < NC8; ++c) acc[c][0] = acc[c][1] = 0.0;
+    // the fragments of step k4 + 4 are loaded into a second register set while the DMMAs of step k4 issue: a DMMA
+    // never waits for a shared-memory load that was issued right before it
+    double fa[2], fb[2][NC8];
+    auto load_frags = [&](int k4, int set) {
+      fa[set] = as[k4];
+#pragma unroll
+      for (int c = 0; c < NC8; ++c) fb[set][c] = bs[k4 * ELD + 8 * c];
+    };
+    auto mma_step = [&](int set) {
+#pragma unroll
+      for (int c = 0; c < NC8; ++c) {
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+            : "+d"(acc[c][0]), "+d"(acc[c][1])
+            : "d"(fa[set]), "d"(fb[set][c]));
+      }
+    };
+    load_frags(0, 0);
+    for (int k4 = 0; k4 < kp; k4 += 8) {
+      if (k4 + 4 < kp) load_frags(k4 + 4, 1);
+      mma_step(0);
+      if (k4 + 4 < kp) {
+        if (k4 + 8 < kp) load_frags(k4 + 8, 0);
+        mma_step(1);
+      }
+    }
+    const int m = row_begin + tile * ET + 8 * warp + g;
+    if (m < M) {
+#pragma unroll
+      for (int c = 0; c < NC8; ++c) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n = 8 * c + 2 * t4 + h;
+          if (n >= N) continue;
+          double v = P.alpha * acc[c][h];
+          if (cs) v *= cs[n];
+          C[int64_t(m) * P.ldc + n] = v;
+        }
+      }
+    }
+  }
+}
+
+bool embed_shape(const GemmProblem& P) {
+  return !P.A.trans && P.A.d && !P.A.gather && P.B.d && !P.B.off && !P.B.gather && !P.B.kscale && P.ksplit <= 1 && P.K > 0 &&
+         P.K <= EKP && P.N > 0 && P.N <= EKP && P.maxM >= 4 * ET;
+}
+
 __global__ void __launch_bounds__(256)
     sum_partials_kernel(const double* __restrict__ part, int n_split, int64_t stride, int64_t n, double* __restrict__ out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -231,6 +352,28 @@ __global__ void __launch_bounds__(256)
 
 int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
   if (P.n_batch <= 0 || P.maxM <= 0 || P.maxN <= 0) return DM_OK;
+  if (embed_shape(P)) {
+    const int chunks = (P.maxM + ET * ETPC - 1) / (ET * ETPC);
+    const int64_t nb = int64_t(P.n_batch) * chunks;
+    if (nb > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "gemm64: grid too large");
+#define DM_EMBED(TB_, NC8_)                                                                                            \
+  do {                                                                                                                \
+    static OncePerDevice once;                                                                                        \
+    if (once.first())                                                                                                 \
+      DM_CUDA_OK(cudaFuncSetAttribute(embed64_kernel<TB_, NC8_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                      int(kEmbedSmem)));                                                              \
+    embed64_kernel<TB_, NC8_><<<unsigned(nb), NT, kEmbedSmem, st>>>(P, chunks);                                        \
+  } while (0)
+    const int nc8 = (P.N + 7) / 8;
+    if (P.B.trans) {
+      if (nc8 <= 4) DM_EMBED(true, 4); else if (nc8 <= 7) DM_EMBED(true, 7); else if (nc8 <= 10) DM_EMBED(true, 10); else DM_EMBED(true, 13);
+    } else {
+      if (nc8 <= 4) DM_EMBED(false, 4); else if (nc8 <= 7) DM_EMBED(false, 7); else if (nc8 <= 10) DM_EMBED(false, 10); else DM_EMBED(false, 13);
+    }
+#undef DM_EMBED
+    DM_LAUNCH_OK("embed64_kernel");
+    return DM_OK;
+  }
   // narrow tiles when the contraction is short (latency-bound) or when they waste less of the N range
   const int waste128 = (P.maxN + 127) / 128 * 128 - P.maxN, waste64 = (P.maxN + 63) / 64 * 64 - P.maxN;
   const int kper = P.ksplit > 1 ? P.kchunk : P.maxK;
