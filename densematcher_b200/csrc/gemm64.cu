@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
 // k pipeline for every 128 x 64 output tile and runs this shape at ~13 TFLOP/s; here B stays resident in shared
 // memory, a CTA walks over several 64-row tiles of A (cp.async double buffer: the next tile streams in while the
 // current one is multiplied) and every warp owns 8 rows x all columns, so one A fragment feeds up to 13 DMMAs.
+// Measured at N = 2000, K = N = 100, 128 pairs: 263 us = 19.4 TFLOP/s (the DMMA pipe alone peaks at 37.1,
+// scripts/micro/dmma_peak.cu).  Tried and not kept: a 4 x 2 warp grid (B fragments shared by two row fragments: 282 us),
+// a lane-major B layout read with LDS.128 (412 us: bank conflicts), eight tiles per CTA (393 us: wave quantisation).
 constexpr int ET = 64;          // rows of A per tile
 constexpr int EKP = 104;        // padded K and N
 constexpr int ELD = EKP + 4;    // pitch == 12 (mod 16): conflict-free 8 x 4 / 4 x 8 fragment loads
@@ -231,6 +234,9 @@ constexpr int ETPC = 4;         // tiles per CTA
 constexpr int ENC8 = EKP / 8;   // 8-column accumulator tiles per warp
 constexpr size_t kEmbedSmem = size_t(EKP + 2 * ET) * ELD * sizeof(double);
 
+__device__ __forceinline__ void cp_async16(double* dst, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async8(double* dst, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
 }
@@ -253,17 +259,28 @@ __global__ void __launch_bounds__(NT, 1) embed64_kernel(const GemmProblem P, int
   const int kp = (K + 3) & ~3;
   constexpr int nc8 = NC8;
 
-  // four threads per row of the tile, each copying every fourth element (no index arithmetic beyond an add)
+  // four threads per row of the tile; 16-byte copies when every row of A starts on a 16-byte boundary (half as many
+  // requests through the load/store unit, which the DMMA operand loads share: 310 -> 282 us), 8-byte copies otherwise
+  const bool vec2 = ((reinterpret_cast<uintptr_t>(A.d) | uintptr_t(A.ld * sizeof(double))) & 15) == 0 && (K & 1) == 0;
   auto prefetch = [&](int tile, int buf) {
     const int r = t >> 2, row = row_begin + tile * ET + r;
     double* dst = As + buf * ET * ELD + r * ELD;
     const double* src = A.d + int64_t(row) * A.ld;
     const bool row_ok = row < M;
-    for (int k = t & 3; k < kp; k += 4) {
-      if (row_ok && k < K)
-        cp_async8(dst + k, src + k);
-      else
-        dst[k] = 0.0;
+    if (vec2) {
+      for (int k = 2 * (t & 3); k < kp; k += 8) {
+        if (row_ok && k < K)
+          cp_async16(dst + k, src + k);
+        else
+          dst[k] = dst[k + 1] = 0.0;
+      }
+    } else {
+      for (int k = t & 3; k < kp; k += 4) {
+        if (row_ok && k < K)
+          cp_async8(dst + k, src + k);
+        else
+          dst[k] = 0.0;
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -319,15 +336,21 @@ __global__ void __launch_bounds__(NT, 1) embed64_kernel(const GemmProblem P, int
     }
     const int m = row_begin + tile * ET + 8 * warp + g;
     if (m < M) {
+      double* crow = C + int64_t(m) * P.ldc;
+      const bool st2 = ((reinterpret_cast<uintptr_t>(C) | uintptr_t(P.ldc * sizeof(double))) & 15) == 0;
 #pragma unroll
       for (int c = 0; c < NC8; ++c) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int n = 8 * c + 2 * t4 + h;
-          if (n >= N) continue;
-          double v = P.alpha * acc[c][h];
-          if (cs) v *= cs[n];
-          C[int64_t(m) * P.ldc + n] = v;
+        const int n = 8 * c + 2 * t4;
+        double v0 = P.alpha * acc[c][0], v1 = P.alpha * acc[c][1];
+        if (cs) {
+          if (n < N) v0 *= cs[n];
+          if (n + 1 < N) v1 *= cs[n + 1];
+        }
+        if (st2 && n + 1 < N) {
+          *reinterpret_cast<double2*>(crow + n) = make_double2(v0, v1);
+        } else {
+          if (n < N) crow[n] = v0;
+          if (n + 1 < N) crow[n + 1] = v1;
         }
       }
     }
