@@ -33,7 +33,7 @@ METRIC = "mesh_pairs_per_sec"
 UNIT = "pairs/s"
 ALG_BYTES_NN = 4 * D_FEAT * 2 * N_VERT + 4 * 2 * N_VERT          # 6.160 MB per pair
 ALG_FLOPS_NN = 2 * N_VERT * N_VERT * D_FEAT                      # 3.072 GFLOP per pair
-NCU_DRAM_BYTES_PER_PAIR = (398.982400e6 + 37.538560e6) / 64      # ncu --set full capture of nn_tc_kernel<1,1,0,1> (CTA-pair mode) at 64 pairs
+NCU_DRAM_BYTES_PER_PAIR = (400.146432e6 + 38.645248e6) / 64      # ncu --set full capture of nn_tc_kernel<1,1,0,1> (CTA-pair mode) at 64 pairs
 
 
 def workload_config(pairs, n_gpus):
@@ -284,7 +284,7 @@ def main():
                 "traffic": NCU_DRAM_BYTES_PER_PAIR * P,
                 "note": "3 bf16 MMA passes per fp32-grade product (split-bf16); peak " + which +
                         "; traffic = dram read+write bytes of this kernel per launch from the ncu --set full capture "
-                        "profiles/r1_end_nn_tc_full_raw.csv (6.82 MB per pair vs 6.16 MB algorithmic)"}
+                        "profiles/r1_end_nn_tc_full_raw.csv (6.86 MB per pair vs 6.16 MB algorithmic)"}
     roof.update({"kernel": "nn score pass (" + engine + ")", "kernel_ms": kern_ms, "nn_stage_ms": nn_stage_ms,
                  "algorithmic_tflops": alg_tflops, "hbm_gbs": hbm_gbs, "hbm_peak_gbs": hbm_peak,
                  "hbm_frac": hbm_gbs / hbm_peak, "peaks": which})
