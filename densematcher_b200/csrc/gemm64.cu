@@ -66,9 +66,37 @@ struct Loader {
   const OpView& v;
   int i0, lim;  // first output index of the tile, number of valid output indices (M or N)
   int t;
-  __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {}
+  // TRANS operands of float64 whose rows start on 16-byte boundaries are moved two output indices at a time (one
+  // 16-byte global load and one 16-byte shared store instead of two of each: the load/store unit is shared with the
+  // DMMA operand loads): thread owns i = 2 (t % (TW / 2)), i + 1 of contraction rows k = t / (TW / 2) + (2 NT / TW) e
+  bool vec2;
+  __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {
+    vec2 = TRANS && v.d != nullptr && ((reinterpret_cast<uintptr_t>(v.d) | uintptr_t(v.ld * sizeof(double))) & 15) == 0 &&
+           (i0 & 1) == 0;
+  }
 
   __device__ __forceinline__ void fetch(int k0, int kend, Staged<NE>& r) const {
+    if (TRANS && vec2) {
+#pragma unroll
+      for (int e = 0; e < NE / 2; ++e) {
+        const int i = i0 + 2 * (t % (TW / 2));
+        const int k = k0 + (t / (TW / 2)) + (2 * NT / TW) * e;
+        r.d[2 * e] = r.d[2 * e + 1] = 0.0;
+        r.s[2 * e] = 1.0;
+        if (i < lim && k < kend) {
+          const int64_t row = v.gather ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : k;
+          const double* src = v.d + row * v.ld + i;
+          if (i + 1 < lim) {
+            const double2 x = __ldg(reinterpret_cast<const double2*>(src));
+            r.d[2 * e] = x.x, r.d[2 * e + 1] = x.y;
+          } else {
+            r.d[2 * e] = __ldg(src);
+          }
+          if (v.kscale) r.s[2 * e] = __ldg(v.kscale + k);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       int i, k;
@@ -97,6 +125,16 @@ struct Loader {
     }
   }
   __device__ __forceinline__ void stash(double* stage, const Staged<NE>& r) const {
+    if (TRANS && vec2) {
+      const bool scaled = v.kscale != nullptr;
+#pragma unroll
+      for (int e = 0; e < NE / 2; ++e) {
+        double x0 = r.d[2 * e], x1 = r.d[2 * e + 1];
+        if (scaled) x0 *= r.s[2 * e], x1 *= r.s[2 * e];
+        *reinterpret_cast<double2*>(stage + ((t / (TW / 2)) + (2 * NT / TW) * e) * LDT + 2 * (t % (TW / 2))) = make_double2(x0, x1);
+      }
+      return;
+    }
     const bool is_d = v.d != nullptr;
     const bool scaled = TRANS && v.kscale != nullptr;
 #pragma unroll
