@@ -71,11 +71,28 @@ struct Loader {
   // DMMA operand loads): thread owns i = 2 (t % (TW / 2)), i + 1 of contraction rows k = t / (TW / 2) + (2 NT / TW) e
   bool vec2;
   __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {
-    vec2 = TRANS && v.d != nullptr && ((reinterpret_cast<uintptr_t>(v.d) | uintptr_t(v.ld * sizeof(double))) & 15) == 0 &&
+    vec2 = v.d != nullptr && ((reinterpret_cast<uintptr_t>(v.d) | uintptr_t(v.ld * sizeof(double))) & 15) == 0 &&
            (i0 & 1) == 0;
   }
 
   __device__ __forceinline__ void fetch(int k0, int kend, Staged<NE>& r) const {
+    if (!TRANS && vec2) {  // thread owns k = 2 (t % 4), k + 1 of rows i = t / 4 + 64 e
+#pragma unroll
+      for (int e = 0; e < NE / 2; ++e) {
+        const int k = k0 + 2 * (t & 3), i = i0 + (t >> 2) + 64 * e;
+        r.d[2 * e] = r.d[2 * e + 1] = 0.0;
+        if (i < lim && k < kend) {
+          const double* src = v.d + int64_t(i) * v.ld + k;
+          if (k + 1 < kend) {
+            const double2 x = __ldg(reinterpret_cast<const double2*>(src));
+            r.d[2 * e] = x.x, r.d[2 * e + 1] = x.y;
+          } else {
+            r.d[2 * e] = __ldg(src);
+          }
+        }
+      }
+      return;
+    }
     if (TRANS && vec2) {
 #pragma unroll
       for (int e = 0; e < NE / 2; ++e) {
@@ -125,6 +142,14 @@ struct Loader {
     }
   }
   __device__ __forceinline__ void stash(double* stage, const Staged<NE>& r) const {
+    if (!TRANS && vec2) {
+#pragma unroll
+      for (int e = 0; e < NE / 2; ++e) {
+        stage[(2 * (t & 3)) * LDT + (t >> 2) + 64 * e] = r.d[2 * e];
+        stage[(2 * (t & 3) + 1) * LDT + (t >> 2) + 64 * e] = r.d[2 * e + 1];
+      }
+      return;
+    }
     if (TRANS && vec2) {
       const bool scaled = v.kscale != nullptr;
 #pragma unroll
