@@ -353,3 +353,23 @@ def test_polar_factor_newton_schulz_and_jacobi_fallback():
                 assert np.abs(C[b] - ref(X[b])).max() < tol, (rows, cols, b, flags)
                 G = C[b].T @ C[b] if rows >= cols else C[b] @ C[b].T
                 assert np.abs(G - np.eye(k)).max() < 1e-11, (rows, cols, b, flags)
+
+
+def test_float64_gemm_paths_with_unaligned_operands(fm):
+    """The float64 GEMMs move operands 16 bytes at a time when rows start on 16-byte boundaries and fall back to
+    8-byte accesses otherwise: odd leading dimensions, odd sizes and column-offset views must give the same numbers."""
+    rng = np.random.default_rng(31)
+    n1, n2 = 700, 650
+    for (k1, k2, ld, c0) in ((21, 19, 45, 1), (20, 20, 44, 0), (33, 30, 47, 2), (104, 100, 104, 0)):
+        big1, big2 = rng.standard_normal((n1, ld + 3)), rng.standard_normal((n2, ld + 3))
+        C = rng.standard_normal((k2, k1))
+        a1 = rng.uniform(0.5, 1.5, n1)
+        P1, P2 = big1[:, c0:c0 + k1], big2[:, c0:c0 + k2]
+        MI = fm.mapped_indicator(dev(C), dev(big1)[:, c0:c0 + k1], dev(big2)[:, c0:c0 + k2], dev(a1)).cpu().numpy()
+        ref = (P2 @ C @ P1.T) * a1[None, :]
+        assert np.abs(MI - ref).max() < 1e-10 * np.abs(ref).max(), (k1, k2, ld, c0)
+        # p2p -> FM (transposed, gathered, scaled operands) on the same views
+        p = rng.integers(0, n1, n2)
+        a2 = rng.uniform(0.5, 1.5, n2)
+        Cg = fm.p2p_to_fm(dev(p), dev(big1)[:, c0:c0 + k1], dev(big2)[:, c0:c0 + k2], dev(a2))[0].cpu().numpy()
+        assert relF(Cg, P2.T @ (a2[:, None] * P1[p])) < 1e-12, (k1, k2, ld, c0)
