@@ -33,7 +33,7 @@ __all__ = [
     "knn_query", "nn_argmax", "knn_bruteforce", "project", "fmap_c00", "ev_sqdiff",
     "fmap_solve_closed_form", "fmap_energy", "fm_to_p2p", "dense_argmax_override",
     "p2p_to_fm", "zoomout_refine", "icp_refine", "surface_map_arrays", "dense_map_energy", "fmap_fit_lbfgs",
-    "hungarian", "tri_closest_point", "project_points_to_triangles", "fm_to_precise_map",
+    "hungarian", "lap_shortest_augmenting_path", "tri_closest_point", "project_points_to_triangles", "fm_to_precise_map",
 ]
 
 
@@ -427,6 +427,79 @@ def hungarian(MI, eta=None):
     eta = np.ones(MI.shape[0]) if eta is None else np.asarray(eta, np.float64)
     return linear_sum_assignment(MI * eta[..., None] - 1000 * (1 - eta[..., None]), maximize=True)
 
+
+
+def lap_shortest_augmenting_path(cost, maximize=False):
+    """Restatement of the solver behind ``scipy.optimize.linear_sum_assignment`` (third-party, scipy 1.18.1 here: the
+    rectangular shortest-augmenting-path algorithm of Crouse 2016), including the details that make its answer unique
+    on tied matrices and that ``dm_lap_solve`` (csrc/lap.cu) follows step for step:
+      * tall matrices are transposed, maximisation negates the costs;
+      * rows are added in order; each Dijkstra search scans the list ``remaining`` -- initialised to nc-1, ..., 0 and
+        updated by moving its last entry into the slot of the column just scanned -- and among equal shortest-path
+        costs keeps the FIRST one met, except that an unassigned column replaces an equal candidate;
+      * ``r = minVal + cost[i, j] - u[i] - v[j]`` is evaluated left to right; the duals are updated as
+        ``u[i] += minVal - spc[col4row[i]]``, ``v[j] -= minVal - spc[j]``.
+    Returns (row_ind, col_ind, number of Dijkstra steps).  Pure Python/numpy: small matrices only."""
+    cost = np.asarray(cost, np.float64)
+    nr, nc = cost.shape
+    transpose = nc < nr
+    if transpose:
+        cost = cost.T.copy()
+        nr, nc = nc, nr
+    if maximize:
+        cost = -cost
+    u, v = np.zeros(nr), np.zeros(nc)
+    path = np.full(nc, -1)
+    col4row, row4col = np.full(nr, -1), np.full(nc, -1)
+    steps = 0
+    for cur in range(nr):
+        remaining = np.arange(nc - 1, -1, -1)
+        nrem = nc
+        SR, SC = np.zeros(nr, bool), np.zeros(nc, bool)
+        spc = np.full(nc, np.inf)
+        minVal, i, sink = 0.0, cur, -1
+        while sink == -1:
+            steps += 1
+            SR[i] = True
+            js = remaining[:nrem]
+            r = ((minVal + cost[i, js]) - u[i]) - v[js]
+            upd = r < spc[js]
+            path[js[upd]] = i
+            spc[js[upd]] = r[upd]
+            s = spc[js]
+            lowest = s.min()
+            if lowest == np.inf:
+                raise ValueError("cost matrix is infeasible")
+            ties = np.nonzero(s == lowest)[0]
+            free = ties[row4col[js[ties]] == -1]
+            index = free[-1] if len(free) else ties[0]
+            minVal = lowest
+            j = js[index]
+            if row4col[j] == -1:
+                sink = j
+            else:
+                i = row4col[j]
+            SC[j] = True
+            nrem -= 1
+            remaining[index] = remaining[nrem]
+        u[cur] += minVal
+        others = SR.copy()
+        others[cur] = False
+        idx = np.nonzero(others)[0]
+        u[idx] += minVal - spc[col4row[idx]]
+        jj = np.nonzero(SC)[0]
+        v[jj] -= minVal - spc[jj]
+        j = sink
+        while True:
+            i = path[j]
+            row4col[j] = i
+            col4row[i], j = j, col4row[i]
+            if i == cur:
+                break
+    if transpose:
+        order = np.argsort(col4row, kind="stable")
+        return col4row[order], order, steps
+    return np.arange(nr), col4row, steps
 
 def tri_closest_point(a, b, c, d, e, f, many=False):
     """Closest point of a triangle B + s E0 + t E1 to a point P, from the six inner products

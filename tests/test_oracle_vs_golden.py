@@ -215,3 +215,23 @@ def test_hungarian_matches_reference(golden_fm, golden_extras):
     assert np.array_equal(c, x["ref_hungarian_cols"])
     rp, cp = orc.hungarian(_csr(x, "ref_precise", (642, 642)).toarray())
     assert np.array_equal(cp, x["ref_hungarian_precise_cols"])
+
+
+def test_lap_restatement_equals_scipy_including_ties():
+    """The solver dm_lap_solve follows (oracle restatement) against scipy itself: generic, integer-tie, constant and
+    rectangular matrices, both directions of optimisation."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(0)
+    cases = [rng.standard_normal((50, 50)), rng.standard_normal((40, 60)), rng.standard_normal((60, 40)),
+             rng.integers(0, 4, (30, 30)).astype(float), rng.integers(0, 4, (30, 45)).astype(float),
+             rng.integers(0, 4, (45, 30)).astype(float), rng.integers(0, 2, (64, 64)).astype(float), np.ones((20, 20)),
+             np.zeros((9, 17))]
+    for c in cases:
+        for mx in (False, True):
+            r, col, _ = orc.lap_shortest_augmenting_path(c, mx)
+            rr, cc = linear_sum_assignment(c, maximize=mx)
+            assert np.array_equal(r, rr) and np.array_equal(col, cc)
+    inf = np.full((4, 4), np.inf)
+    inf[:, 0] = 1.0
+    with pytest.raises(ValueError):
+        orc.lap_shortest_augmenting_path(inf)
