@@ -111,8 +111,10 @@ __device__ __forceinline__ int warp_argmin(double val, unsigned key, double& vmi
   return src;
 }
 
-template <int CPT>
-__global__ void __launch_bounds__(kLapThreads, 1) lap_kernel(LapArgs A) {
+// MINB = 2 caps the kernel at 64 registers so that two problems share an SM: 20 % slower for one problem, 20 % more
+// throughput once there are more problems than SMs (124 ms instead of 156 ms for 296 problems of 2562 x 2562)
+template <int CPT, int MINB>
+__global__ void __launch_bounds__(kLapThreads, MINB) lap_kernel(LapArgs A) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r0 = A.row_off[b];
@@ -274,14 +276,22 @@ size_t lap_smem_bytes(int max_small, int max_big) {
   return size_t(max_small) * 12 + size_t(max_big) * 8 + 2 * kLapWarps * (8 + 4 + 4 + 4) + 64;
 }
 
-template <int CPT>
-int lap_launch(const LapArgs& A, int n_batch, size_t smem, cudaStream_t st) {
+template <int CPT, int MINB>
+int lap_launch_b(const LapArgs& A, int n_batch, size_t smem, cudaStream_t st) {
   static OncePerDevice once;
   if (once.first())
-    DM_CUDA_OK(cudaFuncSetAttribute(lap_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  lap_kernel<CPT><<<n_batch, kLapThreads, smem, st>>>(A);
+    DM_CUDA_OK(cudaFuncSetAttribute(lap_kernel<CPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  lap_kernel<CPT, MINB><<<n_batch, kLapThreads, smem, st>>>(A);
   DM_LAUNCH_OK("lap_kernel");
   return DM_OK;
+}
+
+template <int CPT>
+int lap_launch(const LapArgs& A, int n_batch, size_t smem, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (CPT <= 8 && n_batch > sms && 2 * (smem + 1024) <= 227 * 1024) return lap_launch_b<CPT, (CPT <= 8 ? 2 : 1)>(A, n_batch, smem, st);
+  return lap_launch_b<CPT, 1>(A, n_batch, smem, st);
 }
 
 }  // namespace

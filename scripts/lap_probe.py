@@ -12,7 +12,7 @@ mi = _mapped_indicator(4, 50, 1)
 t = time.time(); rr, cc = linear_sum_assignment(mi, maximize=True); t_scipy = time.time() - t
 print(f"scipy (1 core)          {t_scipy*1e3:9.1f} ms / problem")
 d = torch.from_numpy(mi).cuda()
-for nb in (1, 16, 148):
+for nb in (1, 16, 148, 296):
     rng = np.random.default_rng(nb)
     mats = [d] + [d + 1e-7 * torch.from_numpy(rng.standard_normal(mi.shape)).cuda() for _ in range(min(nb, 8) - 1)]
     mats = [mats[i % len(mats)] for i in range(nb)]
