@@ -141,9 +141,10 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
     return out
 
 
-def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: int = 32):
+def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: int = 256):
     """Hungarian assignment of every pair's mapped indicator  Phi2 C Phi1^T A1  (functional_map.py:57,78), maximised,
-    for a device-resident batch: the float64 (n2, n1) matrices of ``chunk_pairs`` pairs are materialised at a time
+    for a device-resident batch: the float64 (n2, n1) matrices of ``chunk_pairs`` pairs are materialised at a time (more
+    problems than SMs let two of them share an SM)
     (32 MB each at N = 2000) and solved together by ``dm_lap_solve``, one CTA per pair.  Returns a list of
     ``(row_ind, col_ind)`` numpy pairs identical to scipy's."""
     k2, k1 = C.shape[1], C.shape[2]
