@@ -99,7 +99,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // order-preserving 64-bit unsigned key and reduced as two 32-bit halves with redux.sync (three REDUX instead of five
 // rounds of 64-bit shuffles + compares: this sits on the critical path of every Dijkstra step, twice).
 __device__ __forceinline__ int warp_argmin(double val, unsigned key, double& vmin, unsigned& kmin) {
-  const long long b = __double_as_longlong(val);
+  const long long b = __double_as_longlong(__dadd_rn(val, 0.0));  // -0.0 -> +0.0: they compare equal as numbers
   const unsigned long long o = static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
   const unsigned hi = unsigned(o >> 32), lo = unsigned(o);
   const unsigned mh = __reduce_min_sync(kFull, hi);
