@@ -1,4 +1,4 @@
-// Functional-map stages: spectral projection, the closed-form C solve, FM -> p2p (four index outputs
+// Functional-map stages: spectral projection, FM -> p2p (four index outputs
 // from one score pass), p2p -> FM and the ZoomOut ladder.  Everything that enters C is float64; the
 // N x N x k score pass runs through the fused NN engine with the float64 near-tie re-evaluation.
 #include "dm_internal.cuh"
@@ -21,238 +21,6 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
   if (lane == 0) out[row] = -0.5 * s;
-}
-
-// Closed-form rows of C: one 128-thread CTA per (pair, row i of C) solves
-//     (w_d Abar Abar^T + w_l diag(Delta_i)) c = w_d Abar (B_i - c_i0 A_0)^T          (n = k1 - 1 unknowns)
-// by a left-looking Cholesky factorisation held in shared memory as a packed lower triangle (40 KB at k = 100, five
-// systems resident per SM).  The right-hand side is carried as an extra matrix row n, so the forward substitution
-// falls out of the factorisation.  The k2 systems of a pair share the Gram matrix and differ only on the diagonal,
-// but there is no factorisation to share.
-// Columns are produced four at a time: each thread owns one matrix row (two beyond 128 rows) and accumulates
-// a[r][j0..j0+3] - sum_{k<j0} L[r][k] L[j0+c][k] in registers, so every L[r][k] read from shared memory feeds four
-// FMAs; the 4x4 diagonal block is then factorised redundantly by every thread (no serial owner, two block barriers
-// per four columns) and each thread finishes its own row.  Row starts r(r+1)/2 put 16 consecutive rows into 16
-// distinct 8-byte banks.  The back substitution runs in warp 0 with the unknowns in registers.
-constexpr int kSolveNB = 4;        // columns per block step (8 was measured slower: registers cut the resident systems per SM)
-constexpr int kSolveThreads = 128;
-
-// 1 / sqrt(v) in float64 from the FP64 reciprocal-square-root estimate (MUFU.RSQ64H, ~2^-22) and two Newton steps
-// (error at rounding level; the factorisation does not need a correctly rounded square root).  On the critical path
-// of every column: 64 cycles of dependent latency, against 123 through an fp32 estimate with its two conversions
-// and 173 for 1 / sqrt() (scripts/micro/fp64_latency.cu).
-__device__ __forceinline__ double rsqrt64(double v) {
-  if (!(v > 1e-300 && v < 1e300)) return 1.0 / sqrt(v);
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
-  const double h = 0.5 * v;
-  y = y * fma(-h * y, y, 1.5);  // 2^-22 -> 2^-43
-  y = y * fma(-h * y, y, 1.5);  // -> rounding level
-  return y;
-}
-
-// w_d * (A A^T)[1:, 1:] of every pair as a packed lower triangle (row r starts at r (r + 1) / 2), the form in which the
-// k2 systems of the pair bulk-copy it into shared memory.  stride = packed length rounded up to an even count.
-__global__ void __launch_bounds__(256)
-    solve_pack_kernel(const double* __restrict__ AAt, double wd, int k1, int64_t stride, double* __restrict__ Lp) {
-  const int n = k1 - 1, n_tri = n * (n + 1) / 2;
-  const double* aat = AAt + int64_t(blockIdx.x) * k1 * k1;
-  double* out = Lp + int64_t(blockIdx.x) * stride;
-  for (int e = threadIdx.x; e < n_tri; e += blockDim.x) {
-    int r = int((sqrtf(8.f * float(e) + 1.f) - 1.f) * 0.5f);
-    while (r * (r + 1) / 2 > e) --r;
-    while ((r + 1) * (r + 2) / 2 <= e) ++r;
-    const int c = e - r * (r + 1) / 2;
-    out[e] = wd * aat[int64_t(r + 1) * k1 + c + 1];
-  }
-  if (threadIdx.x == 0 && stride > n_tri) out[n_tri] = 0.0;
-}
-
-template <int RPT>  // rows per thread: (n + 1) <= 128 * RPT
-__global__ void __launch_bounds__(kSolveThreads, RPT == 1 ? 5 : 1)
-    fmap_solve_kernel(const double* __restrict__ AAt, const double* __restrict__ BAt, const double* __restrict__ Lp,
-                      int64_t lp_stride, const double* __restrict__ ev1, const double* __restrict__ ev2,
-                      const double* __restrict__ c00, double wd, double wl, int k1, int k2, double* __restrict__ C,
-                      int* __restrict__ status) {
-  extern __shared__ __align__(16) double sm[];
-  constexpr int RPL = 4 * RPT;  // unknowns per lane in the single-warp back substitution
-  const int n = k1 - 1;
-  const int t = threadIdx.x, lane = t & 31;
-  const int sys = blockIdx.x;
-  const int n_tri = n * (n + 1) / 2;
-  double* L = sm;                                        // row r starts at r (r + 1) / 2; row n = right-hand side
-  double* Dbuf = sm + size_t(n + 1) * (n + 2) / 2 + 1;   // [2][4][4] accumulated diagonal blocks (double-buffered)
-  double* invd = Dbuf + 2 * kSolveNB * kSolveNB;                           // [n] reciprocals of the diagonal of L
-  __shared__ double s_scale[kSolveThreads / 32];
-  __shared__ __align__(8) unsigned long long s_bar;
-  const int b = sys / k2, i = sys % k2;
-  const double* aat = AAt + int64_t(b) * k1 * k1;
-  const double* bat = BAt + int64_t(b) * k2 * k1;
-  const double* l1 = ev1 + int64_t(b) * k1;
-  const double* l2 = ev2 + int64_t(b) * k2;
-  // the shared part of the matrix arrives by one bulk copy while the threads prepare the system-specific part
-  const uint32_t bar = tc::smem_u32(&s_bar);
-  if (t == 0) {
-    tc::mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = uint32_t(lp_stride * sizeof(double));
-    tc::mbar_expect_tx(bar, bytes);
-    tc::tma_load_1d(tc::smem_u32(L), Lp + int64_t(b) * lp_stride, bytes, bar);
-  }
-  double scale = -INFINITY;
-  for (int j = t; j < k1; j += kSolveThreads) scale = fmax(scale, l1[j]);
-  for (int j = t; j < k2; j += kSolveThreads) scale = fmax(scale, l2[j]);
-#pragma unroll
-  for (int sh = 16; sh > 0; sh >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, sh));
-  if (lane == 0) s_scale[t >> 5] = scale;
-  __syncthreads();  // also publishes the barrier initialisation to the waiting threads
-  scale = fmax(fmax(s_scale[0], s_scale[1]), fmax(s_scale[2], s_scale[3]));
-  const double ci0 = (i == 0) ? c00[b] : 0.0;
-  const double l2i = l2[i] / scale;
-  double dg[RPT], rh[RPT];
-#pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    const int c = t + kSolveThreads * q;
-    dg[q] = rh[q] = 0.0;
-    if (c < n) {
-      const double df = l1[c + 1] / scale - l2i;
-      dg[q] = wl * (df * df);
-      rh[q] = wd * (bat[int64_t(i) * k1 + c + 1] - ci0 * aat[c + 1]);
-    }
-  }
-  tc::mbar_wait(bar, 0);
-#pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    const int c = t + kSolveThreads * q;
-    if (c < n) {
-      L[size_t(c) * (c + 1) / 2 + c] += dg[q];
-      L[n_tri + c] = rh[q];
-    }
-  }
-  __syncthreads();
-  bool bad = false;
-  int par = 0;
-  for (int j0 = 0; j0 < n; j0 += kSolveNB, par ^= 1) {
-    const int nb = min(kSolveNB, n - j0);
-    // rows of this block step, thread-cyclic from j0: r = j0 + t + 128 q  (row n = right-hand side included)
-    double acc[RPT][kSolveNB];
-    const double* rowr[RPT];
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      const int r = j0 + t + kSolveThreads * q;
-      const int rc = min(r, n);
-      rowr[q] = L + size_t(rc) * (rc + 1) / 2;
-#pragma unroll
-      for (int c = 0; c < kSolveNB; ++c) acc[q][c] = (r <= n && c < nb && j0 + c <= min(r, n - 1)) ? rowr[q][j0 + c] : 0.0;
-    }
-    const double* rowc[kSolveNB];
-#pragma unroll
-    for (int c = 0; c < kSolveNB; ++c) {
-      const int jc = min(j0 + c, n - 1);
-      rowc[c] = L + size_t(jc) * (jc + 1) / 2;
-    }
-    if (j0 + (t & ~31) <= n) {  // warps whose rows all lie beyond the matrix skip the bulk (warp-uniform)
-#pragma unroll 4
-      for (int k = 0; k < j0; ++k) {
-        double lc[kSolveNB];
-#pragma unroll
-        for (int c = 0; c < kSolveNB; ++c) lc[c] = rowc[c][k];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-          const double lr = rowr[q][k];
-#pragma unroll
-          for (int c = 0; c < kSolveNB; ++c) acc[q][c] = fma(-lr, lc[c], acc[q][c]);
-        }
-      }
-    }
-    // publish the accumulated diagonal block (rows j0 .. j0+3 live in threads 0 .. 3, slot 0)
-    double* D = Dbuf + par * kSolveNB * kSolveNB;
-    if (t < kSolveNB) {
-#pragma unroll
-      for (int c = 0; c < kSolveNB; ++c) D[t * kSolveNB + c] = acc[0][c];
-    }
-    __syncthreads();
-    // every thread factorises the 4x4 block: l[c][c2], c2 < c, and the reciprocal diagonal li[c]
-    double l[kSolveNB][kSolveNB], li[kSolveNB];
-#pragma unroll
-    for (int c = 0; c < kSolveNB; ++c) {
-#pragma unroll
-      for (int c2 = 0; c2 <= c; ++c2) {
-        double v = D[c * kSolveNB + c2];
-#pragma unroll
-        for (int c3 = 0; c3 < c2; ++c3) v = fma(-l[c][c3], l[c2][c3], v);
-        if (c2 == c) {
-          if (c < nb && !(v > 0.0)) bad = true;
-          li[c] = c < nb ? rsqrt64(v) : 1.0;
-          l[c][c] = v * li[c];
-        } else {
-          l[c][c2] = c < nb ? v * li[c2] : 0.0;
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < kSolveNB; ++c)
-      if (t == c && c < nb) invd[j0 + c] = li[c];
-    // own rows: forward substitution against the block, then store the four new entries of L
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      const int r = j0 + t + kSolveThreads * q;
-      if (r <= n) {
-        double* row = L + size_t(r) * (r + 1) / 2;
-        double v[kSolveNB];
-#pragma unroll
-        for (int c = 0; c < kSolveNB; ++c) {
-          double x = acc[q][c];
-#pragma unroll
-          for (int c2 = 0; c2 < c; ++c2) x = fma(-v[c2], l[c][c2], x);
-          v[c] = (r == j0 + c) ? l[c][c] : x * li[c];
-          if (c < nb && j0 + c <= min(r, n - 1)) row[j0 + c] = v[c];
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (t == 0 && bad) atomicExch(status, 1);
-  if (t >= 32) return;
-  // back substitution L^T x = y with y = row n; unknown r lives in lane r % 32, slot r / 32
-  double x[RPL];
-  {
-    const double* y = L + n_tri;
-#pragma unroll
-    for (int q = 0; q < RPL; ++q) {
-      const int r = lane + 32 * q;
-      x[q] = r < n ? y[r] : 0.0;
-    }
-  }
-  // slots from the top; inside a slot the 32 unknowns are finished from lane 31 down (static register indexing)
-#pragma unroll
-  for (int qj = RPL - 1; qj >= 0; --qj) {
-    if (32 * qj >= n) continue;
-    for (int lj = min(31, n - 1 - 32 * qj); lj >= 0; --lj) {
-      const int j = 32 * qj + lj;
-      const double* row = L + size_t(j) * (j + 1) / 2;
-      const double xj = __shfl_sync(0xffffffffu, x[qj], lj) * invd[j];
-#pragma unroll
-      for (int q = 0; q < RPL; ++q) {
-        if (q > qj) continue;
-        const int r = lane + 32 * q;
-        if (r == j) x[q] = xj;
-        else if (r < j) x[q] = fma(-row[r], xj, x[q]);
-      }
-    }
-  }
-  double* Ci = C + (int64_t(b) * k2 + i) * k1;
-  if (lane == 0) Ci[0] = ci0;
-#pragma unroll
-  for (int q = 0; q < RPL; ++q) {
-    const int r = lane + 32 * q;
-    if (r < n) Ci[r + 1] = x[q];
-  }
-}
-
-int64_t solve_lp_stride(int k1) {  // packed lower triangle of the (k1 - 1)^2 system, rounded up to an even count
-  const int64_t n = k1 - 1, n_tri = n * (n + 1) / 2;
-  return (n_tri + 1) & ~int64_t(1);
 }
 
 int neg_half_sqnorm(const double* M, int64_t ld, int64_t rows, int d, double* out, cudaStream_t st) {
@@ -399,67 +167,6 @@ int dm_project(const double* Phi, int64_t ldPhi, const double* area, const float
                void* workspace, size_t workspace_bytes, dm_stream_t stream) {
   return dm_project_ex(Phi, ldPhi, area, F, ldF, row_off, total_n, max_n, n_meshes, k, d, out, 0, workspace,
                        workspace_bytes, stream);
-}
-
-// ------------------------------------------------------------------ closed-form C
-size_t dm_fmap_solve_workspace_bytes(int n_pairs, int k1, int k2, int d) {
-  (void)d;
-  Carver c(nullptr);
-  c.take<double>(size_t(n_pairs) * k1 * k1);
-  c.take<double>(size_t(n_pairs) * k2 * k1);
-  c.take<int>(4);
-  c.take<double>(size_t(n_pairs) * solve_lp_stride(k1));
-  return c.bytes();
-}
-
-int dm_fmap_solve(const double* A, const double* B, const double* evals1, const double* evals2, const double* c00,
-                  double w_descr, double w_lap, int n_pairs, int k1, int k2, int d, double* C, void* workspace,
-                  size_t workspace_bytes, dm_stream_t stream) {
-  if (n_pairs < 0 || k1 < 2 || k2 < 1 || d <= 0) DM_FAIL(DM_ERR_BADARG, "bad size (need k1 >= 2)");
-  if (n_pairs == 0) return DM_OK;
-  if (!A || !B || !evals1 || !evals2 || !c00 || !C) DM_FAIL(DM_ERR_BADARG, "null argument");
-  const size_t need = dm_fmap_solve_workspace_bytes(n_pairs, k1, k2, d);
-  if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
-  const int n = k1 - 1;
-  const size_t per = sizeof(double) * (size_t(n + 1) * (n + 2) / 2);
-  if (per > 220 * 1024 || n + 1 > 256) DM_FAIL(DM_ERR_UNSUPPORTED, "k1 = %d too large for the in-shared-memory Cholesky (max 236)", k1);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  Carver c(workspace);
-  double* AAt = c.take<double>(size_t(n_pairs) * k1 * k1);
-  double* BAt = c.take<double>(size_t(n_pairs) * k2 * k1);
-  int* status = c.take<int>(4);
-  const int64_t lp_stride = solve_lp_stride(k1);
-  double* Lp = c.take<double>(size_t(n_pairs) * lp_stride);
-  DM_CUDA_OK(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
-  int rc;
-  GemmProblem G;
-  G.A.d = A, G.A.ld = d, G.A.batch_stride = int64_t(k1) * d, G.A.trans = 0;
-  G.B = G.A;
-  G.M = k1, G.N = k1, G.K = d, G.maxM = k1, G.maxN = k1, G.maxK = d, G.n_batch = n_pairs;
-  G.C = AAt, G.ldc = k1, G.c_batch_stride = int64_t(k1) * k1;
-  if ((rc = gemm64_launch(G, st))) return rc;
-  G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
-  G.M = k2, G.maxM = k2, G.C = BAt, G.c_batch_stride = int64_t(k2) * k1;
-  if ((rc = gemm64_launch(G, st))) return rc;
-  const size_t shm = per + (1 + 2 * kSolveNB * kSolveNB + size_t(n)) * sizeof(double);
-  const int64_t n_sys = int64_t(n_pairs) * k2;
-  if (n_sys > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many systems");
-  solve_pack_kernel<<<unsigned(n_pairs), 256, 0, st>>>(AAt, w_descr, k1, lp_stride, Lp);
-  DM_LAUNCH_OK("solve_pack_kernel");
-#define DM_SOLVE(RPT)                                                                                              \
-  do {                                                                                                             \
-    if (shm > 48 * 1024)                                                                                           \
-      DM_CUDA_OK(cudaFuncSetAttribute(fmap_solve_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
-    fmap_solve_kernel<RPT><<<unsigned(n_sys), kSolveThreads, shm, st>>>(AAt, BAt, Lp, lp_stride, evals1, evals2, c00,  \
-                                                                        w_descr, w_lap, k1, k2, C, status);        \
-  } while (0)
-  if (n + 1 <= kSolveThreads)
-    DM_SOLVE(1);
-  else
-    DM_SOLVE(2);
-#undef DM_SOLVE
-  DM_LAUNCH_OK("fmap_solve_kernel");
-  return DM_OK;
 }
 
 // ------------------------------------------------------------------ FM -> p2p
@@ -679,6 +386,7 @@ IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, i
                     int flags) {
   Carver c(ws);
   IcpLayout L;
+  L.status = c.take<int>(64);  // first: dm_icp_read_status needs no sizes
   L.G = c.take<double>(size_t(n_pairs) * k2 * k2);
   L.Ginv = c.take<double>(size_t(n_pairs) * k2 * k2);
   L.Phi2p = c.take<double>(size_t(total_n2) * k2);
@@ -687,7 +395,6 @@ IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, i
                                                                                      : polar_scratch_doubles(k2, k1);
   L.lin = c.take<double>(lin * n_pairs);
   L.ns = c.take<double>(polar_ns_scratch_doubles(k2, k1, n_pairs));
-  L.status = c.take<int>(4);
   L.S.lde = k2, L.S.ldf = pad4(k2);
   L.S.emb1 = c.take<double>(size_t(total_n1) * k2);
   const bool tc = nn_use_tc(flags);
@@ -725,7 +432,7 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
   int rc;
-  DM_CUDA_OK(cudaMemsetAsync(L.status, 0, 4 * sizeof(int), st));
+  DM_CUDA_OK(cudaMemsetAsync(L.status, 0, 64 * sizeof(int), st));
   if (nit > 0) {
     // lstsq(Phi2, Phi1[p]) = (Phi2 G^-1)^T Phi1[p] with G = Phi2^T Phi2, factorised once   (icp.py:38 -> convert.py:51)
     if ((rc = p2p_to_fm_run(nullptr, 0, Phi2, ld2, off2, Phi2, ld2, off2, max_n2, nullptr, n_pairs, k2, k2, L.G, L.pf_ws,
@@ -808,6 +515,10 @@ MatchLayout match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n
                         int flags) {
   Carver c(ws);
   MatchLayout L;
+  // the solve workspace leads: its status words are then the first bytes of the whole workspace
+  // (dm_match_pairs_read_status == dm_fmap_solve_read_status)
+  L.solve_bytes = dm_fmap_solve_workspace_bytes(n_pairs, k, k, d);
+  L.solve_ws = c.take<char>(L.solve_bytes);
   L.nn_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, d, 1, 1, flags | kFlagSplit3);
   L.nn_ws = c.take<char>(L.nn_bytes);
   L.A = c.take<double>(size_t(n_pairs) * k * d);
@@ -817,8 +528,6 @@ MatchLayout match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n
   const size_t p2 = proj_tc_workspace_bytes(n_pairs, total_n2, max_n2, k, d);
   L.proj_bytes = p1 > p2 ? p1 : p2;
   L.proj_ws = c.take<char>(L.proj_bytes);
-  L.solve_bytes = dm_fmap_solve_workspace_bytes(n_pairs, k, k, d);
-  L.solve_ws = c.take<char>(L.solve_bytes);
   L.p2p_bytes = dm_fm_to_p2p_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k, k, flags);
   L.p2p_ws = c.take<char>(L.p2p_bytes);
   L.bytes = c.bytes();
@@ -885,6 +594,18 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
   if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) return DM_OK;
   return dm_fm_to_p2p(C, k, k, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs, p2p_21,
                       p2p_12, dense_21, dense_12, flags, L.p2p_ws, L.p2p_bytes, stream);
+}
+
+int dm_match_pairs_read_status(const void* workspace, int* out_h, dm_stream_t stream) {
+  return dm_fmap_solve_read_status(workspace, out_h, stream);
+}
+
+int dm_icp_read_status(const void* workspace, int* out_h, dm_stream_t stream) {
+  if (!workspace || !out_h) DM_FAIL(DM_ERR_BADARG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DM_CUDA_OK(cudaMemcpyAsync(out_h, workspace, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DM_CUDA_OK(cudaStreamSynchronize(st));
+  return DM_OK;
 }
 
 // ------------------------------------------------------------------ polar factor (the SVD step of ICP, exposed)

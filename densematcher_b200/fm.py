@@ -22,6 +22,23 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _read_status(fn_name, ws, dev):
+    """The four status words a solve-type call left at the head of its workspace (synchronises the stream)."""
+    import ctypes
+    out = (ctypes.c_int * 4)()
+    with torch.cuda.device(dev):
+        rc = getattr(_lib.load(), fn_name)(ws.data_ptr(), out, _stream(dev))
+    _lib.check(rc, fn_name)
+    return [int(v) for v in out]
+
+
+def _raise_if_singular(st, what):
+    if st[0]:
+        raise _lib.DMError(
+            f"{what}: a linear system was not positive definite even in float64 (rank-deficient descriptors / basis, "
+            "or zero weights); the reference's optimiser would return a finite map here, this closed-form path cannot")
+
+
 def _f64(t):
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
@@ -75,10 +92,13 @@ def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = Non
     return out
 
 
-def fmap_solve(A, B, evals1, evals2, c00, w_descr, w_lap, workspace: Optional[Workspace] = None):
+def fmap_solve(A, B, evals1, evals2, c00, w_descr, w_lap, workspace: Optional[Workspace] = None, check: bool = True,
+               return_status: bool = False):
     """Closed-form minimiser of the descriptor + Laplacian energy, column 0 pinned.
     A [P,k1,d], B [P,k2,d], evals1 [P,k1], evals2 [P,k2], c00 [P] -> C [P,k2,k1] float64.
-    (FunctionalMapping.fit pyFM/functional.py:352-487 with only w_descr / w_lap active)"""
+    (FunctionalMapping.fit pyFM/functional.py:352-487 with only w_descr / w_lap active)
+    ``check`` (default) synchronises and raises ``DMError`` when a system was singular; ``return_status`` also
+    returns [singular, float64 fallbacks, -, refinement steps]."""
     lib = _lib.load()
     dev = A.device
     A, B = _f64(A).contiguous(), _f64(B).contiguous()
@@ -95,6 +115,12 @@ def fmap_solve(A, B, evals1, evals2, c00, w_descr, w_lap, workspace: Optional[Wo
                                float(w_descr), float(w_lap), P, k1, k2, d, C.data_ptr(), ws.data_ptr(), ws.numel(),
                                _stream(dev))
     _lib.check(rc, "dm_fmap_solve")
+    if check or return_status:
+        st = _read_status("dm_fmap_solve_read_status", ws, dev)
+        if check:
+            _raise_if_singular(st, "dm_fmap_solve")
+        if return_status:
+            return C, st
     return C
 
 
@@ -232,7 +258,7 @@ def zoomout(C0, Phi1, Phi2, area2, nit, step=1, off1=None, off2=None, return_p2p
 
 
 def icp(C0, Phi1, Phi2, nit=10, off1=None, off2=None, return_p2p=False, flags=0, out_dtype=torch.int64,
-        workspace: Optional[Workspace] = None):
+        workspace: Optional[Workspace] = None, check: bool = True):
     """Spectral ICP (pyFM/refine/icp.py:10-107).  C0 [P,k2,k1] -> refined C (and its p2p_21)."""
     lib = _lib.load()
     dev = C0.device
@@ -258,11 +284,13 @@ def icp(C0, Phi1, Phi2, nit=10, off1=None, off2=None, return_p2p=False, flags=0,
                         Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, P, C.data_ptr(),
                         p2p.data_ptr() if p2p is not None else None, flags, ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "dm_icp")
+    if check:
+        _raise_if_singular(_read_status("dm_icp_read_status", ws, dev), "dm_icp")
     return (C, p2p) if return_p2p else C
 
 
 def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k, w_descr, w_lap, flags=0,
-                out_dtype=torch.int32, workspace: Optional[Workspace] = None):
+                out_dtype=torch.int32, workspace: Optional[Workspace] = None, check: bool = True):
     """The whole per-pair hot path in ONE library call (``dm_match_pairs``): feature NN both directions, both
     projections (reusing the feature splits of the NN stage), closed-form C, the four FM->p2p index maps.
     Returns a dict like ``pipeline.match_pairs_device``."""
@@ -295,6 +323,13 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
                                 out["p2p_21"].data_ptr(), out["p2p_12"].data_ptr(), flags, ws.data_ptr(), ws.numel(),
                                 _stream(dev))
     _lib.check(rc, "dm_match_pairs")
+    # the solve stage's status words ([singular, float64 fallbacks, -, refinement steps]) lead the workspace: a
+    # stream-ordered copy travels with the results, so that a caller that defers the check (check=False; the staged host
+    # entry does, to keep its copy/compute overlap) can still make it after its own synchronisation
+    if check:
+        _raise_if_singular(ws[:16].view(torch.int32).tolist(), "dm_match_pairs")
+    else:
+        out["status"] = ws[:16].view(torch.int32).clone()
     return out
 
 

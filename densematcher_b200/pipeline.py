@@ -109,7 +109,7 @@ def fmap_c00(batch: PairBatchDevice):
 
 def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr: float = 1e4, w_lap: float = 1e3,
                        feature_nn: bool = True, functional_map: bool = True, out_dtype=torch.int32, flags: int = 0,
-                       fused: bool = True):
+                       fused: bool = True, check: bool = True):
     """Runs the hot path on a device-resident batch.  Returns a dict of device tensors:
     ``nn_p2p_21`` / ``nn_p2p_12`` (feature NN), ``C`` [P,k,k], ``p2p_21`` / ``p2p_12`` (dense-argmax override,
     what compute_surface_map returns in slots 0/1) and ``p2p_21_adjoint`` / ``p2p_12_adjoint`` (kd-tree-equivalent
@@ -120,7 +120,8 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
         # one library call for the whole path; the projections reuse the feature splits of the NN stage
         k = batch.Phi1.shape[1] if k is None else int(k)
         return _fm.match_pairs(batch.F1, batch.F2, batch.Phi1, batch.Phi2, batch.area1, batch.area2, batch.evals1,
-                               batch.evals2, batch.o1, batch.o2, k, w_descr, w_lap, flags=flags, out_dtype=out_dtype)
+                               batch.evals2, batch.o1, batch.o2, k, w_descr, w_lap, flags=flags, out_dtype=out_dtype,
+                               check=check)
     if feature_nn:
         # for each vertex of mesh 2 its nearest feature on mesh 1 (rows), and the reverse (columns)
         (r,), (c,) = _nn.nn_argmax(batch.F2, batch.F1, batch.off2, batch.off1, row_epi=(_nn.COSINE_UNIT,),
@@ -133,7 +134,7 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
         k = batch.Phi1.shape[1] if k is None else int(k)
         A = _fm.project(batch.Phi1, batch.area1, batch.F1, batch.o1, k=k)
         B = _fm.project(batch.Phi2, batch.area2, batch.F2, batch.o2, k=k)
-        C = _fm.fmap_solve(A, B, batch.evals1[:, :k], batch.evals2[:, :k], fmap_c00(batch), w_descr, w_lap)
+        C = _fm.fmap_solve(A, B, batch.evals1[:, :k], batch.evals2[:, :k], fmap_c00(batch), w_descr, w_lap, check=check)
         res = _fm.fm_to_p2p(C, batch.Phi1[:, :k], batch.Phi2[:, :k], batch.area1, batch.o1, batch.o2,
                             flags=flags, out_dtype=out_dtype)
         out.update(C=C, p2p_21=res["dense_21"], p2p_12=res["dense_12"], p2p_21_adjoint=res["p2p_21"],
@@ -216,7 +217,7 @@ class HostStager:
         for s in (self.h2d, self.comp, self.d2h):
             s.wait_stream(cur)
         off1, off2 = np.asarray(batch.off1, np.int64), np.asarray(batch.off2, np.int64)
-        keep, outs = [], {}
+        keep, outs, n_status = [], {}, 0
         for ci, lo in enumerate(range(0, P, chunk_pairs)):
             hi = min(P, lo + chunk_pairs)
             slot = self.slots[ci % self.N_SLOTS]
@@ -250,20 +251,28 @@ class HostStager:
                 self.comp.wait_event(slot["in_ev"])
                 dev = PairBatchDevice(off1_h=_nn.Offsets(offd[0], o1h), off2_h=_nn.Offsets(offd[1], o2h),
                                       device=self.device, **dev_t)
-                res = match_pairs_device(dev, **kw)
+                res = match_pairs_device(dev, check=False, **kw)  # the status words are checked after the final wait
                 slot["done_ev"] = torch.cuda.Event()
                 slot["done_ev"].record(self.comp)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(slot["done_ev"])
+                st = res.pop("status", None)
+                if st is not None:
+                    sb = self._out_buf("_status", (P + chunk_pairs - 1) // chunk_pairs, st[None])
+                    sb[ci].copy_(st, non_blocking=True)
+                    n_status = ci + 1
                 for name, t in res.items():
                     rows, sl = ((P, rp) if name == "C" else
                                 (int(off2[-1]), r2) if "_21" in name else (int(off1[-1]), r1))
                     ob = self._out_buf(name, rows, t)
                     ob[sl].copy_(t, non_blocking=True)
                     outs[name] = rows
-            keep.append(res)  # results stay alive until the D2H copies have run
+            keep.append((res, st))  # results stay alive until the D2H copies have run
         self.d2h.synchronize()
         cur.wait_stream(self.comp)
+        if n_status and bool(self.out["_status"][:n_status, 0].any()):
+            raise _lib.DMError("match_pairs_host: a functional-map system was not positive definite (rank-deficient "
+                               "descriptors or zero weights)")
         if copy:
             return {n: self.out[n][:rows].numpy().copy() for n, rows in outs.items()}
         return {n: self.out[n][:rows].numpy() for n, rows in outs.items()}

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DM_VERSION 100
+#define DM_VERSION 200
 
 typedef void* dm_stream_t; /* a cudaStream_t */
 
@@ -166,13 +166,21 @@ int dm_project_ex(const double* Phi, int64_t ldPhi, const double* area, const fl
  * Functional-map solve: exact minimiser of  w_descr/2 |C A - B|^2 + w_lap/2 sum C^2 Delta  with column 0
  * pinned to c00 * e_0 -- the energy FunctionalMapping.fit minimises with L-BFGS-B when only the
  * descriptor and Laplacian terms are active (pyFM/functional.py:352-487, :629-660;
- * optimize/base_functions.py:31-56, :79-102, :480-763).  Rows decouple into k2 SPD systems (float64
- * Cholesky).  A [n_pairs,k1,d], B [n_pairs,k2,d], evals1 [n_pairs,k1], evals2 [n_pairs,k2], c00 [n_pairs].
+ * optimize/base_functions.py:31-56, :79-102, :480-763).  Rows decouple into k2 SPD systems: float32 Cholesky
+ * as a preconditioner + float64 iterative refinement against the float64 Gram matrix (converges to the float64
+ * solution; systems that do not contract fall back to a float64 Cholesky).  A [n_pairs,k1,d], B [n_pairs,k2,d], evals1 [n_pairs,k1], evals2 [n_pairs,k2], c00 [n_pairs].
  * ---------------------------------------------------------------------------------------- */
 size_t dm_fmap_solve_workspace_bytes(int n_pairs, int k1, int k2, int d);
 int dm_fmap_solve(const double* A, const double* B, const double* evals1, const double* evals2,
                   const double* c00, double w_descr, double w_lap, int n_pairs, int k1, int k2, int d,
                   double* C /* [n_pairs, k2, k1] */, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+/* Outcome of the last dm_fmap_solve (or dm_match_pairs) that used `workspace`; synchronises the stream.
+ *   out_h[0] != 0  a system was not positive definite even in float64 (rank-deficient descriptors with w_lap = 0,
+ *                  w_descr = 0, ...): its row of C holds NaN.  The reference's L-BFGS returns a finite map there;
+ *                  callers must treat this as an error (the Python layer raises).
+ *   out_h[1]       systems the float32 factorisation + float64 refinement could not finish and the float64 kernel redid
+ *   out_h[2]       reserved        out_h[3]  refinement steps taken in total */
+int dm_fmap_solve_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * FM -> point-to-point maps, all four index outputs from one pass over S = (Phi2 C) Phi1^T.
@@ -241,6 +249,9 @@ int dm_icp(const double* C0, int k1, int k2, int nit,
            const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
            int n_pairs, double* C_out, void* p2p_out,
            int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+/* out_h[0] != 0: the Gram matrix Phi2^T Phi2 of some pair was not positive definite (rank-deficient basis); the
+ * refined maps of the call are then meaningless.  Synchronises the stream. */
+int dm_icp_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense-map energy terms of the fit and their gradient with respect to C, without materialising the n2 x n1 map
@@ -276,6 +287,8 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
                    int n_pairs, int d, int k, double w_descr, double w_lap,
                    void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12, void* dense_21,
                    void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+/* status of the solve stage of the last dm_match_pairs on `workspace` (see dm_fmap_solve_read_status) */
+int dm_match_pairs_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Nearest (partial) isometry  C[b] = U I V^T  of  X[b] = U S V^T  (the SVD step of icp.py:39-40), float64,

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_build_info(lib):
-    assert lib.dm_version() == 100
+    assert lib.dm_version() == 200
     info = lib.dm_build_info().decode()
     assert "sm_100a" in info
 
