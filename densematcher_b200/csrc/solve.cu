@@ -710,33 +710,39 @@ __device__ __forceinline__ bool wfactor_step(const float* __restrict__ L, float*
     acc[q] = *reinterpret_cast<const float4*>(Lb + ro[q]);
   }
   const float* Lk = L + 4 * j0;  // row j0 of block column 0; block column K + 1 starts 4 (n + 1) - 16 (K + 1) floats later
-  float4 c0, c1, c2, c3, o[NQ];
-  if (J > 0) {
-    c0 = *reinterpret_cast<const float4*>(Lk), c1 = *reinterpret_cast<const float4*>(Lk + 4);
-    c2 = *reinterpret_cast<const float4*>(Lk + 8), c3 = *reinterpret_cast<const float4*>(Lk + 12);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) o[q] = *reinterpret_cast<const float4*>(Lk + ro[q]);
-  }
-  for (int K = 0; K < J; ++K) {
-    const float4 d0 = c0, d1 = c1, d2 = c2, d3 = c3;
-    float4 p[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) p[q] = o[q];
+  // two register sets (A: even K, B: odd K) alternate, so that the loads of block column K + 1 are in flight while the
+  // FMAs of block column K issue and no register moves are needed
+  float4 ca[4], oa[NQ], cb[4], ob[NQ];
+#define DM_WF_LOAD(C, O)                                                  \
+  do {                                                                    \
+    C[0] = *reinterpret_cast<const float4*>(Lk);                          \
+    C[1] = *reinterpret_cast<const float4*>(Lk + 4);                      \
+    C[2] = *reinterpret_cast<const float4*>(Lk + 8);                      \
+    C[3] = *reinterpret_cast<const float4*>(Lk + 12);                     \
+    _Pragma("unroll") for (int q = 0; q < NQ; ++q) O[q] = *reinterpret_cast<const float4*>(Lk + ro[q]); \
+  } while (0)
+#define DM_WF_FMA(C, O)                                                                                               \
+  do {                                                                                                                \
+    _Pragma("unroll") for (int q = 0; q < NQ; ++q) {                                                                  \
+      acc[q].x = fmaf(-O[q].w, C[0].w, fmaf(-O[q].z, C[0].z, fmaf(-O[q].y, C[0].y, fmaf(-O[q].x, C[0].x, acc[q].x)))); \
+      acc[q].y = fmaf(-O[q].w, C[1].w, fmaf(-O[q].z, C[1].z, fmaf(-O[q].y, C[1].y, fmaf(-O[q].x, C[1].x, acc[q].y)))); \
+      acc[q].z = fmaf(-O[q].w, C[2].w, fmaf(-O[q].z, C[2].z, fmaf(-O[q].y, C[2].y, fmaf(-O[q].x, C[2].x, acc[q].z)))); \
+      acc[q].w = fmaf(-O[q].w, C[3].w, fmaf(-O[q].z, C[3].z, fmaf(-O[q].y, C[3].y, fmaf(-O[q].x, C[3].x, acc[q].w)))); \
+    }                                                                                                                 \
+  } while (0)
+  if (J > 0) DM_WF_LOAD(ca, oa);
+  int K = 0;
+  for (; K + 2 <= J; K += 2) {
     Lk += 4 * (n + 1) - 16 * (K + 1);
-    if (K + 1 < J) {
-      c0 = *reinterpret_cast<const float4*>(Lk), c1 = *reinterpret_cast<const float4*>(Lk + 4);
-      c2 = *reinterpret_cast<const float4*>(Lk + 8), c3 = *reinterpret_cast<const float4*>(Lk + 12);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) o[q] = *reinterpret_cast<const float4*>(Lk + ro[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      acc[q].x = fmaf(-p[q].w, d0.w, fmaf(-p[q].z, d0.z, fmaf(-p[q].y, d0.y, fmaf(-p[q].x, d0.x, acc[q].x))));
-      acc[q].y = fmaf(-p[q].w, d1.w, fmaf(-p[q].z, d1.z, fmaf(-p[q].y, d1.y, fmaf(-p[q].x, d1.x, acc[q].y))));
-      acc[q].z = fmaf(-p[q].w, d2.w, fmaf(-p[q].z, d2.z, fmaf(-p[q].y, d2.y, fmaf(-p[q].x, d2.x, acc[q].z))));
-      acc[q].w = fmaf(-p[q].w, d3.w, fmaf(-p[q].z, d3.z, fmaf(-p[q].y, d3.y, fmaf(-p[q].x, d3.x, acc[q].w))));
-    }
+    DM_WF_LOAD(cb, ob);
+    DM_WF_FMA(ca, oa);
+    Lk += 4 * (n + 1) - 16 * (K + 2);
+    if (K + 2 < J) DM_WF_LOAD(ca, oa);
+    DM_WF_FMA(cb, ob);
   }
+  if (K < J) DM_WF_FMA(ca, oa);
+#undef DM_WF_LOAD
+#undef DM_WF_FMA
   if (lane < 4) *reinterpret_cast<float4*>(Dbuf + 4 * lane) = acc[0];  // rows j0 .. j0 + 3
   __syncwarp();
   bool bad = false;
@@ -883,38 +889,42 @@ __global__ void __launch_bounds__(32, 10)
   float rho_prev = 1.f;
   if (!any_bad) {
     for (; steps < kMaxRefine && !converged; ++steps) {
+      // column c + 1 of rows 1 .. n of the float64 Gram matrix (symmetric: coalesced over the lanes); lanes beyond the
+      // matrix read a clamped column and discard the result.  JU rows per slot are in flight at a time.
       double r0[RPT], r1[RPT];
-      const double* g[RPT];  // column c + 1 of rows 1 .. n (the Gram matrix is symmetric: coalesced over the lanes)
+      const double* g[RPT];
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
         r0[q] = r1[q] = 0.0;
         g[q] = aat + k1 + (min(lane + 32 * q, n - 1) + 1);
       }
-      constexpr int JU = RPT >= 4 ? 4 : 8;  // rows of the Gram matrix in flight per slot (JU * RPT loads per lane)
+      constexpr int JU = RPT >= 4 ? 4 : 8;
+      const double* gj = g[0];  // row cursor (slot 0); the other slots sit 32 q columns to the right
+      int qoff[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) qoff[q] = int(g[q] - g[0]);
       int j = 0;
       for (; j + JU <= n; j += JU) {
         double gv[RPT][JU];
 #pragma unroll
         for (int u = 0; u < JU; ++u)
 #pragma unroll
-          for (int q = 0; q < RPT; ++q)
-            if (32 * q < n) gv[q][u] = g[q][int64_t(j + u) * k1];
+          for (int q = 0; q < RPT; ++q) gv[q][u] = gj[u * k1 + qoff[q]];
+        gj += JU * k1;
 #pragma unroll
         for (int u = 0; u < JU; ++u) {
           const double xv = x64[j + u];
 #pragma unroll
-          for (int q = 0; q < RPT; ++q)
-            if (32 * q < n) {
-              if (u & 1) r1[q] = fma(gv[q][u], xv, r1[q]);
-              else r0[q] = fma(gv[q][u], xv, r0[q]);
-            }
+          for (int q = 0; q < RPT; ++q) {
+            if (u & 1) r1[q] = fma(gv[q][u], xv, r1[q]);
+            else r0[q] = fma(gv[q][u], xv, r0[q]);
+          }
         }
       }
-      for (; j < n; ++j) {
+      for (; j < n; ++j, gj += k1) {
         const double xa = x64[j];
 #pragma unroll
-        for (int q = 0; q < RPT; ++q)
-          if (32 * q < n) r0[q] = fma(g[q][int64_t(j) * k1], xa, r0[q]);
+        for (int q = 0; q < RPT; ++q) r0[q] = fma(gj[qoff[q]], xa, r0[q]);
       }
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
@@ -1043,15 +1053,21 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
   SolveLayout L = solve_carve(workspace, n_pairs, k1, k2);
   DM_CUDA_OK(cudaMemsetAsync(L.status, 0, 64 * sizeof(int), st));
   int rc;
-  GemmProblem G;
-  G.A.d = A, G.A.ld = d, G.A.batch_stride = int64_t(k1) * d, G.A.trans = 0;
-  G.B = G.A;
-  G.M = k1, G.N = k1, G.K = d, G.maxM = k1, G.maxN = k1, G.maxK = d, G.n_batch = n_pairs;
-  G.C = L.AAt, G.ldc = k1, G.c_batch_stride = int64_t(k1) * k1;
-  if ((rc = gemm64_launch(G, st))) return rc;
-  G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
-  G.M = k2, G.maxM = k2, G.C = L.BAt, G.c_batch_stride = int64_t(k2) * k1;
-  if ((rc = gemm64_launch(G, st))) return rc;
+  // profiling (DM_SOLVE_SKIP_PREP=1): reuse the Gram matrices and the packed factor input a previous identical call left
+  // in the workspace, so that the factor / refine kernel can be timed alone with CUDA events
+  const char* sp_env = getenv("DM_SOLVE_SKIP_PREP");
+  const bool skip_prep = sp_env && sp_env[0] == '1';
+  if (!skip_prep) {
+    GemmProblem G;
+    G.A.d = A, G.A.ld = d, G.A.batch_stride = int64_t(k1) * d, G.A.trans = 0;
+    G.B = G.A;
+    G.M = k1, G.N = k1, G.K = d, G.maxM = k1, G.maxN = k1, G.maxK = d, G.n_batch = n_pairs;
+    G.C = L.AAt, G.ldc = k1, G.c_batch_stride = int64_t(k1) * k1;
+    if ((rc = gemm64_launch(G, st))) return rc;
+    G.A.d = B, G.A.batch_stride = int64_t(k2) * d;
+    G.M = k2, G.maxM = k2, G.C = L.BAt, G.c_batch_stride = int64_t(k2) * k1;
+    if ((rc = gemm64_launch(G, st))) return rc;
+  }
   const int64_t n_sys = int64_t(n_pairs) * k2;
   if (n_sys > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many systems");
   const int mode = solve_mode();
@@ -1074,8 +1090,10 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
       DM_SOLVE64(2, n_sys, nullptr, nullptr);
     return DM_OK;
   }
-  solve_pack32_kernel<<<unsigned(n_pairs), 256, 0, st>>>(L.AAt, w_descr, k1, L.stride32, L.Lp32);
-  DM_LAUNCH_OK("solve_pack32_kernel");
+  if (!skip_prep) {
+    solve_pack32_kernel<<<unsigned(n_pairs), 256, 0, st>>>(L.AAt, w_descr, k1, L.stride32, L.Lp32);
+    DM_LAUNCH_OK("solve_pack32_kernel");
+  }
 #define DM_SOLVE32(T, RPT, MINB)                                                                                    \
   do {                                                                                                              \
     const size_t shm = solve32_shmem(n, T);                                                                         \

@@ -21,8 +21,8 @@ from . import _lib
 from . import fm as _fm
 from . import nn as _nn
 
-__all__ = ["PairBatchHost", "PairBatchDevice", "MeshBankDevice", "match_pairs_device", "match_pairs_host",
-           "match_bank_pairs", "intra_category_pairs", "shard_pairs", "gather_results"]
+__all__ = ["PairBatchHost", "PairBatchDevice", "MeshBankDevice", "MeshBankHost", "match_pairs_device", "match_pairs_host",
+           "match_bank_pairs", "match_bank_pairs_host", "intra_category_pairs", "shard_pairs", "gather_results"]
 
 
 @dataclass
@@ -336,6 +336,125 @@ class MeshBankDevice:
                                device=self.device, Phi1=g(self.Phi, r1), Phi2=g(self.Phi, r2),
                                evals1=g(self.evals, i1), evals2=g(self.evals, i2), area1=g(self.area, r1),
                                area2=g(self.area, r2))
+
+
+@dataclass
+class MeshBankHost:
+    """A dataset of meshes in host memory (numpy, pinned once by ``pin()``): the input of the BANK-shaped host entry
+    ``match_bank_pairs_host``.  Same fields as ``MeshBankDevice``.  ``Phi`` may be float32 (the DiffusionNet operator
+    cache stores float32 eigenvectors, diffusion_net/geometry.py:539-560): it is then uploaded as float32 -- half the
+    bytes -- and widened on the device, which is exact."""
+    F: np.ndarray            # [sum n, d] float32
+    off: np.ndarray          # [M + 1] int64
+    Phi: np.ndarray          # [sum n, K] float64 | float32
+    evals: np.ndarray        # [M, K] float64
+    area: np.ndarray         # [sum n] float64
+    _pinned: Dict[str, torch.Tensor] = field(default_factory=dict, repr=False)
+
+    FIELDS = ("F", "Phi", "evals", "area")
+
+    def pin(self):
+        for name in self.FIELDS:
+            if name not in self._pinned:
+                t = torch.from_numpy(np.ascontiguousarray(getattr(self, name)))
+                self._pinned[name] = t.pin_memory() if torch.cuda.is_available() else t
+        return self
+
+    def h2d_bytes(self):
+        return int(sum(np.asarray(getattr(self, n)).nbytes for n in self.FIELDS) + np.asarray(self.off).nbytes)
+
+
+class _BankStager:
+    """Grow-only device copies of a host bank + pinned result buffers for ``match_bank_pairs_host``."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.h2d, self.comp, self.d2h = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.dev, self.out_sets, self.calls = {}, [{}, {}], 0
+
+    def dev_buf(self, name, like):
+        b = self.dev.get(name)
+        if b is None or b.shape[0] < like.shape[0] or b.shape[1:] != like.shape[1:] or b.dtype != like.dtype:
+            b = torch.empty((int(like.shape[0] * 1.05) + 1,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.device)
+            b.record_stream(self.comp)
+            self.dev[name] = b
+        return b[:like.shape[0]]
+
+    def out_buf(self, out, name, rows, like):
+        b = out.get(name)
+        if b is None or b.shape[0] < rows or b.shape[1:] != like.shape[1:] or b.dtype != like.dtype:
+            b = torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype, pin_memory=True)
+            out[name] = b
+        return b
+
+
+_bank_stagers = {}
+
+
+def match_bank_pairs_host(bank: "MeshBankHost", src_ids, dst_ids, device=None, chunk_pairs: int = 128, copy: bool = True,
+                          **kw):
+    """Host buffers in, host results out, for DATASET-shaped work (BASELINE config 5): the meshes of ``bank`` cross
+    PCIe ONCE per call (pinned H2D of features, eigenbasis, eigenvalues, areas), the pairs are two id lists, the
+    batches are assembled on the device, and the index maps / C of every chunk are copied back while the next chunk
+    computes.  Against the pair-shaped entry (``match_pairs_host``: 9.4 MB per pair at N = 2000, d = 384, K = 100)
+    this moves 4.7 MB per MESH.  Returns a dict of numpy arrays packed in pair order (index maps local to each pair)
+    plus ``off1`` / ``off2`` (row offsets of the pairs in those arrays)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _bank_stagers.setdefault(str(device), _BankStager(device))
+    if not bank._pinned:
+        bank.pin()
+    st.calls += 1
+    out = st.out_sets[st.calls & 1]
+    src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
+    sizes = np.diff(np.asarray(bank.off, np.int64))
+    off1 = np.concatenate([[0], np.cumsum(sizes[src_ids])]).astype(np.int64)
+    off2 = np.concatenate([[0], np.cumsum(sizes[dst_ids])]).astype(np.int64)
+    P = len(src_ids)
+    cur = torch.cuda.current_stream(device)
+    for s_ in (st.h2d, st.comp, st.d2h):
+        s_.wait_stream(cur)
+    with torch.cuda.stream(st.h2d):
+        d = {n: st.dev_buf(n, bank._pinned[n]) for n in MeshBankHost.FIELDS}
+        for n in MeshBankHost.FIELDS:
+            d[n].copy_(bank._pinned[n], non_blocking=True)
+        up = torch.cuda.Event()
+        up.record(st.h2d)
+    keep, rows_of, statuses = [], {}, []
+    with torch.cuda.stream(st.comp):
+        st.comp.wait_event(up)
+        Phi = d["Phi"] if d["Phi"].dtype == torch.float64 else d["Phi"].to(torch.float64)  # exact widening on the device
+        dbank = MeshBankDevice.__new__(MeshBankDevice)
+        dbank.device, dbank.F, dbank.Phi, dbank.area, dbank.evals = device, d["F"], Phi, d["area"], d["evals"]
+        dbank.off_h = np.ascontiguousarray(np.asarray(bank.off, np.int64))
+        dbank.off = torch.from_numpy(dbank.off_h).to(device, non_blocking=True)
+        dbank.n_meshes, dbank.sizes_h = len(dbank.off_h) - 1, sizes
+    for lo in range(0, P, chunk_pairs):
+        hi = min(P, lo + chunk_pairs)
+        with torch.cuda.stream(st.comp):
+            res = match_pairs_device(dbank.assemble(src_ids[lo:hi], dst_ids[lo:hi]), check=False, **kw)
+            done = torch.cuda.Event()
+            done.record(st.comp)
+        with torch.cuda.stream(st.d2h):
+            st.d2h.wait_event(done)
+            stt = res.pop("status", None)
+            if stt is not None:
+                sb = st.out_buf(out, "_status", (P + chunk_pairs - 1) // chunk_pairs, stt[None])
+                sb[lo // chunk_pairs].copy_(stt, non_blocking=True)
+                statuses.append(lo // chunk_pairs)
+            for name, t in res.items():
+                rows, sl = ((P, slice(lo, hi)) if name == "C" else
+                            (int(off2[-1]), slice(off2[lo], off2[hi])) if "_21" in name else
+                            (int(off1[-1]), slice(off1[lo], off1[hi])))
+                st.out_buf(out, name, rows, t)[sl].copy_(t, non_blocking=True)
+                rows_of[name] = rows
+        keep.append((res, stt))
+    st.d2h.synchronize()
+    cur.wait_stream(st.comp)
+    if statuses and bool(out["_status"][: max(statuses) + 1, 0].any()):
+        raise _lib.DMError("match_bank_pairs_host: a functional-map system was not positive definite")
+    res = {n: (out[n][:r].numpy().copy() if copy else out[n][:r].numpy()) for n, r in rows_of.items()}
+    res["off1"], res["off2"] = off1, off2
+    return res
 
 
 def intra_category_pairs(categories):

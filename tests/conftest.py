@@ -56,3 +56,13 @@ def golden_zo():
 @pytest.fixture(scope="session")
 def golden_extras():
     return load_golden("extras_ico3.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_full():
+    """Reference outputs at BASELINE size (icosphere(4): 2562 vertices, K = 200, k = 100); the eigenbases are stored as
+    float32 and used as float64(float32(.)) by the reference run that minted the file and by everything under test."""
+    g = load_golden("fm_full_ico4.npz")
+    g["Phi1"] = g.pop("Phi1_f32").astype(np.float64)
+    g["Phi2"] = g.pop("Phi2_f32").astype(np.float64)
+    return g

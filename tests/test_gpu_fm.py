@@ -228,6 +228,42 @@ def test_host_entry_equals_device_pipeline():
     assert np.array_equal(ref["nn_p2p_12"][s1], orc.nn_argmax(host.F2[s2], host.F1[s1], axis=0))
 
 
+def test_full_size_reference_golden_fm_to_p2p_p2p_to_fm_icp(fm, golden_full):
+    """BASELINE size against the REFERENCE (fm_full_ico4: icosphere(4), 2562 vertices, k = 100): all four index maps of
+    FM_to_p2p + dense argmax, p2p_to_FM, and the 10-iteration icp_refine, on the reference's own inputs."""
+    g = golden_full
+    k = int(g["k"])
+    P1, P2 = dev(g["Phi1"][:, :k]), dev(g["Phi2"][:, :k])
+    C = dev(g["C_closed_form"])[None]
+    out = fm.fm_to_p2p(C, P1, P2, dev(g["area1"]))
+    assert np.array_equal(out["p2p_21"].cpu().numpy(), g["ref_p2p_21"])
+    assert np.array_equal(out["p2p_12"].cpu().numpy(), g["ref_p2p_12"])
+    assert np.array_equal(out["dense_21"].cpu().numpy(), g["ref_MI_argmax1"])
+    assert np.array_equal(out["dense_12"].cpu().numpy(), g["ref_MI_argmax0"])
+    Ca = fm.p2p_to_fm(dev(g["ref_p2p_21"]), P1, P2, dev(g["area2"]))[0].cpu().numpy()
+    assert relF(Ca, g["ref_C_area"]) < 1e-12
+    Ci, pi = fm.icp(C, P1, P2, nit=10, return_p2p=True)
+    assert relF(Ci[0].cpu().numpy(), g["ref_C_icp"]) < 1e-9
+    assert np.array_equal(pi.cpu().numpy(), g["ref_p2p_icp"])
+    # projection + closed-form solve from the stored descriptors land on the stored C (tcgen05 projection: fp32-grade)
+    A = fm.project(P1, dev(g["area1"]), dev(g["c1"]), k=k)
+    B = fm.project(P2, dev(g["area2"]), dev(g["c2"]), k=k)
+    c00 = orc.fmap_c00(g["Phi1"], g["Phi2"], g["area1"], g["area2"])
+    Cs = fm.fmap_solve(A, B, dev(g["evals1"][:k])[None], dev(g["evals2"][:k])[None], dev(np.array([c00])),
+                       float(g["w_descr"]), float(g["w_lap"]))[0].cpu().numpy()
+    assert relF(Cs, g["C_closed_form"]) < 1e-4          # north-star bar; ~1e-6 in practice
+
+
+def test_full_size_reference_golden_zoomout_ladder(fm, golden_full):
+    """ZoomOut 30 -> 200 (170 rungs) at N = 2562 against the ladder composed from the REFERENCE's knn_query / p2p_to_FM:
+    final C and final p2p; the default (float64 C) mode must reproduce them exactly."""
+    g = golden_full
+    C0 = dev(g["C_closed_form"][:30, :30].copy())[None]
+    Cz, pz = fm.zoomout(C0, dev(g["Phi1"]), dev(g["Phi2"]), dev(g["area2"]), nit=170, step=1, return_p2p=True)
+    assert relF(Cz[0].cpu().numpy(), g["ref_C_zo"]) < 1e-10
+    assert np.array_equal(pz.cpu().numpy(), g["ref_p2p_zo"])
+
+
 def test_zoomout_ladder_full_size_30_to_200():
     """BASELINE config 4 shape for one pair: N = 2000, ladder k = 30 -> 200 step 1 (170 iterations).  Every
     intermediate p2p must match for the final C to match: C within 1e-4 (in practice ~1e-10) and

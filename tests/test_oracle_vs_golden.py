@@ -235,3 +235,48 @@ def test_lap_restatement_equals_scipy_including_ties():
     inf[:, 0] = 1.0
     with pytest.raises(ValueError):
         orc.lap_shortest_augmenting_path(inf)
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE size (N = 2562, k = 100)
+def _zo_hash(p):
+    return int((p.astype(np.int64) * (np.arange(len(p)) % 1009 + 1)).sum())
+
+
+def test_full_size_fm_to_p2p_and_p2p_to_fm_equal_the_reference(golden_full):
+    g = golden_full
+    k = int(g["k"])
+    P1, P2 = g["Phi1"][:, :k], g["Phi2"][:, :k]
+    C = g["C_closed_form"]
+    # the closed-form C stored in the file is what the oracle computes from the stored inputs
+    A, B = orc.project(P1, g["area1"], g["c1"]), orc.project(P2, g["area2"], g["c2"])
+    Co = orc.fmap_solve_closed_form(A, B, g["evals1"][:k], g["evals2"][:k], orc.fmap_c00(P1, P2, g["area1"], g["area2"]),
+                                    float(g["w_descr"]), float(g["w_lap"]))
+    assert relF(Co, C) < 1e-12
+    p21, p12, MI = orc.fm_to_p2p(C, P1, P2, g["area1"])
+    assert np.array_equal(p21, g["ref_p2p_21"]) and np.array_equal(p12, g["ref_p2p_12"])
+    assert np.array_equal(MI.argmax(1), g["ref_MI_argmax1"]) and np.array_equal(MI.argmax(0), g["ref_MI_argmax0"])
+    assert abs(MI.sum() - g["ref_MI_sum"]) < 1e-8 * abs(g["ref_MI_sum"]) + 1e-8
+    assert relF(orc.p2p_to_fm(g["ref_p2p_21"], P1, P2, g["area2"]), g["ref_C_area"]) < 1e-13
+
+
+def test_full_size_icp_equals_the_reference(golden_full):
+    g = golden_full
+    k = int(g["k"])
+    C, p = orc.icp_refine(g["C_closed_form"], g["Phi1"][:, :k], g["Phi2"][:, :k], nit=10, return_p2p=True)
+    assert relF(C, g["ref_C_icp"]) < 1e-9
+    assert np.array_equal(p, g["ref_p2p_icp"])
+
+
+def test_full_size_zoomout_ladder_equals_the_reference_primitives(golden_full):
+    """30 -> 200, 170 rungs: the brute-force float64 oracle walks the same p2p sequence as the ladder composed from the
+    reference's kd-tree knn_query + p2p_to_FM, rung by rung (hashes) and at the end (C, p2p)."""
+    g = golden_full
+    C = g["C_closed_form"][:30, :30].copy()
+    P1, P2, a2 = g["Phi1"], g["Phi2"], g["area2"]
+    for it in range(170):
+        kk = C.shape[0]
+        p = orc.knn_bruteforce(P1[:, :kk] @ C.T, P2[:, :kk])   # upstream p2p_21: knn(tree = Phi1 C^T, query = Phi2)
+        assert _zo_hash(p) == int(g["ref_zo_p2p_hashes"][it]), it
+        C = orc.p2p_to_fm(p, P1[:, :kk + 1], P2[:, :kk + 1], a2)
+    assert relF(C, g["ref_C_zo"]) < 1e-12
+    assert np.array_equal(orc.knn_bruteforce(P1 @ C.T, P2), g["ref_p2p_zo"])
