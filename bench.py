@@ -371,21 +371,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    comm_stream = torch.cuda.Stream(device) if world > 1 else None
+    gather_state = {"pad": None, "bufs": [None, None], "i": 0}
+
     def gather_all(res):
-        """The path's one collective, EVERY step: all index maps and C of all shards (equal shard shapes -> one padded
-        all_gather_into_tensor per tensor; ragged shards are padded to the largest)."""
+        """The path's one collective, EVERY step: all index maps and C of all shards.  The results of a step are packed
+        into one int32 buffer (C viewed as int32 words; ragged shards padded to the largest shard, whose size is agreed
+        once) and gathered with ONE all_gather_into_tensor on a side stream, so that the NVLink transfer of step i
+        overlaps the kernels of step i + 1 (two buffer sets alternate; the timed region ends after the last gather)."""
         if world == 1:
             return
-        for name, t in res.items():
-            if name == "status" or t is None:
-                continue
-            flat = t.reshape(-1)
-            n = torch.tensor([flat.numel()], device=device)
+        parts = [t.reshape(-1).view(torch.int32) for n_, t in sorted(res.items()) if n_ != "status" and t is not None]
+        total = sum(p_.numel() for p_ in parts)
+        if gather_state["pad"] is None:
+            n = torch.tensor([total], device=device)
             dist.all_reduce(n, op=dist.ReduceOp.MAX)
-            m = int(n.item()) if cfg in ("cfg3", "cfg5") else flat.numel()
-            buf = flat if flat.numel() == m else torch.cat([flat, flat.new_zeros(m - flat.numel())])
-            out = torch.empty(world * m, dtype=flat.dtype, device=device)
-            dist.all_gather_into_tensor(out, buf.contiguous())
+            gather_state["pad"] = int(n.item())
+        m = gather_state["pad"]
+        i = gather_state["i"] = gather_state["i"] ^ 1
+        if gather_state["bufs"][i] is None:
+            gather_state["bufs"][i] = (torch.zeros(m, dtype=torch.int32, device=device),
+                                       torch.empty(world * m, dtype=torch.int32, device=device), torch.cuda.Event())
+        send, recv, done = gather_state["bufs"][i]
+        cur = torch.cuda.current_stream(device)
+        cur.wait_event(done)                       # the gather that last used this buffer set has finished
+        torch.cat(parts, out=send[:total])
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ready)
+            dist.all_gather_into_tensor(recv, send)
+            done.record(comm_stream)
+
+    def finish_gathers():
+        if world > 1:
+            torch.cuda.current_stream(device).wait_stream(comm_stream)
 
     host = dev = bank = None
     extra = {}
@@ -490,6 +510,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         res = step()
+    finish_gathers()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -658,6 +679,8 @@ def main():
     verify = None
     if cfg == "cfg4" and args.verify > 0:
         from oracle import dm_oracle as orc  # the checker, outside every timed region
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=max(1, (os.cpu_count() or 8) // world))  # the ranks check their samples side by side
         nv = min(args.verify, units_per_rank)
         pb, C0, Cz, pz = run_chunk(lo, lo + nv)
         torch.cuda.synchronize()

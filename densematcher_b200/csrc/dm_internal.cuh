@@ -208,6 +208,7 @@ struct NNProblem {
   float eps;             // relative error bound of one score: |S~ - S| <= eps |y| |x|
   int probe_skip_epilogue;  // profiling (DM_NN_PROBE=1): tcgen05 kernel runs TMA + MMA only; results are garbage
   float col_trunc;       // extra relative error of the column scores (tcgen05 engine: 5 low mantissa bits carry the row)
+  float row_trunc;       // the same for the row scores (dual-accumulator engine nn_tc2.cu: packed keys on both sides)
   int i64_out;
   int recheck_all;
   // scratch
@@ -229,7 +230,7 @@ __device__ __forceinline__ void emit_result(const NNProblem& P, const EpiDev& E,
   store_index(E.out, gpos, idx, P.i64_out != 0);
   if (P.flags == nullptr) return;
   const float thr = 2.f * P.eps * own_norm * E.G[pair] + 9.6e-7f * (fabsf(s.m1) + E.Bm[pair]);
-  const float tr = is_col ? P.col_trunc : 0.f;  // per-value truncation error of the column partials
+  const float tr = is_col ? P.col_trunc : P.row_trunc;  // per-value truncation error of packed-key partials
   const bool safe = (s.m1 - s.m2) > thr + tr * (fabsf(s.m1) + fabsf(s.m2));  // NaN -> not safe
   if (!safe || P.recheck_all) {
     const bool two = !P.recheck_all && (s.m1 - s.m3) > thr + tr * (fabsf(s.m1) + fabsf(s.m3)) && s.i2 != kNoIdx;
@@ -257,6 +258,11 @@ int nn_tc_kp(int d);
 int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, float* dbgS,
                  int64_t ldS, cudaStream_t st);
 inline bool nn_use_tc(int flags) { return !(flags & DM_ENGINE_FFMA); }
+// dual-accumulator tcgen05 engine for the four-output FM -> p2p pass with a short contraction (nn_tc2.cu)
+bool nn_tc2_applicable(int n_row, int n_col, int kp);
+int nn_tc2_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, cudaStream_t st);
+// 2-D TMA descriptor over a row-major [rows, kp] bf16 matrix with boxes of [box_rows x 64], 128-byte swizzle (nn_tc.cu)
+int tc_make_map_bf16(void* tensor_map /* CUtensorMap* */, const void* base, int64_t rows, int kp, int box_rows);
 
 // shared stages (nn_common.cu)
 struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of one side

@@ -550,6 +550,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   P.counters = L.counters;
   P.kp = nn_tc_kp(R.d);
   P.col_trunc = 0.f;
+  P.row_trunc = 0.f;
   {
     static const bool probe = [] { const char* e = getenv("DM_NN_PROBE"); return e && e[0] == '1'; }();
     P.probe_skip_epilogue = probe ? 1 : 0;
@@ -586,7 +587,10 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
       return rc;
   }
   if (splits) *splits = NNSplits{L.yh, L.yl, L.yl2, L.xh, L.xl, L.xl2, P.kp};
-  if (tc) {
+  if (tc && nn_tc2_applicable(P.n_row, P.n_col, P.kp)) {
+    P.row_trunc = P.col_trunc;  // packed keys on both sides
+    if ((rc = nn_tc2_launch(P, L.yh, L.yl, L.xh, L.xl, st))) return rc;
+  } else if (tc) {
     if ((rc = nn_tc_launch(P, L.yh, L.yl, L.xh, L.xl, nullptr, 0, st))) return rc;
   } else {
     if ((rc = nn_ffma_launch(P, st))) return rc;

@@ -581,6 +581,10 @@ int launch(const TcMaps& maps, const TcMaps& maps_pair, const NNProblem& P, cons
 
 int nn_tc_kp(int d) { return (d + TBK - 1) / TBK * TBK; }
 
+int tc_make_map_bf16(void* tensor_map, const void* base, int64_t rows, int kp, int box_rows) {
+  return make_map(static_cast<CUtensorMap*>(tensor_map), base, rows, kp, box_rows);
+}
+
 int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, float* dbgS,
                  int64_t ldS, cudaStream_t st) {
   if (P.n_pairs <= 0 || P.total_q <= 0) return DM_OK;
