@@ -283,6 +283,33 @@ int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, i
 int nn_col_finalize(const NNProblem& P, cudaStream_t st);
 int nn_recheck(const NNProblem& P, cudaStream_t st);
 
+// where nn_run carves its scratch (public so that the functional-map stages can fill parts of it themselves)
+struct NNLayout {
+  unsigned int* counters;
+  float *norm_q, *norm_db;
+  struct Arr {
+    float *sf, *bf;
+    double *sd, *bd;
+    float *G, *Bm;
+  } row[kMaxEpi], col[kMaxEpi];
+  Top3* col_partial;
+  FlagEntry* flags;
+  int64_t flag_cap;
+  uint16_t *yh, *yl, *xh, *xl;  // bf16 split operands of the tensor-core engine [rows, kp]
+  uint16_t *yl2, *xl2;          // third split (kFlagSplit3 only)
+  size_t bytes;
+};
+struct NNRequest;
+// Optional stage overrides of nn_run (the factored FM -> p2p path, embed_tc.cu): the query operand is produced by a
+// tensor-core embedding kernel instead of nn_prep_side, and float64 values are filled in on demand before the
+// re-evaluation.
+struct NNHooks {
+  void* ctx = nullptr;
+  int (*prep_y)(void* ctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) = nullptr;
+  int (*after_prep)(void* ctx, const NNLayout& L, NNProblem& P, cudaStream_t st) = nullptr;
+  int (*before_recheck)(void* ctx, const NNLayout& L, NNProblem& P, cudaStream_t st) = nullptr;
+};
+
 // full driver used by the extern "C" entry points and by the FM kernels
 struct NNRequest {
   const float* Y;
@@ -303,6 +330,7 @@ struct NNRequest {
   dm_nn_epi col[kMaxEpi];
   int n_col;
   int flags;
+  const NNHooks* hooks = nullptr;
 };
 size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                           int n_col, int flags);
@@ -323,6 +351,14 @@ int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float
                 const double* b_scale, const void* b_gather, int b_gather_i64, const int64_t* b_gather_src_off,
                 const int64_t* off, int64_t total_n, int max_n, int n_batch, int k, int d, double* out, void* ws,
                 size_t ws_bytes, cudaStream_t st, const void* const* b_presplit = nullptr);
+
+// FM -> p2p with tensor-core embeddings and on-demand float64 (embed_tc.cu); k1, k2 <= 128
+bool f2p_factored_applicable(int k1, int k2, int flags);
+size_t f2p_factored_workspace_bytes(int n_pairs, int64_t n1, int64_t n2, int max_n1, int max_n2, int k1, int k2, int flags);
+int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
+                     int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                     const double* area1, int n_pairs, void* p2p_21, void* p2p_12, void* dense_21, void* dense_12, int flags,
+                     void* ws, cudaStream_t st);
 
 int num_sms();
 // true exactly once per (call site, device): function attributes such as the dynamic shared-memory limit are

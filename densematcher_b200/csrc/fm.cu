@@ -179,7 +179,9 @@ size_t dm_fm_to_p2p_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total
   c.take<float>(size_t(total_n2) * pad4(k1));   // fp32 emb2
   c.take<float>(size_t(total_n1) * pad4(k1));   // fp32 Phi1
   c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k1, 2, 2, flags));
-  return c.bytes();
+  const size_t fact = f2p_factored_applicable(k1, k2, flags)
+                          ? f2p_factored_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k1, k2, flags) : 0;
+  return c.bytes() > fact ? c.bytes() : fact;
 }
 
 int dm_fm_to_p2p(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1,
@@ -196,6 +198,10 @@ int dm_fm_to_p2p(const double* C, int k1, int k2, const double* Phi1, int64_t ld
   if (!workspace || need > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", need);
   if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // default: embeddings on the tensor cores, float64 on demand for the re-evaluated results only (embed_tc.cu)
+  if (f2p_factored_applicable(k1, k2, flags))
+    return f2p_factored_run(C, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs,
+                            p2p_21, p2p_12, dense_21, dense_12, flags, workspace, st);
   Carver c(workspace);
   double* emb2 = c.take<double>(size_t(total_n2) * k1);
   double* emb1 = c.take<double>(size_t(total_n1) * k2);

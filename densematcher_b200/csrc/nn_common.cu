@@ -433,22 +433,6 @@ int nn_recheck(const NNProblem& P, cudaStream_t st) {
 
 // ---------------------------------------------------------------- driver
 namespace {
-struct NNLayout {
-  unsigned int* counters;
-  float *norm_q, *norm_db;
-  struct Arr {
-    float *sf, *bf;
-    double *sd, *bd;
-    float *G, *Bm;
-  } row[kMaxEpi], col[kMaxEpi];
-  Top3* col_partial;
-  FlagEntry* flags;
-  int64_t flag_cap;
-  uint16_t *yh, *yl, *xh, *xl;  // bf16 split operands of the tensor-core engine [rows, kp]
-  uint16_t *yl2, *xl2;          // third split (kFlagSplit3 only)
-  size_t bytes;
-};
-
 int pick_rt_rows(int /*d*/, int /*flags*/) { return kFfmaRowTile; }  // both engines tile 128 query rows per CTA
 
 NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
@@ -582,9 +566,12 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
     if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row,
                            L.xh, L.xl, L.xl2, P.kp, st)))
       return rc;
-    if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col,
-                           L.yh, L.yl, L.yl2, P.kp, st)))
+    if (R.hooks && R.hooks->prep_y) {
+      if ((rc = R.hooks->prep_y(R.hooks->ctx, L, P, R, st))) return rc;
+    } else if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col,
+                                  L.yh, L.yl, L.yl2, P.kp, st)))
       return rc;
+    if (R.hooks && R.hooks->after_prep && (rc = R.hooks->after_prep(R.hooks->ctx, L, P, st))) return rc;
   }
   if (splits) *splits = NNSplits{L.yh, L.yl, L.yl2, L.xh, L.xl, L.xl2, P.kp};
   if (tc && nn_tc2_applicable(P.n_row, P.n_col, P.kp)) {
@@ -597,6 +584,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   }
   if (R.flags & DM_SKIP_FINISH) return DM_OK;
   if ((rc = nn_col_finalize(P, st))) return rc;
+  if (R.hooks && R.hooks->before_recheck && P.flags && (rc = R.hooks->before_recheck(R.hooks->ctx, L, P, st))) return rc;
   if ((rc = nn_recheck(P, st))) return rc;
   return DM_OK;
 }

@@ -72,10 +72,19 @@ struct T2Maps {
 
 constexpr float kMaskedScore = -3.0e38f;  // finite: packed keys must not become NaN
 
+// key = (score bits & mask) | column as ONE LOP3 (LUT 0xEA = (a & b) | c).  `mask` (= ~31) must sit in a register the
+// assembler cannot fold -- it arrives as a kernel parameter -- otherwise the two immediates cost two ALU-pipe
+// instructions, and the ALU pipe (min / max / logic) is what bounds this kernel (ncu: 81 % busy, FMA pipe 10 %).
+__device__ __forceinline__ float t2_key(float w, uint32_t mask, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(w)), "r"(mask), "r"(c));
+  return __uint_as_float(r);
+}
+
 // Top-2 of one 32-column chunk on packed keys.  w_c = v_c * s_c + b_c (IDENT: w_c = v_c); key = (w & ~31) | c.
 template <bool IDENT>
 __device__ __forceinline__ void t2_chunk_top2(const float (&v)[32], const float* __restrict__ sc,
-                                              const float* __restrict__ bi, float& k1, float& k2) {
+                                              const float* __restrict__ bi, uint32_t mask, float& k1, float& k2) {
   k1 = k2 = -INFINITY;
 #pragma unroll
   for (int c4 = 0; c4 < T2_CH / 4; ++c4) {
@@ -84,10 +93,8 @@ __device__ __forceinline__ void t2_chunk_top2(const float (&v)[32], const float*
       const float4 s = *reinterpret_cast<const float4*>(sc + 4 * c4), b = *reinterpret_cast<const float4*>(bi + 4 * c4);
       w0 = fmaf(w0, s.x, b.x), w1 = fmaf(w1, s.y, b.y), w2 = fmaf(w2, s.z, b.z), w3 = fmaf(w3, s.w, b.w);
     }
-    const float ka = __int_as_float((__float_as_int(w0) & ~31) | (4 * c4 + 0));
-    const float kb = __int_as_float((__float_as_int(w1) & ~31) | (4 * c4 + 1));
-    const float kc = __int_as_float((__float_as_int(w2) & ~31) | (4 * c4 + 2));
-    const float kd = __int_as_float((__float_as_int(w3) & ~31) | (4 * c4 + 3));
+    const float ka = t2_key(w0, mask, 4 * c4 + 0), kb = t2_key(w1, mask, 4 * c4 + 1);
+    const float kc = t2_key(w2, mask, 4 * c4 + 2), kd = t2_key(w3, mask, 4 * c4 + 3);
     const float h1 = fmaxf(ka, kb), l1 = fminf(ka, kb), h2 = fmaxf(kc, kd), l2 = fminf(kc, kd);
     const float t1 = fmaxf(h1, h2);
     const float t2 = fmaxf(fmaxf(fminf(h1, h2), l1), l2);
@@ -96,14 +103,50 @@ __device__ __forceinline__ void t2_chunk_top2(const float (&v)[32], const float*
   }
 }
 
-__device__ __forceinline__ void t2_merge_chunk(Top3& st, float k1, float k2, int base) {
+// Third-largest key of a chunk, given its two leaders (only needed in the rare case below)
+template <bool IDENT>
+__device__ __forceinline__ float t2_chunk_third(const float (&v)[32], const float* __restrict__ sc, const float* __restrict__ bi,
+                                             uint32_t mask, float k1, float k2) {
+  float k3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < T2_CH; ++c) {
+    const float w = IDENT ? v[c] : fmaf(v[c], sc[c], bi[c]);
+    const float k = t2_key(w, mask, c);
+    k3 = fmaxf(k3, (k == k1 || k == k2) ? -INFINITY : k);
+  }
+  return k3;
+}
+
+// Merges the chunk's leaders into the running (best, runner-up, third).  Everything else of the chunk is <= its
+// runner-up m2, which serves as the chunk's (conservative) third value.  That bound is loose in exactly one case: the
+// chunk's two leaders are also the two running leaders -- then third == runner-up and a near tie could only be settled
+// by a scan of ALL candidates.  In that case (rare after the first few chunks, warp-uniform test) the chunk's true third
+// is computed from the scores still in registers.
+template <bool IDENT>
+__device__ __forceinline__ void t2_merge_chunk(Top3& st, float k1, float k2, int base, const float (&v)[32],
+                                               const float* __restrict__ sc, const float* __restrict__ bi, uint32_t mask,
+                                               float thr_base) {
   const float m1 = __int_as_float(__float_as_int(k1) & ~31), m2 = __int_as_float(__float_as_int(k2) & ~31);
-  // everything else of the chunk is <= m2: conservative third value
-  top3_merge(st, m1, base + (__float_as_int(k1) & 31), m2, base + (__float_as_int(k2) & 31), m2);
+  const int i1 = base + (__float_as_int(k1) & 31), i2 = base + (__float_as_int(k2) & 31);
+  // ... and it only matters when the chunk's two leaders are close enough to be re-evaluated at all (the window of
+  // emit_result, with slack): a fraction of a percent of the (row, chunk) pairs, so the common path is the plain merge
+  const bool near = !((m1 - m2) > 1.25f * thr_base + 8.0e-6f * (fabsf(m1) + fabsf(m2)));
+  if (!__any_sync(0xffffffffu, near)) {
+    top3_merge(st, m1, i1, m2, i2, m2);
+    return;
+  }
+  const Top3 prev = st;
+  top3_merge(st, m1, i1, m2, i2, m2);
+  if (near && ((st.i1 == i1 && st.i2 == i2) || (st.i1 == i2 && st.i2 == i1))) {
+    const float k3 = t2_chunk_third<IDENT>(v, sc, bi, mask, k1, k2);
+    st = prev;
+    top3_merge(st, m1, i1, m2, i2, __int_as_float(__float_as_int(k3) & ~31));
+  }
 }
 
 template <int KC>  // 64-wide K chunks: kp = 64 KC
-__global__ void __launch_bounds__(T2_THREADS, 1) f2p_tc_kernel(const __grid_constant__ T2Maps maps, const NNProblem P) {
+__global__ void __launch_bounds__(T2_THREADS, 1)
+    f2p_tc_kernel(const __grid_constant__ T2Maps maps, const NNProblem P, const uint32_t keymask) {
   constexpr uint32_t OPB = t2_operand_bytes(KC);
   const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
   const int64_t q0 = P.q_off[p];
@@ -228,6 +271,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) f2p_tc_kernel(const __grid_cons
     }
     const bool full_rows = row0 + T2_ROWS <= nq;
     Top3 st = top3_init();
+    // the re-evaluation window of this thread's result without its score-dependent part (emit_result)
+    const float gE = E.G[p], bE = 9.6e-7f * E.Bm[p];
+    float thr_base = on_s ? 2.f * P.eps * ((row0 + trow < nq) ? P.norm_q[q0 + row0 + trow] : 0.f) * gE + bE : 0.f;
 
     for (int ct = 0; ct < n_ct; ++ct) {
       const int acc = ct & 1, col0 = ct * T2_TN;
@@ -246,6 +292,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) f2p_tc_kernel(const __grid_cons
       } else {
         sc = csb + (e * 2 + 0) * T2_ROWS, bi = csb + (e * 2 + 1) * T2_ROWS;
         st = top3_init();
+        const int j = col0 + trow;
+        thr_base = 2.f * P.eps * (j < nd ? P.norm_db[d0 + j] : 0.f) * gE + bE;
       }
       const bool plain = ident && (on_s ? full_cols : full_rows);  // no scale / bias and nothing to mask
 
@@ -259,11 +307,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) f2p_tc_kernel(const __grid_cons
         float v[32];
         tmem_ld32(taddr + ch * T2_CH, v);
         float k1, k2;
-        if (plain)
-          t2_chunk_top2<true>(v, nullptr, nullptr, k1, k2);
-        else
-          t2_chunk_top2<false>(v, sc + ch * T2_CH, bi + ch * T2_CH, k1, k2);
-        t2_merge_chunk(st, k1, k2, base0 + ch * T2_CH);
+        if (plain) {
+          t2_chunk_top2<true>(v, nullptr, nullptr, keymask, k1, k2);
+          t2_merge_chunk<true>(st, k1, k2, base0 + ch * T2_CH, v, nullptr, nullptr, keymask, thr_base);
+        } else {
+          t2_chunk_top2<false>(v, sc + ch * T2_CH, bi + ch * T2_CH, keymask, k1, k2);
+          t2_merge_chunk<false>(st, k1, k2, base0 + ch * T2_CH, v, sc + ch * T2_CH, bi + ch * T2_CH, keymask, thr_base);
+        }
       }
       tc_fence_before();
       if (!on_s) {
@@ -295,7 +345,7 @@ int t2_launch(const T2Maps& maps, const NNProblem& P, cudaStream_t st) {
     DM_CUDA_OK(cudaFuncSetAttribute(f2p_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t2_smem_bytes(KC))));
   const int64_t nblk = int64_t(P.n_pairs) * P.max_rt;
   if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles (%lld)", (long long)nblk);
-  f2p_tc_kernel<KC><<<unsigned(nblk), T2_THREADS, t2_smem_bytes(KC), st>>>(maps, P);
+  f2p_tc_kernel<KC><<<unsigned(nblk), T2_THREADS, t2_smem_bytes(KC), st>>>(maps, P, ~uint32_t(T2_CH - 1));
   DM_LAUNCH_OK("f2p_tc_kernel");
   return DM_OK;
 }
