@@ -55,6 +55,8 @@ SIGNATURES = {
     "dm_nn_debug_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_nn_debug_scores_f32": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_vp,
                                        c_sz, c_vp]),
+    "dm_knn_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "dm_knn_f64": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "dm_match_dist_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
     "dm_project_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_int, c_int]),
     "dm_project": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp,
@@ -76,6 +78,8 @@ SIGNATURES = {
     "dm_p2p_to_fm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_p2p_to_fm": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp,
                              c_int, c_vp, c_sz, c_vp]),
+    "dm_spd_solve_workspace_bytes": (c_sz, [c_int, c_int]),
+    "dm_spd_solve": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "dm_zoomout_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int]),
     "dm_zoomout": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64,

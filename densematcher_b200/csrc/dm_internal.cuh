@@ -331,6 +331,10 @@ struct NNRequest {
   int n_col;
   int flags;
   const NNHooks* hooks = nullptr;
+  // ladders (ZoomOut / ICP) search the same static query matrix at every rung: its split may be prepared once with
+  // y_prep_d >= d columns (columns beyond d meet zeros on the database side) and reused while skip_prep_y is set
+  int y_prep_d = 0;
+  int skip_prep_y = 0;
 };
 size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                           int n_col, int flags);

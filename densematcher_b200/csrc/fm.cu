@@ -33,7 +33,7 @@ int neg_half_sqnorm(const double* M, int64_t ld, int64_t rows, int d, double* ou
 int pad4(int x) { return (x + 3) / 4 * 4; }
 
 // ---- p2p -> FM (internal, with split-K workspace)
-constexpr int kP2PChunk = 256;
+static const int kP2PChunk = [] { const char* e = getenv("DM_P2P_CHUNK"); return e ? atoi(e) : 256; }();
 size_t p2p_to_fm_ws(int n_pairs, int max_n2, int k1, int k2) {
   const int ks = (max_n2 + kP2PChunk - 1) / kP2PChunk;
   Carver c(nullptr);
@@ -82,7 +82,7 @@ struct P2P21Scratch {
 int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
               int max_n1, const double* Phi2, int64_t ld2, const float* Phi2f, int ldPhi2f, const int64_t* off2,
               int64_t total_n2, int max_n2, int n_pairs, void* p2p_out, int flags, const P2P21Scratch& S,
-              cudaStream_t st) {
+              cudaStream_t st, int* y_kp_state = nullptr) {
   int rc;
   GemmProblem G;
   G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
@@ -102,6 +102,14 @@ int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, 
   R.n_row = 1, R.n_col = 0;
   R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NEG_HALF_SQNORM, nullptr, nullptr, p2p_out};
   R.flags = flags;
+  if (tc && y_kp_state) {
+    // the query matrix Phi2 is the same at every rung: split it once per padded width (64 / 128 / 192 / 256), with all
+    // the columns of that width (those beyond k2 meet the zero padding of the database side)
+    const int kp = nn_tc_kp(k2);
+    R.y_prep_d = int(ld2 < kp ? ld2 : kp);
+    R.skip_prep_y = (*y_kp_state == kp);
+    *y_kp_state = kp;
+  }
   return nn_run(R, S.nn_ws, S.nn_ws_bytes, st);
 }
 
@@ -351,10 +359,11 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
   const double* Ccur = C0;
   int k1 = k1_0, k2 = k2_0;
+  int y_kp = -1;  // padded width for which the split of Phi2 in the workspace is valid
   for (int it = 0; it < nit; ++it) {
     // the fp32 copy of emb1 is re-made with the current width; stale columns beyond k2 are zeroed by cvt
     if ((rc = p2p21_run(Ccur, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2, total_n2,
-                        max_n2, n_pairs, p2p, flags, S, st)))
+                        max_n2, n_pairs, p2p, flags, S, st, &y_kp)))
       return rc;
     double* Cnext = (it == nit - 1) ? C_out : Cbuf[it & 1];
     if (fast_fm) {
@@ -372,7 +381,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
     DM_CUDA_OK(cudaMemcpyAsync(C_out, C0, sizeof(double) * size_t(n_pairs) * k1 * k2, cudaMemcpyDeviceToDevice, st));
   if (p2p_out) {
     if ((rc = p2p21_run(nit == 0 ? C0 : C_out, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2,
-                        total_n2, max_n2, n_pairs, p2p_out, flags, S, st)))
+                        total_n2, max_n2, n_pairs, p2p_out, flags, S, st, &y_kp)))
       return rc;
   }
   return DM_OK;
@@ -455,10 +464,11 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
   }
   if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2, L.Phi2f, L.S.ldf, st))) return rc;
   const double* Ccur = C0;
+  int y_kp = -1;  // the split of the static query matrix Phi2 is made once
   for (int it = 0; it < nit; ++it) {
     // p = p2p_21(C)  (icp.py:37; the other two outputs of FM_to_p2p are discarded there)
     if ((rc = p2p21_run(Ccur, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, L.Phi2f, L.S.ldf, off2, total_n2,
-                        max_n2, n_pairs, L.p2p, flags, L.S, st)))
+                        max_n2, n_pairs, L.p2p, flags, L.S, st, &y_kp)))
       return rc;
     if ((rc = p2p_to_fm_run(L.p2p, i64, Phi1, ld1, off1, L.Phi2p, k2, off2, max_n2, nullptr, n_pairs, k1, k2, L.X,
                             L.pf_ws, st)))
@@ -471,7 +481,7 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
     DM_CUDA_OK(cudaMemcpyAsync(C_out, C0, sizeof(double) * size_t(n_pairs) * k1 * k2, cudaMemcpyDeviceToDevice, st));
   if (p2p_out) {
     if ((rc = p2p21_run(nit == 0 ? C0 : C_out, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, L.Phi2f, L.S.ldf,
-                        off2, total_n2, max_n2, n_pairs, p2p_out, flags, L.S, st)))
+                        off2, total_n2, max_n2, n_pairs, p2p_out, flags, L.S, st, &y_kp)))
       return rc;
   }
   return DM_OK;
@@ -613,6 +623,39 @@ int dm_icp_read_status(const void* workspace, int* out_h, dm_stream_t stream) {
   DM_CUDA_OK(cudaMemcpyAsync(out_h, workspace, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DM_CUDA_OK(cudaStreamSynchronize(st));
   return DM_OK;
+}
+
+// ------------------------------------------------------------------ batched SPD solve (normal equations of the lstsq branch)
+size_t dm_spd_solve_workspace_bytes(int n_batch, int n) {
+  if (n_batch < 0 || n <= 0) return 0;
+  Carver c(nullptr);
+  c.take<int>(64);
+  c.take<double>(size_t(n_batch) * n * n);
+  c.take<double>(spd_inverse_scratch_doubles(n) * size_t(n_batch));
+  return c.bytes();
+}
+
+int dm_spd_solve(const double* G, const double* B, int n, int m, int n_batch, double* X, void* workspace,
+                 size_t workspace_bytes, dm_stream_t stream) {
+  if (n_batch < 0 || n <= 0 || m <= 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_batch == 0) return DM_OK;
+  if (!G || !B || !X) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (!workspace || dm_spd_solve_workspace_bytes(n_batch, n) > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  int* status = c.take<int>(64);  // first: dm_icp_read_status reads it
+  double* Ginv = c.take<double>(size_t(n_batch) * n * n);
+  double* lin = c.take<double>(spd_inverse_scratch_doubles(n) * size_t(n_batch));
+  DM_CUDA_OK(cudaMemsetAsync(status, 0, 64 * sizeof(int), st));
+  int rc;
+  if ((rc = spd_inverse_launch(G, Ginv, n, n_batch, lin, status, st))) return rc;
+  GemmProblem P;
+  P.A.d = Ginv, P.A.ld = n, P.A.batch_stride = int64_t(n) * n, P.A.rows = n, P.A.trans = 0;
+  P.B.d = B, P.B.ld = m, P.B.batch_stride = int64_t(n) * m, P.B.rows = n, P.B.trans = 1;
+  P.M = n, P.N = m, P.K = n, P.maxM = n, P.maxN = m, P.maxK = n, P.n_batch = n_batch;
+  P.C = X, P.ldc = m, P.c_batch_stride = int64_t(n) * m;
+  return gemm64_launch(P, st);
 }
 
 // ------------------------------------------------------------------ polar factor (the SVD step of ICP, exposed)

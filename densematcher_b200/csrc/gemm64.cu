@@ -214,6 +214,9 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
   const int g = lane >> 2, t4 = lane & 3;  // fragment coordinates: A[row g][k t4], B[k t4][col g], C[row g][col 2 t4 + {0,1}]
 
+  // 8 x 8 output blocks of this warp that lie inside the matrix (warp-uniform)
+  const int na = max(0, min(4, (M - (m0 + wm) + 7) / 8)), nc = max(0, min(NT8, (N - (n0 + wn) + 7) / 8));
+
   double acc[4][NT8][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -238,20 +241,42 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
     }
     const double* as = As[buf] + wm + g;
     const double* bs = Bs[buf] + wn + g;
+    if (na == 4 && nc == NT8) {
 #pragma unroll
-    for (int k4 = 0; k4 < TK; k4 += 4) {
-      double av[4], bv[NT8];
+      for (int k4 = 0; k4 < TK; k4 += 4) {
+        double av[4], bv[NT8];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = as[(k4 + t4) * LDT + 8 * a];
+        for (int a = 0; a < 4; ++a) av[a] = as[(k4 + t4) * LDT + 8 * a];
 #pragma unroll
-      for (int c = 0; c < NT8; ++c) bv[c] = bs[(k4 + t4) * LDT + 8 * c];
+        for (int c = 0; c < NT8; ++c) bv[c] = bs[(k4 + t4) * LDT + 8 * c];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < NT8; ++c)
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                       : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
-                       : "d"(av[a]), "d"(bv[c]));
+          for (int c = 0; c < NT8; ++c)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
+                         : "d"(av[a]), "d"(bv[c]));
+      }
+    } else if (na > 0 && nc > 0) {
+      // ragged edge of the output (the ZoomOut ladder's (k + 1) x (k + 1) maps: k + 1 is rarely a multiple of the tile):
+      // only the 8 x 8 blocks that hold output issue MMAs (warp-uniform), so the FP64 tensor pipe is not spent on padding
+#pragma unroll
+      for (int k4 = 0; k4 < TK; k4 += 4) {
+        double av[4], bv[NT8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = as[(k4 + t4) * LDT + 8 * a];
+#pragma unroll
+        for (int c = 0; c < NT8; ++c) bv[c] = bs[(k4 + t4) * LDT + 8 * c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (a < na)
+#pragma unroll
+            for (int c = 0; c < NT8; ++c)
+              if (c < nc)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
+                             : "d"(av[a]), "d"(bv[c]));
+      }
     }
     if (more) {
       la.stash(As[buf ^ 1], ra);
@@ -463,7 +488,10 @@ int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
   // narrow tiles when the contraction is short (latency-bound) or when they waste less of the N range
   const int waste128 = (P.maxN + 127) / 128 * 128 - P.maxN, waste64 = (P.maxN + 63) / 64 * 64 - P.maxN;
   const int kper = P.ksplit > 1 ? P.kchunk : P.maxK;
-  const bool narrow = kper <= 512 || waste64 < waste128;
+  static const int force_wide = [] { const char* e = getenv("DM_GEMM_WIDE"); return e ? atoi(e) : 0; }();
+  bool narrow = kper <= 512 || waste64 < waste128;
+  if (force_wide == 1 && P.maxN > 64) narrow = false;
+  if (force_wide == 2 && P.maxN > 96) narrow = waste64 + 32 < waste128;
   const int tnw = narrow ? 64 : 128;
   const int tiles_m = (P.maxM + TM - 1) / TM, tiles_n = (P.maxN + tnw - 1) / tnw;
   const int64_t nblk = int64_t(P.n_batch) * (P.ksplit > 0 ? P.ksplit : 1) * tiles_m * tiles_n;

@@ -220,7 +220,6 @@ __global__ void __launch_bounds__(kLapThreads, MINB) lap_kernel(LapArgs A) {
       // remaining[index] = remaining[--num_remaining]: the column at the last position moves to `index`; the chosen
       // column leaves the list
       const unsigned last_u = unsigned(nc - nrem), last_a = 0x80000000u | unsigned(nrem - 1);
-#pragma unroll
       const unsigned moved_u = unsigned(nc - 1) - index, moved_a = 0x80000000u | index;
       const int mstar = (jstar - tid) / kLapThreads;  // own slot of the chosen column, if it is one of this thread's
       const bool mine = jstar - tid == mstar * kLapThreads;

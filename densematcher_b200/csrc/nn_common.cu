@@ -568,8 +568,9 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
       return rc;
     if (R.hooks && R.hooks->prep_y) {
       if ((rc = R.hooks->prep_y(R.hooks->ctx, L, P, R, st))) return rc;
-    } else if ((rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q, R.d, L.norm_q, cs, R.n_col,
-                                  L.yh, L.yl, L.yl2, P.kp, st)))
+    } else if (!R.skip_prep_y &&
+               (rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q,
+                                  R.y_prep_d > R.d ? R.y_prep_d : R.d, L.norm_q, cs, R.n_col, L.yh, L.yl, L.yl2, P.kp, st)))
       return rc;
     if (R.hooks && R.hooks->after_prep && (rc = R.hooks->after_prep(R.hooks->ctx, L, P, st))) return rc;
   }

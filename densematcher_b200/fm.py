@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
-__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "zoomout", "icp", "polar_factor",
+__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "spd_solve", "zoomout", "icp", "polar_factor",
            "match_pairs", "dense_energy", "DENSE_TERMS", "PairBatch"]
 
 
@@ -78,6 +78,8 @@ def project(Phi, area, F, off=None, k=None, workspace: Optional[Workspace] = Non
     k = Phi.shape[1] if k is None else int(k)
     if k > Phi.shape[1]:
         raise ValueError("not enough eigenvectors")
+    if F.shape[0] != total or area.numel() != total:
+        raise ValueError(f"Phi has {total} rows but F has {F.shape[0]} and area {area.numel()}")
     d = F.shape[1]
     od, oh, max_n = _offsets(off, total, dev)
     n_m = len(oh) - 1
@@ -186,7 +188,7 @@ def mapped_indicator(C, Phi1, Phi2, area1):
 
 
 def p2p_to_fm(p2p_21, Phi1, Phi2, area2=None, off1=None, off2=None, k1=None, k2=None,
-              workspace: Optional[Workspace] = None):
+              workspace: Optional[Workspace] = None, check_indices: bool = True):
     """C[p] = Phi2[:, :k2]^T (area2 * Phi1[p2p_21, :k1]) -> [P,k2,k1] float64 (convert.py:39-48).
     ``area2=None`` gives the un-weighted product Phi2^T Phi1[p] (the normal-equation right-hand side)."""
     lib = _lib.load()
@@ -203,6 +205,13 @@ def p2p_to_fm(p2p_21, Phi1, Phi2, area2=None, off1=None, off2=None, k1=None, k2=
     p2p_21 = p2p_21.contiguous()
     if p2p_21.numel() != n2:
         raise ValueError("p2p_21 must have one entry per target vertex")
+    if len(o1h) != len(o2h):
+        raise ValueError("off1 and off2 describe different numbers of pairs")
+    if check_indices and n2 > 0:
+        # indices are local to each pair: 0 <= p < rows of the pair's source mesh (numpy would raise IndexError)
+        n1_of = torch.repeat_interleave(torch.as_tensor(np.diff(o1h), device=dev), torch.as_tensor(np.diff(o2h), device=dev))
+        if bool(((p2p_21 < 0) | (p2p_21 >= n1_of)).any()):
+            raise IndexError("p2p_21 holds an index outside its source mesh")
     flags = _lib.DM_I64_OUT if p2p_21.dtype == torch.int64 else 0
     a2 = _f64(area2).contiguous() if area2 is not None else None
     C = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
@@ -214,6 +223,29 @@ def p2p_to_fm(p2p_21, Phi1, Phi2, area2=None, off1=None, off2=None, k1=None, k2=
                               C.data_ptr(), flags, ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "dm_p2p_to_fm")
     return C
+
+
+def spd_solve(G, B, check: bool = True):
+    """X[b] = G[b]^-1 B[b] for symmetric positive definite G [P, n, n], B [P, n, m] (float64): the normal equations of the
+    least-squares branch of p2p_to_FM (convert.py:51)."""
+    lib = _lib.load()
+    G, B = _f64(G), _f64(B)
+    if G.dim() == 2:
+        G, B = G[None], B[None]
+    G, B = G.contiguous(), B.contiguous()
+    P, n, m = B.shape
+    if G.shape != (P, n, n):
+        raise ValueError("shape mismatch in spd_solve")
+    dev = G.device
+    X = torch.empty_like(B)
+    need = lib.dm_spd_solve_workspace_bytes(P, n)
+    ws = default_workspace(dev, "fm").get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_spd_solve(G.data_ptr(), B.data_ptr(), n, m, P, X.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_spd_solve")
+    if check:
+        _raise_if_singular(_read_status("dm_icp_read_status", ws, dev), "dm_spd_solve")
+    return X
 
 
 def zoomout(C0, Phi1, Phi2, area2, nit, step=1, off1=None, off2=None, return_p2p=False, flags=0,
@@ -273,6 +305,8 @@ def icp(C0, Phi1, Phi2, nit=10, off1=None, off2=None, return_p2p=False, flags=0,
         raise AssertionError("At least k eigenvectors should be provided")
     o1, o1h, max1 = _offsets(off1, n1, dev)
     o2, o2h, max2 = _offsets(off2, n2, dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P:
+        raise ValueError("offsets / batch mismatch")
     if out_dtype == torch.int64:
         flags |= _lib.DM_I64_OUT
     C = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)
@@ -307,6 +341,11 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
     o1, o1h, max1 = _offsets(off1, n1, dev)
     o2, o2h, max2 = _offsets(off2, n2, dev)
     P = len(o1h) - 1
+    if len(o2h) - 1 != P:
+        raise ValueError("off1 and off2 describe different numbers of pairs")
+    if (Phi1.shape[0] != n1 or Phi2.shape[0] != n2 or area1.numel() != n1 or area2.numel() != n2 or F2.shape[1] != d
+            or evals1.shape[0] != P or evals2.shape[0] != P):
+        raise ValueError("match_pairs: operand shapes do not agree (rows of F / Phi / area per side, one eigenvalue row per pair)")
     if out_dtype == torch.int64:
         flags |= _lib.DM_I64_OUT
     mk = lambda n: torch.empty(n, dtype=out_dtype, device=dev)
@@ -352,6 +391,8 @@ def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace:
     n1, n2 = Phi1.shape[0], Phi2.shape[0]
     o1, o1h, max1 = _offsets(off1, n1, dev)
     o2, o2h, max2 = _offsets(off2, n2, dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P or area1.numel() != n1:
+        raise ValueError("offsets / batch mismatch")
     w = [float(weights.get(t, 0.0)) for t in DENSE_TERMS]
     energy = torch.zeros(P, 5, dtype=torch.float64, device=dev)
     grad = torch.empty(P, k2, k1, dtype=torch.float64, device=dev)

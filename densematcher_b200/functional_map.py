@@ -48,7 +48,7 @@ def compute_surface_map(mesh1_t, mesh2_t, c1, c2, n_ev=50, compute_extra=False, 
     model = FunctionalMapping(mesh1, mesh2, partial=False, optimizer=optimizer)
     model.preprocess(n_ev=(n_ev, n_ev), n_descr=c1.shape[1], landmarks=None, descr1=to_np(c1), descr2=to_np(c2),
                      subsample_step=1)
-    model.fit(**(fit_params or {}))
+    model.fit(**fit_params)  # fit_params=None raises TypeError like the reference (functional_map.py:47)
 
     def assign():
         if hungarian == "scipy":                              # host solver on the materialised indicator

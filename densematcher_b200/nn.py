@@ -208,3 +208,23 @@ def match_dist(Y, X, idx):
                                    Y.shape[1], out.data_ptr(), flags, torch.cuda.current_stream(Y.device).cuda_stream)
     _lib.check(rc, "dm_match_dist_f32")
     return out
+
+
+def knn_topk(Y: torch.Tensor, X: torch.Tensor, k: int):
+    """(dist [nq, k] float64, idx [nq, k] int64): the k nearest rows of X for every row of Y, ordered by (distance,
+    index) -- ``knn_query(..., k > 1)`` of the reference (nn_utils.py:4-38).  float64 CUDA tensors, one pair."""
+    lib = _lib.load()
+    if not (Y.is_cuda and X.is_cuda):
+        raise ValueError("knn_topk needs CUDA tensors (there is no CPU path)")
+    Y, X = Y.to(torch.float64).contiguous(), X.to(torch.float64).contiguous()
+    nq, d = Y.shape
+    ndb = X.shape[0]
+    idx = torch.empty(nq, k, dtype=torch.int64, device=Y.device)
+    dist = torch.empty(nq, k, dtype=torch.float64, device=Y.device)
+    need = lib.dm_knn_workspace_bytes(nq, ndb, d, k)
+    ws = default_workspace(Y.device, "knn").get(max(need, 256))
+    with torch.cuda.device(Y.device):
+        rc = lib.dm_knn_f64(Y.data_ptr(), Y.stride(0), nq, X.data_ptr(), X.stride(0), ndb, d, int(k), idx.data_ptr(),
+                            dist.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(Y.device).cuda_stream)
+    _lib.check(rc, "dm_knn_f64")
+    return dist, idx

@@ -142,13 +142,18 @@ def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr:
     return out
 
 
-def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: int = 256):
+def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: Optional[int] = None, max_bytes: int = 4 << 30):
     """Hungarian assignment of every pair's mapped indicator  Phi2 C Phi1^T A1  (functional_map.py:57,78), maximised,
-    for a device-resident batch: the float64 (n2, n1) matrices of ``chunk_pairs`` pairs are materialised at a time (more
-    problems than SMs let two of them share an SM)
-    (32 MB each at N = 2000) and solved together by ``dm_lap_solve``, one CTA per pair.  Returns a list of
-    ``(row_ind, col_ind)`` numpy pairs identical to scipy's."""
+    for a device-resident batch.  The float64 (n2, n1) matrices (32 MB each at N = 2000) are materialised one chunk of
+    pairs at a time -- ``chunk_pairs`` pairs, by default as many as fit in ``max_bytes`` (tall problems need a transposed
+    copy as well), at least one -- and each chunk is solved by one ``dm_lap_solve`` launch, one CTA per pair (more
+    problems than SMs let two of them share an SM).  Returns a list of ``(row_ind, col_ind)`` numpy pairs identical to
+    scipy's.  ``dm_lap_solve`` handles up to 8192 rows / columns per problem."""
     k2, k1 = C.shape[1], C.shape[2]
+    n1s, n2s = np.diff(batch.off1_h), np.diff(batch.off2_h)
+    if chunk_pairs is None:
+        per_pair = float(np.max(n1s * n2s)) * 8.0 * 2.0 if len(n1s) else 1.0
+        chunk_pairs = int(max(1, min(256, max_bytes // max(per_pair, 1.0))))
     res = []
     for lo in range(0, batch.n_pairs, chunk_pairs):
         mats = []
@@ -314,24 +319,28 @@ class MeshBankDevice:
         self.sizes_h = np.diff(self.off_h)
 
     def _rows(self, mesh_ids_h):
-        """global row indices of the listed meshes, concatenated (device int64) + packed offsets (host)."""
+        """global row indices of the listed meshes, concatenated (device int64) + packed offsets (host, device).
+        No host synchronisation: the id list goes up through a pinned staging buffer, every size that the device ops
+        need is known on the host."""
         sizes = self.sizes_h[mesh_ids_h]
         o = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        ids = torch.from_numpy(np.ascontiguousarray(mesh_ids_h, dtype=np.int64)).to(self.device)
+        n, total = len(sizes), int(o[-1])
+        stage = torch.empty(2 * n + 1, dtype=torch.int64, pin_memory=True)
+        stage[:n] = torch.from_numpy(np.ascontiguousarray(mesh_ids_h, dtype=np.int64))
+        stage[n:] = torch.from_numpy(o)
+        dev = stage.to(self.device, non_blocking=True)
+        ids, od = dev[:n], dev[n:]
         start = self.off[ids]                                                    # [P]
-        od = torch.from_numpy(o).to(self.device)
-        seg = torch.repeat_interleave(torch.arange(len(sizes), device=self.device), torch.from_numpy(sizes).to(self.device))
-        rows = start[seg] + (torch.arange(int(o[-1]), device=self.device) - od[:-1][seg])
-        return rows, o, od
+        seg = torch.repeat_interleave(torch.arange(n, device=self.device), od[1:] - od[:-1], output_size=total)
+        rows = start[seg] + (torch.arange(total, device=self.device) - od[:-1][seg])
+        return rows, o, od, ids
 
     def assemble(self, src_ids, dst_ids):
         """PairBatchDevice of the pairs (src_ids[p] -> mesh 1, dst_ids[p] -> mesh 2), gathered on the device."""
         src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
-        r1, o1h, o1d = self._rows(src_ids)
-        r2, o2h, o2d = self._rows(dst_ids)
+        r1, o1h, o1d, i1 = self._rows(src_ids)
+        r2, o2h, o2d, i2 = self._rows(dst_ids)
         g = lambda t, r: None if t is None else t.index_select(0, r)
-        i1 = torch.from_numpy(src_ids).to(self.device)
-        i2 = torch.from_numpy(dst_ids).to(self.device)
         return PairBatchDevice(F1=g(self.F, r1), F2=g(self.F, r2), off1_h=_nn.Offsets(o1d, o1h), off2_h=_nn.Offsets(o2d, o2h),
                                device=self.device, Phi1=g(self.Phi, r1), Phi2=g(self.Phi, r2),
                                evals1=g(self.evals, i1), evals2=g(self.evals, i2), area1=g(self.area, r1),

@@ -138,12 +138,14 @@ class FunctionalMapping:
         x0[0, 0] = ev_sign * np.sqrt(self.mesh2.area / self.mesh1.area)
         return x0
 
-    def fit(self, w_descr=1e-1, w_lap=1e-3, w_dcomm=0, w_orient=0, w_area=0, w_conformal=0, w_p2p=0, w_stochastic=0,
+    def fit(self, w_descr=1e-1, w_lap=1e-3, w_dcomm=1, w_orient=0, w_area=0, w_conformal=0, w_p2p=0, w_stochastic=0,
             w_ent=0, w_range01=0, w_sumto1=0, w_area_difference=0, w_mumford_shah=0, mumford_shah_var=0.1,
             w_eta_entropy=0, orient_reversing=False, optinit="zeros", verbose=False, maxiter=1000000, device=None):
         """Minimiser of  w_descr/2 |C A - B|^2 + w_lap/2 sum C^2 Delta  with column 0 pinned (functional.py:352-487,
-        base_functions.py:31-56, :79-102, :759).  NB the reference's default ``w_dcomm=1`` is a §8f term: pass
-        ``w_dcomm=0`` (the DenseMatcher notebook does, example.ipynb cell 11)."""
+        base_functions.py:31-56, :79-102, :759).  The defaults are the reference's (functional.py:352-356), including
+        ``w_dcomm=1`` -- a term that is not implemented here, so a call relying on the defaults raises
+        ``NotImplementedError`` instead of silently minimising a different energy; pass ``w_dcomm=0`` as the DenseMatcher
+        notebook does (example.ipynb cell 11)."""
         given = dict(w_dcomm=w_dcomm, w_orient=w_orient, w_area=w_area, w_conformal=w_conformal, w_p2p=w_p2p,
                      w_stochastic=w_stochastic, w_ent=w_ent, w_range01=w_range01, w_sumto1=w_sumto1,
                      w_area_difference=w_area_difference, w_mumford_shah=w_mumford_shah, w_eta_entropy=w_eta_entropy)

@@ -16,7 +16,7 @@ def p2p_to_FM(p2p_21, evects1, evects2, A2=None):
     With a (diagonal) target mass ``A2`` -- 1-D areas, scipy sparse or dense -- the product
     ``evects2.T @ A2 @ evects1[p2p_21]`` runs on the GPU in float64.  Without ``A2`` the reference
     solves a least-squares problem (convert.py:51); here it is solved through the normal equations
-    with both Gram products on the GPU.  A (n2, n1) matrix map (convert.py:39) is applied on the host.
+    with both Gram products and the Cholesky solve (``dm_spd_solve``) on the GPU.  A (n2, n1) matrix map (convert.py:39) is applied on the host.
     """
     evects1, evects2 = np.asarray(evects1), np.asarray(evects2)
     p = p2p_21
@@ -38,7 +38,7 @@ def p2p_to_FM(p2p_21, evects1, evects2, A2=None):
     # least squares: (Phi2^T Phi2) C = Phi2^T Phi1[p]
     rhs = _fm.p2p_to_fm(ident, P1, P2, None)[0]
     gram = _fm.p2p_to_fm(torch.arange(P2.shape[0], device=P2.device), P2, P2, None)[0]
-    return torch.linalg.solve(gram, rhs).cpu().numpy()
+    return _fm.spd_solve(gram, rhs)[0].cpu().numpy()
 
 
 def mesh_p2p_to_FM(p2p_21, mesh1, mesh2, dims=None, subsample=None):

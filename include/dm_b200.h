@@ -138,6 +138,13 @@ int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, 
                            float* S_out, int64_t ldS, int flags, void* workspace, size_t workspace_bytes,
                            dm_stream_t stream);
 
+/* k nearest neighbours (k > 1) of every row of Y among the rows of X, Euclidean, float64, one pair: knn_query with k > 1
+ * (nn_utils.py:4-38; caller projection_utils.py:178).  idx [nq, k] int64 and dist [nq, k] float64, each row ordered by
+ * (distance, index) like the kd-tree's result.  k <= 16, k <= ndb.  API parity, not the throughput path. */
+size_t dm_knn_workspace_bytes(int nq, int ndb, int d, int k);
+int dm_knn_f64(const double* Y, int64_t ldY, int nq, const double* X, int64_t ldX, int ndb, int d, int k, int64_t* idx,
+               double* dist, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
 /* Euclidean distance of matched rows: dist[i] = | Y[i] - X[idx[i]] |_2 in float64
  * (the `dists` return of knn_query, nn_utils.py:30-38).  idx is int32|int64 per flags, global row ids into X. */
 int dm_match_dist_f32(const float* Y, int64_t ldY, const float* X, int64_t ldX, const void* idx, int64_t n,
@@ -220,6 +227,14 @@ int dm_p2p_to_fm(const void* p2p_21, const double* Phi1, int64_t ld1, const int6
                  const double* area2, int n_pairs, int k1, int k2,
                  double* C /* [n_pairs, k2, k1] */, int flags, void* workspace, size_t workspace_bytes,
                  dm_stream_t stream);
+
+/* Batched symmetric positive definite solve  X[b] = G[b]^-1 B[b]  (G [n_batch, n, n], B / X [n_batch, n, m], float64,
+ * contiguous): the normal equations (Phi2^T Phi2) C = Phi2^T Phi1[p] of the least-squares branch of p2p_to_FM
+ * (convert.py:51, A2 = None; scipy.linalg.lstsq in the reference).  Cholesky inverse + one GEMM; dm_icp_read_status on
+ * the same workspace reports a non-positive pivot. */
+size_t dm_spd_solve_workspace_bytes(int n_batch, int n);
+int dm_spd_solve(const double* G, const double* B, int n, int m, int n_batch, double* X, void* workspace,
+                 size_t workspace_bytes, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ZoomOut ladder (upstream pyFM semantics; pyFM/refine/zoomout.py:7-115, the shipped call at :40 is

@@ -62,8 +62,14 @@ def test_knn_query_shim_small_nonunit(golden_nn_small):
     # float64 inputs take the f64 entry point
     m3 = knn_query(g["X"].astype(np.float64), g["Y"].astype(np.float64))
     assert np.array_equal(m3, g["ref_match"])
-    with pytest.raises(NotImplementedError):
-        knn_query(g["X"], g["Y"], k=3)
+    # k > 1: the reference's (n2, k) result, ordered by distance (golden minted from the reference kd-tree)
+    d3, m3 = knn_query(g["X"], g["Y"], k=3, return_distance=True)
+    assert m3.shape == (193, 3) and m3.dtype == np.int64
+    assert np.array_equal(m3, g["ref_match_k3"]) and np.allclose(d3, g["ref_dist_k3"], rtol=0, atol=1e-12)
+    assert np.array_equal(knn_query(g["X"], g["Y"], k=3), g["ref_match_k3"])
+    assert np.array_equal(knn_query(g["X"], g["Y"], k=16)[:, :3], g["ref_match_k3"])
+    with pytest.raises(ValueError):
+        knn_query(g["X"][:2], g["Y"], k=3)
     with pytest.raises(ValueError):
         knn_query(g["X"][:0], g["Y"])
     assert knn_query(g["X"], g["Y"][:0]).shape == (0,)
