@@ -15,7 +15,7 @@ from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
 __all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "spd_solve", "zoomout", "icp", "polar_factor",
-           "match_pairs", "dense_energy", "DENSE_TERMS", "PairBatch"]
+           "match_pairs", "dense_energy", "fit_dense", "DENSE_TERMS", "PairBatch"]
 
 
 def _stream(dev):
@@ -404,6 +404,112 @@ def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace:
                                  energy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "dm_dense_energy")
     return energy, grad
+
+
+def fit_dense(A, B, evals1, evals2, c00, Phi1, Phi2, area1, weights, w_descr, w_lap, off1=None, off2=None,
+              maxiter: int = 1000, history: int = 10, gtol: float = 1e-5, ftol: float = 2.220446049250313e-09,
+              check_every: int = 2, return_info: bool = False):
+    """Batched ON-DEVICE fit of the functional map with the dense-map energy terms of the notebook's default
+    ``fit_params`` (example.ipynb cell 11: w_ent, w_sumto1, ...; reference: FunctionalMapping.fit functional.py:352-487
+    driving scipy L-BFGS-B over energy_func_std / grad_energy_std, optimize/base_functions.py:480-763, one pair at a time
+    with a host round trip per callback).
+
+        E(C) = w_descr/2 |C A - B|^2 + w_lap/2 sum C^2 Delta + sum_t weights[t] * term_t(Phi2 C Phi1^T A1),   C[:, 0] pinned
+
+    Here P pairs are minimised together: an L-BFGS iteration (two-loop recursion over `history` pairs, Armijo
+    backtracking) is a handful of batched tensor operations on the device plus ONE ``dm_dense_energy`` launch per trial
+    point for all pairs; the host only reads a convergence flag every `check_every` iterations.  The stopping rules and
+    their defaults are scipy's L-BFGS-B (what the reference runs with): max |g| <= gtol (pgtol = 1e-5) or
+    (E_prev - E) / max(|E_prev|, |E|, 1) <= ftol (factr 1e7 * eps); converged pairs are frozen by a mask.
+    A [P,k1,d], B [P,k2,d], evals1 [P,k1], evals2 [P,k2], c00 [P]; Phi / area / offsets as in ``dense_energy``.
+    Returns C [P,k2,k1] float64 (and ``(iterations, energy evaluations)`` with ``return_info``)."""
+    dev = A.device
+    A, B = _f64(A).contiguous(), _f64(B).contiguous()
+    P, k1, _ = A.shape
+    k2 = B.shape[1]
+    ev1, ev2 = _f64(evals1).reshape(P, k1), _f64(evals2).reshape(P, k2)
+    scale = torch.maximum(ev1.max(dim=1).values, ev2.max(dim=1).values)[:, None, None]
+    Delta = (ev1[:, None, :] / scale - ev2[:, :, None] / scale) ** 2                      # functional.py:404-405
+    AAt = torch.bmm(A, A.transpose(1, 2))                                                 # [P,k1,k1]
+    BAt = torch.bmm(B, A.transpose(1, 2))                                                 # [P,k2,k1]
+    bb = 0.5 * w_descr * (B * B).sum(dim=(1, 2))
+    wvec = torch.tensor([float(weights.get(t, 0.0)) for t in DENSE_TERMS], dtype=torch.float64, device=dev)
+    free = torch.ones(k1, dtype=torch.float64, device=dev)
+    free[0] = 0.0                                                                         # base_functions.py:759
+    n_eval = 0
+
+    def energy(C):
+        nonlocal n_eval
+        n_eval += 1
+        CA = torch.bmm(C, AAt)
+        e = 0.5 * w_descr * (C * CA).sum(dim=(1, 2)) - w_descr * (C * BAt).sum(dim=(1, 2)) + bb
+        e = e + 0.5 * w_lap * (C * C * Delta).sum(dim=(1, 2))
+        g = w_descr * (CA - BAt) + w_lap * (C * Delta)
+        ed, gd = dense_energy(C, Phi1, Phi2, area1, weights, off1, off2)
+        return e + ed @ wvec, (g + gd) * free
+
+    C = torch.zeros(P, k2, k1, dtype=torch.float64, device=dev)
+    C[:, 0, 0] = _f64(c00).reshape(P)                                                     # functional.py:654-658
+    f, g = energy(C)
+    S, Y, rho = [], [], []
+    active = torch.ones(P, dtype=torch.bool, device=dev)
+    dot = lambda a, b: (a * b).sum(dim=(1, 2))
+    it = 0
+    while it < maxiter:
+        # two-loop recursion, batched over the pairs
+        q = g.clone()
+        alphas = []
+        for s_, y_, r_ in zip(reversed(S), reversed(Y), reversed(rho)):
+            a_ = r_ * dot(s_, q)
+            alphas.append(a_)
+            q = q - a_[:, None, None] * y_
+        if S:
+            gamma = dot(S[-1], Y[-1]) / dot(Y[-1], Y[-1]).clamp_min(1e-300)
+        else:
+            gamma = 1.0 / dot(g, g).sqrt().clamp_min(1e-300)                              # first step: unit length
+        q = q * gamma[:, None, None]
+        for (s_, y_, r_), a_ in zip(zip(S, Y, rho), reversed(alphas)):
+            b_ = r_ * dot(y_, q)
+            q = q + (a_ - b_)[:, None, None] * s_
+        d = -q
+        gd0 = dot(g, d)
+        bad_dir = gd0 >= 0                                                                # not a descent direction: steepest descent
+        d = torch.where(bad_dir[:, None, None], -g, d)
+        gd0 = torch.where(bad_dir, -dot(g, g), gd0)
+        # Armijo backtracking (per pair: accepted pairs keep their point while the others shrink the step)
+        t = torch.ones(P, dtype=torch.float64, device=dev)
+        done = ~active
+        Cn, fn, gn = C, f, g
+        for _ls in range(30):
+            Ct = C + t[:, None, None] * d
+            ft, gt = energy(Ct)
+            ok = (ft <= f + 1e-4 * t * gd0) & ~done
+            Cn = torch.where(ok[:, None, None], Ct, Cn)
+            fn = torch.where(ok, ft, fn)
+            gn = torch.where(ok[:, None, None], gt, gn)
+            done = done | ok
+            if bool(done.all()):
+                break
+            t = torch.where(done, t, 0.5 * t)
+        s_ = Cn - C
+        y_ = gn - g
+        sy = dot(s_, y_)
+        good = sy > 1e-30
+        if bool(good.any()):
+            # pairs whose curvature condition failed contribute a zero update (rho = 0)
+            S.append(torch.where(good[:, None, None], s_, torch.zeros_like(s_)))
+            Y.append(torch.where(good[:, None, None], y_, torch.zeros_like(y_)))
+            rho.append(torch.where(good, 1.0 / sy.clamp_min(1e-300), torch.zeros_like(sy)))
+            if len(S) > history:
+                S.pop(0), Y.pop(0), rho.pop(0)
+        df = (f - fn).abs()
+        C, f_prev, f, g = Cn, f, fn, gn
+        it += 1
+        conv = ((g.abs().amax(dim=(1, 2)) <= gtol) | (df <= ftol * torch.maximum(f_prev.abs(), f.abs()).clamp_min(1.0)) | ~done)
+        active = active & ~conv
+        if it % check_every == 0 and not bool(active.any()):
+            break
+    return (C, (it, n_eval)) if return_info else C
 
 
 def polar_factor(X, flags=0):

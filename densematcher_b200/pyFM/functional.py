@@ -170,8 +170,16 @@ class FunctionalMapping:
         if not dense:
             C = _fm.fmap_solve(A, B, ev1, ev2, torch.tensor([c00], dtype=torch.float64, device=A.device), w_descr, w_lap)
             self.FM = C[0].cpu().numpy()
-        else:
+        elif self.optimizer == "scipy":
+            # the reference's host loop (scipy L-BFGS-B, one host round trip per callback) around dm_dense_energy
             self.FM = self._fit_lbfgs(A[0], B[0], c00, P1, P2, a1, w_descr, w_lap, dense, maxiter)
+        else:
+            # default: the batched on-device L-BFGS (fm.fit_dense) -- same energy, same pinned column, no host round
+            # trip per iteration
+            C, info = _fm.fit_dense(A, B, ev1, ev2, torch.tensor([c00], dtype=torch.float64, device=A.device), P1, P2, a1,
+                                    dense, w_descr, w_lap, maxiter=min(int(maxiter), 2000), return_info=True)
+            self.FM = C[0].cpu().numpy()
+            self.fit_result = type("FitResult", (), {"nit": info[0], "nfev": info[1], "x": self.FM.ravel()})()
         self.eta = np.ones(self.mesh2.eigenvectors.shape[0])              # functional.py:483
         self._mi = None
         return self
@@ -201,7 +209,7 @@ class FunctionalMapping:
 
         x0 = np.zeros((k2, k1))
         x0[0, 0] = c00
-        method = "L-BFGS-B" if self.optimizer in ("fmin_l_bfgs_b", "L-BFGS-B") else self.optimizer
+        method = "L-BFGS-B" if self.optimizer in ("fmin_l_bfgs_b", "L-BFGS-B", "scipy") else self.optimizer
         res = scipy.optimize.minimize(fun, x0.ravel(), jac=True, method=method, options={"maxiter": int(maxiter)})
         self.fit_result = res
         return res.x.reshape(k2, k1)

@@ -223,6 +223,45 @@ def test_fit_with_notebook_default_weights(golden_fm):
         model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=1.0)
 
 
+def test_batched_device_fit_matches_reference_and_host_loop(golden_fm):
+    """fm.fit_dense: the notebook's energy (w_ent = 0.1, w_sumto1 = 10 next to w_descr / w_lap) minimised for a BATCH of
+    pairs by the on-device L-BFGS.  Every pair lands on the reference's own fit (< 1e-3: its float32 energy leaves
+    ~1e-4 of noise) and on the host scipy loop around the same kernel (< 1e-5), with the same p2p as the reference C."""
+    import torch
+    from conftest import load_golden
+    from densematcher_b200 import fm, _lib
+    from densematcher_b200.pyFM import FunctionalMapping
+    e = load_golden("energy_ico3.npz")
+    g = golden_fm
+    k = int(e["k"])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    P1, P2, a1, a2 = g["Phi1"][:, :k], g["Phi2"][:, :k], g["area1"], g["area2"]
+    A = fm.project(dev(P1), dev(a1), dev(g["c1"]), flags=_lib.DM_F64_GEMM)
+    B = fm.project(dev(P2), dev(a2), dev(g["c2"]), flags=_lib.DM_F64_GEMM)
+    c00 = orc.fmap_c00(g["Phi1"], g["Phi2"], a1, a2)
+    n1, n2 = len(a1), len(a2)
+    reps = 3   # the same pair three times, as a ragged batch
+    cat = lambda x: dev(np.concatenate([x] * reps))
+    off1, off2 = np.arange(reps + 1) * n1, np.arange(reps + 1) * n2
+    C, info = fm.fit_dense(A.repeat(reps, 1, 1), B.repeat(reps, 1, 1), dev(np.tile(g["evals1"][:k], (reps, 1))),
+                           dev(np.tile(g["evals2"][:k], (reps, 1))), dev(np.full(reps, c00)), cat(P1), cat(P2), cat(a1),
+                           {"ent": 1e-1, "sumto1": 1e1}, 1e4, 1e3, off1=off1, off2=off2, return_info=True)
+    C = C.cpu().numpy()
+    assert 5 < info[0] < 500
+    for p in range(reps):
+        assert relF(C[p], e["ref_C_notebook"]) < 1e-3
+        assert relF(C[p], C[0]) < 1e-9                          # batch entries do not interact
+    m1, m2 = _meshes(g)
+    model = FunctionalMapping(m1, m2, partial=False, optimizer="scipy")
+    model.projection_flags = _lib.DM_F64_GEMM
+    model.preprocess(n_ev=(k, k), descr1=g["c1"], descr2=g["c2"])
+    model.fit(w_descr=1e4, w_lap=1e3, w_dcomm=0, w_ent=1e-1, w_sumto1=1e1, maxiter=5000)
+    assert relF(C[0], model.FM) < 2e-4                          # two optimisers stopped by the same (scipy) tolerances
+    r21, r12, _ = orc.fm_to_p2p(e["ref_C_notebook"], P1, P2, a1)
+    o21, o12, _ = orc.fm_to_p2p(C[0], P1, P2, a1)
+    assert np.mean(o21 != r21) < 0.01 and np.mean(o12 != r12) < 0.01
+
+
 def test_cfg2_full_size_pipeline_against_oracle():
     """BASELINE config 2 at full size (N = M = 2000, d = 384, k = 100, notebook weights) for a small batch through the
     single-call pipeline: feature NN bit-exact, C within 1e-4 of the float64 closed form, and -- given that C -- all
