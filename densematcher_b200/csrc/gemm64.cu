@@ -57,6 +57,8 @@ struct Staged {
   double d[NE];
   float f[NE];
   double s[NE];
+  long long row[NE];  // gathered operands: source rows of the NEXT stage, loaded one stage ahead of the data (the row
+                      // index -> row data dependency would otherwise sit inside one stage's latency budget)
 };
 
 // TW = tile width along the output index (128 or 64); a thread moves NE = TW * TK / NT elements per stage
@@ -73,6 +75,24 @@ struct Loader {
   __device__ __forceinline__ Loader(const OpView& view, int i0_, int lim_, int t_) : v(view), i0(i0_), lim(lim_), t(t_) {
     vec2 = v.d != nullptr && ((reinterpret_cast<uintptr_t>(v.d) | uintptr_t(v.ld * sizeof(double))) & 15) == 0 &&
            (i0 & 1) == 0;
+  }
+
+  // source rows of the stage starting at k0 (TRANS operands with a row gather only)
+  __device__ __forceinline__ void prefetch_rows(int k0, int kend, Staged<NE>& r) const {
+    if (!TRANS || !v.gather) return;
+    if (vec2) {
+#pragma unroll
+      for (int e = 0; e < NE / 2; ++e) {
+        const int k = k0 + (t / (TW / 2)) + (2 * NT / TW) * e;
+        r.row[2 * e] = k < kend ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : 0;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int k = k0 + (t / TW) + (NT / TW) * e;
+        r.row[e] = k < kend ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : 0;
+      }
+    }
   }
 
   __device__ __forceinline__ void fetch(int k0, int kend, Staged<NE>& r) const {
@@ -101,7 +121,7 @@ struct Loader {
         r.d[2 * e] = r.d[2 * e + 1] = 0.0;
         r.s[2 * e] = 1.0;
         if (i < lim && k < kend) {
-          const int64_t row = v.gather ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : k;
+          const int64_t row = v.gather ? r.row[2 * e] : k;
           const double* src = v.d + row * v.ld + i;
           if (i + 1 < lim) {
             const double2 x = __ldg(reinterpret_cast<const double2*>(src));
@@ -130,7 +150,7 @@ struct Loader {
         if (!TRANS) {
           idx = int64_t(i) * v.ld + k;
         } else {
-          const int64_t row = v.gather ? load_index(v.gather, v.gbase + k, v.gather_i64 != 0) : k;
+          const int64_t row = v.gather ? r.row[e] : k;
           idx = row * v.ld + i;
         }
         if (v.d)
@@ -226,8 +246,12 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
   Staged<Loader<TA, TM>::NE> ra;
   Staged<Loader<TB, TNW>::NE> rb;
   if (kbeg < kend) {
+    la.prefetch_rows(kbeg, kend, ra);
+    lb.prefetch_rows(kbeg, kend, rb);
     la.fetch(kbeg, kend, ra);
     lb.fetch(kbeg, kend, rb);
+    la.prefetch_rows(kbeg + TK, kend, ra);
+    lb.prefetch_rows(kbeg + TK, kend, rb);
     la.stash(As[0], ra);
     lb.stash(Bs[0], rb);
   }
@@ -238,6 +262,8 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
     if (more) {
       la.fetch(k0 + TK, kend, ra);
       lb.fetch(k0 + TK, kend, rb);
+      la.prefetch_rows(k0 + 2 * TK, kend, ra);
+      lb.prefetch_rows(k0 + 2 * TK, kend, rb);
     }
     const double* as = As[buf] + wm + g;
     const double* bs = Bs[buf] + wn + g;
@@ -304,6 +330,170 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// "Both transposed" shape: C[b] (M x N) = sum_k A[b][k][m] * B[b][gather(k)][n] * kscale[k] -- the p2p -> FM product
+// Phi2^T A2 Phi1[p] of every ZoomOut / ICP rung and the Gram products (convert.py:39-48).  The contraction runs over
+// the VERTICES, both operands are row-major [vertex, column], so a stage of TK vertices is a set of contiguous row
+// segments: they go global -> shared with 16-byte cp.async through a KSTAGES-deep ring (no register staging, the gather
+// indices of a stage are fetched KSTAGES stages ahead), which is what the register-staged generic kernel above lacked
+// on this shape: it restarted a dependent (index -> row) load chain every 8 vertices and ran at 8 TFLOP/s.
+// Same 128 x 64 tile, warp grid and edge-block skipping as gemm64_kernel<.., .., 4>; the vertex scale is applied to the
+// A fragments as they are read.
+constexpr int KSTAGES = 4;
+constexpr int TT_TNW = 64;
+constexpr size_t kTTSmem = size_t(KSTAGES) * TK * (LDT + (TT_TNW + 4)) * sizeof(double) + size_t(KSTAGES) * TK * sizeof(double);
+
+__device__ __forceinline__ void cp_async16_zfill(double* dst, const double* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
+  constexpr int TNW = TT_TNW, LDB = TNW + 4;
+  int bid = blockIdx.x;
+  const int tn = bid % tiles_n;
+  bid /= tiles_n;
+  const int tm = bid % tiles_m;
+  bid /= tiles_m;
+  const int ks = bid % P.ksplit;
+  const int b = bid / P.ksplit;
+  if (P.skip && P.skip[b]) return;
+  const int M = P.M, N = P.N;
+  int K = ragged_k(P.A, b);
+  if (K < 0) K = ragged_k(P.B, b);
+  if (K < 0) K = P.K;
+  const int m0 = tm * TM, n0 = tn * TNW;
+  if (m0 >= M || n0 >= N) return;
+  int kbeg = 0, kend = K;
+  if (P.ksplit > 1) {
+    kbeg = min(K, ks * P.kchunk);
+    kend = min(K, kbeg + P.kchunk);
+  }
+  extern __shared__ __align__(16) double tsm[];
+  double* As = tsm;                                 // [KSTAGES][TK][LDT]
+  double* Bs = As + KSTAGES * TK * LDT;             // [KSTAGES][TK][LDB]
+  double* Ss = Bs + KSTAGES * TK * LDB;             // [KSTAGES][TK] vertex scale
+  const OpView A = resolve(P.A, b), B = resolve(P.B, b);
+  const int t = threadIdx.x;
+  // A stage: TK rows x 64 16-byte chunks = 512 chunks -> 2 per thread; B stage: TK rows x 32 chunks = 256 -> 1 per thread
+  const int a_row = t >> 6, a_ch = t & 63;          // rows a_row, a_row + 4
+  const int b_row = t >> 5, b_ch = t & 31;
+  const int n_stage = (kend - kbeg + TK - 1) / TK;
+  auto a_src_row = [&](int k) -> int64_t { return A.gather ? load_index(A.gather, A.gbase + k, A.gather_i64 != 0) : k; };
+  auto b_src_row = [&](int k) -> int64_t { return B.gather ? load_index(B.gather, B.gbase + k, B.gather_i64 != 0) : k; };
+  // gather rows of the stage that will be ISSUED next (fetched one issue ahead: KSTAGES stages before use)
+  int64_t ra0 = 0, ra1 = 0, rb = 0;
+  auto load_rows = [&](int stage) {
+    const int k = kbeg + stage * TK;
+    ra0 = (k + a_row < kend) ? a_src_row(k + a_row) : 0;
+    ra1 = (k + a_row + 4 < kend) ? a_src_row(k + a_row + 4) : 0;
+    rb = (k + b_row < kend) ? b_src_row(k + b_row) : 0;
+  };
+  auto issue = [&](int stage) {
+    const int k = kbeg + stage * TK, buf = stage % KSTAGES;
+    double* as = As + buf * TK * LDT;
+    double* bs = Bs + buf * TK * LDB;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = a_row + 4 * h, i = m0 + 2 * a_ch;
+      const int valid = (k + kk < kend) ? max(0, min(2, M - i)) : 0;
+      const double* src = A.d + (h == 0 ? ra0 : ra1) * A.ld + min(i, max(M - 1, 0));
+      cp_async16_zfill(as + kk * LDT + 2 * a_ch, valid > 0 ? src : A.d, 8 * valid);
+    }
+    {
+      const int i = n0 + 2 * b_ch;
+      const int valid = (k + b_row < kend) ? max(0, min(2, N - i)) : 0;
+      const double* src = B.d + rb * B.ld + min(i, max(N - 1, 0));
+      cp_async16_zfill(bs + b_row * LDB + 2 * b_ch, valid > 0 ? src : B.d, 8 * valid);
+    }
+    if (t < TK) {
+      const double* ksc = A.kscale ? A.kscale : B.kscale;
+      Ss[buf * TK + t] = (k + t < kend) ? (ksc ? ksc[k + t] : 1.0) : 0.0;
+    }
+  };
+  // warp grid 4 (M) x 2 (N): warp tile 32 x 32
+  constexpr int WN = TNW / 2, NT8 = WN / 8;
+  const int lane = t & 31, warp = t >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int na = max(0, min(4, (M - (m0 + wm) + 7) / 8)), nc = max(0, min(NT8, (N - (n0 + wn) + 7) / 8));
+  double acc[4][NT8][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < NT8; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+
+  load_rows(0);
+  for (int s0 = 0; s0 < KSTAGES - 1; ++s0) {
+    if (s0 < n_stage) {
+      issue(s0);
+      load_rows(s0 + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int st = 0; st < n_stage; ++st) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(KSTAGES - 2) : "memory");
+    __syncthreads();  // stage st has landed for every thread, and everyone is done with the buffer reused below
+    const int nxt = st + KSTAGES - 1;
+    if (nxt < n_stage) {
+      issue(nxt);
+      load_rows(nxt + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int buf = st % KSTAGES;
+    const double* as = As + buf * TK * LDT + wm + g;
+    const double* bs = Bs + buf * TK * LDB + wn + g;
+    const double* ss = Ss + buf * TK;
+    if (na > 0 && nc > 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < TK; k4 += 4) {
+        const double sc = ss[k4 + t4];
+        double av[4], bv[NT8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = as[(k4 + t4) * LDT + 8 * a] * sc;
+#pragma unroll
+        for (int c = 0; c < NT8; ++c) bv[c] = bs[(k4 + t4) * LDB + 8 * c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (a < na)
+#pragma unroll
+            for (int c = 0; c < NT8; ++c)
+              if (c < nc)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[a][c][0]), "+d"(acc[a][c][1])
+                             : "d"(av[a]), "d"(bv[c]));
+      }
+    }
+  }
+  double* C = P.C + int64_t(ks) * P.split_stride + (P.c_off ? P.c_off[b] * P.ldc : int64_t(b) * P.c_batch_stride);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int m = m0 + wm + 8 * a + g;
+    if (m >= M) continue;
+#pragma unroll
+    for (int c = 0; c < NT8; ++c) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = n0 + wn + 8 * c + 2 * t4 + h;
+        if (n >= N) continue;
+        C[int64_t(m) * P.ldc + n] = P.alpha * acc[a][c][h];
+      }
+    }
+  }
+}
+
+// the cp.async path needs float64 operands whose rows and column windows start on 16-byte boundaries
+bool tt_shape(const GemmProblem& P) {
+  static const bool off = [] { const char* e = getenv("DM_GEMM_NO_TT"); return e && e[0] == '1'; }();
+  if (off || P.A.trans != 1 || P.B.trans != 1 || !P.A.d || !P.B.d || P.c_colscale) return false;
+  if (P.A.kscale && P.B.kscale) return false;
+  auto ok = [](const GemmOperand& o) {
+    return ((reinterpret_cast<uintptr_t>(o.d) | uintptr_t(o.ld * sizeof(double)) | uintptr_t(o.col0 * sizeof(double))) & 15) == 0;
+  };
+  return ok(P.A) && ok(P.B);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -483,6 +673,19 @@ int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
     }
 #undef DM_EMBED
     DM_LAUNCH_OK("embed64_kernel");
+    return DM_OK;
+  }
+  if (tt_shape(P)) {
+    const int tiles_m = (P.maxM + TM - 1) / TM, tiles_n = (P.maxN + TT_TNW - 1) / TT_TNW;
+    GemmProblem Q = P;
+    if (Q.ksplit < 1) Q.ksplit = 1;
+    const int64_t nblk = int64_t(P.n_batch) * Q.ksplit * tiles_m * tiles_n;
+    if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "gemm64: grid too large");
+    static OncePerDevice once;
+    if (once.first())
+      DM_CUDA_OK(cudaFuncSetAttribute(gemm64_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTTSmem)));
+    gemm64_tt_kernel<<<unsigned(nblk), NT, kTTSmem, st>>>(Q, tiles_m, tiles_n);
+    DM_LAUNCH_OK("gemm64_tt_kernel");
     return DM_OK;
   }
   // narrow tiles when the contraction is short (latency-bound) or when they waste less of the N range
