@@ -306,6 +306,7 @@ struct NNRequest;
 struct NNHooks {
   void* ctx = nullptr;
   int (*prep_y)(void* ctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) = nullptr;
+  int (*prep_x)(void* ctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) = nullptr;
   int (*after_prep)(void* ctx, const NNLayout& L, NNProblem& P, cudaStream_t st) = nullptr;
   int (*before_recheck)(void* ctx, const NNLayout& L, NNProblem& P, cudaStream_t st) = nullptr;
 };
@@ -363,6 +364,16 @@ int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_
                      int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
                      const double* area1, int n_pairs, void* p2p_21, void* p2p_12, void* dense_21, void* dense_12, int flags,
                      void* ws, cudaStream_t st);
+
+// p2p_21 of a functional map (the ZoomOut / ICP inner conversion) with the database side Phi1 C^T embedded on the tensor
+// cores and float64 rows filled on demand (embed_tc.cu); k1, k2 <= 128.  `scratch` holds the three-way split of Phi1
+// (valid while *x_kp_state == pad64(k1)), the splits of C and the flags.
+bool p2p21_factored_applicable(int k1, int k2, int flags);
+size_t p2p21_factored_scratch_bytes(int n_pairs, int64_t total_n1, int k1m, int k2m);
+int p2p21_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
+                       int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                       int n_pairs, void* p2p_out, int flags, void* scratch, double* emb1, int lde, void* nn_ws,
+                       size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state);
 
 int num_sms();
 // true exactly once per (call site, device): function attributes such as the dynamic shared-memory limit are

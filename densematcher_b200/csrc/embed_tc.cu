@@ -30,7 +30,8 @@ constexpr int EB_UK = 16;
 constexpr uint32_t EB_TILE = EB_ROWS * EB_BK * 2;  // one [128 x 64] bf16 box
 constexpr int EB_THREADS = 192;
 
-__host__ __device__ constexpr uint32_t eb_smem_bytes(int kc) { return uint32_t(kc) * 6 * EB_TILE + 64 + 1024; }
+__host__ __device__ constexpr int eb_a_stages(int kc) { return kc == 1 ? 2 : 1; }  // A buffers that fit beside the resident B
+__host__ __device__ constexpr uint32_t eb_smem_bytes(int kc) { return uint32_t(kc) * 3 * (eb_a_stages(kc) + 1) * EB_TILE + 128 + 1024; }
 
 __device__ __forceinline__ uint64_t eb_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -50,8 +51,13 @@ constexpr uint32_t kEbIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(EB_
 __global__ void __launch_bounds__(256)
     csplit_kernel(const double* __restrict__ C, int k1, int k2, int kp0, int kp1, __nv_bfloat16* __restrict__ h0,
                   __nv_bfloat16* __restrict__ m0, __nv_bfloat16* __restrict__ l0, __nv_bfloat16* __restrict__ h1,
-                  __nv_bfloat16* __restrict__ m1, __nv_bfloat16* __restrict__ l1, float* __restrict__ c_fro) {
-  const int p = blockIdx.x, side = blockIdx.y;
+                  __nv_bfloat16* __restrict__ m1, __nv_bfloat16* __restrict__ l1, float* __restrict__ c_fro,
+                  int first_side, double* __restrict__ Ct) {
+  const int p = blockIdx.x, side = blockIdx.y + first_side;
+  if (Ct) {  // float64 transpose [k1, k2] for the on-demand products Phi1_j C^T
+    for (int e = threadIdx.x; e < k1 * k2; e += blockDim.x)
+      Ct[int64_t(p) * k1 * k2 + e] = C[int64_t(p) * k1 * k2 + int64_t(e % k2) * k1 + e / k2];
+  }
   const double* Cp = C + int64_t(p) * k1 * k2;
   const int n_out = side == 0 ? k1 : k2, n_in = side == 0 ? k2 : k1, kp = side == 0 ? kp0 : kp1;
   __nv_bfloat16* h = (side == 0 ? h0 : h1) + int64_t(p) * EB_ROWS * kp;
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(256)
     const __nv_bfloat16 vm = __float2bfloat16_rn(r1);
     h[e] = vh, m[e] = vm, l[e] = __float2bfloat16_rn(r1 - __bfloat162float(vm));
   }
-  if (side == 0) {
+  if (side == first_side) {
     __shared__ double red[8];
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sh);
@@ -111,27 +117,45 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
   atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// A CTA owns EB_TPC consecutive 128-row tiles of one pair: the B operand (the split of C, up to 96 KB) is fetched once and
+// stays resident, the A tiles (48 KB per 64-wide K chunk triple) and the two accumulators are double-buffered, so the TMA
+// loads of tile t + 1 and the epilogue of tile t - 1 overlap the MMAs of tile t (the first version ran load -> MMA ->
+// epilogue back to back in a one-CTA-per-SM kernel: 143 us per embedding).
+constexpr int EB_TPC = 4;
+
 template <int KC>
 __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_constant__ EbMaps maps, const EbParams P) {
-  const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
+  const int ctas_per_pair = (P.max_rt + EB_TPC - 1) / EB_TPC;
+  const int p = blockIdx.x / ctas_per_pair, rt0 = (blockIdx.x % ctas_per_pair) * EB_TPC;
   const int64_t r0 = P.off[p];
   const int n = int(P.off[p + 1] - r0);
-  const int row0 = rt * EB_ROWS;
-  if (row0 >= n) return;
+  if (rt0 * EB_ROWS >= n) return;
+  const int n_tiles = min(EB_TPC, (n - rt0 * EB_ROWS + EB_ROWS - 1) / EB_ROWS);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  constexpr uint32_t OFF_B = KC * 3 * EB_TILE, OFF_BAR = KC * 6 * EB_TILE;
-  const uint32_t bar_full = sbase + OFF_BAR, bar_done = bar_full + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + OFF_BAR + 16);
+  constexpr uint32_t A_BYTES = KC * 3 * EB_TILE;
+  constexpr int AST = eb_a_stages(KC);
+  constexpr uint32_t OFF_B = AST * A_BYTES, OFF_BAR = OFF_B + KC * 3 * EB_TILE;
+  const uint32_t bar_b = sbase + OFF_BAR;       // B resident
+  const uint32_t bar_afull = bar_b + 8;         // [2]
+  const uint32_t bar_aempty = bar_afull + 16;   // [2]
+  const uint32_t bar_tfull = bar_aempty + 16;   // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + OFF_BAR + 80);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_done, 1);
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,112 +167,133 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[i]) : "memory");
       }
-      mbar_expect_tx(bar_full, KC * 6 * EB_TILE);
-      const int arow = int(r0 + row0), brow = p * EB_ROWS;
+      mbar_expect_tx(bar_b, KC * 3 * EB_TILE);
+      const int brow = p * EB_ROWS;
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          tma_load_2d(sbase + (kc * 3 + i) * EB_TILE, &maps.a[i], kc * EB_BK, arow, bar_full);
-          tma_load_2d(sbase + OFF_B + (kc * 3 + i) * EB_TILE, &maps.b[i], kc * EB_BK, brow, bar_full);
-        }
+        for (int i = 0; i < 3; ++i) tma_load_2d(sbase + OFF_B + (kc * 3 + i) * EB_TILE, &maps.b[i], kc * EB_BK, brow, bar_b);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % AST;
+        mbar_wait_backoff(bar_aempty + 8 * s, ((t / AST) & 1) ^ 1);
+        mbar_expect_tx(bar_afull + 8 * s, A_BYTES);
+        const int arow = int(r0 + int64_t(rt0 + t) * EB_ROWS);
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            tma_load_2d(sbase + s * A_BYTES + (kc * 3 + i) * EB_TILE, &maps.a[i], kc * EB_BK, arow, bar_afull + 8 * s);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait_backoff(bar_full, 0);
-      tc_fence_after();
-      const uint32_t t_hh = tmem_base, t_cor = tmem_base + EB_ROWS;
+      mbar_wait_backoff(bar_b, 0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t & 1, sa = t % AST;
+        mbar_wait_backoff(bar_tempty + 8 * s, ((t >> 1) & 1) ^ 1);
+        mbar_wait_backoff(bar_afull + 8 * sa, (t / AST) & 1);
+        tc_fence_after();
+        const uint32_t t_hh = tmem_base + s * 2 * EB_ROWS, t_cor = t_hh + EB_ROWS;
 #pragma unroll
-      for (int kc = 0; kc < KC; ++kc) {
-        uint64_t da[3], db[3];
+        for (int kc = 0; kc < KC; ++kc) {
+          uint64_t da[3], db[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          da[i] = eb_desc_sw128(sbase + (kc * 3 + i) * EB_TILE);
-          db[i] = eb_desc_sw128(sbase + OFF_B + (kc * 3 + i) * EB_TILE);
+          for (int i = 0; i < 3; ++i) {
+            da[i] = eb_desc_sw128(sbase + sa * A_BYTES + (kc * 3 + i) * EB_TILE);
+            db[i] = eb_desc_sw128(sbase + OFF_B + (kc * 3 + i) * EB_TILE);
+          }
+#pragma unroll
+          for (int k = 0; k < EB_BK / EB_UK; ++k) {
+            const uint64_t ko = uint64_t((k * EB_UK * 2) >> 4);
+            const uint32_t first = (kc | k) != 0;
+            tc_mma_bf16(t_hh, da[0] + ko, db[0] + ko, kEbIdesc, first);   // h h
+            tc_mma_bf16(t_cor, da[0] + ko, db[1] + ko, kEbIdesc, first);  // h m
+            tc_mma_bf16(t_cor, da[1] + ko, db[0] + ko, kEbIdesc, 1);      // m h
+            tc_mma_bf16(t_cor, da[1] + ko, db[1] + ko, kEbIdesc, 1);      // m m
+            tc_mma_bf16(t_cor, da[0] + ko, db[2] + ko, kEbIdesc, 1);      // h l
+            tc_mma_bf16(t_cor, da[2] + ko, db[0] + ko, kEbIdesc, 1);      // l h
+          }
         }
-#pragma unroll
-        for (int k = 0; k < EB_BK / EB_UK; ++k) {
-          const uint64_t ko = uint64_t((k * EB_UK * 2) >> 4);
-          const uint32_t first = (kc | k) != 0;
-          tc_mma_bf16(t_hh, da[0] + ko, db[0] + ko, kEbIdesc, first);   // h h
-          tc_mma_bf16(t_cor, da[0] + ko, db[1] + ko, kEbIdesc, first);  // h m
-          tc_mma_bf16(t_cor, da[1] + ko, db[0] + ko, kEbIdesc, 1);      // m h
-          tc_mma_bf16(t_cor, da[1] + ko, db[1] + ko, kEbIdesc, 1);      // m m
-          tc_mma_bf16(t_cor, da[0] + ko, db[2] + ko, kEbIdesc, 1);      // h l
-          tc_mma_bf16(t_cor, da[2] + ko, db[0] + ko, kEbIdesc, 1);      // l h
-        }
+        tc_commit(bar_aempty + 8 * sa);
+        tc_commit(bar_tfull + 8 * s);
       }
-      tc_commit(bar_done);
     }
   } else {
     const int q = warp & 3;
-    const int i = row0 + 32 * q + lane;  // row inside the pair
-    const bool ok = i < n;
-    const int64_t gi = r0 + i;
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(32 * q) << 16);
-    float ss = 0.f;
-    const int n_ch = P.kp_out / 32;
-    for (int ch = 0; ch < n_ch; ++ch) {
-      float a[32], c[32];
-      if (ch * 32 < P.k_out) {
-        tmem_ld32(taddr + ch * 32, a);
-        tmem_ld32(taddr + EB_ROWS + ch * 32, c);
-      } else {
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
+      const int i = (rt0 + t) * EB_ROWS + 32 * q + lane;  // row inside the pair
+      const bool ok = i < n;
+      const int64_t gi = r0 + i;
+      mbar_wait(bar_tfull + 8 * s, (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + s * 2 * EB_ROWS + (uint32_t(32 * q) << 16);
+      float ss = 0.f;
+      const int n_ch = P.kp_out / 32;
+      for (int ch = 0; ch < n_ch; ++ch) {
+        float a[32], c[32];
+        if (ch * 32 < P.k_out) {
+          tmem_ld32(taddr + ch * 32, a);
+          tmem_ld32(taddr + EB_ROWS + ch * 32, c);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) a[e] = c[e] = 0.f;
-      }
-      uint32_t ph[16], pl[16];
+          for (int e = 0; e < 32; ++e) a[e] = c[e] = 0.f;
+        }
+        uint32_t ph[16], pl[16];
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float y0 = a[e] + c[e], y1 = a[e + 1] + c[e + 1];
-        ss = fmaf(y0, y0, ss);
-        ss = fmaf(y1, y1, ss);
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-        ph[e >> 1] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-        pl[e >> 1] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
-      }
-      if (ok && P.hi) {
-        uint4* dh = reinterpret_cast<uint4*>(P.hi + gi * P.kp_out + ch * 32);
-        uint4* dl = reinterpret_cast<uint4*>(P.lo + gi * P.kp_out + ch * 32);
+        for (int e = 0; e < 32; e += 2) {
+          const float y0 = a[e] + c[e], y1 = a[e + 1] + c[e + 1];
+          ss = fmaf(y0, y0, ss);
+          ss = fmaf(y1, y1, ss);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+          ph[e >> 1] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+          pl[e >> 1] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+        }
+        if (ok && P.hi) {
+          uint4* dh = reinterpret_cast<uint4*>(P.hi + gi * P.kp_out + ch * 32);
+          uint4* dl = reinterpret_cast<uint4*>(P.lo + gi * P.kp_out + ch * 32);
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
-          dh[v4] = make_uint4(ph[4 * v4], ph[4 * v4 + 1], ph[4 * v4 + 2], ph[4 * v4 + 3]);
-          dl[v4] = make_uint4(pl[4 * v4], pl[4 * v4 + 1], pl[4 * v4 + 2], pl[4 * v4 + 3]);
+          for (int v4 = 0; v4 < 4; ++v4) {
+            dh[v4] = make_uint4(ph[4 * v4], ph[4 * v4 + 1], ph[4 * v4 + 2], ph[4 * v4 + 3]);
+            dl[v4] = make_uint4(pl[4 * v4], pl[4 * v4 + 1], pl[4 * v4 + 2], pl[4 * v4 + 3]);
+          }
         }
       }
-    }
-    // |row| rounded up (fp32 sum of squares: relative error <= (k_out + 2) 2^-24), embedding error e_i, inflated norm
-    const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
-    const float e_i = ok ? P.eps_e * P.a_norm[gi] * P.c_fro[p] : 0.f;
-    const float own = (nrm + e_i) + e_i * P.inv_eps;  // eps * own >= eps |row| + e_i
-    if (ok && P.norm) P.norm[gi] = own;
-    for (int e = 0; e < P.n_epi; ++e) {
-      const EbEpi& E = P.epi[e];
-      float g = 0.f, bm = 0.f;
-      if (ok) {
-        const float sc = E.scale ? float(E.scale[gi]) : 1.f;
-        const float bi = E.bias_sqnorm ? -0.5f * ss : 0.f;
-        E.sf[gi] = sc;
-        E.bf[gi] = bi;
-        if (E.sd) E.sd[gi] = E.scale ? E.scale[gi] : 1.0;
-        if (E.bd) E.bd[gi] = 0.0;
-        g = own * fabsf(sc) * 1.000001f;
-        // the float64 bias differs from bi by <= |row| e_i + e_i^2 / 2 + the fp32 rounding of the sum of squares;
-        // it enters the threshold through Bm (emit_result: 9.6e-7 (|s| + Bm)), hence the division
-        const float db = E.bias_sqnorm ? (nrm * e_i + 0.5f * e_i * e_i + fabsf(bi) * float(P.k_out + 4) * 1.2e-7f) : 0.f;
-        bm = fabsf(bi) + db * (2.f / 9.6e-7f);
-      }
+      // the accumulators of this tile are free again
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+      // |row| rounded up (fp32 sum of squares: relative error <= (k_out + 2) 2^-24), embedding error e_i, inflated norm
+      const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[gi] * P.c_fro[p] : 0.f;
+      const float own = (nrm + e_i) + e_i * P.inv_eps;  // eps * own >= eps |row| + e_i
+      if (ok && P.norm) P.norm[gi] = own;
+      for (int e = 0; e < P.n_epi; ++e) {
+        const EbEpi& E = P.epi[e];
+        float g = 0.f, bm = 0.f;
+        if (ok) {
+          const float sc = E.scale ? float(E.scale[gi]) : 1.f;
+          const float bi = E.bias_sqnorm ? -0.5f * ss : 0.f;
+          E.sf[gi] = sc;
+          E.bf[gi] = bi;
+          if (E.sd) E.sd[gi] = E.scale ? E.scale[gi] : 1.0;
+          if (E.bd) E.bd[gi] = 0.0;
+          g = own * fabsf(sc) * 1.000001f;
+          // the float64 bias differs from bi by <= |row| e_i + e_i^2 / 2 + the fp32 rounding of the sum of squares;
+          // it enters the threshold through Bm (emit_result: 9.6e-7 (|s| + Bm)), hence the division
+          const float db = E.bias_sqnorm ? (nrm * e_i + 0.5f * e_i * e_i + fabsf(bi) * float(P.k_out + 4) * 1.2e-7f) : 0.f;
+          bm = fabsf(bi) + db * (2.f / 9.6e-7f);
+        }
 #pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) {
-        g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, sh));
-        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, sh));
-      }
-      if (lane == 0) {
-        atomic_max_nonneg(E.G + p, g);
-        atomic_max_nonneg(E.Bm + p, bm);
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, sh));
+          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, sh));
+        }
+        if (lane == 0) {
+          atomic_max_nonneg(E.G + p, g);
+          atomic_max_nonneg(E.Bm + p, bm);
+        }
       }
     }
   }
@@ -256,7 +301,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -416,7 +461,7 @@ int eb_launch(const EbMaps& maps, const EbParams& P, int n_pairs, cudaStream_t s
   static OncePerDevice once;
   if (once.first())
     DM_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(eb_smem_bytes(KC))));
-  const int64_t nblk = int64_t(n_pairs) * P.max_rt;
+  const int64_t nblk = int64_t(n_pairs) * ((P.max_rt + EB_TPC - 1) / EB_TPC);
   if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles");
   embed_tc_kernel<KC><<<unsigned(nblk), EB_THREADS, eb_smem_bytes(KC), st>>>(maps, P);
   DM_LAUNCH_OK("embed_tc_kernel");
@@ -471,7 +516,7 @@ int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
   csplit_kernel<<<dim3(unsigned(X.n_pairs), 2), 256, 0, st>>>(
       X.C, X.k1, X.k2, X.kp2, X.kp1, reinterpret_cast<__nv_bfloat16*>(X.c0h), reinterpret_cast<__nv_bfloat16*>(X.c0m),
       reinterpret_cast<__nv_bfloat16*>(X.c0l), reinterpret_cast<__nv_bfloat16*>(X.c1h),
-      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.c_fro);
+      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.c_fro, 0, nullptr);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
   E.off = X.off2, E.max_rt = (X.max_n2 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k1, E.kp_out = P.kp, E.n_epi = R.n_col;
@@ -584,6 +629,110 @@ F2PLayout f2p_carve(void* ws, int n_pairs, int64_t n1, int64_t n2, int max_n1, i
   return L;
 }
 
+// ---------------------------------------------------------------- the ladder conversion p2p_21(C) (ZoomOut / ICP)
+// queries = Phi2[:, :k2] as they are, database = Phi1[:, :k1] C^T embedded on the tensor cores, one Euclidean row epilogue
+struct P21Ctx {
+  const double *C, *Phi1;
+  int64_t ld1;
+  const int64_t* off1;
+  int64_t total_n1;
+  int max_n1, n_pairs, k1, k2, kp1;
+  uint16_t *p1h, *p1m, *p1l;  // three-way split of Phi1 [total_n1, kp1] (resident across rungs)
+  float* p1norm;
+  uint16_t *c1h, *c1m, *c1l;  // split of C (rows o < k2, contraction k < k1) [n_pairs * 128, kp1]
+  float* c_fro;
+  double* Ct;                 // [n_pairs, k1, k2] float64 transpose of C
+  double* emb1;               // [total_n1, lde] float64 database rows, filled on demand
+  int lde;
+  int* skip_x;
+};
+
+__global__ void __launch_bounds__(256) ladder_fill_kernel(const NNProblem P, const double* __restrict__ Phi1, int64_t ld1,
+                                                          const double* __restrict__ Ct, int k1, int k2,
+                                                          double* __restrict__ emb1, int lde, double* __restrict__ bd,
+                                                          int* __restrict__ skip_x) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
+  const unsigned n_cand = P.counters[0], n_full = P.counters[3];
+  for (unsigned f = warp; f < n_cand + n_full; f += nwarp) {
+    const bool full = f >= n_cand;
+    const FlagEntry e = full ? P.flags[P.flag_cap - 1 - int64_t(f - n_cand)] : P.flags[f];
+    const int p = e.pair;
+    if (full) {
+      if (lane == 0) skip_x[p] = 0;  // every float64 database row of this pair is needed
+      continue;
+    }
+    const int64_t d0 = P.db_off[p];
+    for (int c = 0; c < 2; ++c) {
+      const int j = c == 0 ? e.c1 : e.c2;
+      // emb1_j[o] = sum_k Phi1[j][k] C[o][k] = sum_k Phi1[j][k] Ct[k][o]
+      const double ss = warp_row_times_C(Phi1 + (d0 + j) * ld1, Ct + int64_t(p) * k1 * k2, k2, k1, lane, emb1 + (d0 + j) * lde);
+      if (lane == 0) bd[d0 + j] = -0.5 * ss;
+    }
+  }
+}
+
+int p21_prep_x(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) {
+  P21Ctx& X = *static_cast<P21Ctx*>(vctx);
+  csplit_kernel<<<dim3(unsigned(X.n_pairs), 1), 256, 0, st>>>(
+      X.C, X.k1, X.k2, 0, X.kp1, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(X.c1h),
+      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.c_fro, 1, X.Ct);
+  DM_LAUNCH_OK("csplit_kernel");
+  EbParams E{};
+  E.off = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = P.kp, E.n_epi = 1;
+  E.hi = reinterpret_cast<__nv_bfloat16*>(L.xh), E.lo = reinterpret_cast<__nv_bfloat16*>(L.xl);
+  E.norm = L.norm_db, E.a_norm = X.p1norm, E.c_fro = X.c_fro;
+  E.eps_e = eb_eps(X.kp1), E.inv_eps = 1.f / P.eps;
+  if (R.n_row != 1 || R.row[0].bias_mode != DM_BIAS_NEG_HALF_SQNORM || R.row[0].scale_mode != DM_SCALE_NONE)
+    DM_FAIL(DM_ERR_UNSUPPORTED, "factored database side: one Euclidean row epilogue expected");
+  E.epi[0] = EbEpi{1, nullptr, L.row[0].sf, L.row[0].bf, L.row[0].G, L.row[0].Bm, L.row[0].sd, L.row[0].bd};
+  DM_CUDA_OK(cudaMemsetAsync(L.row[0].G, 0, sizeof(float) * X.n_pairs, st));
+  DM_CUDA_OK(cudaMemsetAsync(L.row[0].Bm, 0, sizeof(float) * X.n_pairs, st));
+  const void* a3[3] = {X.p1h, X.p1m, X.p1l};
+  const void* b3[3] = {X.c1h, X.c1m, X.c1l};
+  return eb_run(a3, X.total_n1, b3, X.kp1, E, X.n_pairs, st);
+}
+
+int p21_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t st) {
+  P21Ctx& X = *static_cast<P21Ctx*>(vctx);
+  DM_CUDA_OK(cudaMemsetAsync(X.skip_x, 1, sizeof(int) * X.n_pairs, st));
+  ladder_fill_kernel<<<num_sms() * 8, 256, 0, st>>>(P, X.Phi1, X.ld1, X.Ct, X.k1, X.k2, X.emb1, X.lde, L.row[0].bd, X.skip_x);
+  DM_LAUNCH_OK("ladder_fill_kernel");
+  GemmProblem G;
+  G.A.d = X.Phi1, G.A.ld = X.ld1, G.A.off = X.off1, G.A.trans = 0;
+  G.B.d = X.C, G.B.ld = X.k1, G.B.batch_stride = int64_t(X.k1) * X.k2, G.B.rows = X.k2, G.B.trans = 0;
+  G.N = X.k2, G.K = X.k1, G.maxM = X.max_n1, G.maxN = X.k2, G.maxK = X.k1, G.n_batch = X.n_pairs;
+  G.C = X.emb1, G.ldc = X.lde, G.c_off = X.off1, G.skip = X.skip_x;
+  int rc;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  bias_rows_flagged_kernel<<<dim3(32, unsigned(X.n_pairs)), 256, 0, st>>>(X.emb1, X.lde, X.off1, X.max_n1, X.k2, X.skip_x,
+                                                                          L.row[0].bd);
+  DM_LAUNCH_OK("bias_rows_flagged_kernel");
+  return DM_OK;
+}
+
+struct P21Layout {
+  P21Ctx c;
+  size_t bytes;
+};
+P21Layout p21_carve(void* ws, int n_pairs, int64_t total_n1, int k1m, int k2m) {
+  Carver c(ws);
+  P21Layout L{};
+  const int kp = nn_tc_kp(k1m < 2 * EB_BK ? k1m : 2 * EB_BK);
+  (void)k2m;
+  L.c.p1h = c.take<uint16_t>(size_t(total_n1) * kp);
+  L.c.p1m = c.take<uint16_t>(size_t(total_n1) * kp);
+  L.c.p1l = c.take<uint16_t>(size_t(total_n1) * kp);
+  L.c.p1norm = c.take<float>(size_t(total_n1));
+  const size_t cb = size_t(n_pairs) * EB_ROWS * kp;
+  L.c.c1h = c.take<uint16_t>(cb), L.c.c1m = c.take<uint16_t>(cb), L.c.c1l = c.take<uint16_t>(cb);
+  L.c.c_fro = c.take<float>(size_t(n_pairs));
+  L.c.Ct = c.take<double>(size_t(n_pairs) * 2 * EB_BK * 2 * EB_BK);
+  L.c.skip_x = c.take<int>(size_t(n_pairs));
+  L.bytes = c.bytes();
+  return L;
+}
+
 }  // namespace
 
 bool f2p_factored_applicable(int k1, int k2, int flags) {
@@ -628,6 +777,56 @@ int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_
   R.flags = flags | kFlagSplit3;
   R.hooks = &H;
   return nn_run(R, L.nn_ws, L.nn_bytes, st);
+}
+
+}  // namespace dm
+
+namespace dm {
+
+bool p2p21_factored_applicable(int k1, int k2, int flags) {
+  static const bool off = [] { const char* e = getenv("DM_P21_F64EMB"); return e && e[0] == '1'; }();
+  return !off && nn_use_tc(flags) && k1 <= 2 * EB_BK && k2 <= 2 * EB_BK && !(flags & (DM_RECHECK_ALL | DM_SKIP_PREP));
+}
+
+size_t p2p21_factored_scratch_bytes(int n_pairs, int64_t total_n1, int k1m, int k2m) {
+  return p21_carve(nullptr, n_pairs, total_n1, k1m, k2m).bytes;
+}
+
+int p2p21_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
+                       int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                       int n_pairs, void* p2p_out, int flags, void* scratch, double* emb1, int lde, void* nn_ws,
+                       size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state) {
+  // the carve uses the widest split the scratch was sized for; this rung uses the first kp1 columns of each row, so the
+  // split of Phi1 is stored with the rung's own pitch kp1 and remade when the pitch changes (64 -> 128)
+  P21Layout L = p21_carve(scratch, n_pairs, total_n1, 2 * EB_BK, 2 * EB_BK);
+  P21Ctx& X = L.c;
+  X.C = C, X.Phi1 = Phi1, X.ld1 = ld1, X.off1 = off1, X.total_n1 = total_n1, X.max_n1 = max_n1, X.n_pairs = n_pairs;
+  X.k1 = k1, X.k2 = k2, X.kp1 = nn_tc_kp(k1), X.emb1 = emb1, X.lde = lde;
+  int rc;
+  if (!x_kp_state || *x_kp_state != X.kp1) {
+    // all the columns of the padded width (those beyond k1 meet the zero padding of the split of C)
+    const int d_all = int(ld1 < X.kp1 ? ld1 : X.kp1);
+    if ((rc = nn_prep_side(Phi1, 1, ld1, off1, n_pairs, total_n1, d_all, X.p1norm, nullptr, 0, X.p1h, X.p1m, X.p1l, X.kp1, st)))
+      return rc;
+    if (x_kp_state) *x_kp_state = X.kp1;
+  }
+  NNHooks H;
+  H.ctx = &X, H.prep_x = p21_prep_x, H.before_recheck = p21_before_recheck;
+  NNRequest R{};
+  R.Y64 = Phi2, R.ldY64 = ld2, R.X64 = emb1, R.ldX64 = lde;
+  R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
+  R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = k2, R.d_fast = 0;
+  R.n_row = 1, R.n_col = 0;
+  R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NEG_HALF_SQNORM, nullptr, nullptr, p2p_out};
+  R.flags = flags;
+  R.hooks = &H;
+  if (y_kp_state) {
+    const int kp = nn_tc_kp(k2);
+    R.y_prep_d = int(ld2 < kp ? ld2 : kp);
+    R.skip_prep_y = (*y_kp_state == kp);
+    *y_kp_state = kp;
+  }
+  return nn_run(R, nn_ws, nn_ws_bytes, st);
 }
 
 }  // namespace dm

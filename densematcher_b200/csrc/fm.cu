@@ -78,12 +78,18 @@ struct P2P21Scratch {
   void* nn_ws;
   size_t nn_ws_bytes;
   int lde, ldf;
+  void* fact = nullptr;  // scratch of the factored (tensor-core embedding) path, k <= 128
+  int x_kp = -1;         // padded width for which the split of Phi1 in `fact` is valid
 };
 int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
               int max_n1, const double* Phi2, int64_t ld2, const float* Phi2f, int ldPhi2f, const int64_t* off2,
-              int64_t total_n2, int max_n2, int n_pairs, void* p2p_out, int flags, const P2P21Scratch& S,
+              int64_t total_n2, int max_n2, int n_pairs, void* p2p_out, int flags, P2P21Scratch& S,
               cudaStream_t st, int* y_kp_state = nullptr) {
   int rc;
+  // k <= 128: the database side Phi1 C^T is embedded on the tensor cores, float64 rows on demand (embed_tc.cu)
+  if (S.fact && p2p21_factored_applicable(k1, k2, flags))
+    return p2p21_factored_run(C, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, n_pairs,
+                              p2p_out, flags, S.fact, S.emb1, S.lde, S.nn_ws, S.nn_ws_bytes, st, &S.x_kp, y_kp_state);
   GemmProblem G;
   G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
   G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 0;
@@ -322,6 +328,7 @@ size_t dm_zoomout_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n
   c.take<int32_t>(size_t(total_n2) * 2);        // p2p (int32 or int64)
   c.take<char>(zoomout_pf_ws(n_pairs, total_n2, max_n2, k1m, k2m, flags));
   c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags));
+  c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1m, k2m));
   return c.bytes();
 }
 
@@ -354,6 +361,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   const bool fast_fm = (flags & DM_FAST_FM) && proj_tc_supported(k2m, k1m);
   S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags);
   S.nn_ws = c.take<char>(S.nn_ws_bytes);
+  S.fact = c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1m, k2m));
   const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
   int rc;
   if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
@@ -422,6 +430,7 @@ IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, i
   L.pf_ws = c.take<char>(L.pf_bytes);
   L.S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2, 1, 0, flags);
   L.S.nn_ws = c.take<char>(L.S.nn_ws_bytes);
+  L.S.fact = c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1, k2));
   L.bytes = c.bytes();
   return L;
 }

@@ -563,8 +563,10 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   int rc;
   if (!(R.flags & DM_SKIP_PREP)) {
     // database side carries the row epilogues' scale/bias, query side the column epilogues'
-    if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs, R.n_row,
-                           L.xh, L.xl, L.xl2, P.kp, st)))
+    if (R.hooks && R.hooks->prep_x) {
+      if ((rc = R.hooks->prep_x(R.hooks->ctx, L, P, R, st))) return rc;
+    } else if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs,
+                                  R.n_row, L.xh, L.xl, L.xl2, P.kp, st)))
       return rc;
     if (R.hooks && R.hooks->prep_y) {
       if ((rc = R.hooks->prep_y(R.hooks->ctx, L, P, R, st))) return rc;
