@@ -343,7 +343,11 @@ __global__ void __launch_bounds__(NT, NB == 8 ? 1 : 2) gemm64_kernel(const GemmP
 // A fragments as they are read.
 constexpr int KSTAGES = 4;
 constexpr int TT_TNW = 64;
-constexpr size_t kTTSmem = size_t(KSTAGES) * TK * (LDT + (TT_TNW + 4)) * sizeof(double) + size_t(KSTAGES) * TK * sizeof(double);
+// TTK vertices per stage: 8 gave 32 DMMAs per warp between two block barriers (barrier stalls were the top stall reason in
+// the first capture, 42 % DMMA pipe); 16 halves the barrier count at 103 KB of shared memory (still two blocks per SM)
+constexpr size_t tt_smem(int ttk) {
+  return size_t(KSTAGES) * ttk * (LDT + (TT_TNW + 4)) * sizeof(double) + size_t(KSTAGES) * ttk * sizeof(double);
+}
 
 __device__ __forceinline__ void cp_async16_zfill(double* dst, const double* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src),
@@ -351,8 +355,10 @@ __device__ __forceinline__ void cp_async16_zfill(double* dst, const double* src,
                : "memory");
 }
 
+template <int TTK>
 __global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, int tiles_m, int tiles_n) {
   constexpr int TNW = TT_TNW, LDB = TNW + 4;
+  constexpr int AH = TTK / 4, BH = TTK / 8;  // 16-byte chunks per thread and stage: A (TTK x 64 chunks), B (TTK x 32)
   int bid = blockIdx.x;
   const int tn = bid % tiles_n;
   bid /= tiles_n;
@@ -373,45 +379,46 @@ __global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, i
     kend = min(K, kbeg + P.kchunk);
   }
   extern __shared__ __align__(16) double tsm[];
-  double* As = tsm;                                 // [KSTAGES][TK][LDT]
-  double* Bs = As + KSTAGES * TK * LDT;             // [KSTAGES][TK][LDB]
-  double* Ss = Bs + KSTAGES * TK * LDB;             // [KSTAGES][TK] vertex scale
+  double* As = tsm;                                  // [KSTAGES][TTK][LDT]
+  double* Bs = As + KSTAGES * TTK * LDT;             // [KSTAGES][TTK][LDB]
+  double* Ss = Bs + KSTAGES * TTK * LDB;             // [KSTAGES][TTK] vertex scale
   const OpView A = resolve(P.A, b), B = resolve(P.B, b);
   const int t = threadIdx.x;
-  // A stage: TK rows x 64 16-byte chunks = 512 chunks -> 2 per thread; B stage: TK rows x 32 chunks = 256 -> 1 per thread
-  const int a_row = t >> 6, a_ch = t & 63;          // rows a_row, a_row + 4
-  const int b_row = t >> 5, b_ch = t & 31;
-  const int n_stage = (kend - kbeg + TK - 1) / TK;
+  const int a_row = t >> 6, a_ch = t & 63;           // A rows a_row + 4 h
+  const int b_row = t >> 5, b_ch = t & 31;           // B rows b_row + 8 h
+  const int n_stage = (kend - kbeg + TTK - 1) / TTK;
   auto a_src_row = [&](int k) -> int64_t { return A.gather ? load_index(A.gather, A.gbase + k, A.gather_i64 != 0) : k; };
   auto b_src_row = [&](int k) -> int64_t { return B.gather ? load_index(B.gather, B.gbase + k, B.gather_i64 != 0) : k; };
   // gather rows of the stage that will be ISSUED next (fetched one issue ahead: KSTAGES stages before use)
-  int64_t ra0 = 0, ra1 = 0, rb = 0;
+  int64_t ra[AH], rb[BH];
   auto load_rows = [&](int stage) {
-    const int k = kbeg + stage * TK;
-    ra0 = (k + a_row < kend) ? a_src_row(k + a_row) : 0;
-    ra1 = (k + a_row + 4 < kend) ? a_src_row(k + a_row + 4) : 0;
-    rb = (k + b_row < kend) ? b_src_row(k + b_row) : 0;
+    const int k = kbeg + stage * TTK;
+#pragma unroll
+    for (int h = 0; h < AH; ++h) ra[h] = (k + a_row + 4 * h < kend) ? a_src_row(k + a_row + 4 * h) : 0;
+#pragma unroll
+    for (int h = 0; h < BH; ++h) rb[h] = (k + b_row + 8 * h < kend) ? b_src_row(k + b_row + 8 * h) : 0;
   };
   auto issue = [&](int stage) {
-    const int k = kbeg + stage * TK, buf = stage % KSTAGES;
-    double* as = As + buf * TK * LDT;
-    double* bs = Bs + buf * TK * LDB;
+    const int k = kbeg + stage * TTK, buf = stage % KSTAGES;
+    double* as = As + buf * TTK * LDT;
+    double* bs = Bs + buf * TTK * LDB;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < AH; ++h) {
       const int kk = a_row + 4 * h, i = m0 + 2 * a_ch;
       const int valid = (k + kk < kend) ? max(0, min(2, M - i)) : 0;
-      const double* src = A.d + (h == 0 ? ra0 : ra1) * A.ld + min(i, max(M - 1, 0));
+      const double* src = A.d + ra[h] * A.ld + min(i, max(M - 1, 0));
       cp_async16_zfill(as + kk * LDT + 2 * a_ch, valid > 0 ? src : A.d, 8 * valid);
     }
-    {
-      const int i = n0 + 2 * b_ch;
-      const int valid = (k + b_row < kend) ? max(0, min(2, N - i)) : 0;
-      const double* src = B.d + rb * B.ld + min(i, max(N - 1, 0));
-      cp_async16_zfill(bs + b_row * LDB + 2 * b_ch, valid > 0 ? src : B.d, 8 * valid);
+#pragma unroll
+    for (int h = 0; h < BH; ++h) {
+      const int kk = b_row + 8 * h, i = n0 + 2 * b_ch;
+      const int valid = (k + kk < kend) ? max(0, min(2, N - i)) : 0;
+      const double* src = B.d + rb[h] * B.ld + min(i, max(N - 1, 0));
+      cp_async16_zfill(bs + kk * LDB + 2 * b_ch, valid > 0 ? src : B.d, 8 * valid);
     }
-    if (t < TK) {
+    if (t < TTK) {
       const double* ksc = A.kscale ? A.kscale : B.kscale;
-      Ss[buf * TK + t] = (k + t < kend) ? (ksc ? ksc[k + t] : 1.0) : 0.0;
+      Ss[buf * TTK + t] = (k + t < kend) ? (ksc ? ksc[k + t] : 1.0) : 0.0;
     }
   };
   // warp grid 4 (M) x 2 (N): warp tile 32 x 32
@@ -444,12 +451,12 @@ __global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, i
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     const int buf = st % KSTAGES;
-    const double* as = As + buf * TK * LDT + wm + g;
-    const double* bs = Bs + buf * TK * LDB + wn + g;
-    const double* ss = Ss + buf * TK;
+    const double* as = As + buf * TTK * LDT + wm + g;
+    const double* bs = Bs + buf * TTK * LDB + wn + g;
+    const double* ss = Ss + buf * TTK;
     if (na > 0 && nc > 0) {
 #pragma unroll
-      for (int k4 = 0; k4 < TK; k4 += 4) {
+      for (int k4 = 0; k4 < TTK; k4 += 4) {
         const double sc = ss[k4 + t4];
         double av[4], bv[NT8];
 #pragma unroll
@@ -681,10 +688,16 @@ int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
     if (Q.ksplit < 1) Q.ksplit = 1;
     const int64_t nblk = int64_t(P.n_batch) * Q.ksplit * tiles_m * tiles_n;
     if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "gemm64: grid too large");
+    static const int ttk = [] { const char* e = getenv("DM_TT_TK"); return e ? atoi(e) : 16; }();
     static OncePerDevice once;
-    if (once.first())
-      DM_CUDA_OK(cudaFuncSetAttribute(gemm64_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTTSmem)));
-    gemm64_tt_kernel<<<unsigned(nblk), NT, kTTSmem, st>>>(Q, tiles_m, tiles_n);
+    if (once.first()) {
+      DM_CUDA_OK(cudaFuncSetAttribute(gemm64_tt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tt_smem(8))));
+      DM_CUDA_OK(cudaFuncSetAttribute(gemm64_tt_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tt_smem(16))));
+    }
+    if (ttk == 8)
+      gemm64_tt_kernel<8><<<unsigned(nblk), NT, tt_smem(8), st>>>(Q, tiles_m, tiles_n);
+    else
+      gemm64_tt_kernel<16><<<unsigned(nblk), NT, tt_smem(16), st>>>(Q, tiles_m, tiles_n);
     DM_LAUNCH_OK("gemm64_tt_kernel");
     return DM_OK;
   }
