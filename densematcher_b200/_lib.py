@@ -98,6 +98,15 @@ SIGNATURES = {
     "dm_precise_map_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_i64, c_i64]),
     "dm_precise_map": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int,
                                c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "dm_lbo_eigs_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "dm_lbo_eigs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_dbl, c_int, c_int, c_vp, c_vp, c_i64, c_vp,
+                            c_vp, c_vp, c_sz, c_vp]),
+    "dm_sym_eig_workspace_bytes": (c_sz, [c_int, c_int]),
+    "dm_sym_eig": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dm_from_basis": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp]),
+    "dm_spectral_diffusion_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_int, c_int]),
+    "dm_spectral_diffusion": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int,
+                                      c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     "dm_icp_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
     "dm_icp": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
                        c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

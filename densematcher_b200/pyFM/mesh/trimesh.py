@@ -84,24 +84,33 @@ class TriMesh:
         return sp.coo_matrix((np.concatenate([-S, -S, S, S]),
                               (np.concatenate([I, J, I, J]), np.concatenate([J, I, I, J]))), shape=(n, n)).tocsc()
 
-    def laplacian_spectrum(self, k, **_):
+    def laplacian_spectrum(self, k, device=None, **_):
+        """Cotangent stiffness + lumped mass, then the k lowest eigenpairs (mesh/laplacian.py:143-182).
+        ``device`` = a CUDA device: the device eigensolver (spectral_ops.lbo_eigs, csrc/spectral.cu);
+        ``device`` = None or "cpu": scipy's shift-invert ``eigsh`` with sigma = -0.01 like the reference (host)."""
         if self.vertlist is None or self.facelist is None:
             raise ValueError("no geometry and no precomputed spectrum: supply eigenvalues / eigenvectors / A")
         self.W = self._cotan_stiffness()
         self.A = None
         self.A = sp.diags(self.vertex_areas).tocsc()
+        if device is not None and str(device) != "cpu":
+            from ... import spectral_ops
+            evals, evects = spectral_ops.lbo_eigs(self.W, self.vertex_areas, k, device=device)
+            self.eigenvalues, self.eigenvectors = evals.cpu().numpy(), evects.cpu().numpy()
+            return self
         evals, evects = spla.eigsh(self.W, k=k, M=self.A, sigma=-0.01)   # mesh/laplacian.py:165-168
         order = np.argsort(evals)
         self.eigenvalues, self.eigenvectors = evals[order], np.ascontiguousarray(evects[:, order])
         return self
 
-    def process(self, k=200, skip_normals=True, intrinsic=False, robust=False, verbose=False):
-        """trimesh.py:498-531: slice a spectrum that is already there, else compute it (host)."""
+    def process(self, k=200, skip_normals=True, intrinsic=False, robust=False, verbose=False, device=None):
+        """trimesh.py:498-531: slice a spectrum that is already there, else compute it (``device``: see
+        ``laplacian_spectrum``)."""
         if self.eigenvectors is not None and self.eigenvalues is not None and len(self.eigenvalues) >= k:
             self.eigenvectors = self.eigenvectors[:, :k]
             self.eigenvalues = self.eigenvalues[:k]
         else:
-            self.laplacian_spectrum(k)
+            self.laplacian_spectrum(k, device=device)
         return self
 
     # ------------------------------------------------------------------ projection (GPU)

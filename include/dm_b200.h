@@ -352,6 +352,45 @@ int dm_precise_map(const double* emb1, int64_t ld1, const int64_t* off1, int64_t
                    int64_t total_n2, int max_n2, int n_pairs, int p, void* face_match, double* bary, int flags,
                    void* workspace, size_t workspace_bytes, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Eigenbasis provider: the k lowest eigenpairs of  W phi = lambda A phi  (W: cotangent stiffness, CSR, float64, symmetric
+ * positive semi-definite; A = diag(mass) lumped vertex areas), evecs^T A evecs = I, eigenvalues ascending.
+ * Replaces: laplacian_spectrum, pyFM/mesh/laplacian.py:143-182 (scipy eigsh(W, k, M=A, sigma=-0.01)) as called by
+ * TriMesh.process (mesh/trimesh.py:498-531) and diffusion_net/geometry.py's operator cache.
+ * Method: Chebyshev-filtered block subspace iteration on A^-1/2 W A^-1/2 (no factorisation); Gram products on the float64
+ * tensor-core GEMM, dense Rayleigh-Ritz eigenproblems on the device (dm_sym_eig's kernel).  Stops when every wanted
+ * residual |S x - theta x| <= tol * theta_k (tol <= 0: 1e-10) or after max_iter outer iterations; `degree` <= 0 selects
+ * the default filter degree.  The call synchronises the stream once per outer iteration (8 bytes read back).
+ * info_h (host, optional) = {iterations, converged, block width, dense-solver status}; residual_h (host, optional).
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_lbo_eigs_workspace_bytes(int n, int64_t nnz, int k);
+int dm_lbo_eigs(const int64_t* indptr, const int32_t* indices, const double* values, int64_t nnz, const double* mass,
+                int n, int k, double tol, int max_iter, int degree, double* evals /* [k] */,
+                double* evecs /* [n, ld_evecs] */, int64_t ld_evecs, int* info_h, double* residual_h, void* workspace,
+                size_t workspace_bytes, dm_stream_t stream);
+
+/* Batched dense symmetric eigen-decomposition, float64: A [n_batch, m, m] -> w [n_batch, m] ascending,
+ * V [n_batch, m, m] with eigenvectors in the columns (numpy.linalg.eigh convention); m <= 512.  Householder
+ * tridiagonalisation + implicit QL, one CTA per matrix. */
+size_t dm_sym_eig_workspace_bytes(int n_batch, int m);
+int dm_sym_eig(const double* A, int m, int n_batch, double* w, double* V, void* workspace, size_t workspace_bytes,
+               dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DiffusionNet spectral transforms (diffusion_net/geometry.py:572-598, layers.py:56-67).
+ * dm_from_basis: out[rows of mesh b, :c] = Phi_b[:, :k] coef[b]   (coef [n_meshes, k, c] float64).
+ * dm_spectral_diffusion: out = Phi (exp(-evals t) * (Phi^T diag(mass) X))  -- to_basis on the tcgen05 projection
+ * engine (dm_project_ex, same flags), the coefficient scaling, from_basis on the float64 tensor-core GEMM.
+ * evals [n_meshes, k], time [c], X [total_n, ldX] float32, out [total_n, ld_out] float64.
+ * ---------------------------------------------------------------------------------------- */
+int dm_from_basis(const double* coef, const double* Phi, int64_t ldPhi, const int64_t* row_off, int max_n, int n_meshes,
+                  int k, int c, double* out, int64_t ld_out, dm_stream_t stream);
+size_t dm_spectral_diffusion_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int k, int c);
+int dm_spectral_diffusion(const double* Phi, int64_t ldPhi, const double* mass, const double* evals, const float* X,
+                          int64_t ldX, const double* time, const int64_t* row_off, int64_t total_n, int max_n,
+                          int n_meshes, int k, int c, double* out, int64_t ld_out, int flags, void* workspace,
+                          size_t workspace_bytes, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
