@@ -107,6 +107,8 @@ SIGNATURES = {
     "dm_spectral_diffusion_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_int, c_int]),
     "dm_spectral_diffusion": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int,
                                       c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "dm_fps_workspace_bytes": (c_sz, [c_i64]),
+    "dm_fps": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
     "dm_icp_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
     "dm_icp": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
                        c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

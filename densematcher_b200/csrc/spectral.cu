@@ -7,7 +7,7 @@
 //      device algorithm is a Chebyshev-filtered block subspace iteration on the symmetrised operator
 //      S = A^-1/2 W A^-1/2 (same spectrum, eigenvectors u = A^1/2 phi):
 //          X <- p_d(S) X          d fused "sparse row times dense block" passes (spmm_cheb_kernel), three-term recurrence
-//          X <- X G^-1/2-like     orthonormalisation from the eigen-decomposition of the Gram matrix (SVQB)
+//          X <- X T               orthonormalisation: Cholesky-QR of the column-scaled Gram matrix (chol_kernel)
 //          H = X^T S X,  H = V Theta V^T,  X <- X V      Rayleigh-Ritz
 //      with the block products on the float64 tensor-core GEMM (gemm64.cu) and the dense m x m symmetric eigenproblems
 //      (m = k + guard columns <= 512) solved by sym_eig_kernel: Householder tridiagonalisation, explicit Q, implicit QL --
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kEigThreads, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kEigThreads / 32;
   const int tx = tid & 255, part = tid >> 8;  // 256 columns x 4 row parts for the matrix-vector products
 
+  long long tq0 = clock64(), t_scalar = 0, t_apply = 0;
   // ---- phase 1: Householder tridiagonalisation A = Q T Q^T (full symmetric trailing block kept up to date)
   for (int j = 0; j + 1 < m; ++j) {
     const int L = m - j - 1, base = j + 1;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kEigThreads, 1)
     S.e[m - 1] = 0.0;
     if (m >= 2) S.tau[m - 1] = 0.0;
   }
+  long long tq1 = clock64();
   // ---- phase 2: Z = Q = H_0 H_1 ... H_{m-2}
   for (int idx = tid; idx < m * m; idx += kEigThreads) {
     const int r = idx / m, c = idx - r * m;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(kEigThreads, 1)
     }
     __syncthreads();
   }
+  long long tq2 = clock64();
   // ---- phase 3: A <- Z^T (row i of A = eigenvector direction i), implicit QL on (d, e) rotating rows of A
   for (int idx = tid; idx < m * m; idx += kEigThreads) {
     const int r = idx / m, c = idx - r * m;
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(kEigThreads, 1)
   double* sn = S.part[1];
   for (int l = 0; l < m; ++l) {
     for (int iter = 0;; ++iter) {
+      long long ta = clock64();
       if (tid == 0) {
         int mm = l;
         for (; mm < m - 1; ++mm) {
@@ -189,23 +193,32 @@ __global__ void __launch_bounds__(kEigThreads, 1)
           double s = 1.0, c = 1.0, p = 0.0;
           int i = mm - 1;
           bool under = false;
+          // e[i], d[i], d[i + 1] of the running step are carried in registers and the next pair is fetched at the top of
+          // the step, before the dependent chain (the stores below would otherwise fence the shared-memory loads)
+          double e_i = S.e[i], d_i = S.d[i], d_i1 = S.d[i + 1];
           for (; i >= l; --i) {
-            const double f = s * S.e[i], b = c * S.e[i];
-            r = sqrt(fma(f, f, g * g));
-            S.e[i + 1] = r;
-            if (r == 0.0) {
-              S.d[i + 1] -= p;
+            const double e_n = i > l ? S.e[i - 1] : 0.0, d_n = i > l ? S.d[i - 1] : 0.0;
+            const double f = s * e_i, b = c * e_i;
+            // r = hypot(f, g), s = f / r, c = g / r through one reciprocal square root (the float64 sqrt and the two
+            // divisions of the textbook form were 2/3 of the whole solve: this chain runs on ONE thread)
+            const double x = fma(f, f, g * g);
+            if (x == 0.0) {
+              S.e[i + 1] = 0.0;
+              S.d[i + 1] = d_i1 - p;
               S.e[mm] = 0.0;
               under = true;
               break;
             }
-            s = f / r, c = g / r;
-            g = S.d[i + 1] - p;
-            r = fma(S.d[i] - g, s, 2.0 * c * b);
+            const double rinv = rsqrt(x);
+            S.e[i + 1] = x * rinv;
+            s = f * rinv, c = g * rinv;
+            g = d_i1 - p;
+            r = fma(d_i - g, s, 2.0 * c * b);
             p = s * r;
             S.d[i + 1] = g + p;
             g = fma(c, r, -b);
             cs[i] = c, sn[i] = s;
+            d_i1 = d_i, d_i = d_n, e_i = e_n;
           }
           lo = i + 1;
           if (!under) {
@@ -218,11 +231,25 @@ __global__ void __launch_bounds__(kEigThreads, 1)
         S.ctl[0] = mm, S.ctl[1] = lo, S.ctl[2] = (mm == l || iter >= 80) ? 1 : 0;
       }
       __syncthreads();
+      long long tb = clock64();
+      t_scalar += tb - ta;
       const int mm = S.ctl[0], lo = S.ctl[1], done = S.ctl[2];
       if (!done && lo < mm) {
         for (int k = tid; k < m; k += kEigThreads) {
           double zi1 = A[int64_t(mm) * lda + k];
-          for (int i = mm - 1; i >= lo; --i) {
+          int i = mm - 1;
+          for (; i - 7 >= lo; i -= 8) {  // the eight loads first: they do not depend on the rotation chain
+            double z[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) z[u] = A[int64_t(i - u) * lda + k];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const double c = cs[i - u], s = sn[i - u];
+              A[int64_t(i - u + 1) * lda + k] = fma(s, z[u], c * zi1);
+              zi1 = fma(c, z[u], -s * zi1);
+            }
+          }
+          for (; i >= lo; --i) {
             const double zi = A[int64_t(i) * lda + k];
             const double c = cs[i], s = sn[i];
             A[int64_t(i + 1) * lda + k] = fma(s, zi, c * zi1);
@@ -232,8 +259,14 @@ __global__ void __launch_bounds__(kEigThreads, 1)
         }
       }
       __syncthreads();
+      t_apply += clock64() - tb;
       if (done) break;
     }
+  }
+  if (tid == 0 && status && blockIdx.x == 0) {
+    long long tq3 = clock64();
+    status[8] = int((tq1 - tq0) >> 10), status[9] = int((tq2 - tq1) >> 10), status[10] = int((tq3 - tq2) >> 10);
+    status[11] = int(t_scalar >> 10), status[12] = int(t_apply >> 10);
   }
   // ---- ascending order
   for (int t = tid; t < m; t += kEigThreads) {
@@ -366,7 +399,7 @@ __global__ void cheb_coef_kernel(const double* __restrict__ theta, int m, const 
   }
 }
 
-// SVQB step 1: dsc[i] = 1 / sqrt(G_ii); G <- diag(dsc) G diag(dsc) symmetrised
+// column scaling of the Gram matrix: dsc[i] = 1 / sqrt(G_ii); G <- diag(dsc) G diag(dsc), symmetrised
 __global__ void __launch_bounds__(256) svqb_scale_kernel(double* __restrict__ G, int m, int ld, double* __restrict__ dsc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * m) return;
@@ -388,15 +421,62 @@ __global__ void __launch_bounds__(256) svqb_diag_kernel(double* __restrict__ G, 
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < m) G[int64_t(r) * ld + r] = dsc[r] > 0.0 ? 1.0 : 0.0;
 }
-// SVQB step 2: T[i][j] = dsc[i] Q[i][j] / sqrt(max(lam_j, eps lam_max))
-__global__ void __launch_bounds__(256)
-    svqb_transform_kernel(const double* __restrict__ Q, const double* __restrict__ lam, const double* __restrict__ dsc, int m,
-                          int ld, double* __restrict__ T) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= m * m) return;
-  const int r = idx / m, c = idx % m;
-  const double floor_ = 1e-15 * fmax(lam[m - 1], 1e-300);
-  T[int64_t(r) * ld + c] = dsc[r] * Q[int64_t(r) * ld + c] * rsqrt(fmax(lam[c], floor_));
+// Cholesky-QR of the block: G' = diag(dsc) X^T X diag(dsc) (unit diagonal, svqb_scale_kernel) = L L^T in place (lower), then
+// T = diag(dsc) L^-T so that (X T)^T (X T) = I.  One CTA: m <= 512 steps of "pivot, scale the column, rank-1 update of the
+// trailing lower triangle".  A pivot below 1e-14 (the block lost rank) is clamped and reported in status[1].
+__global__ void __launch_bounds__(1024, 1) chol_kernel(double* __restrict__ G, int m, int ld, int* __restrict__ status) {
+  __shared__ double col[kEigMaxM];
+  __shared__ double inv_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = 0; j < m; ++j) {
+    if (tid == 0) {
+      double p = G[int64_t(j) * ld + j];
+      if (!(p > 1e-14)) {
+        p = 1e-14;
+        if (status) status[1] = 1;
+      }
+      const double piv = sqrt(p);
+      G[int64_t(j) * ld + j] = piv;
+      inv_s = 1.0 / piv;
+    }
+    __syncthreads();
+    const double inv = inv_s;
+    for (int r = j + 1 + tid; r < m; r += blockDim.x) {
+      const double v = G[int64_t(r) * ld + j] * inv;
+      G[int64_t(r) * ld + j] = v;
+      col[r] = v;
+    }
+    __syncthreads();
+    for (int r = j + 1 + warp; r < m; r += 32) {
+      const double vr = col[r];
+      double* row = G + int64_t(r) * ld;
+      for (int c = j + 1 + lane; c <= r; c += 32) row[c] = fma(-vr, col[c], row[c]);
+    }
+    __syncthreads();
+  }
+}
+// T[c][i] = dsc[c] (L^-1)[i][c]: one warp per column c of L^-1 (forward substitution, the running column kept in T's row c)
+__global__ void __launch_bounds__(1024, 1)
+    chol_transform_kernel(const double* __restrict__ L, const double* __restrict__ dsc, int m, int ld, double* __restrict__ T) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < m; c += 32) {
+    double* z = T + int64_t(c) * ld;  // z[i] = (L^-1)[i][c], i >= c
+    for (int i = lane; i < c; i += 32) z[i] = 0.0;
+    if (lane == 0) z[c] = 1.0 / L[int64_t(c) * ld + c];
+    __syncwarp();
+    for (int r = c + 1; r < m; ++r) {
+      const double* lr = L + int64_t(r) * ld;
+      double acc = 0.0;
+      for (int i = c + lane; i < r; i += 32) acc = fma(lr[i], z[i], acc);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+      if (lane == 0) z[r] = -acc / lr[r];
+      __syncwarp();
+    }
+    const double dc = dsc[c];
+    for (int i = c + lane; i < m; i += 32) z[i] *= dc;
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(256) symmetrise_kernel(double* __restrict__ H, int m, int ld) {
@@ -554,15 +634,14 @@ int dm_lbo_eigs(const int64_t* indptr, const int32_t* indices, const double* val
   const double plain[3] = {1.0, 0.0, 0.0};
   DM_CUDA_OK(cudaMemcpyAsync(L.coef + 3 * kMaxDegree, plain, sizeof(plain), cudaMemcpyHostToDevice, st));
 
-  auto orthonormalise = [&](double* X, double* out) -> int {  // out = X T with out^T out = I
+  auto orthonormalise = [&](double* X, double* out) -> int {  // out = X T with out^T out = I (Cholesky-QR, scaled columns)
     int r;
     if ((r = gram(X, X, n, m, ld, L, L.G, st))) return r;
     svqb_scale_kernel<<<sq_blocks, 256, 0, st>>>(L.G, m, ld, L.dsc);
     svqb_diag_kernel<<<unsigned((m + 255) / 256), 256, 0, st>>>(L.G, m, ld, L.dsc);
-    DM_LAUNCH_OK("svqb_scale_kernel");
-    if ((r = sym_eig_launch(L.G, ld, m, L.Zs, L.lam, L.V, ld, 1, 0, 0, L.status, st))) return r;
-    svqb_transform_kernel<<<sq_blocks, 256, 0, st>>>(L.V, L.lam, L.dsc, m, ld, L.T);
-    DM_LAUNCH_OK("svqb_transform_kernel");
+    chol_kernel<<<1, 1024, 0, st>>>(L.G, m, ld, L.status);
+    chol_transform_kernel<<<1, 1024, 0, st>>>(L.G, L.dsc, m, ld, L.T);
+    DM_LAUNCH_OK("chol_kernel");
     return times_small(X, L.T, n, m, ld, out, st);
   };
 
@@ -610,10 +689,10 @@ int dm_lbo_eigs(const int64_t* indptr, const int32_t* indices, const double* val
   }
   eigs_output_kernel<<<unsigned((int64_t(n) * k + 255) / 256), 256, 0, st>>>(X, ld, L.theta, L.dinv, n, k, evecs, ld_evecs, evals);
   DM_LAUNCH_OK("eigs_output_kernel");
-  int status = 0;
-  DM_CUDA_OK(cudaMemcpyAsync(&status, L.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int status[2] = {0, 0};  // [0] dense eigensolver (2 = QL did not converge), [1] Cholesky-QR met a rank-deficient block
+  DM_CUDA_OK(cudaMemcpyAsync(status, L.status, sizeof(status), cudaMemcpyDeviceToHost, st));
   DM_CUDA_OK(cudaStreamSynchronize(st));
-  if (info_h) info_h[0] = it + 1, info_h[1] = converged, info_h[2] = m, info_h[3] = status;
+  if (info_h) info_h[0] = it + 1, info_h[1] = converged, info_h[2] = m, info_h[3] = status[0] | (status[1] << 4);
   if (residual_h) *residual_h = res;
   return DM_OK;
 }
@@ -691,6 +770,90 @@ int dm_spectral_diffusion(const double* Phi, int64_t ldPhi, const double* mass, 
   diffusion_scale_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(coef, evals, time, n_meshes, k, c);
   DM_LAUNCH_OK("diffusion_scale_kernel");
   return dm_from_basis(coef, Phi, ldPhi, row_off, max_n, n_meshes, k, c, out, ld_out, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Farthest point sampling, Euclidean (TriMesh.extract_fps(geodesic=False), mesh/trimesh.py:870-876 ->
+// geometry.farthest_point_sampling_call, mesh/geometry.py:813-851): idx[0] = first, then size - 1 times
+// "argmax of the running distances, minimum with the distances to the new point".  One CTA per mesh; distances
+// sqrt((dx^2 + dy^2) + dz^2) rounded exactly like numpy's norm (no fused multiply-add), argmax ties to the lowest index.
+// ---------------------------------------------------------------------------------------------------------------
+namespace dm {
+namespace {
+__global__ void __launch_bounds__(1024, 1)
+    fps_kernel(const double* __restrict__ V, const int64_t* __restrict__ off, const int64_t* __restrict__ first, int size,
+               int64_t* __restrict__ out, double* __restrict__ dist_all) {
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int cur_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = off[b];
+  const int n = int(off[b + 1] - r0);
+  const double* Vb = V + 3 * r0;
+  double* dist = dist_all + r0;
+  int64_t* ob = out + int64_t(b) * size;
+  int cur = int(first[b]);
+  if (cur < 0 || cur >= n) cur = 0;
+  for (int it = 0; it < size; ++it) {
+    if (tid == 0) ob[it] = cur;
+    if (it + 1 == size) break;
+    const double cx = Vb[3 * cur], cy = Vb[3 * cur + 1], cz = Vb[3 * cur + 2];
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const double dx = Vb[3 * i] - cx, dy = Vb[3 * i + 1] - cy, dz = Vb[3 * i + 2] - cz;
+      const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      const double m = it == 0 ? d : fmin(dist[i], d);
+      dist[i] = m;
+      if (m > best) best = m, bi = i;  // ascending i inside a thread: strict '>' keeps the lowest index
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, sh);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, sh);
+      if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+    }
+    if (lane == 0) red_v[warp] = best, red_i[warp] = bi;
+    __syncthreads();
+    if (warp == 0) {
+      best = red_v[lane], bi = red_i[lane];
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, sh);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, sh);
+        if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+      }
+      if (lane == 0) cur_s = bi;
+    }
+    __syncthreads();
+    cur = cur_s;
+  }
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" {
+
+size_t dm_fps_workspace_bytes(int64_t total_n) {
+  if (total_n < 0) return 0;
+  Carver c(nullptr);
+  c.take<double>(size_t(total_n));
+  return c.bytes();
+}
+
+int dm_fps(const double* verts, const int64_t* row_off, int64_t total_n, int n_meshes, const int64_t* first, int size,
+           int64_t* idx, void* workspace, size_t workspace_bytes, dm_stream_t stream) {
+  if (n_meshes < 0 || size < 0 || total_n < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_meshes == 0 || size == 0) return DM_OK;
+  if (!verts || !row_off || !first || !idx) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (!workspace || dm_fps_workspace_bytes(total_n) > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small");
+  Carver c(workspace);
+  double* dist = c.take<double>(size_t(total_n));
+  fps_kernel<<<n_meshes, 1024, 0, static_cast<cudaStream_t>(stream)>>>(verts, row_off, first, size, idx, dist);
+  DM_LAUNCH_OK("fps_kernel");
+  return DM_OK;
 }
 
 }  // extern "C"

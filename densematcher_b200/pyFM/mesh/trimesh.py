@@ -113,6 +113,17 @@ class TriMesh:
             self.laplacian_spectrum(k, device=device)
         return self
 
+    def extract_fps(self, size, random_init=True, geodesic=False, no_load=False, verbose=False, first=None):
+        """(size,) indices of a farthest point sample (trimesh.py:847-893), on the GPU.  Euclidean distances only: the
+        reference's default ``geodesic=True`` runs the heat method of the un-vendored ``potpourri3d`` wheel
+        (trimesh.py:880-888), which is outside the accelerated path -- asking for it raises.  ``first`` pins the start
+        vertex (drawn at random like geometry.py:839 otherwise)."""
+        if geodesic:
+            raise NotImplementedError("geodesic farthest point sampling needs potpourri3d's heat method "
+                                      "(trimesh.py:880-888); use geodesic=False")
+        from ... import spectral_ops
+        return spectral_ops.farthest_point_sampling(self.vertlist, int(size), first=first).cpu().numpy()
+
     # ------------------------------------------------------------------ projection (GPU)
     def project(self, func, k=None):
         """(k,p) or (k,) coefficients of ``func`` in the basis: eigenvectors[:, :k].T @ A @ func

@@ -67,10 +67,11 @@ def zoomout_refine(FM_12, evects1, evects2, nit=10, step=1, A2=None, subsample=N
 
 def mesh_zoomout_refine(FM_12, mesh1, mesh2, nit=10, step=1, subsample=None, return_p2p=False, n_jobs=1,
                         verbose=False):
-    """zoomout.py:118-161 (``subsample`` must be a pair of index arrays; integer FPS sampling needs the
-    geodesic machinery that is outside the hot path)."""
+    """zoomout.py:118-161.  An integer ``subsample`` draws a farthest point sample of that size on both meshes
+    (:150-156) -- Euclidean, on the GPU (``TriMesh.extract_fps``; the reference's geodesic variant needs the un-vendored
+    potpourri3d heat method)."""
     if np.issubdtype(type(subsample), np.integer):
-        raise NotImplementedError("integer subsample (farthest point sampling) is outside the hot path")
+        subsample = (mesh1.extract_fps(subsample, geodesic=False), mesh2.extract_fps(subsample, geodesic=False))
     return zoomout_refine(FM_12, mesh1.eigenvectors, mesh2.eigenvectors, nit, step=step, A2=mesh2.A,
                           subsample=subsample, return_p2p=return_p2p, n_jobs=n_jobs, verbose=verbose)
 
@@ -79,15 +80,16 @@ def mesh_zoomout_refine_p2p(p2p_21, mesh1, mesh2, k_init, nit=10, step=1, subsam
                             p2p_on_sub=False, verbose=False):
     """zoomout.py:164-217: start the ladder from a vertex map."""
     if np.issubdtype(type(subsample), np.integer):
-        raise NotImplementedError("integer subsample (farthest point sampling) is outside the hot path")
+        if p2p_on_sub:
+            raise ValueError("P2P can't be defined on undefined subsample")          # zoomout.py:200-201
+        subsample = (mesh1.extract_fps(subsample, geodesic=False), mesh2.extract_fps(subsample, geodesic=False))
     k1_0, k2_0 = (k_init, k_init) if np.issubdtype(type(k_init), np.integer) else k_init
-    if subsample is None:
+    if subsample is None or not p2p_on_sub:
+        # the vertex map lives on the full meshes: initial map from all the vertices (zoomout.py:211 ->
+        # convert.py:89-90), the ladder itself on the samples
         FM_12 = _convert.p2p_to_FM(p2p_21, mesh1.eigenvectors[:, :k1_0], mesh2.eigenvectors[:, :k2_0], A2=mesh2.A)
     else:
         sub1, sub2 = subsample
-        p = p2p_21 if p2p_on_sub else None
-        if p is None:
-            raise NotImplementedError("p2p_on_sub=False with subsample needs a host-side index search")
-        FM_12 = _convert.p2p_to_FM(p, mesh1.eigenvectors[sub1, :k1_0], mesh2.eigenvectors[sub2, :k2_0], A2=None)
+        FM_12 = _convert.p2p_to_FM(p2p_21, mesh1.eigenvectors[sub1, :k1_0], mesh2.eigenvectors[sub2, :k2_0], A2=None)
     return mesh_zoomout_refine(FM_12, mesh1, mesh2, nit=nit, step=step, subsample=subsample, return_p2p=return_p2p,
                                n_jobs=n_jobs, verbose=verbose)

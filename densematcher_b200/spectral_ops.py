@@ -19,7 +19,7 @@ import torch
 from . import _lib, fm as _fm
 from .nn import default_workspace
 
-__all__ = ["load_operator_cache", "to_basis", "from_basis", "spectral_diffusion", "lbo_eigs", "sym_eig"]
+__all__ = ["load_operator_cache", "to_basis", "from_basis", "spectral_diffusion", "lbo_eigs", "sym_eig", "farthest_point_sampling"]
 
 
 def load_operator_cache(path, k_eig=None):
@@ -174,3 +174,33 @@ def lbo_eigs(W, mass, k, device=None, tol=1e-10, max_iter=40, degree=0, return_i
         import warnings
         warnings.warn(f"lbo_eigs: residual {res.value:.2e} after {info[0]} iterations (tol {tol:g})")
     return (evals, evecs, d) if return_info else (evals, evecs)
+
+
+def farthest_point_sampling(verts, size, first=None, off=None):
+    """Euclidean farthest point sampling on the device (``TriMesh.extract_fps(size, geodesic=False)``,
+    mesh/trimesh.py:870-876; geometry.py:813-851).  ``verts`` (n,3) or ragged (total,3) with ``off``; ``first``: start
+    vertex per mesh (the reference draws it at random: ``None`` does the same).  -> int64 CUDA tensor (size,) or
+    (n_meshes, size) of mesh-local indices, identical to the numpy loop for the same start vertex."""
+    lib = _lib.load()
+    V = verts if torch.is_tensor(verts) else torch.from_numpy(np.ascontiguousarray(verts, dtype=np.float64))
+    if not V.is_cuda:
+        V = V.cuda()
+    V = V.to(torch.float64).contiguous()
+    dev = V.device
+    single = off is None
+    oh = np.array([0, V.shape[0]], dtype=np.int64) if single else np.asarray(off, dtype=np.int64)
+    n_m = len(oh) - 1
+    sizes = np.diff(oh)
+    if size > int(sizes.min()):
+        raise ValueError(f"cannot sample {size} points of a mesh with {int(sizes.min())} vertices")
+    if first is None:
+        first = np.random.default_rng().integers(0, sizes)           # geometry.py:839
+    f = torch.from_numpy(np.atleast_1d(np.asarray(first, dtype=np.int64))).to(dev)
+    od = torch.from_numpy(oh).to(dev)
+    out = torch.empty(n_m, size, dtype=torch.int64, device=dev)
+    ws = default_workspace(dev, "eig").get(max(lib.dm_fps_workspace_bytes(V.shape[0]), 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_fps(V.data_ptr(), od.data_ptr(), V.shape[0], n_m, f.data_ptr(), int(size), out.data_ptr(),
+                        ws.data_ptr(), ws.numel(), _fm._stream(dev))
+    _lib.check(rc, "dm_fps")
+    return out[0] if single else out

@@ -391,6 +391,17 @@ int dm_spectral_diffusion(const double* Phi, int64_t ldPhi, const double* mass, 
                           int n_meshes, int k, int c, double* out, int64_t ld_out, int flags, void* workspace,
                           size_t workspace_bytes, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Farthest point sampling with Euclidean distances, batched over meshes: the vertex subsample ZoomOut takes when
+ * `subsample` is an integer (pyFM/refine/zoomout.py:150-156, 199-206 -> TriMesh.extract_fps, mesh/trimesh.py:847-893 with
+ * geodesic=False -> mesh/geometry.py:813-851).  verts [total_n, 3] float64 ragged-packed by row_off, first [n_meshes]
+ * start vertex per mesh (the reference draws it at random), idx [n_meshes, size] int64 (mesh-local indices).
+ * Same float64 rounding as numpy's norm and lowest-index argmax: identical samples for the same start vertex.
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_fps_workspace_bytes(int64_t total_n);
+int dm_fps(const double* verts, const int64_t* row_off, int64_t total_n, int n_meshes, const int64_t* first, int size,
+           int64_t* idx, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,6 +275,33 @@ def zoomout_refine(FM_12, Phi1, Phi2, nit=10, step=1, A2=None, subsample=None,
     return C
 
 
+def fps_euclidean(V, size, first):
+    """Euclidean farthest point sampling from a given start vertex: ``TriMesh.extract_fps(size, geodesic=False)``
+    (densematcher/pyFM/mesh/trimesh.py:870-876) -> ``farthest_point_sampling_call`` (mesh/geometry.py:813-851), whose
+    random start vertex (:839) is the ``first`` argument here."""
+    V = np.asarray(V, dtype=np.float64)
+    dist_func = lambda i: np.linalg.norm(V - V[i, None, :], axis=1)     # trimesh.py:871-872
+    inds = [int(first)]
+    dists = dist_func(inds[0])
+    for _ in range(size - 1):                                           # geometry.py:842-848
+        newid = int(np.argmax(dists))
+        inds.append(newid)
+        dists = np.minimum(dists, dist_func(newid))
+    return np.asarray(inds, dtype=np.int64)
+
+
+def mesh_zoomout_refine_p2p(p2p_21, Phi1, Phi2, A2, k_init, nit=10, step=1, subsample=None, p2p_on_sub=False,
+                            return_p2p=False):
+    """densematcher/pyFM/refine/zoomout.py:164-217 on bare arrays: initial map from the vertex map (on the samples when
+    ``p2p_on_sub``, else on all the vertices: :208-211 -> convert.py:89-93), then ``zoomout_refine``."""
+    k1, k2 = (k_init, k_init) if np.issubdtype(type(k_init), np.integer) else k_init
+    if subsample is not None and p2p_on_sub:
+        C0 = p2p_to_fm(p2p_21, Phi1[subsample[0], :k1], Phi2[subsample[1], :k2], A2=None)
+    else:
+        C0 = p2p_to_fm(p2p_21, Phi1[:, :k1], Phi2[:, :k2], A2=A2)
+    return zoomout_refine(C0, Phi1, Phi2, nit=nit, step=step, A2=A2, subsample=subsample, return_p2p=return_p2p)
+
+
 def icp_refine(FM_12, Phi1, Phi2, nit=10, tol=1e-10, return_p2p=False, nn="brute"):
     """Spectral ICP.
 

@@ -134,6 +134,56 @@ def test_lbo_eigs_rejects_bad_sizes():
         spectral_ops.lbo_eigs(W, a, 0, device=DEV)
 
 
+def test_fps_matches_the_numpy_loop_exactly():
+    """Ragged batch of three clouds + a single mesh call, start vertices pinned: identical index sequences."""
+    from oracle import dm_oracle as orc
+    rng = np.random.default_rng(11)
+    sizes = [2000, 777, 1313]
+    clouds = [rng.standard_normal((n, 3)) * rng.uniform(0.5, 2.0, 3) for n in sizes]
+    clouds[1][5] = clouds[1][9]                                               # duplicate points: ties in the argmax
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    first = [17, 0, 1312]
+    got = spectral_ops.farthest_point_sampling(np.concatenate(clouds), 300, first=first, off=off).cpu().numpy()
+    for b, V in enumerate(clouds):
+        assert np.array_equal(got[b], orc.fps_euclidean(V, 300, first[b])), b
+    V, F, _, _ = _mesh(3, 1)
+    from densematcher_b200.pyFM.mesh import TriMesh
+    m = TriMesh(V, F)
+    assert np.array_equal(m.extract_fps(642, first=3), orc.fps_euclidean(V, 642, 3))      # every vertex, once
+    assert len(np.unique(m.extract_fps(100))) == 100                                      # random start
+    with pytest.raises(NotImplementedError):
+        m.extract_fps(10, geodesic=True)
+    with pytest.raises(ValueError):
+        spectral_ops.farthest_point_sampling(V, 643)
+
+
+def test_mesh_zoomout_refine_p2p_subsample_variants(golden_zo):
+    """zoomout.py:164-217: explicit subsamples with the vertex map on the samples / on the full meshes, and an integer
+    subsample (device FPS) -- against the oracle composition of the same primitives."""
+    from oracle import dm_oracle as orc
+    from densematcher_b200.pyFM import refine
+    from densematcher_b200.pyFM.mesh import TriMesh
+    g = golden_zo
+    V1, F, _, _ = _mesh(3, 1)
+    V2, _, _, _ = _mesh(3, 2)
+    m1 = TriMesh.from_basis(g["evals1"], g["Phi1"], g["area1"], V1, F)
+    m2 = TriMesh.from_basis(g["evals2"], g["Phi2"], g["area2"], V2, F)
+    rng = np.random.default_rng(5)
+    p_full = rng.integers(0, 642, 642)
+    sub = (g["sub1"], g["sub2"])
+    p_sub = rng.integers(0, len(sub[0]), len(sub[1]))
+    for p, on_sub in ((p_sub, True), (p_full, False)):
+        C, pz = refine.mesh_zoomout_refine_p2p(p, m1, m2, 10, nit=6, step=1, subsample=sub, return_p2p=True,
+                                                p2p_on_sub=on_sub)
+        Co, po = orc.mesh_zoomout_refine_p2p(p, g["Phi1"], g["Phi2"], g["area2"], 10, nit=6, step=1, subsample=sub,
+                                             p2p_on_sub=on_sub, return_p2p=True)
+        assert np.abs(C - Co).max() <= 1e-9 * np.abs(Co).max() and np.array_equal(pz, po)
+    C = refine.mesh_zoomout_refine_p2p(p_full, m1, m2, 10, nit=4, step=1, subsample=200)
+    assert C.shape == (14, 14) and np.all(np.isfinite(C))
+    with pytest.raises(ValueError):
+        refine.mesh_zoomout_refine_p2p(p_full, m1, m2, 10, nit=4, subsample=200, p2p_on_sub=True)
+
+
 def _diffusion_reference(x, mass, evals, evecs, t):
     xs = torch.matmul(evecs.transpose(-2, -1), x * mass.unsqueeze(-1))         # geometry.py:572-583
     coefs = torch.exp(-evals.unsqueeze(-1) * t.unsqueeze(0))                   # layers.py:60-61
