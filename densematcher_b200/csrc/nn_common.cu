@@ -581,6 +581,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
     P.row_trunc = P.col_trunc;  // packed keys on both sides
     if ((rc = nn_tc2_launch(P, L.yh, L.yl, L.xh, L.xl, st))) return rc;
   } else if (tc) {
+    if (P.n_col == 0) P.row_trunc = P.col_trunc;  // row-only passes scan packed keys (nn_tc.cu)
     if ((rc = nn_tc_launch(P, L.yh, L.yl, L.xh, L.xl, nullptr, 0, st))) return rc;
   } else {
     if ((rc = nn_ffma_launch(P, st))) return rc;

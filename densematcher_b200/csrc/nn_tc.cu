@@ -19,6 +19,7 @@
 // near-tie re-evaluation in nn_common.cu.
 #include "dm_internal.cuh"
 #include "tc_ptx.cuh"
+#include "tc_scan.cuh"
 
 namespace dm {
 namespace tc {
@@ -49,9 +50,15 @@ constexpr int TBK = 64;       // K elements per pipeline stage (one 128-byte swi
 __host__ __device__ constexpr int n_stages(bool pair) { return pair ? 3 : 2; }
 constexpr int UMMA_K = 16;
 constexpr int kGroupWarps = 4;              // one warp per TMEM lane quarter
-// Two epilogue groups, or three when there are two row epilogues AND column epilogues (see the kernel)
+// Two epilogue groups, or three when there are two row epilogues AND column epilogues (see the kernel).  Row epilogues
+// only: FOUR groups share the chunks of every tile -- the sequential top-3 scan is latency-bound, not issue-bound (two
+// warps per scheduler left the ZoomOut conversion at 520 us per 128 pairs where its MMAs need 160), so twice the warps
+// is the cheapest way to hide it
 __host__ __device__ constexpr bool three_groups(int nr, int nc, bool debug) { return nr == 2 && nc > 0 && !debug; }
-__host__ __device__ constexpr int epi_warps(int nr, int nc, bool debug) { return (three_groups(nr, nc, debug) ? 3 : 2) * kGroupWarps; }
+__host__ __device__ constexpr int n_groups(int nr, int nc, bool debug) {
+  return three_groups(nr, nc, debug) ? 3 : ((nc == 0 && nr > 0 && !debug) ? 4 : 2);
+}
+__host__ __device__ constexpr int epi_warps(int nr, int nc, bool debug) { return n_groups(nr, nc, debug) * kGroupWarps; }
 __host__ __device__ constexpr int n_threads(int nr, int nc, bool debug) { return 32 * (2 + epi_warps(nr, nc, debug)); }
 constexpr int CCH = 32;  // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
 
@@ -132,7 +139,7 @@ struct DebugOut {
 // ------------------------------------------------------------------ the kernel
 template <int NR, int NC, bool DEBUG, bool PAIR>
 __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
-    nn_tc_kernel(const __grid_constant__ TcMaps maps, const NNProblem P, const DebugOut dbg) {
+    nn_tc_kernel(const __grid_constant__ TcMaps maps, const NNProblem P, const DebugOut dbg, const uint32_t keymask) {
   constexpr int STAGES = n_stages(PAIR);
   constexpr uint32_t SZ_X = sz_x(PAIR), STAGE_BYTES = stage_bytes(PAIR);
   constexpr uint32_t kIdesc = idesc(PAIR);
@@ -278,7 +285,11 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
     const int trow = 32 * q + lane;            // accumulator row of this thread
     const int gt = (threadIdx.x - 64) & 127;   // thread index inside its group
     constexpr bool kSplitRoles = (NR > 0 && NC > 0);
-    constexpr bool kShareRows = (NC == 0);     // both groups work on rows (also the DEBUG dump)
+    constexpr bool kShareRows = (NC == 0);     // all the groups work on rows (also the DEBUG dump)
+    // Row epilogues only: the scan runs on packed keys (tc_scan.cuh: 4 ALU-pipe instructions per score instead of the ~12
+    // of the branchy top-3 chains below -- ncu on the ZoomOut conversion: ALU pipe 67 % busy, 16 instructions per score,
+    // tensor pipe 20 %); the 2^-18 truncation of the scores is covered by NNProblem::row_trunc
+    constexpr bool kPacked = (NC == 0 && NR > 0 && !DEBUG);
     const bool do_rows = kSplitRoles ? group != 1 : (NC == 0 ? true : false);
     const bool do_cols = NC > 0 && group == 1;
     const int r_base = kG3 && group == 2 ? 1 : 0;  // first row epilogue of this thread
@@ -286,7 +297,8 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
     float* patch = reinterpret_cast<float*>(sgen + OFF_PATCH + q * PATCH_BYTES);
     Top3* colred = reinterpret_cast<Top3*>(sgen + OFF_COLRED);          // [2][kMaxEpi][4][CCH]
     float* rowsb = reinterpret_cast<float*>(sgen + OFF_ROWSB);          // [e][0=scale,1=bias][TN]
-    const int row_threads = kShareRows ? 2 * kGroupWarps * 32 : kGroupWarps * 32;
+    constexpr int kGroups = n_groups(NR, NC, DEBUG);
+    const int row_threads = kShareRows ? kGroups * kGroupWarps * 32 : kGroupWarps * 32;
 
     Top3 rowst[NRS > 0 ? NRS : 1], rowsu[NRS > 0 ? NRS : 1];  // two chains per row epilogue (merged at the end)
 #pragma unroll
@@ -301,6 +313,15 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       rsf[r] = second ? P.row[NR > 1 ? 1 : 0].sf : P.row[0].sf;
       rbf[r] = second ? P.row[NR > 1 ? 1 : 0].bf : P.row[0].bf;
       rident[r] = second ? P.row[NR > 1 ? 1 : 0].identity : P.row[0].identity;
+    }
+
+    // the re-evaluation window of this thread's results without its score-dependent part (emit_result), packed scans only
+    float thr_base[NRS > 0 ? NRS : 1];
+#pragma unroll
+    for (int r = 0; r < NRS; ++r) {
+      const EpiDev& E = P.row[(kG3 ? r_base : r) < NR ? (kG3 ? r_base : r) : 0];
+      const float nq_i = (kPacked && row0 + trow < nq) ? P.norm_q[q0 + row0 + trow] : 0.f;
+      thr_base[r] = kPacked ? 2.f * P.eps * nq_i * E.G[p] + 9.6e-7f * E.Bm[p] : 0.f;
     }
 
     // scale / bias of THIS thread's accumulator row for the column epilogues (applied before the transposition)
@@ -326,7 +347,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
             const int j = col0 + jj;
             const bool v = j < nd;
             rowsb[((r_base + r) * 2 + 0) * TN + jj] = v ? __ldg(rsf[r] + d0 + j) : 0.f;
-            rowsb[((r_base + r) * 2 + 1) * TN + jj] = v ? __ldg(rbf[r] + d0 + j) : -INFINITY;
+            rowsb[((r_base + r) * 2 + 1) * TN + jj] = v ? __ldg(rbf[r] + d0 + j) : (kPacked ? kMaskedScore : -INFINITY);
           }
         bar_sync_n(row_bar, row_threads);
       }
@@ -335,8 +356,8 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TN + (uint32_t(32 * q) << 16);
       const int n_ch = min(TN, nd - col0 + CCH - 1) / CCH;  // chunks that hold at least one valid column
-      const int ch_beg = kShareRows ? group * (TN / CCH / 2) : 0;
-      const int ch_end = kShareRows ? ch_beg + TN / CCH / 2 : TN / CCH;
+      const int ch_beg = kShareRows ? group * (TN / CCH / kGroups) : 0;
+      const int ch_end = kShareRows ? ch_beg + TN / CCH / kGroups : TN / CCH;
       for (int ch = ch_beg; ch < ch_end; ++ch) {
         if (ch >= n_ch) break;  // uniform over the group
         if ((!do_rows && !do_cols && !DEBUG) || P.probe_skip_epilogue) break;
@@ -354,7 +375,21 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
         if (NR > 0 && do_rows) {
           const bool full_tile = col0 + TN <= nd;  // no masked tail columns in this tile
           const int jb = col0 + ch * CCH;
-          if (NRS == 2 && !(full_tile && (rident[0] || rident[NRS - 1]))) {
+          if (kPacked) {
+#pragma unroll
+            for (int r = 0; r < NRS; ++r) {
+              float k1, k2;
+              if (rident[r] && full_tile) {
+                t2_chunk_top2<true>(v, nullptr, nullptr, keymask, k1, k2);
+                t2_merge_chunk<true>(rowst[r], k1, k2, jb, v, nullptr, nullptr, keymask, thr_base[r]);
+              } else {
+                const float* sc = rowsb + ((r_base + r) * 2 + 0) * TN + ch * CCH;
+                const float* bi = rowsb + ((r_base + r) * 2 + 1) * TN + ch * CCH;
+                t2_chunk_top2<false>(v, sc, bi, keymask, k1, k2);
+                t2_merge_chunk<false>(rowst[r], k1, k2, jb, v, sc, bi, keymask, thr_base[r]);
+              }
+            }
+          } else if (NRS == 2 && !(full_tile && (rident[0] || rident[NRS - 1]))) {
             // both epilogues carry scale / bias: interleave them (one vote, four independent chains)
             const float4* s40 = reinterpret_cast<const float4*>(rowsb + 0 * TN + ch * CCH);
             const float4* b40 = reinterpret_cast<const float4*>(rowsb + 1 * TN + ch * CCH);
@@ -474,16 +509,20 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
 #pragma unroll
       for (int r = 0; r < NRS; ++r) top3_merge(rowst[r], rowsu[r]);
       if (kShareRows) {
-        // group 1 hands its per-row states to group 0 through shared memory (the patch area is free: NC == 0)
-        Top3* xch = reinterpret_cast<Top3*>(sgen + OFF_PATCH);  // [NR][128]
-        if (group == 1) {
+        // the other groups hand their per-row states to group 0 through shared memory (the patch area is free: NC == 0);
+        // merged in ascending chunk order, i.e. ascending column index inside every tile
+        static_assert((kGroups - 1) * (NR > 0 ? NR : 1) * TM_ROWS * sizeof(Top3) <= kGroupWarps * PATCH_BYTES, "exchange area");
+        Top3* xch = reinterpret_cast<Top3*>(sgen + OFF_PATCH);  // [kGroups - 1][NR][128]
+        if (group > 0) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) xch[r * TM_ROWS + trow] = rowst[r];
+          for (int r = 0; r < NR; ++r) xch[((group - 1) * NR + r) * TM_ROWS + trow] = rowst[r];
         }
         bar_sync_n(1, row_threads);
         if (group == 0) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) top3_merge(rowst[r], xch[r * TM_ROWS + trow]);
+          for (int g2 = 1; g2 < kGroups; ++g2)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) top3_merge(rowst[r], xch[((g2 - 1) * NR + r) * TM_ROWS + trow]);
         }
       }
       const int i = row0 + trow;
@@ -545,7 +584,7 @@ int launch_mode(const TcMaps& maps, const NNProblem& P, const DebugOut& dbg, cud
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 1 : 0;
-  DM_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_tc_kernel<NR, NC, DEBUG, PAIR>, maps, P, dbg));
+  DM_CUDA_OK(cudaLaunchKernelEx(&cfg, nn_tc_kernel<NR, NC, DEBUG, PAIR>, maps, P, dbg, ~uint32_t(T2_CH - 1)));
   return DM_OK;
 }
 
