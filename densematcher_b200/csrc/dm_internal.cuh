@@ -375,6 +375,15 @@ int p2p21_factored_run(const double* C, int k1, int k2, const double* Phi1, int6
                        int n_pairs, void* p2p_out, int flags, void* scratch, double* emb1, int lde, void* nn_ws,
                        size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state);
 
+// incremental p2p -> FM of the ZoomOut ladder (zoomout_delta.cu): the full-width map M = Phi2^T A2 Phi1[p] is kept resident
+// and corrected with the changed entries of the vertex map; every rung reads its leading block
+bool p2p_to_fm_delta_applicable();
+size_t p2p_to_fm_delta_ws(int n_pairs, int64_t total_n2);
+int p2p_to_fm_delta_run(const void* p_new, const void* p_old, int i64, const double* Phi1, int64_t ld1, const int64_t* off1,
+                        const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2, const double* area2,
+                        int n_pairs, int K1, int K2, double* M, void* ws, cudaStream_t st);
+int extract_block_run(const double* M, int K1, int K2, int k1, int k2, int n_pairs, double* C, cudaStream_t st);
+
 int num_sms();
 // true exactly once per (call site, device): function attributes such as the dynamic shared-memory limit are
 // per-device state, and one process may drive several devices

@@ -326,6 +326,9 @@ size_t dm_zoomout_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n
   c.take<float>(size_t(total_n1) * pad4(k2m));  // fp32 emb1
   c.take<float>(size_t(total_n2) * pad4(k2m));  // fp32 Phi2
   c.take<int32_t>(size_t(total_n2) * 2);        // p2p (int32 or int64)
+  c.take<int32_t>(size_t(total_n2) * 2);        // p2p of the previous rung
+  c.take<char>(p2p_to_fm_delta_ws(n_pairs, total_n2));
+  c.take<double>(size_t(n_pairs) * k1m * k2m);  // M: the full-width map kept resident by the incremental rungs
   c.take<char>(zoomout_pf_ws(n_pairs, total_n2, max_n2, k1m, k2m, flags));
   c.take<char>(nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags));
   c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1m, k2m));
@@ -355,7 +358,11 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   S.emb1 = c.take<double>(size_t(total_n1) * k2m);
   S.Xf = c.take<float>(size_t(total_n1) * S.ldf);
   float* Phi2f = c.take<float>(size_t(total_n2) * S.ldf);
-  void* p2p = c.take<int32_t>(size_t(total_n2) * 2);
+  void* p2p_buf[2];
+  p2p_buf[0] = c.take<int32_t>(size_t(total_n2) * 2);
+  p2p_buf[1] = c.take<int32_t>(size_t(total_n2) * 2);
+  void* delta_ws = c.take<char>(p2p_to_fm_delta_ws(n_pairs, total_n2));
+  double* Mfull = c.take<double>(size_t(n_pairs) * k1m * k2m);
   const size_t pf_bytes = zoomout_pf_ws(n_pairs, total_n2, max_n2, k1m, k2m, flags);
   void* pf_ws = c.take<char>(pf_bytes);
   const bool fast_fm = (flags & DM_FAST_FM) && proj_tc_supported(k2m, k1m);
@@ -368,17 +375,33 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   const double* Ccur = C0;
   int k1 = k1_0, k2 = k2_0;
   int y_kp = -1;  // padded width for which the split of Phi2 in the workspace is valid
+  // The rungs keep M = Phi2[:, :k2m]^T A2 Phi1[p, :k1m] (the widths of the LAST rung) resident and correct it with the
+  // vertices whose image changed since the previous rung (zoomout_delta.cu); a rung's map is M's leading block.  A full
+  // product re-anchors M every kZoAnchor rungs, and the last rung is always a fresh product of its own.
+  // (the gathered correction runs on the cp.async GEMM: rows of both bases on 16-byte boundaries)
+  constexpr int kZoAnchor = 32;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(Phi1) | reinterpret_cast<uintptr_t>(Phi2)) & 15) == 0 && !((ld1 | ld2) & 1);
+  const bool delta_ok = !fast_fm && aligned16 && nit > 2 && p2p_to_fm_delta_applicable();
   for (int it = 0; it < nit; ++it) {
+    void* p2p = p2p_buf[it & 1];
     // the fp32 copy of emb1 is re-made with the current width; stale columns beyond k2 are zeroed by cvt
     if ((rc = p2p21_run(Ccur, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, Phi2f, S.ldf, off2, total_n2,
                         max_n2, n_pairs, p2p, flags, S, st, &y_kp)))
       return rc;
     double* Cnext = (it == nit - 1) ? C_out : Cbuf[it & 1];
     if (fast_fm) {
-      // C = Phi2[:, :k2+s]^T (a2 * Phi1[p, :k1+s]) on the tensor cores: A operand = Phi2, B operand = gathered, scaled Phi1
+      // C = Phi2[:, :k2+s2]^T (a2 * Phi1[p, :k1+s1]) on the tensor cores: A operand = Phi2, B operand = gathered, scaled Phi1
       if ((rc = proj_tc_run(Phi2, ld2, nullptr, nullptr, Phi1, ld1, area2, p2p, i64, off1, off2, total_n2, max_n2, n_pairs,
                             k2 + step2, k1 + step1, Cnext, pf_ws, pf_bytes, st)))
         return rc;
+    } else if (delta_ok && it != nit - 1) {
+      if (it % kZoAnchor == 0) {
+        if ((rc = p2p_to_fm_run(p2p, i64, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs, k1m, k2m, Mfull, pf_ws, st)))
+          return rc;
+      } else if ((rc = p2p_to_fm_delta_run(p2p, p2p_buf[(it - 1) & 1], i64, Phi1, ld1, off1, Phi2, ld2, off2, total_n2, max_n2,
+                                           area2, n_pairs, k1m, k2m, Mfull, delta_ws, st)))
+        return rc;
+      if ((rc = extract_block_run(Mfull, k1m, k2m, k1 + step1, k2 + step2, n_pairs, Cnext, st))) return rc;
     } else if ((rc = p2p_to_fm_run(p2p, i64, Phi1, ld1, off1, Phi2, ld2, off2, max_n2, area2, n_pairs, k1 + step1,
                                    k2 + step2, Cnext, pf_ws, st)))
       return rc;

@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, i
       for (int h = 0; h < 2; ++h) {
         const int n = n0 + wn + 8 * c + 2 * t4 + h;
         if (n >= N) continue;
-        C[int64_t(m) * P.ldc + n] = P.alpha * acc[a][c][h];
+        double v = P.alpha * acc[a][c][h];
+        if (P.c_add) v += P.c_add[int64_t(b) * P.c_add_batch_stride + int64_t(m) * P.c_add_ld + n];
+        C[int64_t(m) * P.ldc + n] = v;
       }
     }
   }
@@ -496,6 +498,7 @@ __global__ void __launch_bounds__(NT, 2) gemm64_tt_kernel(const GemmProblem P, i
 bool tt_shape(const GemmProblem& P) {
   static const bool off = [] { const char* e = getenv("DM_GEMM_NO_TT"); return e && e[0] == '1'; }();
   if (off || P.A.trans != 1 || P.B.trans != 1 || !P.A.d || !P.B.d || P.c_colscale) return false;
+  if (P.c_add && P.ksplit > 1) return false;
   if (P.A.kscale && P.B.kscale) return false;
   auto ok = [](const GemmOperand& o) {
     return ((reinterpret_cast<uintptr_t>(o.d) | uintptr_t(o.ld * sizeof(double)) | uintptr_t(o.col0 * sizeof(double))) & 15) == 0;
@@ -660,6 +663,7 @@ __global__ void __launch_bounds__(256)
 
 int gemm64_launch(const GemmProblem& P, cudaStream_t st) {
   if (P.n_batch <= 0 || P.maxM <= 0 || P.maxN <= 0) return DM_OK;
+  if (P.c_add && !tt_shape(P)) DM_FAIL(DM_ERR_UNSUPPORTED, "gemm64: an addend needs the both-transposed cp.async shape");
   if (embed_shape(P)) {
     const int chunks = (P.maxM + ET * ETPC - 1) / (ET * ETPC);
     const int64_t nb = int64_t(P.n_batch) * chunks;

@@ -37,6 +37,9 @@ struct GemmProblem {
   const double* c_colscale = nullptr;  // optional: C[m][n] *= c_colscale[colscale_base + n]
   const int64_t* c_colscale_off = nullptr;
   double alpha = 1.0;
+  // optional addend of the "both transposed" shape (gemm64_tt_kernel): C[b][m][n] = alpha acc + c_add[b][m][n]
+  const double* c_add = nullptr;
+  int64_t c_add_ld = 0, c_add_batch_stride = 0;
   int ksplit = 1;                 // number of K chunks; chunk s writes to C + s * split_stride
   int kchunk = 0;
   int64_t split_stride = 0;
