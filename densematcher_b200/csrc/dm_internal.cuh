@@ -372,8 +372,8 @@ bool p2p21_factored_applicable(int k1, int k2, int flags);
 size_t p2p21_factored_scratch_bytes(int n_pairs, int64_t total_n1, int k1m, int k2m);
 int p2p21_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
                        int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
-                       int n_pairs, void* p2p_out, int flags, void* scratch, double* emb1, int lde, void* nn_ws,
-                       size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state);
+                       int n_pairs, void* p2p_out, int flags, void* scratch, int scratch_k1m, int scratch_k2m, double* emb1,
+                       int lde, void* nn_ws, size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state);
 
 // incremental p2p -> FM of the ZoomOut ladder (zoomout_delta.cu): the full-width map M = Phi2^T A2 Phi1[p] is kept resident
 // and corrected with the changed entries of the vertex map; every rung reads its leading block

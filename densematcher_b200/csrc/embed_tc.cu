@@ -47,24 +47,26 @@ constexpr uint32_t kEbIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(EB_
 // ---------------------------------------------------------------- B operand: three-way bf16 split of C or C^T per pair
 // side 0: Bt[o][k] = C[k][o]   (rows o < k1, contraction k < k2: emb2 = Phi2 C)
 // side 1: Bt[o][k] = C[o][k]   (rows o < k2, contraction k < k1: emb1 = Phi1 C^T)
-// output rows are padded to 128 per pair and the contraction to kp (zeros); c_fro[p] >= |C|_F.
+// output rows are padded to rb (128 or 256) per pair and the contraction to kp (zeros); c_fro[p] >= |C|_F.
+constexpr int kCsplitChunks = 8;  // CTAs per (pair, side): the kernel is a latency-bound walk over <= 256 x 256 entries
 __global__ void __launch_bounds__(256)
     csplit_kernel(const double* __restrict__ C, int k1, int k2, int kp0, int kp1, __nv_bfloat16* __restrict__ h0,
                   __nv_bfloat16* __restrict__ m0, __nv_bfloat16* __restrict__ l0, __nv_bfloat16* __restrict__ h1,
-                  __nv_bfloat16* __restrict__ m1, __nv_bfloat16* __restrict__ l1, float* __restrict__ c_fro,
-                  int first_side, double* __restrict__ Ct) {
-  const int p = blockIdx.x, side = blockIdx.y + first_side;
+                  __nv_bfloat16* __restrict__ m1, __nv_bfloat16* __restrict__ l1, double* __restrict__ fro_part,
+                  int first_side, double* __restrict__ Ct, int rb) {
+  const int p = blockIdx.x, side = blockIdx.y + first_side, chunk = blockIdx.z;
   if (Ct) {  // float64 transpose [k1, k2] for the on-demand products Phi1_j C^T
-    for (int e = threadIdx.x; e < k1 * k2; e += blockDim.x)
+    for (int e = chunk * blockDim.x + threadIdx.x; e < k1 * k2; e += blockDim.x * kCsplitChunks)
       Ct[int64_t(p) * k1 * k2 + e] = C[int64_t(p) * k1 * k2 + int64_t(e % k2) * k1 + e / k2];
   }
   const double* Cp = C + int64_t(p) * k1 * k2;
   const int n_out = side == 0 ? k1 : k2, n_in = side == 0 ? k2 : k1, kp = side == 0 ? kp0 : kp1;
-  __nv_bfloat16* h = (side == 0 ? h0 : h1) + int64_t(p) * EB_ROWS * kp;
-  __nv_bfloat16* m = (side == 0 ? m0 : m1) + int64_t(p) * EB_ROWS * kp;
-  __nv_bfloat16* l = (side == 0 ? l0 : l1) + int64_t(p) * EB_ROWS * kp;
+  __nv_bfloat16* h = (side == 0 ? h0 : h1) + int64_t(p) * rb * kp;
+  __nv_bfloat16* m = (side == 0 ? m0 : m1) + int64_t(p) * rb * kp;
+  __nv_bfloat16* l = (side == 0 ? l0 : l1) + int64_t(p) * rb * kp;
   double ss = 0.0;
-  for (int e = threadIdx.x; e < EB_ROWS * kp; e += blockDim.x) {
+  const int rows_per = rb / kCsplitChunks;
+  for (int e = chunk * rows_per * kp + threadIdx.x; e < (chunk + 1) * rows_per * kp; e += blockDim.x) {
     const int o = e / kp, k = e % kp;
     double v = 0.0;
     if (o < n_out && k < n_in) v = side == 0 ? Cp[int64_t(k) * k1 + o] : Cp[int64_t(o) * k1 + k];
@@ -83,9 +85,17 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < 8; ++w) ss += red[w];
-      c_fro[p] = __double2float_ru(sqrt(ss)) * 1.000001f;
+      fro_part[p * kCsplitChunks + chunk] = ss;
     }
   }
+}
+// c_fro[p] >= |C_p|_F from the chunk sums (fixed order)
+__global__ void __launch_bounds__(128) cfro_kernel(const double* __restrict__ fro_part, int n_pairs, float* __restrict__ c_fro) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  double ss = 0.0;
+  for (int c = 0; c < kCsplitChunks; ++c) ss += fro_part[p * kCsplitChunks + c];
+  c_fro[p] = __double2float_ru(sqrt(ss)) * 1.000001f;
 }
 
 // ---------------------------------------------------------------- the embedding kernel
@@ -305,6 +315,196 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------- wide embeddings: 128 < k <= 256 (upper ZoomOut rungs)
+// The split of C no longer fits beside the A tiles (3 x 256 rows x 256 columns of bf16 = 384 KB), so BOTH operands are
+// streamed per 64-wide K chunk through a two-stage ring (48 KB of A + 48 KB of B per stage; B comes from L2, every CTA of a
+// pair re-reads it), and the output columns are produced in halves of 128 -- a work unit is (row tile, half), its two
+// accumulators (hh / corrections) double-buffered in tensor memory exactly as above.  The epilogue thread carries the
+// running sum of squares of its row across the halves and finalises norm / bias / maxima after the last one.
+constexpr uint32_t EBS_STAGE = 6 * EB_TILE;  // A triple + B triple of one K chunk: 96 KB
+constexpr uint32_t kEbsSmem = 2 * EBS_STAGE + 128 + 1024;
+
+__global__ void __launch_bounds__(EB_THREADS, 1)
+    embed_tc_stream_kernel(const __grid_constant__ EbMaps maps, const EbParams P, const int n_kc, const int n_half) {
+  const int ctas_per_pair = (P.max_rt + EB_TPC - 1) / EB_TPC;
+  const int p = blockIdx.x / ctas_per_pair, rt0 = (blockIdx.x % ctas_per_pair) * EB_TPC;
+  const int64_t r0 = P.off[p];
+  const int n = int(P.off[p + 1] - r0);
+  if (rt0 * EB_ROWS >= n) return;
+  const int n_tiles = min(EB_TPC, (n - rt0 * EB_ROWS + EB_ROWS - 1) / EB_ROWS);
+  const int n_units = n_tiles * n_half;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  constexpr uint32_t OFF_BAR = 2 * EBS_STAGE;
+  const uint32_t bar_full = sbase + OFF_BAR;    // [2]
+  const uint32_t bar_empty = bar_full + 16;     // [2]
+  const uint32_t bar_tfull = bar_empty + 16;    // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + OFF_BAR + 80);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[i]) : "memory");
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = 0; u < n_units; ++u) {
+        const int t = u / n_half, h = u % n_half;
+        const int arow = int(r0 + int64_t(rt0 + t) * EB_ROWS), brow = (p * n_half + h) * EB_ROWS;
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, EBS_STAGE);
+          const uint32_t sb = sbase + stage * EBS_STAGE;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            tma_load_2d(sb + i * EB_TILE, &maps.a[i], kc * EB_BK, arow, bar_full + 8 * stage);
+            tma_load_2d(sb + (3 + i) * EB_TILE, &maps.b[i], kc * EB_BK, brow, bar_full + 8 * stage);
+          }
+          if (++stage == 2) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = 0; u < n_units; ++u) {
+        const int s = u & 1;
+        mbar_wait_backoff(bar_tempty + 8 * s, ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t t_hh = tmem_base + s * 2 * EB_ROWS, t_cor = t_hh + EB_ROWS;
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait_backoff(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sb = sbase + stage * EBS_STAGE;
+          uint64_t da[3], db[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            da[i] = eb_desc_sw128(sb + i * EB_TILE);
+            db[i] = eb_desc_sw128(sb + (3 + i) * EB_TILE);
+          }
+#pragma unroll
+          for (int k = 0; k < EB_BK / EB_UK; ++k) {
+            const uint64_t ko = uint64_t((k * EB_UK * 2) >> 4);
+            const uint32_t first = (kc | k) != 0;
+            tc_mma_bf16(t_hh, da[0] + ko, db[0] + ko, kEbIdesc, first);   // h h
+            tc_mma_bf16(t_cor, da[0] + ko, db[1] + ko, kEbIdesc, first);  // h m
+            tc_mma_bf16(t_cor, da[1] + ko, db[0] + ko, kEbIdesc, 1);      // m h
+            tc_mma_bf16(t_cor, da[1] + ko, db[1] + ko, kEbIdesc, 1);      // m m
+            tc_mma_bf16(t_cor, da[0] + ko, db[2] + ko, kEbIdesc, 1);      // h l
+            tc_mma_bf16(t_cor, da[2] + ko, db[0] + ko, kEbIdesc, 1);      // l h
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == 2) stage = 0, phase ^= 1;
+        }
+        tc_commit(bar_tfull + 8 * s);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int i = (rt0 + t) * EB_ROWS + 32 * q + lane;  // row inside the pair
+      const bool ok = i < n;
+      const int64_t gi = r0 + i;
+      float ss = 0.f;
+      for (int h = 0; h < n_half; ++h) {
+        const int u = t * n_half + h, s = u & 1;
+        mbar_wait(bar_tfull + 8 * s, (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + s * 2 * EB_ROWS + (uint32_t(32 * q) << 16);
+        const int col_base = h * EB_ROWS;
+        const int n_ch = min(4, (P.kp_out - col_base) / 32);
+        for (int ch = 0; ch < n_ch; ++ch) {
+          float a[32], c[32];
+          if (col_base + ch * 32 < P.k_out) {
+            tmem_ld32(taddr + ch * 32, a);
+            tmem_ld32(taddr + EB_ROWS + ch * 32, c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) a[e] = c[e] = 0.f;
+          }
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float y0 = a[e] + c[e], y1 = a[e + 1] + c[e + 1];
+            ss = fmaf(y0, y0, ss);
+            ss = fmaf(y1, y1, ss);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+            ph[e >> 1] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+            pl[e >> 1] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+          }
+          if (ok && P.hi) {
+            uint4* dh = reinterpret_cast<uint4*>(P.hi + gi * P.kp_out + col_base + ch * 32);
+            uint4* dl = reinterpret_cast<uint4*>(P.lo + gi * P.kp_out + col_base + ch * 32);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              dh[v4] = make_uint4(ph[4 * v4], ph[4 * v4 + 1], ph[4 * v4 + 2], ph[4 * v4 + 3]);
+              dl[v4] = make_uint4(pl[4 * v4], pl[4 * v4 + 1], pl[4 * v4 + 2], pl[4 * v4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+      }
+      const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[gi] * P.c_fro[p] : 0.f;
+      const float own = (nrm + e_i) + e_i * P.inv_eps;
+      if (ok && P.norm) P.norm[gi] = own;
+      for (int e = 0; e < P.n_epi; ++e) {
+        const EbEpi& E = P.epi[e];
+        float g = 0.f, bm = 0.f;
+        if (ok) {
+          const float sc = E.scale ? float(E.scale[gi]) : 1.f;
+          const float bi = E.bias_sqnorm ? -0.5f * ss : 0.f;
+          E.sf[gi] = sc;
+          E.bf[gi] = bi;
+          if (E.sd) E.sd[gi] = E.scale ? E.scale[gi] : 1.0;
+          if (E.bd) E.bd[gi] = 0.0;
+          g = own * fabsf(sc) * 1.000001f;
+          const float db = E.bias_sqnorm ? (nrm * e_i + 0.5f * e_i * e_i + fabsf(bi) * float(P.k_out + 4) * 1.2e-7f) : 0.f;
+          bm = fabsf(bi) + db * (2.f / 9.6e-7f);
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, sh));
+          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, sh));
+        }
+        if (lane == 0) {
+          atomic_max_nonneg(E.G + p, g);
+          atomic_max_nonneg(E.Bm + p, bm);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------- on-demand float64 for the queued re-evaluations
 struct FillParams {
   // Y side: query rows are Phi2[:, :k2] C                      (row i -> emb64[q0 + i], k1 values)
@@ -324,40 +524,40 @@ struct FillParams {
 
 // out[o] = sum_k phi[k] C[k][o], o < k1 (lanes over o: coalesced rows of C); returns sum_o out[o]^2 (all lanes).
 // The row of Phi is held in registers (lane l: entries l, l + 32, ...) and broadcast by shuffles; four rows of C are in
-// flight per step (the loop is otherwise one dependent L2 round trip per k: 15 us per product).
+// flight per step (the loop is otherwise one dependent L2 round trip per k: 15 us per product).  T slabs of 32: k <= 32 T.
+template <int T>
 __device__ __forceinline__ double warp_row_times_C(const double* __restrict__ phi, const double* __restrict__ Cp, int k1,
                                                    int k2, int lane, double* __restrict__ out) {
-  double f[4];
+  double f[T];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) f[t] = (lane + 32 * t < k2) ? phi[lane + 32 * t] : 0.0;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  const int o0 = lane, o1 = lane + 32, o2 = lane + 64, o3 = lane + 96;
+  for (int t = 0; t < T; ++t) f[t] = (lane + 32 * t < k2) ? phi[lane + 32 * t] : 0.0;
+  double acc[T];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int a = 0; a < T; ++a) acc[a] = 0.0;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
     if (32 * t >= k2) break;
     for (int kk = 0; kk < 32 && 32 * t + kk < k2; kk += 4) {
-      double c[4][4];
+      double c[4][T];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = min(32 * t + kk + u, k2 - 1);
         const double* row = Cp + int64_t(k) * k1;
-        c[u][0] = o0 < k1 ? row[o0] : 0.0;
-        c[u][1] = o1 < k1 ? row[o1] : 0.0;
-        c[u][2] = o2 < k1 ? row[o2] : 0.0;
-        c[u][3] = o3 < k1 ? row[o3] : 0.0;
+#pragma unroll
+        for (int a = 0; a < T; ++a) c[u][a] = lane + 32 * a < k1 ? row[lane + 32 * a] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         double fk = __shfl_sync(0xffffffffu, f[t], kk + u);
         if (32 * t + kk + u >= k2) fk = 0.0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a] = fma(fk, c[u][a], acc[a]);
+        for (int a = 0; a < T; ++a) acc[a] = fma(fk, c[u][a], acc[a]);
       }
     }
   }
   double ss = 0.0;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < T; ++t) {
     const int o = lane + 32 * t;
     if (o < k1) {
       if (out) out[o] = acc[t];
@@ -410,7 +610,7 @@ __global__ void __launch_bounds__(256) factored_fill_kernel(const NNProblem P, c
     const double* Cp = F.C + int64_t(p) * F.k1 * F.k2;
     if (!is_col) {
       // the result of query row `local`: its float64 embedding row, and the float64 biases of its candidates
-      warp_row_times_C(F.Phi2 + (q0 + e.local) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + e.local) * F.k1);
+      warp_row_times_C<4>(F.Phi2 + (q0 + e.local) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + e.local) * F.k1);
       if (epi == F.row_bias_epi) {
         if (full) {
           if (lane == 0) F.skip_x[p] = 0;
@@ -429,7 +629,7 @@ __global__ void __launch_bounds__(256) factored_fill_kernel(const NNProblem P, c
       } else {
         for (int c = 0; c < 2; ++c) {
           const int i = c == 0 ? e.c1 : e.c2;
-          const double ss = warp_row_times_C(F.Phi2 + (q0 + i) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + i) * F.k1);
+          const double ss = warp_row_times_C<4>(F.Phi2 + (q0 + i) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + i) * F.k1);
           if (lane == 0 && epi == F.col_bias_epi) F.col_bd[q0 + i] = -0.5 * ss;
         }
       }
@@ -468,15 +668,28 @@ int eb_launch(const EbMaps& maps, const EbParams& P, int n_pairs, cudaStream_t s
   return DM_OK;
 }
 
+// kp_in <= 128 and k_out <= 128: resident-B kernel; wider: the streaming kernel (the B operand then holds
+// 128 * ceil(k_out / 128) rows per pair)
+int eb_b_rows(int k_out) { return k_out <= EB_ROWS ? EB_ROWS : 2 * EB_ROWS; }
 int eb_run(const void* const a3[3], int64_t a_rows, const void* const b3[3], int kp_in, const EbParams& P, int n_pairs,
            cudaStream_t st) {
   EbMaps maps;
   int rc;
+  const bool wide = kp_in > 2 * EB_BK || P.k_out > EB_ROWS;
+  const int rb = wide ? eb_b_rows(P.k_out) : EB_ROWS;
   for (int i = 0; i < 3; ++i) {
     if ((rc = tc_make_map_bf16(&maps.a[i], a3[i], a_rows, kp_in, EB_ROWS))) return rc;
-    if ((rc = tc_make_map_bf16(&maps.b[i], b3[i], int64_t(n_pairs) * EB_ROWS, kp_in, EB_ROWS))) return rc;
+    if ((rc = tc_make_map_bf16(&maps.b[i], b3[i], int64_t(n_pairs) * rb, kp_in, EB_ROWS))) return rc;
   }
-  return kp_in <= EB_BK ? eb_launch<1>(maps, P, n_pairs, st) : eb_launch<2>(maps, P, n_pairs, st);
+  if (!wide) return kp_in <= EB_BK ? eb_launch<1>(maps, P, n_pairs, st) : eb_launch<2>(maps, P, n_pairs, st);
+  static OncePerDevice once;
+  if (once.first())
+    DM_CUDA_OK(cudaFuncSetAttribute(embed_tc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kEbsSmem)));
+  const int64_t nblk = int64_t(n_pairs) * ((P.max_rt + EB_TPC - 1) / EB_TPC);
+  if (nblk > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many row tiles");
+  embed_tc_stream_kernel<<<unsigned(nblk), EB_THREADS, kEbsSmem, st>>>(maps, P, kp_in / EB_BK, rb / EB_ROWS);
+  DM_LAUNCH_OK("embed_tc_stream_kernel");
+  return DM_OK;
 }
 
 // ---------------------------------------------------------------- the FM -> p2p hooks
@@ -493,6 +706,7 @@ struct F2PCtx {
   float* p2norm;
   uint16_t *c0h, *c0m, *c0l, *c1h, *c1m, *c1l;  // B operands [n_pairs * 128, kp]
   float* c_fro;
+  double* fro_part;  // [n_pairs, kCsplitChunks] partial sums of squares of C
   float* g_scratch;
   double* emb2;   // [total_n2, k1] float64 query rows, filled on demand
   double* emb1;   // [total_n1, k2] float64, only for pairs that need every bias
@@ -513,10 +727,11 @@ int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
   if ((rc = nn_prep_side(X.Phi2, 1, X.ld2, X.off2, X.n_pairs, X.total_n2, X.k2, X.p2norm, nullptr, 0, X.p2h, X.p2m, X.p2l,
                          X.kp2, st)))
     return rc;
-  csplit_kernel<<<dim3(unsigned(X.n_pairs), 2), 256, 0, st>>>(
+  csplit_kernel<<<dim3(unsigned(X.n_pairs), 2, kCsplitChunks), 256, 0, st>>>(
       X.C, X.k1, X.k2, X.kp2, X.kp1, reinterpret_cast<__nv_bfloat16*>(X.c0h), reinterpret_cast<__nv_bfloat16*>(X.c0m),
       reinterpret_cast<__nv_bfloat16*>(X.c0l), reinterpret_cast<__nv_bfloat16*>(X.c1h),
-      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.c_fro, 0, nullptr);
+      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.fro_part, 0, nullptr, EB_ROWS);
+  cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
   E.off = X.off2, E.max_rt = (X.max_n2 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k1, E.kp_out = P.kp, E.n_epi = R.n_col;
@@ -618,6 +833,7 @@ F2PLayout f2p_carve(void* ws, int n_pairs, int64_t n1, int64_t n2, int max_n1, i
   L.c.c0h = c.take<uint16_t>(cb0), L.c.c0m = c.take<uint16_t>(cb0), L.c.c0l = c.take<uint16_t>(cb0);
   L.c.c1h = c.take<uint16_t>(cb1), L.c.c1m = c.take<uint16_t>(cb1), L.c.c1l = c.take<uint16_t>(cb1);
   L.c.c_fro = c.take<float>(size_t(n_pairs));
+  L.c.fro_part = c.take<double>(size_t(n_pairs) * kCsplitChunks);
   L.c.g_scratch = c.take<float>(size_t(n_pairs));
   L.c.emb2 = c.take<double>(size_t(n2) * k1);
   L.c.emb1 = c.take<double>(size_t(n1) * k2);
@@ -641,12 +857,14 @@ struct P21Ctx {
   float* p1norm;
   uint16_t *c1h, *c1m, *c1l;  // split of C (rows o < k2, contraction k < k1) [n_pairs * 128, kp1]
   float* c_fro;
+  double* fro_part;           // [n_pairs, kCsplitChunks]
   double* Ct;                 // [n_pairs, k1, k2] float64 transpose of C
   double* emb1;               // [total_n1, lde] float64 database rows, filled on demand
   int lde;
   int* skip_x;
 };
 
+template <int T>
 __global__ void __launch_bounds__(256) ladder_fill_kernel(const NNProblem P, const double* __restrict__ Phi1, int64_t ld1,
                                                           const double* __restrict__ Ct, int k1, int k2,
                                                           double* __restrict__ emb1, int lde, double* __restrict__ bd,
@@ -666,7 +884,7 @@ __global__ void __launch_bounds__(256) ladder_fill_kernel(const NNProblem P, con
     for (int c = 0; c < 2; ++c) {
       const int j = c == 0 ? e.c1 : e.c2;
       // emb1_j[o] = sum_k Phi1[j][k] C[o][k] = sum_k Phi1[j][k] Ct[k][o]
-      const double ss = warp_row_times_C(Phi1 + (d0 + j) * ld1, Ct + int64_t(p) * k1 * k2, k2, k1, lane, emb1 + (d0 + j) * lde);
+      const double ss = warp_row_times_C<T>(Phi1 + (d0 + j) * ld1, Ct + int64_t(p) * k1 * k2, k2, k1, lane, emb1 + (d0 + j) * lde);
       if (lane == 0) bd[d0 + j] = -0.5 * ss;
     }
   }
@@ -674,9 +892,12 @@ __global__ void __launch_bounds__(256) ladder_fill_kernel(const NNProblem P, con
 
 int p21_prep_x(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) {
   P21Ctx& X = *static_cast<P21Ctx*>(vctx);
-  csplit_kernel<<<dim3(unsigned(X.n_pairs), 1), 256, 0, st>>>(
+  const bool wide = X.kp1 > 2 * EB_BK || X.k2 > EB_ROWS;
+  csplit_kernel<<<dim3(unsigned(X.n_pairs), 1, kCsplitChunks), 256, 0, st>>>(
       X.C, X.k1, X.k2, 0, X.kp1, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(X.c1h),
-      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.c_fro, 1, X.Ct);
+      reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.fro_part, 1, X.Ct,
+      wide ? eb_b_rows(X.k2) : EB_ROWS);
+  cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
   E.off = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = P.kp, E.n_epi = 1;
@@ -696,7 +917,10 @@ int p21_prep_x(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
 int p21_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t st) {
   P21Ctx& X = *static_cast<P21Ctx*>(vctx);
   DM_CUDA_OK(cudaMemsetAsync(X.skip_x, 1, sizeof(int) * X.n_pairs, st));
-  ladder_fill_kernel<<<num_sms() * 8, 256, 0, st>>>(P, X.Phi1, X.ld1, X.Ct, X.k1, X.k2, X.emb1, X.lde, L.row[0].bd, X.skip_x);
+  if (X.k1 <= 128 && X.k2 <= 128)
+    ladder_fill_kernel<4><<<num_sms() * 8, 256, 0, st>>>(P, X.Phi1, X.ld1, X.Ct, X.k1, X.k2, X.emb1, X.lde, L.row[0].bd, X.skip_x);
+  else
+    ladder_fill_kernel<8><<<num_sms() * 8, 256, 0, st>>>(P, X.Phi1, X.ld1, X.Ct, X.k1, X.k2, X.emb1, X.lde, L.row[0].bd, X.skip_x);
   DM_LAUNCH_OK("ladder_fill_kernel");
   GemmProblem G;
   G.A.d = X.Phi1, G.A.ld = X.ld1, G.A.off = X.off1, G.A.trans = 0;
@@ -715,19 +939,22 @@ struct P21Layout {
   P21Ctx c;
   size_t bytes;
 };
+constexpr int kP21MaxK = 4 * EB_BK;  // widest rung embedded on the tensor cores
 P21Layout p21_carve(void* ws, int n_pairs, int64_t total_n1, int k1m, int k2m) {
   Carver c(ws);
   P21Layout L{};
-  const int kp = nn_tc_kp(k1m < 2 * EB_BK ? k1m : 2 * EB_BK);
-  (void)k2m;
+  const int kp = nn_tc_kp(k1m < kP21MaxK ? k1m : kP21MaxK);
+  const int rb = (k2m < kP21MaxK ? k2m : kP21MaxK) <= EB_ROWS && kp <= 2 * EB_BK ? EB_ROWS : 2 * EB_ROWS;
   L.c.p1h = c.take<uint16_t>(size_t(total_n1) * kp);
   L.c.p1m = c.take<uint16_t>(size_t(total_n1) * kp);
   L.c.p1l = c.take<uint16_t>(size_t(total_n1) * kp);
   L.c.p1norm = c.take<float>(size_t(total_n1));
-  const size_t cb = size_t(n_pairs) * EB_ROWS * kp;
+  const size_t cb = size_t(n_pairs) * rb * kp;
   L.c.c1h = c.take<uint16_t>(cb), L.c.c1m = c.take<uint16_t>(cb), L.c.c1l = c.take<uint16_t>(cb);
   L.c.c_fro = c.take<float>(size_t(n_pairs));
-  L.c.Ct = c.take<double>(size_t(n_pairs) * 2 * EB_BK * 2 * EB_BK);
+  L.c.fro_part = c.take<double>(size_t(n_pairs) * kCsplitChunks);
+  const int kt = k1m < kP21MaxK ? k1m : kP21MaxK, ku = k2m < kP21MaxK ? k2m : kP21MaxK;
+  L.c.Ct = c.take<double>(size_t(n_pairs) * kt * ku);
   L.c.skip_x = c.take<int>(size_t(n_pairs));
   L.bytes = c.bytes();
   return L;
@@ -785,7 +1012,9 @@ namespace dm {
 
 bool p2p21_factored_applicable(int k1, int k2, int flags) {
   static const bool off = [] { const char* e = getenv("DM_P21_F64EMB"); return e && e[0] == '1'; }();
-  return !off && nn_use_tc(flags) && k1 <= 2 * EB_BK && k2 <= 2 * EB_BK && !(flags & (DM_RECHECK_ALL | DM_SKIP_PREP));
+  static const bool narrow = [] { const char* e = getenv("DM_P21_NARROW"); return e && e[0] == '1'; }();
+  const int lim = narrow ? 2 * EB_BK : kP21MaxK;
+  return !off && nn_use_tc(flags) && k1 <= lim && k2 <= lim && !(flags & (DM_RECHECK_ALL | DM_SKIP_PREP));
 }
 
 size_t p2p21_factored_scratch_bytes(int n_pairs, int64_t total_n1, int k1m, int k2m) {
@@ -794,11 +1023,13 @@ size_t p2p21_factored_scratch_bytes(int n_pairs, int64_t total_n1, int k1m, int 
 
 int p2p21_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
                        int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
-                       int n_pairs, void* p2p_out, int flags, void* scratch, double* emb1, int lde, void* nn_ws,
-                       size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state) {
+                       int n_pairs, void* p2p_out, int flags, void* scratch, int scratch_k1m, int scratch_k2m, double* emb1,
+                       int lde, void* nn_ws, size_t nn_ws_bytes, cudaStream_t st, int* x_kp_state, int* y_kp_state) {
   // the carve uses the widest split the scratch was sized for; this rung uses the first kp1 columns of each row, so the
   // split of Phi1 is stored with the rung's own pitch kp1 and remade when the pitch changes (64 -> 128)
-  P21Layout L = p21_carve(scratch, n_pairs, total_n1, 2 * EB_BK, 2 * EB_BK);
+  // carved with the widths the scratch was sized for (p2p21_factored_scratch_bytes): the layout is the same at every rung
+  if (k1 > scratch_k1m || k2 > scratch_k2m) DM_FAIL(DM_ERR_WORKSPACE, "factored conversion: scratch sized for narrower maps");
+  P21Layout L = p21_carve(scratch, n_pairs, total_n1, scratch_k1m, scratch_k2m);
   P21Ctx& X = L.c;
   X.C = C, X.Phi1 = Phi1, X.ld1 = ld1, X.off1 = off1, X.total_n1 = total_n1, X.max_n1 = max_n1, X.n_pairs = n_pairs;
   X.k1 = k1, X.k2 = k2, X.kp1 = nn_tc_kp(k1), X.emb1 = emb1, X.lde = lde;

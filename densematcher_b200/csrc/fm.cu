@@ -78,7 +78,8 @@ struct P2P21Scratch {
   void* nn_ws;
   size_t nn_ws_bytes;
   int lde, ldf;
-  void* fact = nullptr;  // scratch of the factored (tensor-core embedding) path, k <= 128
+  void* fact = nullptr;  // scratch of the factored (tensor-core embedding) path, k <= 256
+  int fact_k1m = 0, fact_k2m = 0;  // widths it was sized for
   int x_kp = -1;         // padded width for which the split of Phi1 in `fact` is valid
 };
 int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
@@ -87,9 +88,10 @@ int p2p21_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, 
               cudaStream_t st, int* y_kp_state = nullptr) {
   int rc;
   // k <= 128: the database side Phi1 C^T is embedded on the tensor cores, float64 rows on demand (embed_tc.cu)
-  if (S.fact && p2p21_factored_applicable(k1, k2, flags))
+  if (S.fact && k1 <= S.fact_k1m && k2 <= S.fact_k2m && p2p21_factored_applicable(k1, k2, flags))
     return p2p21_factored_run(C, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, n_pairs,
-                              p2p_out, flags, S.fact, S.emb1, S.lde, S.nn_ws, S.nn_ws_bytes, st, &S.x_kp, y_kp_state);
+                              p2p_out, flags, S.fact, S.fact_k1m, S.fact_k2m, S.emb1, S.lde, S.nn_ws, S.nn_ws_bytes, st, &S.x_kp,
+                              y_kp_state);
   GemmProblem G;
   G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
   G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 0;
@@ -369,6 +371,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2m, 1, 0, flags);
   S.nn_ws = c.take<char>(S.nn_ws_bytes);
   S.fact = c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1m, k2m));
+  S.fact_k1m = k1m, S.fact_k2m = k2m;
   const int i64 = (flags & DM_I64_OUT) ? 1 : 0;
   int rc;
   if (!nn_use_tc(flags) && (rc = cvt_f64_f32(Phi2, ld2, total_n2, k2m, Phi2f, S.ldf, st))) return rc;
@@ -454,6 +457,7 @@ IcpLayout icp_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, i
   L.S.nn_ws_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, k2, 1, 0, flags);
   L.S.nn_ws = c.take<char>(L.S.nn_ws_bytes);
   L.S.fact = c.take<char>(p2p21_factored_scratch_bytes(n_pairs, total_n1, k1, k2));
+  L.S.fact_k1m = k1, L.S.fact_k2m = k2;
   L.bytes = c.bytes();
   return L;
 }
