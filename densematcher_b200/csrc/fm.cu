@@ -382,7 +382,7 @@ int dm_zoomout(const double* C0, int k1_0, int k2_0, int nit, int step1, int ste
   // vertices whose image changed since the previous rung (zoomout_delta.cu); a rung's map is M's leading block.  A full
   // product re-anchors M every kZoAnchor rungs, and the last rung is always a fresh product of its own.
   // (the gathered correction runs on the cp.async GEMM: rows of both bases on 16-byte boundaries)
-  constexpr int kZoAnchor = 32;
+  constexpr int kZoAnchor = 64;
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(Phi1) | reinterpret_cast<uintptr_t>(Phi2)) & 15) == 0 && !((ld1 | ld2) & 1);
   const bool delta_ok = !fast_fm && aligned16 && nit > 2 && p2p_to_fm_delta_applicable();
   for (int it = 0; it < nit; ++it) {

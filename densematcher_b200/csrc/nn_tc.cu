@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
   const int nd = int(P.db_off[p + 1] - d0);
   const int n_ct = (nd + TN - 1) / TN;
   const int n_kc = P.kp / TBK;
+  const int n_k16 = max(1, min(P.kp / UMMA_K, (P.d + UMMA_K - 1) / UMMA_K));
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -249,8 +250,12 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
           const uint32_t sb = sbase + stage * STAGE_BYTES;
           const uint64_t dyh = umma_desc_sw128(sb), dyl = umma_desc_sw128(sb + SZ_Y);
           const uint64_t dxh = umma_desc_sw128(sb + 2 * SZ_Y), dxl = umma_desc_sw128(sb + 2 * SZ_Y + SZ_X);
+          // the database side is zero beyond column d: the K steps of the last chunk that only meet padding are skipped
+          // (k = 150 pads to 192 columns but needs 160; the upper ZoomOut rungs are bound by these MMAs)
+          const int ksteps = min(TBK / UMMA_K, n_k16 - kc * (TBK / UMMA_K));
 #pragma unroll
           for (int k = 0; k < TBK / UMMA_K; ++k) {
+            if (k >= ksteps) break;
             const uint64_t ko = uint64_t((k * UMMA_K * 2) >> 4);  // 32 bytes per K step inside the swizzle row
             if (PAIR) {
               tc_mma_bf16_pair(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);

@@ -12,7 +12,7 @@
 //                                           interleaved (+a2, p) / (-a2, p_old) entries of a gather list
 //   gemm64_tt_kernel                        the correction as a gathered "both transposed" GEMM with M as its addend
 //   extract_block_kernel                    the dense leading block for the next conversion
-// The ladder re-anchors M with a full product every 32 rungs, and the last rung is always a fresh product, so the rounding
+// The ladder re-anchors M with a full product every 64 rungs, and the last rung is always a fresh product, so the rounding
 // of the running sum never exceeds that of a few dozen float64 additions per entry.
 #include "dm_internal.cuh"
 #include "gemm64.cuh"
