@@ -653,7 +653,7 @@ def main():
         hbank = MeshBankHost(F=np.concatenate(pool["feats"]), off=np.arange(9, dtype=np.int64) * N_VERT,
                              Phi=np.concatenate([b[1] for b in pool["bases"]]), evals=np.stack([b[0] for b in pool["bases"]]),
                              area=np.concatenate([b[2] for b in pool["bases"]])).pin()
-        kwb = dict(k=K_EIG, w_descr=W_DESCR, w_lap=W_LAP, chunk_pairs=max(8, P // 4), copy=False)
+        kwb = dict(k=K_EIG, w_descr=W_DESCR, w_lap=W_LAP, chunk_pairs=P, copy=False)   # one launch set per call (19.3 k vs 14.6 k pairs/s at P // 4)
         bank_call = lambda: pipeline.match_bank_pairs_host(hbank, pool["ia"], pool["ib"], device, **kwb)
         for _ in range(2):
             outb = bank_call()

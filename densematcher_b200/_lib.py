@@ -66,6 +66,7 @@ SIGNATURES = {
     "dm_fmap_solve_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_fmap_solve": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_vp, c_vp,
                               c_sz, c_vp]),
+    "dm_fmap_c00": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "dm_fmap_solve_read_status": (c_int, [c_vp, C.POINTER(c_int), c_vp]),
     "dm_match_pairs_read_status": (c_int, [c_vp, C.POINTER(c_int), c_vp]),
     "dm_icp_read_status": (c_int, [c_vp, C.POINTER(c_int), c_vp]),

@@ -718,3 +718,17 @@ int dm_polar_factor(const double* X, int rows, int cols, int n_batch, double* C,
 }
 
 }  // extern "C"
+
+extern "C" {
+// c00[p] = sign(Phi1[first vertex of pair p][0] * Phi2[...][0]) * sqrt(area(mesh 2) / area(mesh 1)): the pinned entry
+// x0[0, 0] of FunctionalMapping.fit (pyFM/functional.py:654-658), for a ragged batch.
+int dm_fmap_c00(const double* Phi1, int64_t ld1, const int64_t* off1, const double* Phi2, int64_t ld2, const int64_t* off2,
+                const double* area1, const double* area2, int n_pairs, double* c00, dm_stream_t stream) {
+  if (n_pairs < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0) return DM_OK;
+  if (!Phi1 || !Phi2 || !off1 || !off2 || !area1 || !area2 || !c00) DM_FAIL(DM_ERR_BADARG, "null argument");
+  c00_kernel<<<unsigned(n_pairs), 256, 0, static_cast<cudaStream_t>(stream)>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, c00);
+  DM_LAUNCH_OK("c00_kernel");
+  return DM_OK;
+}
+}  // extern "C"

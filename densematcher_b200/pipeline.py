@@ -94,17 +94,18 @@ class PairBatchDevice:
         self.max1, self.max2 = self.o1.max, self.o2.max
 
 
-def _segment_sum(x, off_dev):
-    return torch.segment_reduce(x, "sum", offsets=off_dev)
-
-
 def fmap_c00(batch: PairBatchDevice):
-    """x0[0, 0] = sign(Phi1[0,0] Phi2[0,0]) sqrt(area2 / area1) per pair (pyFM/functional.py:654-658)."""
-    a1 = _segment_sum(batch.area1, batch.off1)
-    a2 = _segment_sum(batch.area2, batch.off2)
-    first1 = batch.Phi1[batch.off1[:-1], 0]
-    first2 = batch.Phi2[batch.off2[:-1], 0]
-    return torch.sign(first1 * first2) * torch.sqrt(a2 / a1)
+    """x0[0, 0] = sign(Phi1[0,0] Phi2[0,0]) sqrt(area2 / area1) per pair (pyFM/functional.py:654-658), ``dm_fmap_c00``."""
+    lib = _lib.load()
+    dev = batch.device
+    P1, P2, a1, a2 = _fm._f64(batch.Phi1), _fm._f64(batch.Phi2), _fm._f64(batch.area1), _fm._f64(batch.area2)
+    out = torch.empty(batch.n_pairs, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.dm_fmap_c00(P1.data_ptr(), P1.stride(0), batch.off1.data_ptr(), P2.data_ptr(), P2.stride(0),
+                             batch.off2.data_ptr(), a1.data_ptr(), a2.data_ptr(), batch.n_pairs, out.data_ptr(),
+                             _fm._stream(dev))
+    _lib.check(rc, "dm_fmap_c00")
+    return out
 
 
 def match_pairs_device(batch: PairBatchDevice, k: Optional[int] = None, w_descr: float = 1e4, w_lap: float = 1e3,
@@ -170,10 +171,13 @@ def precise_maps(batch: PairBatchDevice, C: torch.Tensor, faces1, face_off):
     ``faces1`` are the packed faces of the meshes 1 (vertex ids local to each mesh), ``face_off`` their offsets.
     Returns (face_match [total_n2], bary [total_n2, 3]) on the device."""
     k2, k1 = C.shape[1], C.shape[2]
-    emb2 = torch.empty((batch.Phi2.shape[0], k1), dtype=torch.float64, device=C.device)
-    for p in range(batch.n_pairs):
-        c, d = int(batch.off2_h[p]), int(batch.off2_h[p + 1])
-        torch.matmul(batch.Phi2[c:d, :k2], C[p], out=emb2[c:d])
+    lib = _lib.load()
+    Phi2, Cc = _fm._f64(batch.Phi2), C.to(torch.float64).contiguous()
+    emb2 = torch.empty((Phi2.shape[0], k1), dtype=torch.float64, device=C.device)
+    with torch.cuda.device(C.device):                       # emb2[rows of pair p] = Phi2_p[:, :k2] C[p], one ragged GEMM
+        rc = lib.dm_from_basis(Cc.data_ptr(), Phi2.data_ptr(), Phi2.stride(0), batch.off2.data_ptr(), batch.max2,
+                               batch.n_pairs, k2, k1, emb2.data_ptr(), emb2.stride(0), _fm._stream(C.device))
+    _lib.check(rc, "dm_from_basis")
     emb1 = batch.Phi1[:, :k1].contiguous()
     return _fm.precise_map(emb1, faces1, emb2, batch.off1_h, face_off, batch.off2_h)
 

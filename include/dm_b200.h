@@ -189,6 +189,12 @@ int dm_fmap_solve(const double* A, const double* B, const double* evals1, const 
  *   out_h[2]       reserved        out_h[3]  refinement steps taken in total */
 int dm_fmap_solve_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
+/* c00[p] = sign(Phi1[first vertex of pair p][0] * Phi2[first vertex][0]) * sqrt(area(mesh 2) / area(mesh 1)): the pinned
+ * entry x0[0, 0] of FunctionalMapping.fit (pyFM/functional.py:654-658) that dm_fmap_solve takes, for a ragged batch. */
+int dm_fmap_c00(const double* Phi1, int64_t ld1, const int64_t* off1, const double* Phi2, int64_t ld2,
+                const int64_t* off2, const double* area1, const double* area2, int n_pairs, double* c00,
+                dm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * FM -> point-to-point maps, all four index outputs from one pass over S = (Phi2 C) Phi1^T.
  * Replaces: FM_to_p2p  pyFM/spectral/convert.py:96-147 and the override functional_map.py:49-50.
