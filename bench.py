@@ -41,7 +41,9 @@ METRIC = "mesh_pairs_per_sec"
 UNIT = "pairs/s"
 ALG_BYTES_NN = 4 * D_FEAT * 2 * N_VERT + 4 * 2 * N_VERT          # 6.160 MB per pair
 ALG_FLOPS_NN = 2 * N_VERT * N_VERT * D_FEAT                      # 3.072 GFLOP per pair
-NCU_DRAM_BYTES_PER_PAIR = (400.146432e6 + 38.645248e6) / 64      # ncu --set full capture of nn_tc_kernel<1,1,0,1> (CTA-pair mode) at 64 pairs
+NCU_DRAM_BYTES_PER_PAIR = (796.788736e6 + 79.306496e6) / 128       # nn_tc_kernel<1,1>: profiles/r2_nn_tc_full_raw.csv (128 pairs)
+NCU_F2P_DRAM_BYTES_PER_PAIR = (272.548096e6 + 139.916544e6) / 128   # f2p_tc_kernel<2>: profiles/r2_f2p_tc_full_raw.csv
+NCU_SOLVE_DRAM_BYTES_PER_PAIR = (23.4176e6 + 0.13184e6) / 128       # fmap_solve32w_kernel<4>: profiles/r2_fmap_solve32w_full_raw.csv
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                # CUDA-core FFMA peak at max clock
 LANE_OPS_PER_S = 148 * 128 * 1.965e9                             # issue-limited lane instructions per second (4 x 32 lanes per SM)
 
@@ -372,14 +374,17 @@ def main():
         torch.cuda.synchronize()
 
     comm_stream = torch.cuda.Stream(device) if world > 1 else None
-    gather_state = {"pad": None, "bufs": [None, None], "i": 0}
+    gather_state = {"pad": None, "bufs": [None, None], "i": 0, "peer": None, "mode": None}
+    gather_mode = os.environ.get("DM_BENCH_GATHER", "peer")   # peer (NVLink copy engines) | nccl | none (diagnostics only)
 
     def gather_all(res):
         """The path's one collective, EVERY step: all index maps and C of all shards.  The results of a step are packed
         into one int32 buffer (C viewed as int32 words; ragged shards padded to the largest shard, whose size is agreed
-        once) and gathered with ONE all_gather_into_tensor on a side stream, so that the NVLink transfer of step i
-        overlaps the kernels of step i + 1 (two buffer sets alternate; the timed region ends after the last gather)."""
-        if world == 1:
+        once) and gathered on a side stream, so that the NVLink transfer of step i overlaps the kernels of step i + 1 (two
+        buffer sets alternate; the timed region ends after the last gather).  Default transport: pipeline.PeerGather
+        (peer-memory writes by the copy engines + a device-side barrier); NCCL's all_gather_into_tensor when symmetric
+        memory is unavailable or DM_BENCH_GATHER=nccl."""
+        if world == 1 or gather_mode == "none":
             return
         parts = [t.reshape(-1).view(torch.int32) for n_, t in sorted(res.items()) if n_ != "status" and t is not None]
         total = sum(p_.numel() for p_ in parts)
@@ -387,15 +392,35 @@ def main():
             n = torch.tensor([total], device=device)
             dist.all_reduce(n, op=dist.ReduceOp.MAX)
             gather_state["pad"] = int(n.item())
+            gather_state["mode"] = "nccl"
+            if gather_mode == "peer":
+                ok = torch.ones(1, device=device)
+                try:
+                    gather_state["peer"] = pipeline.PeerGather(gather_state["pad"], device)
+                except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory setup: every rank falls back
+                    ok.zero_()
+                    if rank == 0:
+                        print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather", file=sys.stderr)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok.item()) > 0:
+                    gather_state["mode"] = "peer"
+                else:
+                    gather_state["peer"] = None
         m = gather_state["pad"]
         i = gather_state["i"] = gather_state["i"] ^ 1
         if gather_state["bufs"][i] is None:
             gather_state["bufs"][i] = (torch.zeros(m, dtype=torch.int32, device=device),
+                                       None if gather_state["mode"] == "peer" else
                                        torch.empty(world * m, dtype=torch.int32, device=device), torch.cuda.Event())
         send, recv, done = gather_state["bufs"][i]
         cur = torch.cuda.current_stream(device)
         cur.wait_event(done)                       # the gather that last used this buffer set has finished
         torch.cat(parts, out=send[:total])
+        if gather_state["mode"] == "peer":
+            pg = gather_state["peer"]
+            pg.gather(send)
+            done.record(pg.stream)
+            return
         ready = torch.cuda.Event()
         ready.record(cur)
         with torch.cuda.stream(comm_stream):
@@ -406,6 +431,8 @@ def main():
     def finish_gathers():
         if world > 1:
             torch.cuda.current_stream(device).wait_stream(comm_stream)
+            if gather_state["peer"] is not None:
+                gather_state["peer"].wait()
 
     host = dev = bank = None
     extra = {}
@@ -419,10 +446,12 @@ def main():
                 res = pipeline.match_pairs_device(dev, k=K_EIG, w_descr=W_DESCR, w_lap=W_LAP, check=False)
                 gather_all(res)
                 return res
-            # launches of OUR kernels per step (profiles/launches_r2_*): feature NN 8 (2 prep, 2 per-pair maxima, score,
-            # column finalise, 2 re-evaluation) + projection 2 x 3 + pinned entry 1 + solve 6 (2 Gram GEMMs, float32 pack,
-            # factor/refine, lazy float64 pack, float64 fallback) + FM->p2p 11 + status copy 1
-            launches_per_step = 8 + 6 + 1 + 6 + 11 + 1
+            # launches of OUR kernels per step (profiles/launches_r2_step.csv, gpurun_out/r4h_step_launches.csv: 36 + the
+            # Frobenius finalise added since): feature NN 8 (2 prep, 2 per-pair maxima, score, column finalise, 2
+            # re-evaluation) + projection 2 x 3 + pinned entry 1 + solve 6 (2 Gram GEMMs, float32 pack, factor/refine, lazy
+            # float64 pack, float64 fallback) + FM->p2p 16 (2 splits, per-pair maxima, split of C + its norm, 2 embeddings,
+            # score pass, column finalise, on-demand fill, 2 flagged GEMMs + 2 bias passes, 2 re-evaluation)
+            launches_per_step = 8 + 6 + 1 + 6 + 16
         else:
             nit = 70
 
@@ -433,7 +462,7 @@ def main():
                 res.update(C_zo=Cz, p2p_zo=pz)
                 gather_all(res)
                 return res
-            launches_per_step = 33 + nit * 10 + 9
+            launches_per_step = 37 + nit * 14 + 12     # 2382 launches per 170-rung ladder (gpurun_out/r4q_zo_launches.csv)
         units_per_rank = P
     elif cfg == "cfg3":
         g = torch.Generator(device=device).manual_seed(3000 + rank)
@@ -483,7 +512,7 @@ def main():
             gather_all(res)
             return res
         n_chunks = (hi - lo + chunk - 1) // chunk
-        launches_per_step = n_chunks * (12 + nit * 10 + 9)
+        launches_per_step = n_chunks * (12 + nit * 14 + 12)
         units_per_rank = hi - lo
     else:  # cfg5
         bank, cats = make_device_bank_cfg5(device)
@@ -497,7 +526,7 @@ def main():
             res = {n: torch.cat([o[n] for o in outs]) for n in outs[0] if n != "status"}
             gather_all(res)
             return res
-        launches_per_step = ((hi - lo + 127) // 128) * 44
+        launches_per_step = ((hi - lo + 127) // 128) * 37
         units_per_rank = hi - lo
     torch.cuda.synchronize()
 
@@ -574,7 +603,7 @@ def main():
                 "hbm_frac": hbm_gbs / hbm_peak, "peaks": which,
                 "note": "3 bf16 MMA passes per fp32-grade product (split-bf16); the pass is tensor-bound (AI ~ 500 flop/B, "
                         "SURVEY.md 8d), hbm_frac is the figure BASELINE.json asks for; traffic = dram read+write bytes per "
-                        "launch from the ncu --set full capture profiles/r1_end_nn_tc_full_raw.csv (6.86 MB per pair vs 6.16 "
+                        "launch from the ncu --set full capture profiles/r2_nn_tc_full_raw.csv (6.84 MB per pair vs 6.16 "
                         "MB algorithmic)"}
         top.append(dict(roof))
     if cfg in ("cfg2a", "cfg2b"):
@@ -594,7 +623,8 @@ def main():
         ach = flops / (solve_kern_ms * 1e-3) / 1e12
         top.append({"kernel": "fmap_solve32w_kernel (float32 Cholesky + float64 refinement, one warp per system)",
                     "kernel_ms": solve_kern_ms, "stage_ms": solve_stage_ms, "bound": "fp32_fma", "achieved": ach,
-                    "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": None,
+                    "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
+                    "traffic": NCU_SOLVE_DRAM_BYTES_PER_PAIR * P,
                     "note": f"{n_sys} SPD systems of size {n}; algorithmic flops n^3/3 + 8 n^2 each; peak = 148 SM x 128 FFMA/clk "
                             "x 1.965 GHz; the kernel is latency-bound (9-10 resident warps per SM: 22 KB of shared memory per "
                             "system), see DESIGN.md 5.3"})
@@ -607,9 +637,10 @@ def main():
         ex = 3 * P * 2.0 * N_VERT * N_VERT * kp / (f2p_kern_ms * 1e-3) / 1e12
         red = P * 4.0 * N_VERT * N_VERT / (f2p_kern_ms * 1e-3)           # score reductions per second (4 index maps)
         alu_peak = LANE_OPS_PER_S / 4.5                                  # ~4.5 lane instructions per tracked score (fma, key, top-2)
-        top.append({"kernel": "nn_tc_kernel<2,2> FM->p2p score pass (4 index maps from one pass)", "kernel_ms": f2p_kern_ms,
+        top.append({"kernel": "f2p_tc_kernel<2> FM->p2p score pass (dual accumulator, 4 index maps from one pass)", "kernel_ms": f2p_kern_ms,
                     "stage_ms": f2p_stage_ms, "bound": "alu", "achieved": red / 1e12, "peak": alu_peak / 1e12,
-                    "unit": "T score-reductions/s", "frac": red / alu_peak, "tensor_frac": ex / tf_peak, "traffic": None,
+                    "unit": "T score-reductions/s", "frac": red / alu_peak, "tensor_frac": ex / tf_peak,
+                    "traffic": NCU_F2P_DRAM_BYTES_PER_PAIR * P,
                     "note": "epilogue (issue / ALU) bound, not tensor bound: 4 argmax reductions over every score; peak model = "
                             "issue slots / 4.5 lane instructions per tracked score; tensor_frac = executed bf16 flops (3 "
                             "passes, K padded to %d) / measured bf16 peak" % kp})
@@ -709,7 +740,7 @@ def main():
                 "dtype": "f32 scores + f64 re-evaluation / f64 functional map", "data": "synthetic",
                 "config": workload_config(cfg, P, world), "roofline": roof, "roofline_top": top, "cpu_baseline": cpu,
                 "e2e": e2e, "e2e_bank": e2e_bank, "gpu_launches": (launches_per_step or 0) * args.steps, "clocks": clocks,
-                "engine": "tcgen05", "lib": info, "numa_binding": numa, "verify": verify, **extra}
+                "engine": "tcgen05", "lib": info, "numa_binding": numa, "gather_transport": gather_state["mode"] if world > 1 else None, "verify": verify, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
