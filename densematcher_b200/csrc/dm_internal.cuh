@@ -336,6 +336,9 @@ struct NNRequest {
   // y_prep_d >= d columns (columns beyond d meet zeros on the database side) and reused while skip_prep_y is set
   int y_prep_d = 0;
   int skip_prep_y = 0;
+  // recorded on the stream once both operands are split (before the score pass): lets a caller fork work that only needs
+  // the splits onto another stream (dm_match_pairs: the projections and the solve run beside the score pass)
+  cudaEvent_t after_prep_event = nullptr;
 };
 size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                           int n_col, int flags);

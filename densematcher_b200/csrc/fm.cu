@@ -617,6 +617,25 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
   if (L.bytes > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", L.bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
+  // The feature search (tensor-bound score pass) and the functional-map chain up to C (HBM-bound splits / reductions,
+  // latency-bound solve) are independent once the features are split: the chain runs on a side stream forked after the
+  // operand preparation and joined before FM -> p2p.  Stream and events are per host thread and device (the call stays
+  // stream-ordered for the caller and capturable: the fork / join are event edges).  DM_MATCH_SERIAL=1: one stream.
+  struct Fork {
+    cudaStream_t side = nullptr;
+    cudaEvent_t prep = nullptr, done = nullptr;
+  };
+  static thread_local Fork forks[64];
+  static const bool serial = [] { const char* e = getenv("DM_MATCH_SERIAL"); return e && e[0] == '1'; }();
+  int devi = 0;
+  DM_CUDA_OK(cudaGetDevice(&devi));
+  Fork* fk = (!serial && devi >= 0 && devi < 64) ? &forks[devi] : nullptr;
+  if (fk && !fk->side) {
+    DM_CUDA_OK(cudaStreamCreateWithFlags(&fk->side, cudaStreamNonBlocking));
+    DM_CUDA_OK(cudaEventCreateWithFlags(&fk->prep, cudaEventDisableTiming));
+    DM_CUDA_OK(cudaEventCreateWithFlags(&fk->done, cudaEventDisableTiming));
+  }
+  cudaStream_t sf = fk ? fk->side : st;  // stream of the functional-map chain
   // 1. feature NN: queries = mesh 2, database = mesh 1 (rows -> p2p_21, columns -> p2p_12); keeps the three-way splits
   NNRequest R{};
   R.Y = F2, R.ldY = ldF2, R.X = F1, R.ldX = ldF1;
@@ -626,23 +645,29 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
   R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_21};
   R.col[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_12};
   R.flags = flags | kFlagSplit3;
+  R.after_prep_event = fk ? fk->prep : nullptr;
   NNSplits sp{};
   if ((rc = nn_run(R, L.nn_ws, L.nn_bytes, st, &sp))) return rc;
+  if (fk) DM_CUDA_OK(cudaStreamWaitEvent(sf, fk->prep, 0));
   // 2. projections, reusing the feature splits (mesh 1 = database side, mesh 2 = query side)
   const void* s1[3] = {sp.xh, sp.xl, sp.xl2};
   const void* s2[3] = {sp.yh, sp.yl, sp.yl2};
   if ((rc = proj_tc_run(Phi1, ld1, area1, F1, nullptr, ldF1, nullptr, nullptr, 0, nullptr, off1, total_n1, max_n1, n_pairs,
-                        k, d, L.A, L.proj_ws, L.proj_bytes, st, s1)))
+                        k, d, L.A, L.proj_ws, L.proj_bytes, sf, s1)))
     return rc;
   if ((rc = proj_tc_run(Phi2, ld2, area2, F2, nullptr, ldF2, nullptr, nullptr, 0, nullptr, off2, total_n2, max_n2, n_pairs,
-                        k, d, L.B, L.proj_ws, L.proj_bytes, st, s2)))
+                        k, d, L.B, L.proj_ws, L.proj_bytes, sf, s2)))
     return rc;
   // 3. pinned entry, closed-form C
-  c00_kernel<<<unsigned(n_pairs), 256, 0, st>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, L.c00);
+  c00_kernel<<<unsigned(n_pairs), 256, 0, sf>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, L.c00);
   DM_LAUNCH_OK("c00_kernel");
   if ((rc = dm_fmap_solve(L.A, L.B, evals1, evals2, L.c00, w_descr, w_lap, n_pairs, k, k, d, C, L.solve_ws, L.solve_bytes,
-                          stream)))
+                          static_cast<dm_stream_t>(sf))))
     return rc;
+  if (fk) {
+    DM_CUDA_OK(cudaEventRecord(fk->done, sf));
+    DM_CUDA_OK(cudaStreamWaitEvent(st, fk->done, 0));
+  }
   // 4. the four index maps
   if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) return DM_OK;
   return dm_fm_to_p2p(C, k, k, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs, p2p_21,

@@ -577,6 +577,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
     if (R.hooks && R.hooks->after_prep && (rc = R.hooks->after_prep(R.hooks->ctx, L, P, st))) return rc;
   }
   if (splits) *splits = NNSplits{L.yh, L.yl, L.yl2, L.xh, L.xl, L.xl2, P.kp};
+  if (R.after_prep_event) DM_CUDA_OK(cudaEventRecord(R.after_prep_event, st));
   if (tc && nn_tc2_applicable(P.n_row, P.n_col, P.kp)) {
     P.row_trunc = P.col_trunc;  // packed keys on both sides
     if ((rc = nn_tc2_launch(P, L.yh, L.yl, L.xh, L.xl, st))) return rc;
