@@ -339,10 +339,28 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       cbi[c] = ok ? __ldg(P.col[c].bf + q0 + i) : -3.0e38f;  // finite: the packed keys below must not become NaN
     }
 
+    // Row-only passes with one epilogue: the per-column scale / bias of the WHOLE database side is staged once per CTA
+    // (the transposition patches, column partials and per-tile arrays are unused here, minus the exchange area of the final
+    // merge: 24 KB = 3072 columns) instead of once per tile behind two group barriers and a round trip to L2 -- with
+    // short contractions those ~1.5 us per tile were a third of the CTA's time
+    constexpr uint32_t kXchBytes = 3 * TM_ROWS * sizeof(Top3);  // (kGroups - 1) x NR = 1 states, see the merge below
+    constexpr int kRowCacheCols = int((kGroupWarps * PATCH_BYTES + COLRED_BYTES + ROWSB_BYTES - kXchBytes) / 8) / TN * TN;
+    const bool cache_rows = kPacked && NRS == 1 && n_ct * TN <= kRowCacheCols;
+    float* rcache = reinterpret_cast<float*>(sgen + OFF_PATCH + kXchBytes);  // [scale: n_ct TN][bias: n_ct TN]
+    if (cache_rows) {
+      const int rt_idx = int(threadIdx.x) - 64, n_all = n_ct * TN;
+      for (int j = rt_idx; j < n_all; j += row_threads) {
+        const bool v = j < nd;
+        rcache[j] = v ? __ldg(rsf[0] + d0 + j) : 0.f;
+        rcache[n_all + j] = v ? __ldg(rbf[0] + d0 + j) : kMaskedScore;
+      }
+      bar_sync_n(row_bar, row_threads);
+    }
+
     for (int ct = 0; ct < n_ct; ++ct) {
       const int acc = ct & 1;
       const int col0 = ct * TN;
-      if (NR > 0 && do_rows) {
+      if (NR > 0 && do_rows && !cache_rows) {
         // per-column scale / bias of the row epilogues for this tile
         bar_sync_n(row_bar, row_threads);  // everyone is done with the previous tile's arrays
         const int rt_idx = kShareRows ? int(threadIdx.x) - 64 : gt;
@@ -388,8 +406,8 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
                 t2_chunk_top2<true>(v, nullptr, nullptr, keymask, k1, k2);
                 t2_merge_chunk<true>(rowst[r], k1, k2, jb, v, nullptr, nullptr, keymask, thr_base[r]);
               } else {
-                const float* sc = rowsb + ((r_base + r) * 2 + 0) * TN + ch * CCH;
-                const float* bi = rowsb + ((r_base + r) * 2 + 1) * TN + ch * CCH;
+                const float* sc = cache_rows ? rcache + col0 + ch * CCH : rowsb + ((r_base + r) * 2 + 0) * TN + ch * CCH;
+                const float* bi = cache_rows ? rcache + n_ct * TN + col0 + ch * CCH : rowsb + ((r_base + r) * 2 + 1) * TN + ch * CCH;
                 t2_chunk_top2<false>(v, sc, bi, keymask, k1, k2);
                 t2_merge_chunk<false>(rowst[r], k1, k2, jb, v, sc, bi, keymask, thr_base[r]);
               }
