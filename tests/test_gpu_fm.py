@@ -454,3 +454,35 @@ def test_float64_gemm_paths_with_unaligned_operands(fm):
         a2 = rng.uniform(0.5, 1.5, n2)
         Cg = fm.p2p_to_fm(dev(p), dev(big1)[:, c0:c0 + k1], dev(big2)[:, c0:c0 + k2], dev(a2))[0].cpu().numpy()
         assert relF(Cg, P2.T @ (a2[:, None] * P1[p])) < 1e-12, (k1, k2, ld, c0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step", [1, (2, 1), (1, 3), (4, 4)])
+def test_zoomout_incremental_rungs_ragged_rectangular(fm, step):
+    """The ladder keeps M = Phi2^T A2 Phi1[p] resident and corrects it with the changed vertices (zoomout_delta.cu): a
+    ragged batch (three pairs of different sizes), square and rectangular steps, int32 and int64 maps, long enough to
+    cross a re-anchoring rung -- every pair against the float64 oracle ladder (final p2p identical, C to 1e-10), i.e.
+    the same result as the full product per rung."""
+    rng = np.random.default_rng(77)
+    meshes = []
+    for sub, scale in ((2, (1, 1.2, 0.8)), (3, (1.1, 0.9, 1.0)), (2, (0.9, 1.0, 1.3))):
+        V, F = meshgen.icosphere(sub)
+        meshes.append(meshgen.lbo_basis(meshgen.deform(V, scale, bump=0.1, phase=(0.2, 0.7)), F, 150))
+    pairs = [(0, 1), (1, 2), (2, 0)]
+    s1, s2 = (step, step) if isinstance(step, int) else step
+    k0 = 6
+    nit = min((150 - k0) // max(s1, s2), 70)                      # 70 rungs at step 1: crosses the anchor at rung 64
+    Phi1 = np.concatenate([meshes[a][1] for a, _ in pairs]); Phi2 = np.concatenate([meshes[b][1] for _, b in pairs])
+    ar2 = np.concatenate([meshes[b][2] for _, b in pairs])
+    o1 = np.concatenate([[0], np.cumsum([meshes[a][1].shape[0] for a, _ in pairs])])
+    o2 = np.concatenate([[0], np.cumsum([meshes[b][1].shape[0] for _, b in pairs])])
+    C0 = np.stack([np.linalg.qr(rng.standard_normal((k0, k0)))[0] for _ in pairs])
+    for dt in (torch.int32, torch.int64):
+        Cz, pz = fm.zoomout(dev(C0), dev(Phi1), dev(Phi2), dev(ar2), nit=nit, step=step, off1=o1, off2=o2, return_p2p=True,
+                            out_dtype=dt)
+        assert pz.dtype == dt
+        for i in range(len(pairs)):
+            a, b = slice(o1[i], o1[i + 1]), slice(o2[i], o2[i + 1])
+            Co, po = orc.zoomout_refine(C0[i], Phi1[a], Phi2[b], nit=nit, step=step, A2=ar2[b], return_p2p=True)
+            assert np.array_equal(pz[b].cpu().numpy(), po), (i, step)
+            assert relF(Cz[i].cpu().numpy(), Co) < 1e-10
