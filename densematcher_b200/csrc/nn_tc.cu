@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
   const int n_ct = (nd + TN - 1) / TN;
   const int n_kc = P.kp / TBK;
   const int n_k16 = max(1, min(P.kp / UMMA_K, (P.d + UMMA_K - 1) / UMMA_K));
+  const int last_ksteps = n_k16 - (n_kc - 1) * (TBK / UMMA_K);  // K steps of the last chunk that meet data (1..4)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -252,10 +253,7 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
           const uint64_t dxh = umma_desc_sw128(sb + 2 * SZ_Y), dxl = umma_desc_sw128(sb + 2 * SZ_Y + SZ_X);
           // the database side is zero beyond column d: the K steps of the last chunk that only meet padding are skipped
           // (k = 150 pads to 192 columns but needs 160; the upper ZoomOut rungs are bound by these MMAs)
-          const int ksteps = min(TBK / UMMA_K, n_k16 - kc * (TBK / UMMA_K));
-#pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            if (k >= ksteps) break;
+          auto issue_kstep = [&](int k) {
             const uint64_t ko = uint64_t((k * UMMA_K * 2) >> 4);  // 32 bytes per K step inside the swizzle row
             if (PAIR) {
               tc_mma_bf16_pair(tacc, dyh + ko, dxh + ko, kIdesc, (kc | k) != 0);
@@ -266,6 +264,12 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
               tc_mma_bf16(tacc, dyh + ko, dxl + ko, kIdesc, 1);
               tc_mma_bf16(tacc, dyl + ko, dxh + ko, kIdesc, 1);
             }
+          };
+          if (kc + 1 < n_kc || last_ksteps == TBK / UMMA_K) {  // full chunk: branch-free issue (the issuing thread is the
+#pragma unroll                                                 // critical path of MMA-bound launches)
+            for (int k = 0; k < TBK / UMMA_K; ++k) issue_kstep(k);
+          } else {
+            for (int k = 0; k < last_ksteps; ++k) issue_kstep(k);
           }
           // smem slot reusable once these MMAs have read it (PAIR: in both CTAs)
           if (PAIR) tc_commit_pair(bar_empty + 8 * stage); else tc_commit(bar_empty + 8 * stage);
