@@ -40,37 +40,58 @@ struct EnergyParams {
   double* partial;   // [n_pairs * max_rt][3]  p2p, ent, range01
 };
 
-// MODE 0: sums of squares only (doubly_stochastic, first sweep); MODE 1: energies + T
-template <int MODE>
-__global__ void __launch_bounds__(kEThreads, 1) dense_energy_kernel(const EnergyParams P) {
+__host__ __device__ inline int energy_ldk(int k1) { return ((k1 + 7) / 8 * 8 + 15) / 16 * 16 + 4; }  // pitch = 4 (mod 16)
+constexpr int kLdG = ET + 4;
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// MODE 0: sums of squares only (doubly_stochastic, first sweep); MODE 1: energies + T.
+// Both contractions run on the float64 tensor cores (mma.sync m8n8k4): the tile S = E P^T (64 x 64 x k1) with eight warps
+// in a 2 x 4 grid (warp tile 32 x 16), the loss and its derivative applied in the accumulator layout, and T += G P
+// (64 x k1 x 64) with the derivative tile staged through shared memory.  Row pitches = 4 (mod 16) doubles make every
+// fragment load conflict-free.  (The first version used 4 x 4 register tiles on the DFMA pipe: 2.8 TFLOP/s, shared-memory
+// bound at 8 loads per 16 FMAs.)
+// NCB: column blocks of T per warp (k1 <= 32 NCB): the small eigenbases of the fit (k = 15 ... 50) leave room for two CTAs
+// per SM, which is what hides the float64 latency of the element-wise part (log, divisions)
+template <int MODE, int NCB>
+__global__ void __launch_bounds__(kEThreads, NCB <= 2 ? 2 : 1) dense_energy_kernel(const EnergyParams P) {
   extern __shared__ double sm[];
   const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
   const int64_t r0 = P.off2[p], c0 = P.off1[p];
   const int n2 = int(P.off2[p + 1] - r0), n1 = int(P.off1[p + 1] - c0);
   const int row0 = rt * ET;
   if (row0 >= n2) return;
-  const int k1 = P.k1, ldk = k1 + 1;
-  double* Es = sm;                 // [ET][ldk]  emb2 rows of this tile
+  const int k1 = P.k1, ldk = energy_ldk(k1), kp4 = (k1 + 3) & ~3, kp8 = (k1 + 7) & ~7;
+  double* Es = sm;                 // [ET][ldk]  emb2 rows of this tile (zero beyond k1)
   double* Ps = Es + ET * ldk;      // [ET][ldk]  Phi1 rows of the current column tile
-  double* Gs = Ps + ET * ldk;      // [ET][ET + 1]  dE/dM * a_j of the current tile
+  double* Gs = Ps + ET * ldk;      // [ET][kLdG] dE/dM * a_j of the current tile
   __shared__ double red[kEThreads / 32][3];
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  for (int e = t; e < ET * k1; e += kEThreads) {
-    const int i = e / k1, k = e % k1;
-    Es[i * ldk + k] = (row0 + i < n2) ? P.emb2[(r0 + row0 + i) * k1 + k] : 0.0;
+  __shared__ double rowsq[4][ET];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int rh = warp & 1, cq = warp >> 1;  // row half (32 rows), column quarter (16 columns) of the score tile
+  for (int e = t; e < ET * kp8; e += kEThreads) {
+    const int i = e / kp8, k = e % kp8;
+    Es[i * ldk + k] = (row0 + i < n2 && k < k1) ? P.emb2[(r0 + row0 + i) * k1 + k] : 0.0;
   }
-  double T[4][kMaxK / 16];
+  // T: rows rh*32 + 8 a + g, column blocks cq + 4 c (interleaved: a small k1 still spreads over the four warp columns)
+  double T[4][NCB][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < kMaxK / 16; ++c) T[a][c] = 0.0;
+    for (int c = 0; c < NCB; ++c) T[a][c][0] = T[a][c][1] = 0.0;
+  const int n_cb = kp8 / 8;  // column blocks of T
   double e_p2p = 0.0, e_ent = 0.0, e_r01 = 0.0, rs2[4] = {0.0, 0.0, 0.0, 0.0};
   const double rbar = P.means ? P.means[2 * p] : 0.0, cbar = P.means ? P.means[2 * p + 1] : 0.0;
   const double n2n1 = double(n2) / double(n1);
   double ri[4], r2i[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int i = row0 + 4 * ty + a;
+    const int i = row0 + rh * 32 + 8 * a + g;
     ri[a] = (P.rs && i < n2) ? P.rs[r0 + i] - rbar : 0.0;
     r2i[a] = (MODE == 1 && P.w_st != 0.0 && i < n2) ? P.rs2[r0 + i] - 1.0 : 0.0;
   }
@@ -78,107 +99,129 @@ __global__ void __launch_bounds__(kEThreads, 1) dense_energy_kernel(const Energy
   for (int ct = 0; ct < nct; ++ct) {
     const int col0 = ct * ET;
     __syncthreads();  // previous tile's Ps / Gs are free
-    for (int e = t; e < ET * k1; e += kEThreads) {
-      const int j = e / k1, k = e % k1;
-      Ps[j * ldk + k] = (col0 + j < n1) ? P.Phi1[(c0 + col0 + j) * P.ld1 + k] : 0.0;
+    for (int e = t; e < ET * kp8; e += kEThreads) {
+      const int j = e / kp8, k = e % kp8;
+      Ps[j * ldk + k] = (col0 + j < n1 && k < k1) ? P.Phi1[(c0 + col0 + j) * P.ld1 + k] : 0.0;
     }
     __syncthreads();
-    double S[4][4];
+    double S[4][2][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) S[a][b] = 0.0;
-    for (int k = 0; k < k1; ++k) {
-      double ev[4], pv[4];
+      for (int b = 0; b < 2; ++b) S[a][b][0] = S[a][b][1] = 0.0;
+    {
+      const double* ea = Es + (rh * 32 + g) * ldk + t4;
+      const double* pb = Ps + (cq * 16 + g) * ldk + t4;
+      for (int k = 0; k < kp4; k += 4) {
+        double av[4], bv[2];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) ev[a] = Es[(4 * ty + a) * ldk + k];
+        for (int a = 0; a < 4; ++a) av[a] = ea[8 * a * ldk + k];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) pv[b] = Ps[(4 * tx + b) * ldk + k];
+        for (int b = 0; b < 2; ++b) bv[b] = pb[8 * b * ldk + k];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) S[a][b] = fma(ev[a], pv[b], S[a][b]);
+          for (int b = 0; b < 2; ++b) dmma884(S[a][b], av[a], bv[b]);
+      }
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int j = col0 + 4 * tx + b;
-      const bool jv = j < n1;
-      const double aj = jv ? P.area1[c0 + j] : 0.0;
-      const double cj = (P.cs && jv) ? P.cs[c0 + j] - cbar : 0.0;
-      const double c2j = (MODE == 1 && P.w_st != 0.0 && jv) ? P.cs2[c0 + j] - n2n1 : 0.0;
-      double colsq = 0.0;
+    for (int b = 0; b < 2; ++b) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const bool v = jv && (row0 + 4 * ty + a < n2);
-        const double m = S[a][b] * aj;
-        if (MODE == 0) {
-          const double mm = v ? m * m : 0.0;
-          rs2[a] += mm;
-          colsq += mm;
-        } else {
-          double g = 0.0;
-          if (v) {
-            if (P.w_p2p != 0.0) {
-              const double q = m * m - m;
-              e_p2p += q * q;
-              g += P.w_p2p * 2.0 * q * (2.0 * m - 1.0);
+      for (int h = 0; h < 2; ++h) {
+        const int jl = cq * 16 + 8 * b + 2 * t4 + h, j = col0 + jl;
+        const bool jv = j < n1;
+        const double aj = jv ? P.area1[c0 + j] : 0.0;
+        const double cj = (P.cs && jv) ? P.cs[c0 + j] - cbar : 0.0;
+        const double c2j = (MODE == 1 && P.w_st != 0.0 && jv) ? P.cs2[c0 + j] - n2n1 : 0.0;
+        double colsq = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int il = rh * 32 + 8 * a + g;
+          const bool v = jv && (row0 + il < n2);
+          const double m = S[a][b][h] * aj;
+          if (MODE == 0) {
+            const double mm = v ? m * m : 0.0;
+            rs2[a] += mm;
+            colsq += mm;
+          } else {
+            double gd = 0.0;
+            if (v) {
+              if (P.w_p2p != 0.0) {
+                const double q = m * m - m;
+                e_p2p += q * q;
+                gd += P.w_p2p * 2.0 * q * (2.0 * m - 1.0);
+              }
+              if (P.w_ent != 0.0) {
+                const double mc = fmin(fmax(m, 0.0), 1.0);
+                const double lg = log(mc + 1e-10);
+                e_ent -= mc * lg;
+                if (m >= 0.0 && m <= 1.0) gd += P.w_ent * (-lg - mc / (mc + 1e-10));
+              }
+              if (P.w_r01 != 0.0) {
+                const double lo = fmax(-m, 0.0), hi = fmax(m - 1.0, 0.0);
+                e_r01 += lo * lo + hi * hi;
+                gd += P.w_r01 * (2.0 * hi - 2.0 * lo);
+              }
+              if (P.w_sum != 0.0) gd += P.w_sum * (2.0 * cj + 2.0 * ri[a]);
+              if (P.w_st != 0.0) gd += P.w_st * 2.0 * m * (2.0 * c2j + 2.0 * r2i[a]);
             }
-            if (P.w_ent != 0.0) {
-              const double mc = fmin(fmax(m, 0.0), 1.0);
-              const double lg = log(mc + 1e-10);
-              e_ent -= mc * lg;
-              if (m >= 0.0 && m <= 1.0) g += P.w_ent * (-lg - mc / (mc + 1e-10));
-            }
-            if (P.w_r01 != 0.0) {
-              const double lo = fmax(-m, 0.0), hi = fmax(m - 1.0, 0.0);
-              e_r01 += lo * lo + hi * hi;
-              g += P.w_r01 * (2.0 * hi - 2.0 * lo);
-            }
-            if (P.w_sum != 0.0) g += P.w_sum * (2.0 * cj + 2.0 * ri[a]);
-            if (P.w_st != 0.0) g += P.w_st * 2.0 * m * (2.0 * c2j + 2.0 * r2i[a]);
+            Gs[il * kLdG + jl] = gd * aj;
           }
-          Gs[(4 * ty + a) * (ET + 1) + 4 * tx + b] = g * aj;
+        }
+        if (MODE == 0) {
+          // column sum of squares over this warp's 32 rows: lanes that share (t4, h) differ in g
+#pragma unroll
+          for (int sh = 4; sh < 32; sh <<= 1) colsq += __shfl_xor_sync(0xffffffffu, colsq, sh);
+          if (g == 0 && jv && colsq != 0.0) atomicAdd(P.cs2 + c0 + j, colsq);
         }
       }
-      if (MODE == 0 && jv && colsq != 0.0) atomicAdd(P.cs2 + c0 + j, colsq);
     }
     if (MODE == 1) {
       __syncthreads();
       // T[i][c] += sum_j G[i][j] Phi1[j][c]
-      for (int j = 0; j < ET; ++j) {
-        double gv[4];
+      const double* ga = Gs + (rh * 32 + g) * kLdG + t4;
+      for (int j = 0; j < ET; j += 4) {
+        double av[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) gv[a] = Gs[(4 * ty + a) * (ET + 1) + j];
+        for (int a = 0; a < 4; ++a) av[a] = ga[8 * a * kLdG + j];
 #pragma unroll
-        for (int c = 0; c < kMaxK / 16; ++c) {
-          if (tx + 16 * c < k1) {
-            const double pv = Ps[j * ldk + tx + 16 * c];
+        for (int c = 0; c < NCB; ++c) {
+          const int cb = cq + 4 * c;
+          if (cb < n_cb) {
+            const double bv = Ps[(j + t4) * ldk + 8 * cb + g];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) T[a][c] = fma(gv[a], pv, T[a][c]);
+            for (int a = 0; a < 4; ++a) dmma884(T[a][c], av[a], bv);
           }
         }
       }
     }
   }
   if (MODE == 0) {
-    // row sums of squares: reduce over the 16 threads (tx) that share a row group
+    // row sums of squares: the four lanes of a row (t4), then the four warps of a row half (cq)
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       double v = rs2[a];
-#pragma unroll
-      for (int sh = 8; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
-      const int i = row0 + 4 * ty + a;
-      if (tx == 0 && i < n2) P.rs2[r0 + i] = v;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t4 == 0) rowsq[cq][rh * 32 + 8 * a + g] = v;
     }
+    __syncthreads();
+    if (t < ET && row0 + t < n2) P.rs2[r0 + row0 + t] = rowsq[0][t] + rowsq[1][t] + rowsq[2][t] + rowsq[3][t];
     return;
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int i = row0 + 4 * ty + a;
+    const int i = row0 + rh * 32 + 8 * a + g;
     if (i >= n2) continue;
 #pragma unroll
-    for (int c = 0; c < kMaxK / 16; ++c)
-      if (tx + 16 * c < k1) P.T[(r0 + i) * k1 + tx + 16 * c] = T[a][c];
+    for (int c = 0; c < NCB; ++c) {
+      const int cb = cq + 4 * c;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = 8 * cb + 2 * t4 + h;
+        if (cb < n_cb && col < k1) P.T[(r0 + i) * k1 + col] = T[a][c][h];
+      }
+    }
   }
   double e3[3] = {e_p2p, e_ent, e_r01};
 #pragma unroll
@@ -353,20 +396,22 @@ int dm_dense_energy(const double* C, int k1, int k2, const double* Phi1, int64_t
     DM_LAUNCH_OK("sums_kernel");
     P.rs = L.rs, P.cs = L.cs, P.means = L.means;
   }
-  const size_t shm = sizeof(double) * (2 * size_t(ET) * (k1 + 1) + size_t(ET) * (ET + 1));
-  static OncePerDevice attr_once;
-  if (attr_once.first()) {
-    DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
+  const size_t shm = sizeof(double) * (2 * size_t(ET) * energy_ldk(k1) + size_t(ET) * kLdG);
   const unsigned grid = unsigned(n_pairs) * L.max_rt;
-  if (w_stochastic != 0.0) {
-    DM_CUDA_OK(cudaMemsetAsync(L.cs2, 0, sizeof(double) * size_t(total_n1), st));
-    dense_energy_kernel<0><<<grid, kEThreads, shm, st>>>(P);
-    DM_LAUNCH_OK("dense_energy_kernel<0>");
-  }
-  dense_energy_kernel<1><<<grid, kEThreads, shm, st>>>(P);
-  DM_LAUNCH_OK("dense_energy_kernel<1>");
+  if (w_stochastic != 0.0) DM_CUDA_OK(cudaMemsetAsync(L.cs2, 0, sizeof(double) * size_t(total_n1), st));
+#define DM_ENERGY(NCB_)                                                                                                   \
+  do {                                                                                                                    \
+    static OncePerDevice once;                                                                                            \
+    if (once.first()) {                                                                                                   \
+      DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<0, NCB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<1, NCB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    }                                                                                                                     \
+    if (w_stochastic != 0.0) dense_energy_kernel<0, NCB_><<<grid, kEThreads, shm, st>>>(P);                               \
+    dense_energy_kernel<1, NCB_><<<grid, kEThreads, shm, st>>>(P);                                                        \
+  } while (0)
+  if (k1 <= 32) DM_ENERGY(1); else if (k1 <= 64) DM_ENERGY(2); else DM_ENERGY(4);
+#undef DM_ENERGY
+  DM_LAUNCH_OK("dense_energy_kernel");
   energy_finalize_kernel<<<n_pairs, 256, 0, st>>>(L.partial, L.max_rt, off1, off2, L.rs, L.cs, L.means, L.rs2, L.cs2,
                                                   w_sumto1 != 0.0, w_stochastic != 0.0, energy);
   DM_LAUNCH_OK("energy_finalize_kernel");
