@@ -23,6 +23,7 @@ DM_SKIP_PREP = 1 << 5
 DM_SKIP_FINISH = 1 << 6
 DM_F64_GEMM = 1 << 7
 DM_FAST_FM = 1 << 8
+DM_FAST_LOSS = 1 << 9
 DM_POLAR_JACOBI = 1 << 9
 SCALE_NONE, SCALE_ARRAY, SCALE_INVNORM = 0, 1, 2
 BIAS_NONE, BIAS_ARRAY, BIAS_NEG_HALF_SQNORM = 0, 1, 2
@@ -88,6 +89,9 @@ SIGNATURES = {
     "dm_dense_energy_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int]),
     "dm_dense_energy": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
                                 c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "dm_dense_energy_ex": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
+                                   c_vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "dm_bmm_nt_f64": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "dm_match_pairs_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
     "dm_match_pairs": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_dbl, c_dbl,

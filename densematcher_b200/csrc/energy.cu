@@ -57,8 +57,19 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // bound at 8 loads per 16 FMAs.)
 // NCB: column blocks of T per warp (k1 <= 32 NCB): the small eigenbases of the fit (k = 15 ... 50) leave room for two CTAs
 // per SM, which is what hides the float64 latency of the element-wise part (log, divisions)
-template <int MODE, int NCB>
+// FAST: the logarithm and the division of the entropy term in float32 (the reference evaluates every term in float32,
+// base_functions.py:363-372 on float32 tensors); everything else, and every accumulation, stays float64.  The float64
+// log / division were ~200 of the 240 instructions per element of M.
+// TERMS: which terms can be active (bit 0 p2p, 1 stochastic, 2 entropy, 3 range01, 4 sumto1).  kAllTerms tests the weights
+// at run time; the notebook's default set (entropy + sumto1) has its own instantiation, without the per-element tests
+// and the dead branches of the others (~150 -> ~50 instructions per element of M).
+constexpr int kTermP2P = 1, kTermSt = 2, kTermEnt = 4, kTermR01 = 8, kTermSum = 16, kAllTerms = 31;
+template <int MODE, int NCB, bool FAST, int TERMS>
 __global__ void __launch_bounds__(kEThreads, NCB <= 2 ? 2 : 1) dense_energy_kernel(const EnergyParams P) {
+  constexpr bool kSpec = TERMS != kAllTerms;  // specialised: every term of TERMS is active, the others are absent
+  const bool on_p2p = (TERMS & kTermP2P) && (kSpec || P.w_p2p != 0.0), on_st = (TERMS & kTermSt) && (kSpec || P.w_st != 0.0);
+  const bool on_ent = (TERMS & kTermEnt) && (kSpec || P.w_ent != 0.0), on_r01 = (TERMS & kTermR01) && (kSpec || P.w_r01 != 0.0);
+  const bool on_sum = (TERMS & kTermSum) && (kSpec || P.w_sum != 0.0);
   extern __shared__ double sm[];
   const int p = blockIdx.x / P.max_rt, rt = blockIdx.x % P.max_rt;
   const int64_t r0 = P.off2[p], c0 = P.off1[p];
@@ -92,8 +103,8 @@ __global__ void __launch_bounds__(kEThreads, NCB <= 2 ? 2 : 1) dense_energy_kern
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int i = row0 + rh * 32 + 8 * a + g;
-    ri[a] = (P.rs && i < n2) ? P.rs[r0 + i] - rbar : 0.0;
-    r2i[a] = (MODE == 1 && P.w_st != 0.0 && i < n2) ? P.rs2[r0 + i] - 1.0 : 0.0;
+    ri[a] = (on_sum && P.rs && i < n2) ? 2.0 * P.w_sum * (P.rs[r0 + i] - rbar) : 0.0;   // row part of the sumto1 gradient
+    r2i[a] = (MODE == 1 && on_st && i < n2) ? P.rs2[r0 + i] - 1.0 : 0.0;
   }
   const int nct = (n1 + ET - 1) / ET;
   for (int ct = 0; ct < nct; ++ct) {
@@ -131,8 +142,8 @@ __global__ void __launch_bounds__(kEThreads, NCB <= 2 ? 2 : 1) dense_energy_kern
         const int jl = cq * 16 + 8 * b + 2 * t4 + h, j = col0 + jl;
         const bool jv = j < n1;
         const double aj = jv ? P.area1[c0 + j] : 0.0;
-        const double cj = (P.cs && jv) ? P.cs[c0 + j] - cbar : 0.0;
-        const double c2j = (MODE == 1 && P.w_st != 0.0 && jv) ? P.cs2[c0 + j] - n2n1 : 0.0;
+        const double cj = (on_sum && P.cs && jv) ? 2.0 * P.w_sum * (P.cs[c0 + j] - cbar) : 0.0;  // column part, as above
+        const double c2j = (MODE == 1 && on_st && jv) ? P.cs2[c0 + j] - n2n1 : 0.0;
         double colsq = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -146,24 +157,32 @@ __global__ void __launch_bounds__(kEThreads, NCB <= 2 ? 2 : 1) dense_energy_kern
           } else {
             double gd = 0.0;
             if (v) {
-              if (P.w_p2p != 0.0) {
+              if (on_p2p) {
                 const double q = m * m - m;
                 e_p2p += q * q;
                 gd += P.w_p2p * 2.0 * q * (2.0 * m - 1.0);
               }
-              if (P.w_ent != 0.0) {
+              if (on_ent) {
                 const double mc = fmin(fmax(m, 0.0), 1.0);
-                const double lg = log(mc + 1e-10);
+                double lg, ratio;
+                if (FAST) {
+                  const float x = float(mc + 1e-10);
+                  lg = double(logf(x));
+                  ratio = double(__fdividef(float(mc), x));
+                } else {
+                  lg = log(mc + 1e-10);
+                  ratio = mc / (mc + 1e-10);
+                }
                 e_ent -= mc * lg;
-                if (m >= 0.0 && m <= 1.0) gd += P.w_ent * (-lg - mc / (mc + 1e-10));
+                if (m >= 0.0 && m <= 1.0) gd += P.w_ent * (-lg - ratio);
               }
-              if (P.w_r01 != 0.0) {
+              if (on_r01) {
                 const double lo = fmax(-m, 0.0), hi = fmax(m - 1.0, 0.0);
                 e_r01 += lo * lo + hi * hi;
                 gd += P.w_r01 * (2.0 * hi - 2.0 * lo);
               }
-              if (P.w_sum != 0.0) gd += P.w_sum * (2.0 * cj + 2.0 * ri[a]);
-              if (P.w_st != 0.0) gd += P.w_st * 2.0 * m * (2.0 * c2j + 2.0 * r2i[a]);
+              if (on_sum) gd += cj + ri[a];
+              if (on_st) gd += P.w_st * 2.0 * m * (2.0 * c2j + 2.0 * r2i[a]);
             }
             Gs[il * kLdG + jl] = gd * aj;
           }
@@ -367,6 +386,15 @@ int dm_dense_energy(const double* C, int k1, int k2, const double* Phi1, int64_t
                     int max_n2, const double* area1, int n_pairs, double w_p2p, double w_stochastic, double w_ent,
                     double w_range01, double w_sumto1, double* energy, double* grad, void* workspace,
                     size_t workspace_bytes, dm_stream_t stream) {
+  return dm_dense_energy_ex(C, k1, k2, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs,
+                            w_p2p, w_stochastic, w_ent, w_range01, w_sumto1, energy, grad, 0, workspace, workspace_bytes, stream);
+}
+
+int dm_dense_energy_ex(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1,
+                       int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2,
+                       int max_n2, const double* area1, int n_pairs, double w_p2p, double w_stochastic, double w_ent,
+                       double w_range01, double w_sumto1, double* energy, double* grad, int flags, void* workspace,
+                       size_t workspace_bytes, dm_stream_t stream) {
   if (n_pairs < 0 || k1 <= 0 || k2 <= 0 || total_n1 < 0 || total_n2 < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
   if (n_pairs == 0) return DM_OK;
   if (!C || !Phi1 || !Phi2 || !off1 || !off2 || !area1 || !energy || !grad) DM_FAIL(DM_ERR_BADARG, "null argument");
@@ -399,17 +427,32 @@ int dm_dense_energy(const double* C, int k1, int k2, const double* Phi1, int64_t
   const size_t shm = sizeof(double) * (2 * size_t(ET) * energy_ldk(k1) + size_t(ET) * kLdG);
   const unsigned grid = unsigned(n_pairs) * L.max_rt;
   if (w_stochastic != 0.0) DM_CUDA_OK(cudaMemsetAsync(L.cs2, 0, sizeof(double) * size_t(total_n1), st));
-#define DM_ENERGY(NCB_)                                                                                                   \
-  do {                                                                                                                    \
-    static OncePerDevice once;                                                                                            \
-    if (once.first()) {                                                                                                   \
-      DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<0, NCB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<1, NCB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    }                                                                                                                     \
-    if (w_stochastic != 0.0) dense_energy_kernel<0, NCB_><<<grid, kEThreads, shm, st>>>(P);                               \
-    dense_energy_kernel<1, NCB_><<<grid, kEThreads, shm, st>>>(P);                                                        \
+  const bool ent_sum = w_p2p == 0.0 && w_stochastic == 0.0 && w_range01 == 0.0 && w_ent != 0.0 && w_sumto1 != 0.0;
+#define DM_ENERGY1(NCB_, FAST_, TERMS_)                                                                                       \
+  do {                                                                                                                        \
+    static OncePerDevice once1;                                                                                               \
+    if (once1.first())                                                                                                        \
+      DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<1, NCB_, FAST_, TERMS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      200 * 1024));                                                                           \
+    dense_energy_kernel<1, NCB_, FAST_, TERMS_><<<grid, kEThreads, shm, st>>>(P);                                             \
+  } while (0)
+#define DM_ENERGY(NCB_)                                                                                                       \
+  do {                                                                                                                        \
+    if (w_stochastic != 0.0) {                                                                                                \
+      static OncePerDevice once0;                                                                                             \
+      if (once0.first())                                                                                                      \
+        DM_CUDA_OK(cudaFuncSetAttribute(dense_energy_kernel<0, NCB_, false, kAllTerms>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                            \
+      dense_energy_kernel<0, NCB_, false, kAllTerms><<<grid, kEThreads, shm, st>>>(P);                                        \
+    }                                                                                                                         \
+    const bool fast = (flags & DM_FAST_LOSS) != 0;                                                                            \
+    if (ent_sum && fast) DM_ENERGY1(NCB_, true, kTermEnt | kTermSum);                                                         \
+    else if (ent_sum) DM_ENERGY1(NCB_, false, kTermEnt | kTermSum);                                                           \
+    else if (fast) DM_ENERGY1(NCB_, true, kAllTerms);                                                                         \
+    else DM_ENERGY1(NCB_, false, kAllTerms);                                                                                  \
   } while (0)
   if (k1 <= 32) DM_ENERGY(1); else if (k1 <= 64) DM_ENERGY(2); else DM_ENERGY(4);
+#undef DM_ENERGY1
 #undef DM_ENERGY
   DM_LAUNCH_OK("dense_energy_kernel");
   energy_finalize_kernel<<<n_pairs, 256, 0, st>>>(L.partial, L.max_rt, off1, off2, L.rs, L.cs, L.means, L.rs2, L.cs2,
@@ -431,3 +474,15 @@ int dm_dense_energy(const double* C, int k1, int k2, const double* Phi1, int64_t
 }
 
 }  // extern "C"
+
+extern "C" int dm_bmm_nt_f64(const double* A, const double* B, int n_batch, int m, int n, int k, double* C, dm_stream_t stream) {
+  if (n_batch < 0 || m <= 0 || n <= 0 || k <= 0) DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_batch == 0) return DM_OK;
+  if (!A || !B || !C) DM_FAIL(DM_ERR_BADARG, "null argument");
+  GemmProblem G;
+  G.A.d = A, G.A.ld = k, G.A.batch_stride = int64_t(m) * k, G.A.rows = m, G.A.trans = 0;
+  G.B.d = B, G.B.ld = k, G.B.batch_stride = int64_t(n) * k, G.B.rows = n, G.B.trans = 0;
+  G.M = m, G.N = n, G.K = k, G.maxM = m, G.maxN = n, G.maxK = k, G.n_batch = n_batch;
+  G.C = C, G.ldc = n, G.c_batch_stride = int64_t(m) * n;
+  return gemm64_launch(G, static_cast<cudaStream_t>(stream));
+}

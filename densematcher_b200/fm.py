@@ -375,9 +375,27 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
 DENSE_TERMS = ("p2p", "stochastic", "ent", "range01", "sumto1")
 
 
-def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace: Optional[Workspace] = None):
-    """Dense-map energy terms and their gradient (``dm_dense_energy``).  ``weights``: dict over ``DENSE_TERMS``.
-    Returns (energies [P, 5] unweighted, in ``DENSE_TERMS`` order; grad [P, k2, k1] of the weighted sum)."""
+def bmm_nt(A, B):
+    """C[b] = A[b] @ B[b]^T for contiguous float64 batches [P,m,k] x [P,n,k] -> [P,m,n] on the library's own DMMA GEMM
+    (``dm_bmm_nt_f64``): the small products of the fit and of the drop-in mirror, without cuBLAS."""
+    lib = _lib.load()
+    A, B = _f64(A).contiguous(), _f64(B).contiguous()
+    P, m, k = A.shape
+    n = B.shape[1]
+    if B.shape[0] != P or B.shape[2] != k:
+        raise ValueError(f"bmm_nt: {tuple(A.shape)} x {tuple(B.shape)}^T")
+    out = torch.empty(P, m, n, dtype=torch.float64, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.dm_bmm_nt_f64(A.data_ptr(), B.data_ptr(), P, m, n, k, out.data_ptr(), _stream(A.device))
+    _lib.check(rc, "dm_bmm_nt_f64")
+    return out
+
+
+def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace: Optional[Workspace] = None,
+                 flags: int = 0):
+    """Dense-map energy terms and their gradient (``dm_dense_energy_ex``).  ``weights``: dict over ``DENSE_TERMS``.
+    Returns (energies [P, 5] unweighted, in ``DENSE_TERMS`` order; grad [P, k2, k1] of the weighted sum).
+    ``flags=_lib.DM_FAST_LOSS``: logarithm / division of the entropy term in float32 (the reference's precision), ~1e-7."""
     lib = _lib.load()
     dev = C.device
     C = _f64(C)
@@ -399,16 +417,16 @@ def dense_energy(C, Phi1, Phi2, area1, weights, off1=None, off2=None, workspace:
     need = lib.dm_dense_energy_workspace_bytes(P, n1, n2, max1, max2, k1, k2)
     ws = (workspace or default_workspace(dev, "energy")).get(max(need, 256))
     with torch.cuda.device(dev):
-        rc = lib.dm_dense_energy(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1, max1,
-                                 Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, area1.data_ptr(), P, *w,
-                                 energy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
-    _lib.check(rc, "dm_dense_energy")
+        rc = lib.dm_dense_energy_ex(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), n1, max1,
+                                    Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), n2, max2, area1.data_ptr(), P, *w,
+                                    energy.data_ptr(), grad.data_ptr(), int(flags), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_dense_energy_ex")
     return energy, grad
 
 
 def fit_dense(A, B, evals1, evals2, c00, Phi1, Phi2, area1, weights, w_descr, w_lap, off1=None, off2=None,
               maxiter: int = 1000, history: int = 10, gtol: float = 1e-5, ftol: float = 2.220446049250313e-09,
-              check_every: int = 2, return_info: bool = False):
+              check_every: int = 2, return_info: bool = False, fast_loss: bool = True):
     """Batched ON-DEVICE fit of the functional map with the dense-map energy terms of the notebook's default
     ``fit_params`` (example.ipynb cell 11: w_ent, w_sumto1, ...; reference: FunctionalMapping.fit functional.py:352-487
     driving scipy L-BFGS-B over energy_func_std / grad_energy_std, optimize/base_functions.py:480-763, one pair at a time
@@ -422,16 +440,19 @@ def fit_dense(A, B, evals1, evals2, c00, Phi1, Phi2, area1, weights, w_descr, w_
     their defaults are scipy's L-BFGS-B (what the reference runs with): max |g| <= gtol (pgtol = 1e-5) or
     (E_prev - E) / max(|E_prev|, |E|, 1) <= ftol (factr 1e7 * eps); converged pairs are frozen by a mask.
     A [P,k1,d], B [P,k2,d], evals1 [P,k1], evals2 [P,k2], c00 [P]; Phi / area / offsets as in ``dense_energy``.
+    ``fast_loss`` (default): the logarithm / division of the entropy term run in float32 (``DM_FAST_LOSS``) -- the
+    reference evaluates all of these terms in float32; the energy moves by ~1e-7 relative, far below the stopping rules.
     Returns C [P,k2,k1] float64 (and ``(iterations, energy evaluations)`` with ``return_info``)."""
     dev = A.device
+    eflags = _lib.DM_FAST_LOSS if fast_loss else 0
     A, B = _f64(A).contiguous(), _f64(B).contiguous()
     P, k1, _ = A.shape
     k2 = B.shape[1]
     ev1, ev2 = _f64(evals1).reshape(P, k1), _f64(evals2).reshape(P, k2)
     scale = torch.maximum(ev1.max(dim=1).values, ev2.max(dim=1).values)[:, None, None]
     Delta = (ev1[:, None, :] / scale - ev2[:, :, None] / scale) ** 2                      # functional.py:404-405
-    AAt = torch.bmm(A, A.transpose(1, 2))                                                 # [P,k1,k1]
-    BAt = torch.bmm(B, A.transpose(1, 2))                                                 # [P,k2,k1]
+    AAt = bmm_nt(A, A)                                                                    # [P,k1,k1]
+    BAt = bmm_nt(B, A)                                                                    # [P,k2,k1]
     bb = 0.5 * w_descr * (B * B).sum(dim=(1, 2))
     wvec = torch.tensor([float(weights.get(t, 0.0)) for t in DENSE_TERMS], dtype=torch.float64, device=dev)
     free = torch.ones(k1, dtype=torch.float64, device=dev)
@@ -441,12 +462,12 @@ def fit_dense(A, B, evals1, evals2, c00, Phi1, Phi2, area1, weights, w_descr, w_
     def energy(C):
         nonlocal n_eval
         n_eval += 1
-        CA = torch.bmm(C, AAt)
+        CA = bmm_nt(C, AAt)                                                               # AAt is symmetric
         e = 0.5 * w_descr * (C * CA).sum(dim=(1, 2)) - w_descr * (C * BAt).sum(dim=(1, 2)) + bb
         e = e + 0.5 * w_lap * (C * C * Delta).sum(dim=(1, 2))
         g = w_descr * (CA - BAt) + w_lap * (C * Delta)
-        ed, gd = dense_energy(C, Phi1, Phi2, area1, weights, off1, off2)
-        return e + ed @ wvec, (g + gd) * free
+        ed, gd = dense_energy(C, Phi1, Phi2, area1, weights, off1, off2, flags=eflags)
+        return e + (ed * wvec).sum(dim=1), (g + gd) * free
 
     C = torch.zeros(P, k2, k1, dtype=torch.float64, device=dev)
     C[:, 0, 0] = _f64(c00).reshape(P)                                                     # functional.py:654-658

@@ -57,8 +57,10 @@ enum {
   DM_SKIP_PREP = 1 << 5,    /* profiling: reuse the operand preparation a previous identical call left in the workspace */
   DM_SKIP_FINISH = 1 << 6,  /* profiling: stop after the score kernel (no column finalisation, no re-evaluation) */
   DM_F64_GEMM = 1 << 7,     /* projection: float64 CUDA-core contraction instead of the tcgen05 split-bf16 engine */
-  DM_FAST_FM = 1 << 8       /* ZoomOut: form C = Phi2^T A2 Phi1[p] on the tcgen05 split-bf16 engine (fp32-grade, ~2e-6)
+  DM_FAST_FM = 1 << 8,      /* ZoomOut: form C = Phi2^T A2 Phi1[p] on the tcgen05 split-bf16 engine (fp32-grade, ~2e-6)
                                instead of float64; p2p near ties may then resolve differently from the float64 reference */
+  DM_FAST_LOSS = 1 << 9     /* dm_dense_energy_ex: logarithm / division of the entropy term in float32 (the reference's own
+                               precision for these terms); energies and gradients then agree with float64 to ~1e-7 */
 };
 
 /* how the per-element scale / bias of one argmax epilogue is obtained */
@@ -274,6 +276,11 @@ int dm_icp(const double* C0, int k1, int k2, int nit,
  * refined maps of the call are then meaningless.  Synchronises the stream. */
 int dm_icp_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
+/* Batched dense float64 product  C[b] = A[b] B[b]^T  (A [n_batch, m, k], B [n_batch, n, k], C [n_batch, m, n], contiguous)
+ * on the library's DMMA GEMM: the small k x k x d products around the fit (A A^T, B A^T, C (A A^T); torch.bmm in the
+ * reference's energy_func_std, pyFM/optimize/base_functions.py:516-532). */
+int dm_bmm_nt_f64(const double* A, const double* B, int n_batch, int m, int n, int k, double* C, dm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense-map energy terms of the fit and their gradient with respect to C, without materialising the n2 x n1 map
  * M = Phi2 C Phi1^T A1 (pyFM/optimize/base_functions.py: p2p :296-325, doubly_stochastic :327-361, entropy :363-372,
@@ -290,6 +297,13 @@ int dm_dense_energy(const double* C, int k1, int k2,
                     const double* area1, int n_pairs,
                     double w_p2p, double w_stochastic, double w_ent, double w_range01, double w_sumto1,
                     double* energy, double* grad, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+int dm_dense_energy_ex(const double* C, int k1, int k2,
+                       const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1, int max_n1,
+                       const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
+                       const double* area1, int n_pairs,
+                       double w_p2p, double w_stochastic, double w_ent, double w_range01, double w_sumto1,
+                       double* energy, double* grad, int flags /* DM_FAST_LOSS */, void* workspace,
+                       size_t workspace_bytes, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * The whole per-pair hot path of compute_surface_map (functional_map.py:44-50) for a ragged batch, in one call:

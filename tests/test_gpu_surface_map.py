@@ -196,6 +196,14 @@ def test_dense_energy_kernel_matches_oracle(golden_fm):
         Eo, Go, parts = orc.dense_map_energy(C[p], Phi1[s1], Phi2[s2], ar1[s1], w)
         assert np.allclose(en[p].cpu().numpy(), [parts[t] for t in orc.DENSE_TERMS], rtol=1e-10)
         assert np.abs(gr[p].cpu().numpy() - Go).max() < 1e-10 * np.abs(Go).max()
+    # DM_FAST_LOSS: float32 logarithm / division in the entropy term (the reference's own precision): 1e-6 of float64
+    from densematcher_b200 import _lib
+    en_f, gr_f = fm.dense_energy(dev(C), dev(Phi1), dev(Phi2), dev(ar1), w, o1, o2, flags=_lib.DM_FAST_LOSS)
+    assert np.allclose(en_f.cpu().numpy(), en.cpu().numpy(), rtol=1e-6)
+    assert float((gr_f - gr).abs().max()) < 1e-6 * float(gr.abs().max())
+    # the small batched products of the fit on the library's own GEMM
+    A3, B3 = rng.standard_normal((3, 13, 40)), rng.standard_normal((3, 9, 40))
+    assert np.abs(fm.bmm_nt(dev(A3), dev(B3)).cpu().numpy() - A3 @ B3.transpose(0, 2, 1)).max() < 1e-12
 
 
 def test_fit_with_notebook_default_weights(golden_fm):
