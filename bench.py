@@ -41,9 +41,9 @@ METRIC = "mesh_pairs_per_sec"
 UNIT = "pairs/s"
 ALG_BYTES_NN = 4 * D_FEAT * 2 * N_VERT + 4 * 2 * N_VERT          # 6.160 MB per pair
 ALG_FLOPS_NN = 2 * N_VERT * N_VERT * D_FEAT                      # 3.072 GFLOP per pair
-NCU_DRAM_BYTES_PER_PAIR = (796.788736e6 + 79.306496e6) / 128       # nn_tc_kernel<1,1>: profiles/r2_nn_tc_full_raw.csv (128 pairs)
-NCU_F2P_DRAM_BYTES_PER_PAIR = (272.548096e6 + 139.916544e6) / 128   # f2p_tc_kernel<2>: profiles/r2_f2p_tc_full_raw.csv
-NCU_SOLVE_DRAM_BYTES_PER_PAIR = (23.4176e6 + 0.13184e6) / 128       # fmap_solve32w_kernel<4>: profiles/r2_fmap_solve32w_full_raw.csv
+NCU_DRAM_BYTES_PER_PAIR = (794.701312e6 + 78.630656e6) / 128       # nn_tc_kernel<1,1>: profiles/r2_nn_tc_full_raw.csv (128 pairs)
+NCU_F2P_DRAM_BYTES_PER_PAIR = (272.526080e6 + 136.424704e6) / 128   # f2p_tc_kernel<2>: profiles/r2_f2p_tc_full_raw.csv
+NCU_SOLVE_DRAM_BYTES_PER_PAIR = (23.4176e6 + 0.112128e6) / 128       # fmap_solve32w_kernel<4>: profiles/r2_fmap_solve32w_full_raw.csv
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                # CUDA-core FFMA peak at max clock
 LANE_OPS_PER_S = 148 * 128 * 1.965e9                             # issue-limited lane instructions per second (4 x 32 lanes per SM)
 
@@ -603,7 +603,7 @@ def main():
                 "hbm_frac": hbm_gbs / hbm_peak, "peaks": which,
                 "note": "3 bf16 MMA passes per fp32-grade product (split-bf16); the pass is tensor-bound (AI ~ 500 flop/B, "
                         "SURVEY.md 8d), hbm_frac is the figure BASELINE.json asks for; traffic = dram read+write bytes per "
-                        "launch from the ncu --set full capture profiles/r2_nn_tc_full_raw.csv (6.84 MB per pair vs 6.16 "
+                        "launch from the ncu --set full capture profiles/r2_nn_tc_full_raw.csv (6.82 MB per pair vs 6.16 "
                         "MB algorithmic)"}
         top.append(dict(roof))
     if cfg in ("cfg2a", "cfg2b"):
