@@ -281,12 +281,8 @@ class FunctionalMapping:
             self.FM_type = "zoomout"
 
     def compute_SD(self):
-        """functional.py:619-627."""
-        from .spectral import area_SD, conformal_SD
-        if not self.fitted:
-            raise ValueError("The Functional map must be fit before computing the shape difference")
-        self.D_a = area_SD(self.FM)
-        self.D_c = conformal_SD(self.FM, self.mesh1.eigenvalues, self.mesh2.eigenvalues)
+        """functional.py:619-627: shape-difference operators are outside the accelerated path."""
+        raise NotImplementedError("shape-difference operators are outside the accelerated path (SURVEY.md section 2 row 9)")
 
     def get_precise_map(self, precompute_dmin=True, use_adj=True, batch_size=None, n_jobs=1, verbose=False):
         """functional.py:221-251: (n2, n1) sparse barycentric map of mesh 2 onto mesh 1."""

@@ -1,6 +1,5 @@
 from .convert import p2p_to_FM, mesh_p2p_to_FM, FM_to_p2p, mesh_FM_to_p2p  # noqa: F401
 from .nn_utils import knn_query  # noqa: F401
-from .shape_difference import area_SD, conformal_SD, compute_SD  # noqa: F401
 
 
 from . import projection_utils  # noqa: F401
