@@ -46,6 +46,7 @@ NCU_F2P_DRAM_BYTES_PER_PAIR = (272.526080e6 + 136.424704e6) / 128   # f2p_tc_ker
 NCU_SOLVE_DRAM_BYTES_PER_PAIR = (23.4176e6 + 0.112128e6) / 128       # fmap_solve32w_kernel<4>: profiles/r2_fmap_solve32w_full_raw.csv
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                # CUDA-core FFMA peak at max clock
 LANE_OPS_PER_S = 148 * 128 * 1.965e9                             # issue-limited lane instructions per second (4 x 32 lanes per SM)
+ALU_PIPE_OPS_PER_S = 148 * 64 * 1.965e9                          # the ALU pipe (min / max / compare / logic) runs at half rate: 16 lanes / clk / scheduler
 
 CONFIG_DEFAULTS = {  # pairs (per GPU for weak configs, total for strong ones), default steps / warmup when not given
     "cfg2a": dict(pairs=128, scaling="weak"), "cfg2b": dict(pairs=64, scaling="weak"),
@@ -636,13 +637,14 @@ def main():
         kp = (k + 63) // 64 * 64
         ex = 3 * P * 2.0 * N_VERT * N_VERT * kp / (f2p_kern_ms * 1e-3) / 1e12
         red = P * 4.0 * N_VERT * N_VERT / (f2p_kern_ms * 1e-3)           # score reductions per second (4 index maps)
-        alu_peak = LANE_OPS_PER_S / 4.5                                  # ~4.5 lane instructions per tracked score (fma, key, top-2)
+        alu_peak = ALU_PIPE_OPS_PER_S / 4.0                              # 4 ALU-pipe instructions per tracked score (1 LOP3 key + 3 FMNMX top-2)
         top.append({"kernel": "f2p_tc_kernel<2> FM->p2p score pass (dual accumulator, 4 index maps from one pass)", "kernel_ms": f2p_kern_ms,
                     "stage_ms": f2p_stage_ms, "bound": "alu", "achieved": red / 1e12, "peak": alu_peak / 1e12,
                     "unit": "T score-reductions/s", "frac": red / alu_peak, "tensor_frac": ex / tf_peak,
                     "traffic": NCU_F2P_DRAM_BYTES_PER_PAIR * P,
-                    "note": "epilogue (issue / ALU) bound, not tensor bound: 4 argmax reductions over every score; peak model = "
-                            "issue slots / 4.5 lane instructions per tracked score; tensor_frac = executed bf16 flops (3 "
+                    "note": "ALU-pipe bound, not tensor bound (ncu profiles/r2_kernels.md: ALU pipe 70 % busy, tensor 45 %): 4 argmax reductions "
+                            "over every score; peak model = half-rate ALU pipe / 4 instructions per tracked score (LOP3 key + 3 "
+                            "FMNMX); tensor_frac = executed bf16 flops (3 "
                             "passes, K padded to %d) / measured bf16 peak" % kp})
         top.sort(key=lambda r: -r["kernel_ms"])
 
