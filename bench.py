@@ -642,7 +642,7 @@ def main():
                     "stage_ms": f2p_stage_ms, "bound": "alu", "achieved": red / 1e12, "peak": alu_peak / 1e12,
                     "unit": "T score-reductions/s", "frac": red / alu_peak, "tensor_frac": ex / tf_peak,
                     "traffic": NCU_F2P_DRAM_BYTES_PER_PAIR * P,
-                    "note": "ALU-pipe bound, not tensor bound (ncu profiles/r2_kernels.md: ALU pipe 70 % busy, tensor 45 %): 4 argmax reductions "
+                    "note": "ALU-pipe bound, not tensor bound (ncu profiles/r2_kernels.md: ALU pipe 70 %% busy, tensor 45 %%): 4 argmax reductions "
                             "over every score; peak model = half-rate ALU pipe / 4 instructions per tracked score (LOP3 key + 3 "
                             "FMNMX); tensor_frac = executed bf16 flops (3 "
                             "passes, K padded to %d) / measured bf16 peak" % kp})
