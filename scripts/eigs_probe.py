@@ -18,3 +18,13 @@ for deg in (16, 24, 32, 48):
 t = time.perf_counter()
 wr = spla.eigsh(W.tocsc(), k=k, M=sp.diags(a).tocsc(), sigma=-0.01)[0]
 print(f"scipy eigsh shift-invert: {(time.perf_counter() - t) * 1e3:.1f} ms; max |d evals| = {np.abs(np.sort(wr) - ev.cpu().numpy()).max():.2e}")
+
+# dataset throughput: many meshes in flight
+M = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+Ws, ms = [W] * M, [a] * M
+for ns in (1, 8, 16, 32):
+    spectral_ops.lbo_eigs_many(Ws[:ns], ms[:ns], k, n_streams=ns)
+    torch.cuda.synchronize(); t = time.perf_counter()
+    spectral_ops.lbo_eigs_many(Ws, ms, k, n_streams=ns)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t
+    print(f"lbo_eigs_many: {M} meshes, {ns} in flight: {dt * 1e3:.0f} ms = {dt / M * 1e3:.1f} ms per mesh")

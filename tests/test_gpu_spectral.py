@@ -126,6 +126,17 @@ def test_trimesh_process_on_device_matches_host():
     assert cos.min() > 1 - 1e-6
 
 
+def test_lbo_eigs_many_equals_one_by_one():
+    """Several meshes in flight on their own streams / workspaces give the same eigenpairs as sequential calls."""
+    meshes = [_mesh(2, 1), _mesh(3, 2), _mesh(2, 2), _mesh(3, 1), _mesh(1, 1)]
+    Ws, ms = [m[2] for m in meshes], [m[3] for m in meshes]
+    many = spectral_ops.lbo_eigs_many(Ws, ms, 12, device=DEV, n_streams=3)
+    for (ev, Phi), W, a in zip(many, Ws, ms):
+        ev1, Phi1 = spectral_ops.lbo_eigs(W, a, 12, device=DEV)
+        assert torch.equal(ev, ev1) and torch.equal(Phi, Phi1)
+        _check_eigenpairs(W, a, ev.cpu().numpy(), Phi.cpu().numpy(), 1e-9)
+
+
 def test_lbo_eigs_rejects_bad_sizes():
     V, F, W, a = _mesh(1, 1)
     with pytest.raises(ValueError):
