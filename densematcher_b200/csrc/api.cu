@@ -191,6 +191,7 @@ int dm_nn_debug_scores_f32(const float* Y, int64_t ldY, int nq, const float* X, 
   if ((rc = nn_prep_side(X, 0, ldX, off + 2, 1, ndb, d, ndv, nullptr, 0, xh, xl, nullptr, kp, st))) return rc;
   NNProblem P{};
   P.q_off = off, P.db_off = off + 2, P.total_q = nq, P.total_db = ndb, P.max_q = nq, P.max_db = ndb;
+  P.q_in = P.q_off, P.db_in = P.db_off, P.rows_q = nq, P.rows_db = ndb;
   P.n_pairs = 1, P.d = d, P.kp = kp, P.rt_rows = kFfmaRowTile, P.max_rt = (nq + kFfmaRowTile - 1) / kFfmaRowTile;
   return nn_tc_launch(P, yh, yl, xh, xl, S_out, ldS, st);
 }

@@ -195,6 +195,13 @@ struct NNProblem {
   int x64_is_double;
   const int64_t* q_off;
   const int64_t* db_off;
+  // first row of pair p inside the OPERAND arrays (the bf16 splits read through TMA and the originals read by the float64
+  // re-evaluation).  Equal to q_off / db_off unless a side lives in a per-mesh bank (NNBankSide): then the operands of
+  // pair p start at q_in[p] / db_in[p] of the bank while every per-row array of the batch (norms, scale / bias, results)
+  // stays packed by q_off / db_off.  rows_q / rows_db: rows of the operand arrays (TMA extents).
+  const int64_t* q_in;
+  const int64_t* db_in;
+  int64_t rows_q, rows_db;
   int64_t total_q, total_db;
   int max_q, max_db;
   int n_pairs, d;
@@ -264,6 +271,15 @@ int nn_tc2_launch(const NNProblem& P, const void* Yh, const void* Yl, const void
 // 2-D TMA descriptor over a row-major [rows, kp] bf16 matrix with boxes of [box_rows x 64], 128-byte swizzle (nn_tc.cu)
 int tc_make_map_bf16(void* tensor_map /* CUtensorMap* */, const void* base, int64_t rows, int kp, int box_rows);
 
+// One side of a search whose operands were prepared ONCE PER MESH (dm_bank_prepare) instead of once per pair: the bf16
+// splits and row norms of the whole bank, and where each pair's mesh starts in it.  The float64 originals (NNRequest::X64 /
+// Y64 or X / Y) are then bank arrays too; scale arrays of the epilogues over this side are indexed by bank rows.
+struct NNBankSide {
+  const int64_t* in;         // [n_pairs] first bank row of the pair's mesh (device)
+  int64_t rows;              // rows of the bank arrays
+  const void *hi, *lo, *lo2; // [rows, kp] bf16 (lo2: third split, may be null)
+  const float* norm;         // [rows] row norms as nn_prep_side leaves them
+};
 // shared stages (nn_common.cu)
 struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of one side
   int scale_mode, bias_mode;
@@ -280,6 +296,10 @@ struct SideEpiSpec {  // how to derive one epilogue's scale/bias for the rows of
 int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, int n_pairs, int64_t total, int d,
                  float* norm_out, const SideEpiSpec* specs, int n_specs, void* hi, void* lo, void* lo2, int kp,
                  cudaStream_t st);
+// the per-pair part of the preparation of a side served from a mesh bank: batch-packed copies of the bank's row norms,
+// the epilogues' scale / bias arrays and the per-pair maxima (no operand is read or split)
+int nn_bank_side_rows(const NNBankSide& B, const int64_t* off, int n_pairs, int max_n, float* norm_out,
+                      const SideEpiSpec* specs, int n_specs, cudaStream_t st);
 int nn_col_finalize(const NNProblem& P, cudaStream_t st);
 int nn_recheck(const NNProblem& P, cudaStream_t st);
 
@@ -339,12 +359,18 @@ struct NNRequest {
   // recorded on the stream once both operands are split (before the score pass): lets a caller fork work that only needs
   // the splits onto another stream (dm_match_pairs: the projections and the solve run beside the score pass)
   cudaEvent_t after_prep_event = nullptr;
+  // sides served from a mesh bank (tensor-core engines only; epilogues over such a side: DM_SCALE_NONE / DM_SCALE_ARRAY
+  // with DM_BIAS_NONE / DM_BIAS_ARRAY, the bias array being a placeholder that a hook fills)
+  const NNBankSide* bank_q = nullptr;
+  const NNBankSide* bank_db = nullptr;
 };
 size_t nn_workspace_bytes(int n_pairs, int64_t total_q, int64_t total_db, int max_q, int max_db, int d, int n_row,
                           int n_col, int flags);
 // internal flag: also keep the third bf16 split (v = hi + lo + lo2) of both operands in the workspace, so that the
 // projection engine can reuse the feature splits of the nearest-neighbour stage (dm_match_pairs)
 constexpr int kFlagSplit3 = 1 << 30;
+// internal flags of nn_workspace_bytes: the split operands of that side come from a mesh bank (none are carved)
+constexpr int kFlagBankQ = 1 << 28, kFlagBankDb = 1 << 29;
 struct NNSplits {  // where nn_run left the split operands ([rows, kp] bf16 each)
   const void *yh, *yl, *yl2, *xh, *xl, *xl2;
   int kp;
@@ -353,7 +379,7 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
 
 // tcgen05 projection engine (proj_tc.cu): out[b] = (a_scale A)^T (b_scale B[gather]) over the rows of batch b
 bool proj_tc_supported(int k, int d);
-size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d);
+size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d, bool b_presplit = false);
 // b_presplit (optional): three [total_n, pad64(d)] bf16 arrays (hi, mid, lo) of the B operand prepared elsewhere
 int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float* Bf, const double* Bd, int64_t ldB,
                 const double* b_scale, const void* b_gather, int b_gather_i64, const int64_t* b_gather_src_off,
@@ -366,7 +392,7 @@ size_t f2p_factored_workspace_bytes(int n_pairs, int64_t n1, int64_t n2, int max
 int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
                      int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
                      const double* area1, int n_pairs, void* p2p_21, void* p2p_12, void* dense_21, void* dense_12, int flags,
-                     void* ws, cudaStream_t st);
+                     void* ws, cudaStream_t st, const NNBankSide* bank1 = nullptr, const NNBankSide* bank2 = nullptr);
 
 // p2p_21 of a functional map (the ZoomOut / ICP inner conversion) with the database side Phi1 C^T embedded on the tensor
 // cores and float64 rows filled on demand (embed_tc.cu); k1, k2 <= 128.  `scratch` holds the three-way split of Phi1

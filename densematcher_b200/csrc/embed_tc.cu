@@ -113,6 +113,7 @@ struct EbEpi {          // one argmax epilogue whose scale / bias live on the em
 
 struct EbParams {
   const int64_t* off;       // rows of pair p: off[p] .. off[p + 1]
+  const int64_t* a_in;      // first row of pair p in the A operand (its split and a_norm): off, or the mesh-bank rows
   int max_rt, k_out, kp_out, n_epi;
   __nv_bfloat16 *hi, *lo;   // [total, kp_out] split of the embedding (nullptr: norms / biases only)
   float* norm;              // inflated row norm (nullptr: not wanted)
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
         const int s = t % AST;
         mbar_wait_backoff(bar_aempty + 8 * s, ((t / AST) & 1) ^ 1);
         mbar_expect_tx(bar_afull + 8 * s, A_BYTES);
-        const int arow = int(r0 + int64_t(rt0 + t) * EB_ROWS);
+        const int arow = int(P.a_in[p] + int64_t(rt0 + t) * EB_ROWS);
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
       if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
       // |row| rounded up (fp32 sum of squares: relative error <= (k_out + 2) 2^-24), embedding error e_i, inflated norm
       const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
-      const float e_i = ok ? P.eps_e * P.a_norm[gi] * P.c_fro[p] : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * P.c_fro[p] : 0.f;
       const float own = (nrm + e_i) + e_i * P.inv_eps;  // eps * own >= eps |row| + e_i
       if (ok && P.norm) P.norm[gi] = own;
       for (int e = 0; e < P.n_epi; ++e) {
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1)
       uint32_t phase = 0;
       for (int u = 0; u < n_units; ++u) {
         const int t = u / n_half, h = u % n_half;
-        const int arow = int(r0 + int64_t(rt0 + t) * EB_ROWS), brow = (p * n_half + h) * EB_ROWS;
+        const int arow = int(P.a_in[p] + int64_t(rt0 + t) * EB_ROWS), brow = (p * n_half + h) * EB_ROWS;
         for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * stage, EBS_STAGE);
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1)
         if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
       }
       const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
-      const float e_i = ok ? P.eps_e * P.a_norm[gi] * P.c_fro[p] : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * P.c_fro[p] : 0.f;
       const float own = (nrm + e_i) + e_i * P.inv_eps;
       if (ok && P.norm) P.norm[gi] = own;
       for (int e = 0; e < P.n_epi; ++e) {
@@ -520,6 +521,7 @@ struct FillParams {
   double *row_bd, *col_bd;  // float64 bias arrays of those epilogues
   int* skip_y;      // per pair: cleared when a result needs ALL float64 query rows of the pair
   int* skip_x;      // ... all float64 database-side biases
+  const int64_t *in1, *in2;  // first row of pair p in Phi1 / Phi2 (the batch offsets, or mesh-bank rows)
 };
 
 // out[o] = sum_k phi[k] C[k][o], o < k1 (lanes over o: coalesced rows of C); returns sum_o out[o]^2 (all lanes).
@@ -610,14 +612,14 @@ __global__ void __launch_bounds__(256) factored_fill_kernel(const NNProblem P, c
     const double* Cp = F.C + int64_t(p) * F.k1 * F.k2;
     if (!is_col) {
       // the result of query row `local`: its float64 embedding row, and the float64 biases of its candidates
-      warp_row_times_C<4>(F.Phi2 + (q0 + e.local) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + e.local) * F.k1);
+      warp_row_times_C<4>(F.Phi2 + (F.in2[p] + e.local) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + e.local) * F.k1);
       if (epi == F.row_bias_epi) {
         if (full) {
           if (lane == 0) F.skip_x[p] = 0;
         } else {
           for (int c = 0; c < 2; ++c) {
             const int j = c == 0 ? e.c1 : e.c2;
-            const double ss = warp_sqnorm_C_times_row(F.Phi1 + (d0 + j) * F.ld1, Cp, F.k1, F.k2, lane);
+            const double ss = warp_sqnorm_C_times_row(F.Phi1 + (F.in1[p] + j) * F.ld1, Cp, F.k1, F.k2, lane);
             if (lane == 0) F.row_bd[d0 + j] = -0.5 * ss;
           }
         }
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(256) factored_fill_kernel(const NNProblem P, c
       } else {
         for (int c = 0; c < 2; ++c) {
           const int i = c == 0 ? e.c1 : e.c2;
-          const double ss = warp_row_times_C<4>(F.Phi2 + (q0 + i) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + i) * F.k1);
+          const double ss = warp_row_times_C<4>(F.Phi2 + (F.in2[p] + i) * F.ld2, Cp, F.k1, F.k2, lane, F.emb64 + (q0 + i) * F.k1);
           if (lane == 0 && epi == F.col_bias_epi) F.col_bd[q0 + i] = -0.5 * ss;
         }
       }
@@ -701,6 +703,10 @@ struct F2PCtx {
   int64_t total_n1, total_n2;
   int max_n1, max_n2, n_pairs, k1, k2;
   int row_bias_epi, col_bias_epi;  // epilogue numbers of p2p_21 / p2p_12 (-1: not requested)
+  // meshes served from a bank (three-way splits of Phi[:, :k] and row norms prepared once per mesh, dm_bank_prepare):
+  // Phi1 / Phi2 are then the bank's matrix and in1 / in2 the first bank row of each pair's mesh; else in = off
+  const NNBankSide *bank1, *bank2;
+  const int64_t *in1, *in2;
   // scratch
   uint16_t *p2h, *p2m, *p2l;  // three-way split of Phi2 [total_n2, kp2]
   float* p2norm;
@@ -723,9 +729,9 @@ float eb_eps(int kp_in) {
 int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, cudaStream_t st) {
   F2PCtx& X = *static_cast<F2PCtx*>(vctx);
   int rc;
-  // three-way split + row norms of Phi2 (the A operand of the embedding)
-  if ((rc = nn_prep_side(X.Phi2, 1, X.ld2, X.off2, X.n_pairs, X.total_n2, X.k2, X.p2norm, nullptr, 0, X.p2h, X.p2m, X.p2l,
-                         X.kp2, st)))
+  // three-way split + row norms of Phi2 (the A operand of the embedding), unless the bank holds them
+  if (!X.bank2 && (rc = nn_prep_side(X.Phi2, 1, X.ld2, X.off2, X.n_pairs, X.total_n2, X.k2, X.p2norm, nullptr, 0, X.p2h, X.p2m,
+                                     X.p2l, X.kp2, st)))
     return rc;
   csplit_kernel<<<dim3(unsigned(X.n_pairs), 2, kCsplitChunks), 256, 0, st>>>(
       X.C, X.k1, X.k2, X.kp2, X.kp1, reinterpret_cast<__nv_bfloat16*>(X.c0h), reinterpret_cast<__nv_bfloat16*>(X.c0m),
@@ -734,9 +740,9 @@ int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
   cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
-  E.off = X.off2, E.max_rt = (X.max_n2 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k1, E.kp_out = P.kp, E.n_epi = R.n_col;
+  E.off = X.off2, E.a_in = X.in2, E.max_rt = (X.max_n2 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k1, E.kp_out = P.kp, E.n_epi = R.n_col;
   E.hi = reinterpret_cast<__nv_bfloat16*>(L.yh), E.lo = reinterpret_cast<__nv_bfloat16*>(L.yl);
-  E.norm = L.norm_q, E.a_norm = X.p2norm, E.c_fro = X.c_fro;
+  E.norm = L.norm_q, E.a_norm = X.bank2 ? X.bank2->norm : X.p2norm, E.c_fro = X.c_fro;
   E.eps_e = eb_eps(X.kp2), E.inv_eps = 1.f / P.eps;
   for (int e = 0; e < R.n_col; ++e) {
     if (R.col[e].scale_mode == DM_SCALE_INVNORM || R.col[e].bias_mode == DM_BIAS_ARRAY)
@@ -747,8 +753,9 @@ int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
     DM_CUDA_OK(cudaMemsetAsync(L.col[e].Bm, 0, sizeof(float) * X.n_pairs, st));
   }
   const void* a3[3] = {X.p2h, X.p2m, X.p2l};
+  const void* a3b[3] = {X.bank2 ? X.bank2->hi : nullptr, X.bank2 ? X.bank2->lo : nullptr, X.bank2 ? X.bank2->lo2 : nullptr};
   const void* b3[3] = {X.c0h, X.c0m, X.c0l};
-  return eb_run(a3, X.total_n2, b3, X.kp2, E, X.n_pairs, st);
+  return eb_run(X.bank2 ? a3b : a3, X.bank2 ? X.bank2->rows : X.total_n2, b3, X.kp2, E, X.n_pairs, st);
 }
 
 // (runs after nn_prep_side of the database side = Phi1, which left its three-way split in L.xh / xl / xl2)
@@ -757,19 +764,19 @@ int f2p_after_prep(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t st)
   if (X.row_bias_epi < 0) return DM_OK;
   const int e = X.row_bias_epi;
   EbParams E{};
-  E.off = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = X.kp2, E.n_epi = 1;
+  E.off = X.off1, E.a_in = X.in1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = X.kp2, E.n_epi = 1;
   E.hi = E.lo = nullptr, E.norm = nullptr;
-  E.a_norm = L.norm_db, E.c_fro = X.c_fro;
+  E.a_norm = X.bank1 ? X.bank1->norm : L.norm_db, E.c_fro = X.c_fro;  // (L.norm_db is the batch-packed copy of the same values)
   E.eps_e = eb_eps(X.kp1), E.inv_eps = 1.f / P.eps;
   // only bf / Bm of the bias epilogue change: the scale stays 1 (the kernel rewrites sf = 1) and G must stay
   // max_j |Phi1_j| from nn_prep_side, so the kernel's G (the norm of emb1, not wanted) goes to a scratch array
   E.epi[0] = EbEpi{1, nullptr, L.row[e].sf, L.row[e].bf, X.g_scratch, L.row[e].Bm, nullptr, nullptr};
   DM_CUDA_OK(cudaMemsetAsync(L.row[e].Bm, 0, sizeof(float) * X.n_pairs, st));
   DM_CUDA_OK(cudaMemsetAsync(X.g_scratch, 0, sizeof(float) * X.n_pairs, st));
-  const void* a3[3] = {L.xh, L.xl, L.xl2};
+  const void* a3[3] = {L.xh, L.xl, L.xl2};  // (the bank's splits when Phi1 is served from a bank, see nn_run)
   const void* b3[3] = {X.c1h, X.c1m, X.c1l};
   (void)P;
-  return eb_run(a3, X.total_n1, b3, X.kp1, E, X.n_pairs, st);
+  return eb_run(a3, X.bank1 ? X.bank1->rows : X.total_n1, b3, X.kp1, E, X.n_pairs, st);
 }
 
 int f2p_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t st) {
@@ -781,6 +788,7 @@ int f2p_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t
   F.Phi2 = X.Phi2, F.ld2 = X.ld2, F.Phi1 = X.Phi1, F.ld1 = X.ld1, F.C = X.C, F.k1 = X.k1, F.k2 = X.k2;
   F.emb64 = X.emb2, F.row_bias_epi = X.row_bias_epi, F.col_bias_epi = X.col_bias_epi;
   F.skip_y = X.skip_y, F.skip_x = X.skip_x;
+  F.in1 = X.in1, F.in2 = X.in2;
   F.row_bd = X.row_bias_epi >= 0 ? L.row[X.row_bias_epi].bd : nullptr;
   F.col_bd = X.col_bias_epi >= 0 ? L.col[X.col_bias_epi].bd : nullptr;
   factored_fill_kernel<<<num_sms() * 8, 256, 0, st>>>(P, F);
@@ -789,7 +797,7 @@ int f2p_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t
   // pairs with a full scan on the query side: every float64 query row (+ its bias)
   {
     GemmProblem G;
-    G.A.d = X.Phi2, G.A.ld = X.ld2, G.A.off = X.off2, G.A.trans = 0;
+    G.A.d = X.Phi2, G.A.ld = X.ld2, G.A.off = X.off2, G.A.in = X.bank2 ? X.in2 : nullptr, G.A.trans = 0;
     G.B.d = X.C, G.B.ld = X.k1, G.B.batch_stride = int64_t(X.k1) * X.k2, G.B.rows = X.k2, G.B.trans = 1;
     G.N = X.k1, G.K = X.k2, G.maxM = X.max_n2, G.maxN = X.k1, G.maxK = X.k2, G.n_batch = X.n_pairs;
     G.C = X.emb2, G.ldc = X.k1, G.c_off = X.off2, G.skip = X.skip_y;
@@ -803,7 +811,7 @@ int f2p_before_recheck(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t
   // pairs with a full scan of a result whose database-side bias is factored: every float64 bias -1/2 |C Phi1_j|^2
   if (X.row_bias_epi >= 0) {
     GemmProblem G;
-    G.A.d = X.Phi1, G.A.ld = X.ld1, G.A.off = X.off1, G.A.trans = 0;
+    G.A.d = X.Phi1, G.A.ld = X.ld1, G.A.off = X.off1, G.A.in = X.bank1 ? X.in1 : nullptr, G.A.trans = 0;
     G.B.d = X.C, G.B.ld = X.k1, G.B.batch_stride = int64_t(X.k1) * X.k2, G.B.rows = X.k2, G.B.trans = 0;
     G.N = X.k2, G.K = X.k1, G.maxM = X.max_n1, G.maxN = X.k2, G.maxK = X.k1, G.n_batch = X.n_pairs;
     G.C = X.emb1, G.ldc = X.k2, G.c_off = X.off1, G.skip = X.skip_x;
@@ -900,7 +908,7 @@ int p21_prep_x(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
   cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
-  E.off = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = P.kp, E.n_epi = 1;
+  E.off = X.off1, E.a_in = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = P.kp, E.n_epi = 1;
   E.hi = reinterpret_cast<__nv_bfloat16*>(L.xh), E.lo = reinterpret_cast<__nv_bfloat16*>(L.xl);
   E.norm = L.norm_db, E.a_norm = X.p1norm, E.c_fro = X.c_fro;
   E.eps_e = eb_eps(X.kp1), E.inv_eps = 1.f / P.eps;
@@ -974,10 +982,11 @@ size_t f2p_factored_workspace_bytes(int n_pairs, int64_t n1, int64_t n2, int max
 int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1, int64_t total_n1,
                      int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2,
                      const double* area1, int n_pairs, void* p2p_21, void* p2p_12, void* dense_21, void* dense_12, int flags,
-                     void* ws, cudaStream_t st) {
+                     void* ws, cudaStream_t st, const NNBankSide* bank1, const NNBankSide* bank2) {
   F2PLayout L = f2p_carve(ws, n_pairs, total_n1, total_n2, max_n1, max_n2, k1, k2, flags);
   F2PCtx& X = L.c;
   X.C = C, X.Phi1 = Phi1, X.Phi2 = Phi2, X.ld1 = ld1, X.ld2 = ld2, X.off1 = off1, X.off2 = off2;
+  X.bank1 = bank1, X.bank2 = bank2, X.in1 = bank1 ? bank1->in : off1, X.in2 = bank2 ? bank2->in : off2;
   X.total_n1 = total_n1, X.total_n2 = total_n2, X.max_n1 = max_n1, X.max_n2 = max_n2, X.n_pairs = n_pairs;
   X.k1 = k1, X.k2 = k2;
   NNHooks H;
@@ -1003,6 +1012,7 @@ int f2p_factored_run(const double* C, int k1, int k2, const double* Phi1, int64_
   if (dense_12) R.col[R.n_col++] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, dense_12};
   R.flags = flags | kFlagSplit3;
   R.hooks = &H;
+  R.bank_db = bank1;  // (area1, the scale of dense_21, is then indexed by bank rows)
   return nn_run(R, L.nn_ws, L.nn_bytes, st);
 }
 

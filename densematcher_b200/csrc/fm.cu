@@ -529,14 +529,17 @@ int dm_icp(const double* C0, int k1, int k2, int nit, const double* Phi1, int64_
 namespace dm {
 namespace {
 // c00[p] = sign(Phi1[first row of p][0] * Phi2[first row][0]) * sqrt(sum area2 / sum area1)   (functional.py:654-658)
+// in1 / in2: first row of pair p in Phi / area (the batch offsets themselves, or the rows of its meshes in a bank)
 __global__ void __launch_bounds__(256)
     c00_kernel(const double* __restrict__ Phi1, int64_t ld1, const int64_t* __restrict__ off1,
                const double* __restrict__ Phi2, int64_t ld2, const int64_t* __restrict__ off2,
-               const double* __restrict__ area1, const double* __restrict__ area2, double* __restrict__ c00) {
+               const double* __restrict__ area1, const double* __restrict__ area2, double* __restrict__ c00,
+               const int64_t* __restrict__ in1, const int64_t* __restrict__ in2) {
   const int p = blockIdx.x, t = threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  for (int64_t r = off1[p] + t; r < off1[p + 1]; r += 256) s1 += area1[r];
-  for (int64_t r = off2[p] + t; r < off2[p + 1]; r += 256) s2 += area2[r];
+  const int64_t b1 = in1[p], e1 = b1 + (off1[p + 1] - off1[p]), b2 = in2[p], e2 = b2 + (off2[p + 1] - off2[p]);
+  for (int64_t r = b1 + t; r < e1; r += 256) s1 += area1[r];
+  for (int64_t r = b2 + t; r < e2; r += 256) s2 += area2[r];
   __shared__ double r1[8], r2[8];
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) {
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (t == 0) {
     for (int w = 1; w < 8; ++w) s1 += r1[w], s2 += r2[w];
-    const double pr = Phi1[off1[p] * ld1] * Phi2[off2[p] * ld2];
+    const double pr = Phi1[b1 * ld1] * Phi2[b2 * ld2];
     const double sg = pr > 0.0 ? 1.0 : (pr < 0.0 ? -1.0 : 0.0);
     c00[p] = sg * sqrt(s2 / s1);
   }
@@ -659,7 +662,7 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
                         k, d, L.B, L.proj_ws, L.proj_bytes, sf, s2)))
     return rc;
   // 3. pinned entry, closed-form C
-  c00_kernel<<<unsigned(n_pairs), 256, 0, sf>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, L.c00);
+  c00_kernel<<<unsigned(n_pairs), 256, 0, sf>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, L.c00, off1, off2);
   DM_LAUNCH_OK("c00_kernel");
   if ((rc = dm_fmap_solve(L.A, L.B, evals1, evals2, L.c00, w_descr, w_lap, n_pairs, k, k, d, C, L.solve_ws, L.solve_bytes,
                           static_cast<dm_stream_t>(sf))))
@@ -752,8 +755,269 @@ int dm_fmap_c00(const double* Phi1, int64_t ld1, const int64_t* off1, const doub
   if (n_pairs < 0) DM_FAIL(DM_ERR_BADARG, "bad size");
   if (n_pairs == 0) return DM_OK;
   if (!Phi1 || !Phi2 || !off1 || !off2 || !area1 || !area2 || !c00) DM_FAIL(DM_ERR_BADARG, "null argument");
-  c00_kernel<<<unsigned(n_pairs), 256, 0, static_cast<cudaStream_t>(stream)>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, c00);
+  c00_kernel<<<unsigned(n_pairs), 256, 0, static_cast<cudaStream_t>(stream)>>>(Phi1, ld1, off1, Phi2, ld2, off2, area1, area2, c00,
+                                                                               off1, off2);
   DM_LAUNCH_OK("c00_kernel");
   return DM_OK;
 }
+}  // extern "C"
+
+// ------------------------------------------------------------------ mesh bank: per-mesh preparation, pairs as id lists
+// Dataset-shaped work (BASELINE config 5: 599 meshes, every intra-category pair; the evaluation loop around
+// compute_surface_map, functional_map.py:9-81) matches each mesh against ~50 others.  Everything of the per-pair path that
+// depends on ONE mesh only is done once per mesh here -- the bf16 splits of its features (feature search operands), the
+// three-way split of its eigenbasis (embedding operands of FM -> p2p), the row norms, the projection Phi^T A F -- and the
+// per-pair call reads those through each pair's mesh rows: no per-pair gather of the meshes' matrices, no per-pair
+// operand preparation, no per-pair projection.  Results are bit-identical to dm_match_pairs on the assembled batch.
+namespace dm {
+namespace {
+struct BankLayout {
+  uint16_t *Fh, *Fl;        // [total_n, pad64(d)] bf16 splits of the features
+  float* Fnorm;             // [total_n]
+  uint16_t *Ph, *Pm, *Pl;   // [total_n, pad64(k)] three-way split of Phi[:, :k]
+  float* Pnorm;             // [total_n]
+  double* A;                // [n_meshes, k, d] Phi^T diag(area) F
+  size_t bytes;
+};
+BankLayout bank_carve(void* state, int n_meshes, int64_t total_n, int d, int k) {
+  Carver c(state);
+  BankLayout L;
+  const size_t kpF = size_t(nn_tc_kp(d)), kpK = size_t(nn_tc_kp(k));
+  L.Fh = c.take<uint16_t>(size_t(total_n) * kpF);
+  L.Fl = c.take<uint16_t>(size_t(total_n) * kpF);
+  L.Fnorm = c.take<float>(size_t(total_n));
+  L.Ph = c.take<uint16_t>(size_t(total_n) * kpK);
+  L.Pm = c.take<uint16_t>(size_t(total_n) * kpK);
+  L.Pl = c.take<uint16_t>(size_t(total_n) * kpK);
+  L.Pnorm = c.take<float>(size_t(total_n));
+  L.A = c.take<double>(size_t(n_meshes) * k * d);
+  L.bytes = c.bytes();
+  return L;
+}
+constexpr int kBankProjChunk = 128;  // meshes per projection launch (bounds the split-K partials)
+
+struct BankPrepLayout {
+  uint16_t* Fl2;  // third split of the features: only the projection reads it
+  void* proj_ws;
+  size_t proj_bytes, bytes;
+};
+BankPrepLayout bank_prep_carve(void* ws, int n_meshes, int64_t total_n, int max_n, int d, int k) {
+  Carver c(ws);
+  BankPrepLayout L;
+  L.Fl2 = c.take<uint16_t>(size_t(total_n) * nn_tc_kp(d));
+  const int nb = n_meshes < kBankProjChunk ? n_meshes : kBankProjChunk;
+  L.proj_bytes = proj_tc_workspace_bytes(nb, total_n, max_n, k, d, true);
+  L.proj_ws = c.take<char>(L.proj_bytes);
+  L.bytes = c.bytes();
+  return L;
+}
+
+// in[p] = bank_off[ids[p]] for both sides; a size mismatch between the batch offsets and the bank raises status word 2
+__global__ void __launch_bounds__(256)
+    bank_starts_kernel(const int64_t* __restrict__ bank_off, int n_meshes, const int64_t* __restrict__ ids1,
+                       const int64_t* __restrict__ ids2, const int64_t* __restrict__ off1, const int64_t* __restrict__ off2,
+                       int n_pairs, int64_t* __restrict__ in1, int64_t* __restrict__ in2, int* __restrict__ bad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int64_t a = ids1[p], b = ids2[p];
+  const bool ok = a >= 0 && a < n_meshes && b >= 0 && b < n_meshes;
+  const int64_t ac = ok ? a : 0, bc = ok ? b : 0;
+  in1[p] = bank_off[ac], in2[p] = bank_off[bc];
+  if (!ok || bank_off[ac + 1] - bank_off[ac] != off1[p + 1] - off1[p] || bank_off[bc + 1] - bank_off[bc] != off2[p + 1] - off2[p])
+    atomicExch(bad, 1);
+}
+
+// dst[p][j] = src[ids[p] * src_stride + j], j < len (per-mesh blocks -> per-pair blocks: projections, eigenvalues)
+__global__ void __launch_bounds__(256)
+    gather_blocks_kernel(const double* __restrict__ src, int64_t src_stride, const int64_t* __restrict__ ids, int len,
+                         double* __restrict__ dst) {
+  const int p = blockIdx.x;
+  const double* s = src + ids[p] * src_stride;
+  double* d = dst + int64_t(p) * len;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < len; j += gridDim.y * blockDim.x) d[j] = s[j];
+}
+
+struct BankMatchLayout {
+  void* solve_ws;
+  size_t solve_bytes;
+  int* bad;
+  int64_t *in1, *in2;
+  double *A, *B, *ev1, *ev2, *c00;
+  void* nn_ws;
+  size_t nn_bytes;
+  void* p2p_ws;
+  size_t p2p_bytes, bytes;
+};
+BankMatchLayout bank_match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d, int k,
+                                 int flags) {
+  Carver c(ws);
+  BankMatchLayout L;
+  L.solve_bytes = dm_fmap_solve_workspace_bytes(n_pairs, k, k, d);  // leads: its status words open the workspace
+  L.solve_ws = c.take<char>(L.solve_bytes);
+  L.bad = c.take<int>(64);
+  L.in1 = c.take<int64_t>(size_t(n_pairs));
+  L.in2 = c.take<int64_t>(size_t(n_pairs));
+  L.A = c.take<double>(size_t(n_pairs) * k * d);
+  L.B = c.take<double>(size_t(n_pairs) * k * d);
+  L.ev1 = c.take<double>(size_t(n_pairs) * k);
+  L.ev2 = c.take<double>(size_t(n_pairs) * k);
+  L.c00 = c.take<double>(size_t(n_pairs));
+  L.nn_bytes = nn_workspace_bytes(n_pairs, total_n2, total_n1, max_n2, max_n1, d, 1, 1, flags | kFlagBankQ | kFlagBankDb);
+  L.nn_ws = c.take<char>(L.nn_bytes);
+  L.p2p_bytes = f2p_factored_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k, k, flags);
+  L.p2p_ws = c.take<char>(L.p2p_bytes);
+  L.bytes = c.bytes();
+  return L;
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" {
+
+size_t dm_bank_state_bytes(int n_meshes, int64_t total_n, int d, int k) {
+  if (n_meshes < 0 || total_n < 0 || d <= 0 || k < 2) return 0;
+  return bank_carve(nullptr, n_meshes, total_n, d, k).bytes;
+}
+
+size_t dm_bank_prepare_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int d, int k) {
+  if (n_meshes < 0 || total_n < 0 || max_n < 0 || d <= 0 || k < 2) return 0;
+  return bank_prep_carve(nullptr, n_meshes, total_n, max_n, d, k).bytes;
+}
+
+int dm_bank_prepare(const float* F, int64_t ldF, const double* Phi, int64_t ldPhi, const double* area, const int64_t* off,
+                    int64_t total_n, int max_n, int n_meshes, int d, int k, void* state, size_t state_bytes, void* workspace,
+                    size_t workspace_bytes, dm_stream_t stream) {
+  if (n_meshes < 0 || total_n < 0 || max_n < 0 || d <= 0 || k < 2) DM_FAIL(DM_ERR_BADARG, "bad size (need k >= 2)");
+  if (n_meshes == 0 || total_n == 0) return DM_OK;
+  if (!F || !Phi || !area || !off || !state) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ldF < d || ldPhi < k) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
+  if (!proj_tc_supported(k, d) || !f2p_factored_applicable(k, k, 0))
+    DM_FAIL(DM_ERR_UNSUPPORTED, "the mesh bank needs the tensor-core engines (d <= 512, k <= 128)");
+  if (reinterpret_cast<uintptr_t>(state) % 256 || (workspace && reinterpret_cast<uintptr_t>(workspace) % 256))
+    DM_FAIL(DM_ERR_ALIGN, "state and workspace must be 256-byte aligned");
+  BankLayout S = bank_carve(state, n_meshes, total_n, d, k);
+  if (S.bytes > state_bytes) DM_FAIL(DM_ERR_WORKSPACE, "bank state too small: need %zu", S.bytes);
+  BankPrepLayout W = bank_prep_carve(workspace, n_meshes, total_n, max_n, d, k);
+  if (!workspace || W.bytes > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", W.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  // the same kernels, per row, as the per-pair preparation of dm_match_pairs / dm_fm_to_p2p: identical bits
+  if ((rc = nn_prep_side(F, 0, ldF, off, n_meshes, total_n, d, S.Fnorm, nullptr, 0, S.Fh, S.Fl, W.Fl2, nn_tc_kp(d), st))) return rc;
+  if ((rc = nn_prep_side(Phi, 1, ldPhi, off, n_meshes, total_n, k, S.Pnorm, nullptr, 0, S.Ph, S.Pm, S.Pl, nn_tc_kp(k), st)))
+    return rc;
+  const void* fs[3] = {S.Fh, S.Fl, W.Fl2};
+  for (int m0 = 0; m0 < n_meshes; m0 += kBankProjChunk) {
+    const int nb = n_meshes - m0 < kBankProjChunk ? n_meshes - m0 : kBankProjChunk;
+    // (the projection of a mesh sums fixed 256-vertex slices: it does not depend on the batch the mesh is in)
+    if ((rc = proj_tc_run(Phi, ldPhi, area, F, nullptr, ldF, nullptr, nullptr, 0, nullptr, off + m0, total_n, max_n, nb, k, d,
+                          S.A + size_t(m0) * k * d, W.proj_ws, W.proj_bytes, st, fs)))
+      return rc;
+  }
+  return DM_OK;
+}
+
+size_t dm_match_bank_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d,
+                                           int k, int flags) {
+  if (n_pairs < 0 || total_n1 < 0 || total_n2 < 0 || d <= 0 || k < 2) return 0;
+  return bank_match_carve(nullptr, n_pairs, total_n1, total_n2, max_n1, max_n2, d, k, flags).bytes;
+}
+
+int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, int64_t ldF, const double* Phi, int64_t ldPhi,
+                        const double* area, const double* evals, int64_t ld_evals, const int64_t* bank_off, int64_t total_n,
+                        int n_meshes, const int64_t* ids1, const int64_t* ids2, const int64_t* off1, int64_t total_n1,
+                        int max_n1, const int64_t* off2, int64_t total_n2, int max_n2, int n_pairs, int d, int k,
+                        double w_descr, double w_lap, void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12,
+                        void* dense_21, void* dense_12, int flags, void* workspace, size_t workspace_bytes,
+                        dm_stream_t stream) {
+  if (n_pairs < 0 || d <= 0 || k < 2 || total_n1 < 0 || total_n2 < 0 || n_meshes <= 0 || total_n <= 0)
+    DM_FAIL(DM_ERR_BADARG, "bad size (need k >= 2 and a non-empty bank)");
+  if (n_pairs == 0) return DM_OK;
+  if (!state || !F || !Phi || !area || !evals || !bank_off || !ids1 || !ids2 || !off1 || !off2 || !C || !nn_p2p_21 || !nn_p2p_12)
+    DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ldF < d || ldPhi < k || ld_evals < k) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
+  if (total_n1 == 0 || total_n2 == 0) DM_FAIL(DM_ERR_BADARG, "empty meshes");
+  if (!nn_use_tc(flags) || !proj_tc_supported(k, d) || !f2p_factored_applicable(k, k, flags))
+    DM_FAIL(DM_ERR_UNSUPPORTED, "dm_match_bank_pairs needs the tensor-core engines (d <= 512, k <= 128)");
+  if (!workspace) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 || reinterpret_cast<uintptr_t>(state) % 256)
+    DM_FAIL(DM_ERR_ALIGN, "state and workspace must be 256-byte aligned");
+  BankLayout S = bank_carve(const_cast<void*>(state), n_meshes, total_n, d, k);
+  if (S.bytes > state_bytes) DM_FAIL(DM_ERR_WORKSPACE, "bank state too small: need %zu (prepared with other sizes?)", S.bytes);
+  BankMatchLayout L = bank_match_carve(workspace, n_pairs, total_n1, total_n2, max_n1, max_n2, d, k, flags);
+  if (L.bytes > workspace_bytes) DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu", L.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  // the functional-map chain up to C (gathers of the per-mesh projections / eigenvalues, pinned entry, solve) only needs
+  // the row starts: it runs on a side stream beside the feature score pass and is joined before FM -> p2p
+  // (stream-ordered for the caller and capturable, like dm_match_pairs).  DM_MATCH_SERIAL=1: one stream.
+  struct Fork {
+    cudaStream_t side = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr;
+  };
+  static thread_local Fork forks[64];
+  static const bool serial = [] { const char* e = getenv("DM_MATCH_SERIAL"); return e && e[0] == '1'; }();
+  int devi = 0;
+  DM_CUDA_OK(cudaGetDevice(&devi));
+  Fork* fk = (!serial && devi >= 0 && devi < 64) ? &forks[devi] : nullptr;
+  if (fk && !fk->side) {
+    DM_CUDA_OK(cudaStreamCreateWithFlags(&fk->side, cudaStreamNonBlocking));
+    DM_CUDA_OK(cudaEventCreateWithFlags(&fk->start, cudaEventDisableTiming));
+    DM_CUDA_OK(cudaEventCreateWithFlags(&fk->done, cudaEventDisableTiming));
+  }
+  cudaStream_t sf = fk ? fk->side : st;
+  DM_CUDA_OK(cudaMemsetAsync(L.bad, 0, 64 * sizeof(int), st));
+  bank_starts_kernel<<<unsigned((n_pairs + 255) / 256), 256, 0, st>>>(bank_off, n_meshes, ids1, ids2, off1, off2, n_pairs, L.in1,
+                                                                     L.in2, L.bad);
+  DM_LAUNCH_OK("bank_starts_kernel");
+  if (fk) {
+    DM_CUDA_OK(cudaEventRecord(fk->start, st));
+    DM_CUDA_OK(cudaStreamWaitEvent(sf, fk->start, 0));
+  }
+  // 1. chain: A / B / eigenvalues of each pair's meshes, pinned entry, closed-form C
+  {
+    const int len = k * d;
+    gather_blocks_kernel<<<dim3(unsigned(n_pairs), unsigned((len + 1023) / 1024)), 256, 0, sf>>>(S.A, int64_t(len), ids1, len, L.A);
+    gather_blocks_kernel<<<dim3(unsigned(n_pairs), unsigned((len + 1023) / 1024)), 256, 0, sf>>>(S.A, int64_t(len), ids2, len, L.B);
+    gather_blocks_kernel<<<dim3(unsigned(n_pairs), 1), 256, 0, sf>>>(evals, ld_evals, ids1, k, L.ev1);
+    gather_blocks_kernel<<<dim3(unsigned(n_pairs), 1), 256, 0, sf>>>(evals, ld_evals, ids2, k, L.ev2);
+    DM_LAUNCH_OK("gather_blocks_kernel");
+    c00_kernel<<<unsigned(n_pairs), 256, 0, sf>>>(Phi, ldPhi, off1, Phi, ldPhi, off2, area, area, L.c00, L.in1, L.in2);
+    DM_LAUNCH_OK("c00_kernel");
+    if ((rc = dm_fmap_solve(L.A, L.B, L.ev1, L.ev2, L.c00, w_descr, w_lap, n_pairs, k, k, d, C, L.solve_ws, L.solve_bytes,
+                            static_cast<dm_stream_t>(sf))))
+      return rc;
+    if (fk) DM_CUDA_OK(cudaEventRecord(fk->done, sf));
+  }
+  // 2. feature search: queries = mesh 2, database = mesh 1, both read from the bank's splits
+  const NNBankSide fq{L.in2, total_n, S.Fh, S.Fl, nullptr, S.Fnorm}, fdb{L.in1, total_n, S.Fh, S.Fl, nullptr, S.Fnorm};
+  NNRequest R{};
+  R.Y = F, R.ldY = ldF, R.X = F, R.ldX = ldF;
+  R.q_off = off2, R.db_off = off1, R.total_q = total_n2, R.total_db = total_n1;
+  R.max_q = max_n2, R.max_db = max_n1, R.n_pairs = n_pairs, R.d = d;
+  R.n_row = 1, R.n_col = 1;
+  R.row[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_21};
+  R.col[0] = dm_nn_epi{DM_SCALE_NONE, DM_BIAS_NONE, nullptr, nullptr, nn_p2p_12};
+  R.flags = flags;
+  R.bank_q = &fq, R.bank_db = &fdb;
+  if ((rc = nn_run(R, L.nn_ws, L.nn_bytes, st))) return rc;
+  if (fk) DM_CUDA_OK(cudaStreamWaitEvent(st, fk->done, 0));
+  // 3. the four index maps
+  if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) return DM_OK;
+  const NNBankSide b1{L.in1, total_n, S.Ph, S.Pm, S.Pl, S.Pnorm}, b2{L.in2, total_n, S.Ph, S.Pm, S.Pl, S.Pnorm};
+  return f2p_factored_run(C, k, k, Phi, ldPhi, off1, total_n1, max_n1, Phi, ldPhi, off2, total_n2, max_n2, area, n_pairs, p2p_21,
+                          p2p_12, dense_21, dense_12, flags, L.p2p_ws, st, &b1, &b2);
+}
+
+// [0..3]: the solve stage's status words (dm_fmap_solve_read_status); [4] != 0: an id was out of range or the batch offsets
+// do not match the sizes of the meshes in the bank (results are then meaningless)
+int dm_match_bank_pairs_read_status(const void* workspace, int n_pairs, int d, int k, int* out_h /* [5] */, dm_stream_t stream) {
+  if (!workspace || !out_h) DM_FAIL(DM_ERR_BADARG, "null argument");
+  BankMatchLayout L = bank_match_carve(const_cast<void*>(workspace), n_pairs, 0, 0, 0, 0, d, k, 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DM_CUDA_OK(cudaMemcpyAsync(out_h, workspace, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DM_CUDA_OK(cudaMemcpyAsync(out_h + 4, L.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DM_CUDA_OK(cudaStreamSynchronize(st));
+  return DM_OK;
+}
+
 }  // extern "C"

@@ -28,7 +28,7 @@ struct OpView {  // an operand resolved for one batch
 __device__ __forceinline__ OpView resolve(const GemmOperand& o, int b) {
   OpView v;
   const int64_t row0 = o.off ? o.off[b] : 0;
-  const int64_t base = (o.off ? 0 : int64_t(b) * o.batch_stride) + row0 * o.ld + o.col0;
+  const int64_t base = (o.off ? 0 : int64_t(b) * o.batch_stride) + ((o.off && o.in) ? o.in[b] : row0) * o.ld + o.col0;
   v.d = o.d ? o.d + base : nullptr;
   v.f = o.f ? o.f + base : nullptr;
   v.ld = o.ld;

@@ -12,6 +12,8 @@ struct GemmOperand {
   const float* f = nullptr;   // float32 data
   int64_t ld = 0;
   const int64_t* off = nullptr;  // ragged: batch b owns matrix rows off[b]..off[b+1]
+  const int64_t* in = nullptr;   // ragged, optional: the DATA of batch b starts at matrix row in[b] instead (mesh bank);
+                                 // sizes, kscale and the output still follow `off`
   int64_t batch_stride = 0;      // else: elements between consecutive batches
   int rows = 0;                  // else: matrix rows per batch
   int col0 = 0;                  // first matrix column used

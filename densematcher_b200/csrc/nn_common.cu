@@ -188,6 +188,28 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// A side served from a mesh bank: pair p's rows are bank rows in[p] .. in[p] + n.  Copies the bank's row norms into the
+// batch packing and fills the epilogues' scale / bias arrays (scale arrays are indexed by bank rows; a DM_BIAS_ARRAY bias is
+// a placeholder that a hook overwrites).  Same values as prep_side_kernel writes for these modes.
+__global__ void __launch_bounds__(256)
+    bank_side_rows_kernel(const int64_t* __restrict__ in, const int64_t* __restrict__ off, const float* __restrict__ norm_bank,
+                          float* __restrict__ norm_out, SpecArr specs, int n_specs) {
+  const int p = blockIdx.x;
+  const int64_t s0 = in[p], r0 = off[p];
+  const int n = int(off[p + 1] - r0);
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+    norm_out[r0 + i] = norm_bank[s0 + i];
+    for (int e = 0; e < n_specs; ++e) {
+      const SideEpiSpec& S = specs.s[e];
+      const double sc = S.scale_mode == DM_SCALE_ARRAY ? S.scale[s0 + i] : 1.0;
+      S.sd[r0 + i] = sc;
+      S.bd[r0 + i] = 0.0;
+      S.sf[r0 + i] = float(sc);
+      S.bf[r0 + i] = 0.f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) col_finalize_kernel(const NNProblem P) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t per_epi = int64_t(P.n_pairs) * P.max_db;
@@ -287,16 +309,17 @@ __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(RC_THREAD
     const int p = e.pair, epi = e.epi & 255;
     const bool is_col = (e.epi & 256) != 0;
     const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
+    const int64_t qi0 = P.q_in[p], di0 = P.db_in[p];  // operand rows (mesh bank) vs batch-packed per-row arrays
     const int nq = int(P.q_off[p + 1] - q0), nd = int(P.db_off[p + 1] - d0);
     const int n = is_col ? nq : nd;
     const int per = (n + kScanCluster - 1) / kScanCluster;
     const int j_beg = min(n, int(rank) * per), j_end = min(n, j_beg + per);
     const EpiDev& E = is_col ? P.col[epi] : P.row[epi];
     if (!is_col)
-      scan64_slice<TY, TX>(vec, sbest, sidx, Y + (q0 + e.local) * P.ldY64, X + d0 * P.ldX64, P.ldX64, j_beg, j_end, P.d,
+      scan64_slice<TY, TX>(vec, sbest, sidx, Y + (qi0 + e.local) * P.ldY64, X + di0 * P.ldX64, P.ldX64, j_beg, j_end, P.d,
                            E.sd + d0, E.bd + d0);
     else
-      scan64_slice<TX, TY>(vec, sbest, sidx, X + (d0 + e.local) * P.ldX64, Y + q0 * P.ldY64, P.ldY64, j_beg, j_end, P.d,
+      scan64_slice<TX, TY>(vec, sbest, sidx, X + (di0 + e.local) * P.ldX64, Y + qi0 * P.ldY64, P.ldY64, j_beg, j_end, P.d,
                            E.sd + q0, E.bd + q0);
     cluster.sync();
     if (rank == 0 && threadIdx.x == 0) {
@@ -339,19 +362,20 @@ __global__ void __launch_bounds__(256) recheck_cand_kernel(const NNProblem P) {
     const int p = e.pair, epi = e.epi & 255;
     const bool is_col = (e.epi & 256) != 0;
     const int64_t q0 = P.q_off[p], d0 = P.db_off[p];
+    const int64_t qi0 = P.q_in[p], di0 = P.db_in[p];
     const int lo = min(e.c1, e.c2), hi = max(e.c1, e.c2);
     double vlo, vhi;
     const EpiDev& E = is_col ? P.col[epi] : P.row[epi];
     if (!is_col) {
-      const TY* y = Y + (q0 + e.local) * P.ldY64;
-      vlo = warp_dot64(y, X + (d0 + lo) * P.ldX64, P.d, lane);
-      vhi = warp_dot64(y, X + (d0 + hi) * P.ldX64, P.d, lane);
+      const TY* y = Y + (qi0 + e.local) * P.ldY64;
+      vlo = warp_dot64(y, X + (di0 + lo) * P.ldX64, P.d, lane);
+      vhi = warp_dot64(y, X + (di0 + hi) * P.ldX64, P.d, lane);
       vlo = __dadd_rn(__dmul_rn(vlo, E.sd[d0 + lo]), E.bd[d0 + lo]);
       vhi = __dadd_rn(__dmul_rn(vhi, E.sd[d0 + hi]), E.bd[d0 + hi]);
     } else {
-      const TX* x = X + (d0 + e.local) * P.ldX64;
-      vlo = warp_dot64(x, Y + (q0 + lo) * P.ldY64, P.d, lane);
-      vhi = warp_dot64(x, Y + (q0 + hi) * P.ldY64, P.d, lane);
+      const TX* x = X + (di0 + e.local) * P.ldX64;
+      vlo = warp_dot64(x, Y + (qi0 + lo) * P.ldY64, P.d, lane);
+      vhi = warp_dot64(x, Y + (qi0 + hi) * P.ldY64, P.d, lane);
       vlo = __dadd_rn(__dmul_rn(vlo, E.sd[q0 + lo]), E.bd[q0 + lo]);
       vhi = __dadd_rn(__dmul_rn(vhi, E.sd[q0 + hi]), E.bd[q0 + hi]);
     }
@@ -383,6 +407,24 @@ int nn_prep_side(const void* M, int is_double, int64_t ld, const int64_t* off, i
                                                        norm_out, arr, n_specs, hi, lo, lo2, kp, need_sq64);
   DM_LAUNCH_OK("prep_side_kernel");
   if (n_specs > 0 && n_pairs > 0) {
+    pair_max_kernel<<<dim3(unsigned(n_pairs), unsigned(n_specs)), 256, 0, st>>>(off, norm_out, arr, n_pairs);
+    DM_LAUNCH_OK("pair_max_kernel");
+  }
+  return DM_OK;
+}
+
+int nn_bank_side_rows(const NNBankSide& B, const int64_t* off, int n_pairs, int max_n, float* norm_out,
+                      const SideEpiSpec* specs, int n_specs, cudaStream_t st) {
+  if (n_pairs <= 0 || max_n <= 0) return DM_OK;
+  SpecArr arr;
+  for (int e = 0; e < kMaxEpi; ++e) arr.s[e] = specs && e < n_specs ? specs[e] : SideEpiSpec{};
+  for (int e = 0; e < n_specs; ++e)
+    if (specs[e].scale_mode == DM_SCALE_INVNORM || specs[e].bias_mode == DM_BIAS_NEG_HALF_SQNORM)
+      DM_FAIL(DM_ERR_UNSUPPORTED, "mesh-bank side: epilogue %d derives its scale / bias from the rows", e);
+  bank_side_rows_kernel<<<dim3(unsigned(n_pairs), unsigned((max_n + 255) / 256)), 256, 0, st>>>(B.in, off, B.norm, norm_out,
+                                                                                                arr, n_specs);
+  DM_LAUNCH_OK("bank_side_rows_kernel");
+  if (n_specs > 0) {
     pair_max_kernel<<<dim3(unsigned(n_pairs), unsigned(n_specs)), 256, 0, st>>>(off, norm_out, arr, n_pairs);
     DM_LAUNCH_OK("pair_max_kernel");
   }
@@ -466,13 +508,14 @@ NNLayout carve(void* ws, int n_pairs, int64_t total_q, int64_t total_db, int max
   L.yh = L.yl = L.xh = L.xl = L.yl2 = L.xl2 = nullptr;
   if (nn_use_tc(flags)) {
     const size_t kp = size_t(nn_tc_kp(d));
-    L.yh = c.take<uint16_t>(size_t(total_q) * kp);
-    L.yl = c.take<uint16_t>(size_t(total_q) * kp);
-    L.xh = c.take<uint16_t>(size_t(total_db) * kp);
-    L.xl = c.take<uint16_t>(size_t(total_db) * kp);
+    const size_t nyq = (flags & kFlagBankQ) ? 0 : size_t(total_q), nxd = (flags & kFlagBankDb) ? 0 : size_t(total_db);
+    L.yh = c.take<uint16_t>(nyq * kp);
+    L.yl = c.take<uint16_t>(nyq * kp);
+    L.xh = c.take<uint16_t>(nxd * kp);
+    L.xl = c.take<uint16_t>(nxd * kp);
     if (flags & kFlagSplit3) {
-      L.yl2 = c.take<uint16_t>(size_t(total_q) * kp);
-      L.xl2 = c.take<uint16_t>(size_t(total_db) * kp);
+      L.yl2 = c.take<uint16_t>(nyq * kp);
+      L.xl2 = c.take<uint16_t>(nxd * kp);
     }
   }
   L.bytes = c.bytes();
@@ -509,9 +552,22 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   }
   if (!ws) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
   if (reinterpret_cast<uintptr_t>(ws) % 256) DM_FAIL(DM_ERR_ALIGN, "workspace must be 256-byte aligned");
-  NNLayout L = carve(ws, R.n_pairs, R.total_q, R.total_db, R.max_q, R.max_db, R.d, R.n_row, R.n_col, R.flags);
+  if ((R.bank_q || R.bank_db) && !tc) DM_FAIL(DM_ERR_UNSUPPORTED, "mesh-bank operands need the tensor-core engine");
+  if ((R.bank_q && R.skip_prep_y) || ((R.bank_q || R.bank_db) && (R.flags & DM_SKIP_PREP)))
+    DM_FAIL(DM_ERR_BADARG, "mesh-bank operands cannot be combined with a skipped preparation");
+  NNLayout L = carve(ws, R.n_pairs, R.total_q, R.total_db, R.max_q, R.max_db, R.d, R.n_row, R.n_col,
+                     R.flags | (R.bank_q ? kFlagBankQ : 0) | (R.bank_db ? kFlagBankDb : 0));
   if (L.bytes > ws_bytes)
     DM_FAIL(DM_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.bytes, ws_bytes);
+  // operands of a bank side: the splits prepared once per mesh (the hooks and the engines below see them through L)
+  if (R.bank_q) {
+    L.yh = static_cast<uint16_t*>(const_cast<void*>(R.bank_q->hi)), L.yl = static_cast<uint16_t*>(const_cast<void*>(R.bank_q->lo));
+    L.yl2 = static_cast<uint16_t*>(const_cast<void*>(R.bank_q->lo2));
+  }
+  if (R.bank_db) {
+    L.xh = static_cast<uint16_t*>(const_cast<void*>(R.bank_db->hi)), L.xl = static_cast<uint16_t*>(const_cast<void*>(R.bank_db->lo));
+    L.xl2 = static_cast<uint16_t*>(const_cast<void*>(R.bank_db->lo2));
+  }
 
   DM_CUDA_OK(cudaMemsetAsync(L.counters, 0, 64 * sizeof(unsigned int), st));
 
@@ -520,6 +576,8 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
   P.Y64 = R.Y64 ? static_cast<const void*>(R.Y64) : R.Y, P.ldY64 = R.Y64 ? R.ldY64 : R.ldY, P.y64_is_double = R.Y64 != nullptr;
   P.X64 = R.X64 ? static_cast<const void*>(R.X64) : R.X, P.ldX64 = R.X64 ? R.ldX64 : R.ldX, P.x64_is_double = R.X64 != nullptr;
   P.q_off = R.q_off, P.db_off = R.db_off;
+  P.q_in = R.bank_q ? R.bank_q->in : R.q_off, P.db_in = R.bank_db ? R.bank_db->in : R.db_off;
+  P.rows_q = R.bank_q ? R.bank_q->rows : R.total_q, P.rows_db = R.bank_db ? R.bank_db->rows : R.total_db;
   P.total_q = R.total_q, P.total_db = R.total_db, P.max_q = R.max_q, P.max_db = R.max_db;
   P.n_pairs = R.n_pairs, P.d = R.d, P.n_row = R.n_row, P.n_col = R.n_col;
   P.d_fast = R.d_fast > 0 ? R.d_fast : R.d;
@@ -565,11 +623,15 @@ int nn_run(const NNRequest& R, void* ws, size_t ws_bytes, cudaStream_t st, NNSpl
     // database side carries the row epilogues' scale/bias, query side the column epilogues'
     if (R.hooks && R.hooks->prep_x) {
       if ((rc = R.hooks->prep_x(R.hooks->ctx, L, P, R, st))) return rc;
+    } else if (R.bank_db) {
+      if ((rc = nn_bank_side_rows(*R.bank_db, R.db_off, R.n_pairs, R.max_db, L.norm_db, rs, R.n_row, st))) return rc;
     } else if ((rc = nn_prep_side(P.X64, P.x64_is_double, P.ldX64, R.db_off, R.n_pairs, R.total_db, R.d, L.norm_db, rs,
                                   R.n_row, L.xh, L.xl, L.xl2, P.kp, st)))
       return rc;
     if (R.hooks && R.hooks->prep_y) {
       if ((rc = R.hooks->prep_y(R.hooks->ctx, L, P, R, st))) return rc;
+    } else if (R.bank_q) {
+      if ((rc = nn_bank_side_rows(*R.bank_q, R.q_off, R.n_pairs, R.max_q, L.norm_q, cs, R.n_col, st))) return rc;
     } else if (!R.skip_prep_y &&
                (rc = nn_prep_side(P.Y64, P.y64_is_double, P.ldY64, R.q_off, R.n_pairs, R.total_q,
                                   R.y_prep_d > R.d ? R.y_prep_d : R.d, L.norm_q, cs, R.n_col, L.yh, L.yl, L.yl2, P.kp, st)))

@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(n_threads(NR, NC, DEBUG), 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.xl) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      const int yrow = int(q0 + row0);
+      // operand rows: the pair's meshes may live in a bank (q_in / db_in), results and per-row arrays are batch-packed
+      const int yrow = int(P.q_in[p] + row0);
+      const int64_t xrow0 = P.db_in[p];
       for (int ct = 0; ct < n_ct; ++ct) {
-        const int xrow = int(d0 + int64_t(ct) * TN) + (PAIR ? int(rank) * (TN / 2) : 0);
+        const int xrow = int(xrow0 + int64_t(ct) * TN) + (PAIR ? int(rank) * (TN / 2) : 0);
         for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait_backoff(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = sbase + stage * STAGE_BYTES, fb = bar_full + 8 * stage;
@@ -654,16 +656,16 @@ int tc_make_map_bf16(void* tensor_map, const void* base, int64_t rows, int kp, i
 int nn_tc_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, float* dbgS,
                  int64_t ldS, cudaStream_t st) {
   if (P.n_pairs <= 0 || P.total_q <= 0) return DM_OK;
-  if (P.total_q > 0x7fffffffLL || P.total_db > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
+  if (P.rows_q > 0x7fffffffLL || P.rows_db > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
   TcMaps maps;
   int rc;
-  if ((rc = make_map(&maps.yh, Yh, P.total_q, P.kp, TM_ROWS))) return rc;
-  if ((rc = make_map(&maps.yl, Yl, P.total_q, P.kp, TM_ROWS))) return rc;
-  if ((rc = make_map(&maps.xh, Xh, P.total_db, P.kp, TN))) return rc;
-  if ((rc = make_map(&maps.xl, Xl, P.total_db, P.kp, TN))) return rc;
+  if ((rc = make_map(&maps.yh, Yh, P.rows_q, P.kp, TM_ROWS))) return rc;
+  if ((rc = make_map(&maps.yl, Yl, P.rows_q, P.kp, TM_ROWS))) return rc;
+  if ((rc = make_map(&maps.xh, Xh, P.rows_db, P.kp, TN))) return rc;
+  if ((rc = make_map(&maps.xl, Xl, P.rows_db, P.kp, TN))) return rc;
   TcMaps maps_pair = maps;  // CTA-pair mode: each CTA stages half of the X tile
-  if ((rc = make_map(&maps_pair.xh, Xh, P.total_db, P.kp, TN / 2))) return rc;
-  if ((rc = make_map(&maps_pair.xl, Xl, P.total_db, P.kp, TN / 2))) return rc;
+  if ((rc = make_map(&maps_pair.xh, Xh, P.rows_db, P.kp, TN / 2))) return rc;
+  if ((rc = make_map(&maps_pair.xl, Xl, P.rows_db, P.kp, TN / 2))) return rc;
   DebugOut dbg{dbgS, ldS};
   if (dbgS) {
     if ((rc = launch<0, 0, true>(maps, maps_pair, P, dbg, st))) return rc;

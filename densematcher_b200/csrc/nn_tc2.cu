@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.yl) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.xh) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.xl) : "memory");
-      const int yrow = int(q0 + row0);
+      const int yrow = int(P.q_in[p] + row0);  // operand rows (a side may live in a mesh bank), see NNProblem::q_in
+      const int64_t xrow0 = P.db_in[p];
       mbar_expect_tx(bar_y, OPB);
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
         const uint32_t phase = (ct / T2_NST) & 1;
         mbar_wait_backoff(bar_xempty + 8 * stage, phase ^ 1);
         const uint32_t sb = sbase + t2_off_x(KC) + stage * OPB, fb = bar_xfull + 8 * stage;
-        const int xrow = int(d0 + int64_t(ct) * T2_TN);
+        const int xrow = int(xrow0 + int64_t(ct) * T2_TN);
         mbar_expect_tx(fb, OPB);
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
@@ -286,13 +287,13 @@ bool nn_tc2_applicable(int n_row, int n_col, int kp) {
 
 int nn_tc2_launch(const NNProblem& P, const void* Yh, const void* Yl, const void* Xh, const void* Xl, cudaStream_t st) {
   if (P.n_pairs <= 0 || P.total_q <= 0) return DM_OK;
-  if (P.total_q > 0x7fffffffLL || P.total_db > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
+  if (P.rows_q > 0x7fffffffLL || P.rows_db > 0x7fffffffLL) DM_FAIL(DM_ERR_BADARG, "too many rows for TMA coordinates");
   T2Maps maps;
   int rc;
-  if ((rc = tc_make_map_bf16(&maps.yh, Yh, P.total_q, P.kp, T2_ROWS))) return rc;
-  if ((rc = tc_make_map_bf16(&maps.yl, Yl, P.total_q, P.kp, T2_ROWS))) return rc;
-  if ((rc = tc_make_map_bf16(&maps.xh, Xh, P.total_db, P.kp, T2_TN))) return rc;
-  if ((rc = tc_make_map_bf16(&maps.xl, Xl, P.total_db, P.kp, T2_TN))) return rc;
+  if ((rc = tc_make_map_bf16(&maps.yh, Yh, P.rows_q, P.kp, T2_ROWS))) return rc;
+  if ((rc = tc_make_map_bf16(&maps.yl, Yl, P.rows_q, P.kp, T2_ROWS))) return rc;
+  if ((rc = tc_make_map_bf16(&maps.xh, Xh, P.rows_db, P.kp, T2_TN))) return rc;
+  if ((rc = tc_make_map_bf16(&maps.xl, Xl, P.rows_db, P.kp, T2_TN))) return rc;
   return P.kp <= T2_BK ? t2_launch<1>(maps, P, st) : t2_launch<2>(maps, P, st);
 }
 

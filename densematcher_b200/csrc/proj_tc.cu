@@ -326,13 +326,13 @@ int proj_tc_ksplit(int /*n_batch*/, int /*m_tiles*/, int max_n) {
   return ks < 1 ? 1 : ks;
 }
 
-size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d) {
+size_t proj_tc_workspace_bytes(int n_batch, int64_t total_n, int max_n, int k, int d, bool b_presplit) {
   const int kpA = pad_to(k, 128), kpB = pad_to(d, 64);
   const int m_tiles = kpA / 128;
   const int64_t a_rows = int64_t(n_batch) * pad_to(max_n, PKC);
   Carver c(nullptr);
   for (int i = 0; i < 3; ++i) c.take<uint16_t>(size_t(a_rows) * kpA);
-  for (int i = 0; i < 3; ++i) c.take<uint16_t>(size_t(total_n) * kpB);
+  for (int i = 0; i < 3; ++i) c.take<uint16_t>(b_presplit ? 0 : size_t(total_n) * kpB);
   c.take<float>(size_t(proj_tc_ksplit(n_batch, m_tiles, max_n)) * n_batch * kpA * kpB);
   return c.bytes();
 }
@@ -355,7 +355,8 @@ int proj_tc_run(const double* A, int64_t ldA, const double* a_scale, const float
   __nv_bfloat16* a3[3];
   __nv_bfloat16* b3[3];
   for (int i = 0; i < 3; ++i) a3[i] = reinterpret_cast<__nv_bfloat16*>(c.take<uint16_t>(size_t(a_rows) * kpA));
-  for (int i = 0; i < 3; ++i) b3[i] = reinterpret_cast<__nv_bfloat16*>(c.take<uint16_t>(size_t(total_n) * kpB));
+  for (int i = 0; i < 3; ++i)
+    b3[i] = reinterpret_cast<__nv_bfloat16*>(c.take<uint16_t>(b_presplit ? 0 : size_t(total_n) * kpB));
   float* partial = c.take<float>(size_t(ksplit) * n_batch * kpA * kpB);
   if (c.bytes() > ws_bytes) DM_FAIL(DM_ERR_WORKSPACE, "projection workspace too small: need %zu", c.bytes());
 

@@ -15,7 +15,8 @@ from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
 __all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "spd_solve", "zoomout", "icp", "polar_factor",
-           "match_pairs", "dense_energy", "fit_dense", "DENSE_TERMS", "PairBatch"]
+           "match_pairs", "bank_prepare", "match_bank_pairs", "BankState", "dense_energy", "fit_dense", "DENSE_TERMS",
+           "PairBatch"]
 
 
 def _stream(dev):
@@ -367,6 +368,97 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
     # entry does, to keep its copy/compute overlap) can still make it after its own synchronisation
     if check:
         _raise_if_singular(ws[:16].view(torch.int32).tolist(), "dm_match_pairs")
+    else:
+        out["status"] = ws[:16].view(torch.int32).clone()
+    return out
+
+
+class BankState:
+    """What ``dm_bank_prepare`` leaves in HBM for a bank of meshes: per-mesh operand splits, row norms and projections
+    (opaque to Python), together with the matrices they were derived from (the per-pair call re-reads those for its
+    float64 re-evaluations)."""
+
+    def __init__(self, F, Phi, area, evals, off_dev, off_host, k, state):
+        self.F, self.Phi, self.area, self.evals = F, Phi, area, evals
+        self.off, self.off_h, self.k, self.state = off_dev, off_host, int(k), state
+        self.n_meshes = len(off_host) - 1
+        self.sizes_h = np.diff(off_host)
+        self.max_n = int(self.sizes_h.max()) if self.n_meshes else 0
+
+
+def bank_prepare(F, Phi, area, evals, off, k, workspace: Optional[Workspace] = None, state: Optional[torch.Tensor] = None):
+    """Once-per-mesh preparation of a bank of meshes (``dm_bank_prepare``): F [N, d] float32, Phi [N, K >= k] float64,
+    area [N], evals [M, K], off [M + 1] row offsets.  Returns a ``BankState`` for ``match_bank_pairs``."""
+    lib = _lib.load()
+    dev = F.device
+    if dev.type != "cuda":
+        raise ValueError("bank_prepare needs CUDA tensors")
+    F = F if (F.dtype == torch.float32 and F.stride(1) == 1) else F.float().contiguous()
+    Phi, area, evals = _f64(Phi), _f64(area).contiguous(), _f64(evals)
+    k = int(k)
+    if k > Phi.shape[1] or k > evals.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    N, d = F.shape
+    od, oh, max_n = _offsets(off, N, dev)
+    M = len(oh) - 1
+    if Phi.shape[0] != N or area.numel() != N or evals.shape[0] != M:
+        raise ValueError("bank_prepare: rows of F / Phi / area, or the number of eigenvalue rows, do not agree")
+    need = lib.dm_bank_state_bytes(M, N, d, k)
+    if state is None or state.numel() < need:
+        state = torch.empty(max(int(need), 256), dtype=torch.uint8, device=dev)
+    wneed = lib.dm_bank_prepare_workspace_bytes(M, N, max_n, d, k)
+    ws = (workspace or default_workspace(dev, "bank_prep")).get(wneed)
+    with torch.cuda.device(dev):
+        rc = lib.dm_bank_prepare(F.data_ptr(), F.stride(0), Phi.data_ptr(), Phi.stride(0), area.data_ptr(), od.data_ptr(), N,
+                                 max_n, M, d, k, state.data_ptr(), state.numel(), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_bank_prepare")
+    return BankState(F, Phi, area, evals, od, np.asarray(oh, np.int64), k, state)
+
+
+def match_bank_pairs(bank: BankState, ids1, ids2, off1, off2, w_descr, w_lap, flags=0, out_dtype=torch.int32,
+                     workspace: Optional[Workspace] = None, check: bool = True):
+    """The per-pair hot path for pairs (ids1[p] -> mesh 1, ids2[p] -> mesh 2) drawn from a prepared bank, in one library
+    call (``dm_match_bank_pairs``).  ids1 / ids2: device int64 [P]; off1 / off2: the packing of the outputs (``Offsets`` or
+    host arrays: cumulative sizes of the pairs' meshes).  Same result dict, bit for bit, as ``match_pairs`` on the
+    assembled batch."""
+    import ctypes
+    lib = _lib.load()
+    dev = bank.F.device
+    P = int(ids1.numel())
+    if int(ids2.numel()) != P or ids1.dtype != torch.int64 or ids2.dtype != torch.int64:
+        raise ValueError("match_bank_pairs: ids1 / ids2 must be int64 device tensors of one length")
+    tot = lambda o: int((o.host if isinstance(o, Offsets) else np.asarray(o))[-1])
+    o1, o1h, max1 = _offsets(off1, tot(off1), dev)
+    o2, o2h, max2 = _offsets(off2, tot(off2), dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P:
+        raise ValueError("match_bank_pairs: off1 / off2 must describe one entry per pair")
+    n1, n2, d, k = int(o1h[-1]), int(o2h[-1]), bank.F.shape[1], bank.k
+    if out_dtype == torch.int64:
+        flags |= _lib.DM_I64_OUT
+    mk = lambda n: torch.empty(n, dtype=out_dtype, device=dev)
+    out = dict(nn_p2p_21=mk(n2), nn_p2p_12=mk(n1), C=torch.empty(P, k, k, dtype=torch.float64, device=dev),
+               p2p_21=mk(n2), p2p_12=mk(n1), p2p_21_adjoint=mk(n2), p2p_12_adjoint=mk(n1))
+    if P == 0:
+        return out
+    need = lib.dm_match_bank_pairs_workspace_bytes(P, n1, n2, max1, max2, d, k, flags)
+    ws = (workspace or default_workspace(dev, "match")).get(need)
+    with torch.cuda.device(dev):
+        rc = lib.dm_match_bank_pairs(
+            bank.state.data_ptr(), bank.state.numel(), bank.F.data_ptr(), bank.F.stride(0), bank.Phi.data_ptr(),
+            bank.Phi.stride(0), bank.area.data_ptr(), bank.evals.data_ptr(), bank.evals.stride(0), bank.off.data_ptr(),
+            bank.F.shape[0], bank.n_meshes, ids1.data_ptr(), ids2.data_ptr(), o1.data_ptr(), n1, max1, o2.data_ptr(), n2, max2,
+            P, d, k, float(w_descr), float(w_lap), out["nn_p2p_21"].data_ptr(), out["nn_p2p_12"].data_ptr(),
+            out["C"].data_ptr(), out["p2p_21_adjoint"].data_ptr(), out["p2p_12_adjoint"].data_ptr(),
+            out["p2p_21"].data_ptr(), out["p2p_12"].data_ptr(), flags, ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_match_bank_pairs")
+    if check:
+        st = (ctypes.c_int * 5)()
+        with torch.cuda.device(dev):
+            rc = lib.dm_match_bank_pairs_read_status(ws.data_ptr(), P, d, k, st, _stream(dev))
+        _lib.check(rc, "dm_match_bank_pairs_read_status")
+        if st[4]:
+            raise ValueError("match_bank_pairs: a mesh id is out of range or off1 / off2 do not match the meshes' sizes")
+        _raise_if_singular([int(v) for v in st[:4]], "dm_match_bank_pairs")
     else:
         out["status"] = ws[:16].view(torch.int32).clone()
     return out

@@ -305,10 +305,13 @@ def match_pairs_host(batch: PairBatchHost, device=None, chunk_pairs: int = 16, c
 
 class MeshBankDevice:
     """A dataset of meshes resident in HBM once (features, eigenbasis, eigenvalues, vertex areas, ragged-packed by
-    ``off``), from which batches of (source, target) pairs are assembled ON THE DEVICE.  This is the layout for
-    dataset-shaped workloads (BASELINE config 5: 599 meshes, every intra-category pair): each mesh is uploaded once
-    (~4.7 MB at N = 2000, d = 384, K = 100) instead of once per pair it takes part in; assembling a pair costs one
-    gather of its rows (~19 MB of HBM traffic, ~3 us) against ~55 us of matching."""
+    ``off``).  This is the layout for dataset-shaped workloads (BASELINE config 5: 599 meshes, every intra-category
+    pair): each mesh is uploaded once (~4.7 MB at N = 2000, d = 384, K = 100) instead of once per pair it takes part in,
+    and -- ``match`` -- everything of the per-pair path that depends on one mesh only (operand splits, row norms, the
+    projection Phi^T A F) is computed once per mesh (``dm_bank_prepare``); the pairs are two id lists and the kernels read
+    each pair's operands through its meshes' rows in the bank (``dm_match_bank_pairs``): nothing is gathered per pair.
+    ``assemble`` (a device gather of the pairs' rows into a ``PairBatchDevice``) remains for the stages that want a
+    packed batch (ZoomOut / ICP ladders, the dense-map fit) and for configurations the bank kernels do not cover."""
 
     def __init__(self, F, off, Phi=None, evals=None, area=None, device=None):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -321,6 +324,47 @@ class MeshBankDevice:
         self.off = torch.from_numpy(self.off_h).to(device)
         self.n_meshes = len(self.off_h) - 1
         self.sizes_h = np.diff(self.off_h)
+        self._states = {}
+
+    def bank_supported(self, k, flags=0):
+        """whether ``dm_match_bank_pairs`` covers this bank (tensor-core engines: d <= 512, k <= 128)"""
+        return (self.Phi is not None and self.evals is not None and self.area is not None and self.F.shape[1] <= 512
+                and 2 <= int(k) <= 128 and not (flags & _lib.DM_ENGINE_FFMA))
+
+    def prepared(self, k):
+        """``fm.BankState`` for eigenbasis width k: the once-per-mesh preparation, made on first use and kept"""
+        k = int(k)
+        st = getattr(self, "_states", None)
+        if st is None:
+            st = self._states = {}
+        if k not in st:
+            st[k] = _fm.bank_prepare(self.F, self.Phi, self.area, self.evals, _nn.Offsets(self.off, self.off_h), k,
+                                     state=getattr(self, "_state_buf", None))
+        return st[k]
+
+    def match(self, src_ids, dst_ids, k=None, w_descr: float = 1e4, w_lap: float = 1e3, out_dtype=torch.int32,
+              flags: int = 0, check: bool = True):
+        """The hot path for the pairs (src_ids[p] -> mesh 1, dst_ids[p] -> mesh 2) without assembling them: same result
+        dict, bit for bit, as ``match_pairs_device(self.assemble(src_ids, dst_ids))``, plus ``off1`` / ``off2`` host
+        offsets of the packed outputs."""
+        src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
+        k = self.Phi.shape[1] if k is None else int(k)
+        bank = self.prepared(k)
+        n = len(src_ids)
+        o1 = np.concatenate([[0], np.cumsum(self.sizes_h[src_ids])]).astype(np.int64)
+        o2 = np.concatenate([[0], np.cumsum(self.sizes_h[dst_ids])]).astype(np.int64)
+        # one pinned staging buffer for ids and offsets: no host synchronisation
+        stage = torch.empty(4 * n + 2, dtype=torch.int64, pin_memory=True)
+        stage[:n] = torch.from_numpy(np.ascontiguousarray(src_ids))
+        stage[n:2 * n] = torch.from_numpy(np.ascontiguousarray(dst_ids))
+        stage[2 * n:3 * n + 1] = torch.from_numpy(o1)
+        stage[3 * n + 1:] = torch.from_numpy(o2)
+        dev = stage.to(self.device, non_blocking=True)
+        res = _fm.match_bank_pairs(bank, dev[:n], dev[n:2 * n], _nn.Offsets(dev[2 * n:3 * n + 1], o1),
+                                   _nn.Offsets(dev[3 * n + 1:], o2), w_descr, w_lap, flags=flags, out_dtype=out_dtype,
+                                   check=check)
+        res["off1"], res["off2"] = o1, o2
+        return res
 
     def _rows(self, mesh_ids_h):
         """global row indices of the listed meshes, concatenated (device int64) + packed offsets (host, device).
@@ -441,10 +485,12 @@ def match_bank_pairs_host(bank: "MeshBankHost", src_ids, dst_ids, device=None, c
         dbank.off_h = np.ascontiguousarray(np.asarray(bank.off, np.int64))
         dbank.off = torch.from_numpy(dbank.off_h).to(device, non_blocking=True)
         dbank.n_meshes, dbank.sizes_h = len(dbank.off_h) - 1, sizes
+        # the once-per-mesh preparation is redone per call (the bank was just uploaded), into a buffer the stager keeps
+        dbank._states, dbank._state_buf = {}, st.dev.get("_bank_state")
     for lo in range(0, P, chunk_pairs):
         hi = min(P, lo + chunk_pairs)
         with torch.cuda.stream(st.comp):
-            res = match_pairs_device(dbank.assemble(src_ids[lo:hi], dst_ids[lo:hi]), check=False, **kw)
+            res = _bank_chunk(dbank, src_ids[lo:hi], dst_ids[lo:hi], check=False, **kw)
             done = torch.cuda.Event()
             done.record(st.comp)
         with torch.cuda.stream(st.d2h):
@@ -461,6 +507,8 @@ def match_bank_pairs_host(bank: "MeshBankHost", src_ids, dst_ids, device=None, c
                 st.out_buf(out, name, rows, t)[sl].copy_(t, non_blocking=True)
                 rows_of[name] = rows
         keep.append((res, stt))
+    for bs in dbank._states.values():
+        st.dev["_bank_state"] = bs.state
     st.d2h.synchronize()
     cur.wait_stream(st.comp)
     if statuses and bool(out["_status"][: max(statuses) + 1, 0].any()):
@@ -468,6 +516,19 @@ def match_bank_pairs_host(bank: "MeshBankHost", src_ids, dst_ids, device=None, c
     res = {n: (out[n][:r].numpy().copy() if copy else out[n][:r].numpy()) for n, r in rows_of.items()}
     res["off1"], res["off2"] = off1, off2
     return res
+
+
+def _bank_chunk(bank: MeshBankDevice, src, dst, check: bool = True, use_bank: bool = True, **kw):
+    """One chunk of pairs of a device bank: through the bank kernels (``MeshBankDevice.match``: nothing gathered, nothing
+    prepared per pair) whenever they cover the request, else assembled into a packed batch for ``match_pairs_device``."""
+    k = kw.get("k") or (bank.Phi.shape[1] if bank.Phi is not None else None)
+    if (use_bank and len(src) > 0 and kw.get("feature_nn", True) and kw.get("functional_map", True) and kw.get("fused", True)
+            and k is not None and bank.bank_supported(k, kw.get("flags", 0))):
+        res = bank.match(src, dst, k=k, w_descr=kw.get("w_descr", 1e4), w_lap=kw.get("w_lap", 1e3),
+                         out_dtype=kw.get("out_dtype", torch.int32), flags=kw.get("flags", 0), check=check)
+        res.pop("off1"), res.pop("off2")
+        return res
+    return match_pairs_device(bank.assemble(src, dst), check=check, **kw)
 
 
 def intra_category_pairs(categories):
@@ -495,7 +556,7 @@ def match_bank_pairs(bank: MeshBankDevice, src_ids, dst_ids, chunk_pairs: int = 
     out = []
     for a in range(lo, hi, chunk_pairs):
         b = min(hi, a + chunk_pairs)
-        res = match_pairs_device(bank.assemble(src_ids[a:b], dst_ids[a:b]), **kw)
+        res = _bank_chunk(bank, src_ids[a:b], dst_ids[a:b], **kw)
         out.append({n: (t.cpu().numpy() if to_host else t) for n, t in res.items()})
     return out, (lo, hi)
 

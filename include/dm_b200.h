@@ -326,6 +326,40 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
 int dm_match_pairs_read_status(const void* workspace, int* out_h /* [4] */, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mesh bank: the same per-pair path for DATASET-shaped work -- every mesh takes part in many pairs (the evaluation
+ * loop around compute_surface_map, densematcher/functional_map.py:9-81, over a test split; BASELINE config 5).
+ * dm_bank_prepare does, ONCE PER MESH, everything of the path that depends on one mesh only: the bf16 splits and row
+ * norms of its features (knn_query operands, pyFM/spectral/nn_utils.py:4-38), the three-way split of Phi[:, :k] (embedding
+ * operands of FM_to_p2p, pyFM/spectral/convert.py:96-147) and the projection Phi^T A F (optimize/base_functions.py:526-532).
+ * dm_match_bank_pairs then takes the pairs as two id lists and reads each pair's operands through its meshes' rows in the
+ * bank: no per-pair copy of the meshes, no per-pair preparation or projection.  Results are bit-identical to
+ * dm_match_pairs on the assembled batch.
+ *   F [total_n, ldF] float32, Phi [total_n, ldPhi >= k] float64, area [total_n], evals [n_meshes, ld_evals >= k],
+ *   bank_off [n_meshes + 1] (device): rows of mesh m = bank_off[m] .. bank_off[m + 1]
+ *   ids1 / ids2 [n_pairs] (device int64): mesh 1 / mesh 2 of each pair; off1 / off2 [n_pairs + 1]: the packing of the
+ *   OUTPUTS (cumulative sizes of the pairs' meshes, as in dm_match_pairs); `state` is opaque device memory of
+ *   dm_bank_state_bytes, filled by dm_bank_prepare with the same (n_meshes, total_n, d, k).
+ * ---------------------------------------------------------------------------------------- */
+size_t dm_bank_state_bytes(int n_meshes, int64_t total_n, int d, int k);
+size_t dm_bank_prepare_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int d, int k);
+int dm_bank_prepare(const float* F, int64_t ldF, const double* Phi, int64_t ldPhi, const double* area,
+                    const int64_t* bank_off, int64_t total_n, int max_n, int n_meshes, int d, int k,
+                    void* state, size_t state_bytes, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+size_t dm_match_bank_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2,
+                                           int d, int k, int flags);
+int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, int64_t ldF, const double* Phi,
+                        int64_t ldPhi, const double* area, const double* evals, int64_t ld_evals,
+                        const int64_t* bank_off, int64_t total_n, int n_meshes, const int64_t* ids1,
+                        const int64_t* ids2, const int64_t* off1, int64_t total_n1, int max_n1, const int64_t* off2,
+                        int64_t total_n2, int max_n2, int n_pairs, int d, int k, double w_descr, double w_lap,
+                        void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12, void* dense_21,
+                        void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+/* out_h[0..3]: the solve stage's status words (dm_fmap_solve_read_status); out_h[4] != 0: a mesh id was out of range or
+ * off1 / off2 do not match the sizes of the meshes in the bank (the results are then meaningless).  Synchronises. */
+int dm_match_bank_pairs_read_status(const void* workspace, int n_pairs, int d, int k, int* out_h /* [5] */,
+                                    dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Nearest (partial) isometry  C[b] = U I V^T  of  X[b] = U S V^T  (the SVD step of icp.py:39-40), float64,
  * X / C [n_batch, rows, cols] contiguous, X != C.  Newton-Schulz iteration on batched GEMMs; matrices it cannot
  * orthonormalise to 1e-12 in its fixed step count (ill-conditioned or rank-deficient) are redone by a one-sided
