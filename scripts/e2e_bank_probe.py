@@ -29,3 +29,14 @@ try:
     print(f"match_pairs_device: {tm(lambda: pipeline.match_pairs_device(b, check=False, k=bench.K_EIG, w_descr=bench.W_DESCR, w_lap=bench.W_LAP)):.2f} ms")
 except Exception as e:
     print("pieces failed:", repr(e))
+# the bank kernels: pairs as id lists, nothing assembled (dm_bank_prepare once + dm_match_bank_pairs)
+kwd = dict(k=bench.K_EIG, w_descr=bench.W_DESCR, w_lap=bench.W_LAP, check=False)
+dbank.prepared(bench.K_EIG)
+print(f"bank.match (prepared): {tm(lambda: dbank.match(pool['ia'], pool['ib'], **kwd)):.2f} ms per {P} pairs")
+def prep():
+    dbank._states.clear()
+    dbank.prepared(bench.K_EIG)
+print(f"bank prepare (8 meshes): {tm(prep):.2f} ms")
+if os.environ.get("PROBE_ONE"):  # one more call for an ncu launch list (skip the warm-up launches with --launch-skip)
+    torch.cuda.synchronize(); torch.cuda.profiler.start()
+    dbank.match(pool['ia'], pool['ib'], **kwd); torch.cuda.synchronize(); torch.cuda.profiler.stop()
