@@ -98,10 +98,11 @@ SIGNATURES = {
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     "dm_bank_state_bytes": (c_sz, [c_int, c_i64, c_int, c_int]),
     "dm_bank_prepare_workspace_bytes": (c_sz, [c_int, c_i64, c_int, c_int, c_int]),
-    "dm_bank_prepare": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp,
-                                c_sz, c_vp]),
+    "dm_bank_prepare": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_i64,
+                                c_i64, c_vp, c_sz, c_vp, c_sz, c_vp]),
     "dm_match_bank_pairs_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]),
-    "dm_match_bank_pairs": (c_int, [c_vp, c_sz, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp,
+    "dm_match_bank_pairs": (c_int, [c_vp, c_sz, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int,
+                                    c_vp, c_vp,
                                     c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_dbl, c_dbl,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     "dm_match_bank_pairs_read_status": (c_int, [c_vp, c_int, c_int, c_int, C.POINTER(c_int), c_vp]),

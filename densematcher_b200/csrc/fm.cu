@@ -812,16 +812,17 @@ BankPrepLayout bank_prep_carve(void* ws, int n_meshes, int64_t total_n, int max_
   return L;
 }
 
-// in[p] = bank_off[ids[p]] for both sides; a size mismatch between the batch offsets and the bank raises status word 2
+// in[p] = bank_off[ids[p]] for both sides; an id outside the prepared range of meshes, or a size mismatch between the batch
+// offsets and the bank, raises the flag that dm_match_bank_pairs_read_status reports
 __global__ void __launch_bounds__(256)
-    bank_starts_kernel(const int64_t* __restrict__ bank_off, int n_meshes, const int64_t* __restrict__ ids1,
+    bank_starts_kernel(const int64_t* __restrict__ bank_off, int mesh_lo, int mesh_hi, const int64_t* __restrict__ ids1,
                        const int64_t* __restrict__ ids2, const int64_t* __restrict__ off1, const int64_t* __restrict__ off2,
                        int n_pairs, int64_t* __restrict__ in1, int64_t* __restrict__ in2, int* __restrict__ bad) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   const int64_t a = ids1[p], b = ids2[p];
-  const bool ok = a >= 0 && a < n_meshes && b >= 0 && b < n_meshes;
-  const int64_t ac = ok ? a : 0, bc = ok ? b : 0;
+  const bool ok = a >= mesh_lo && a < mesh_hi && b >= mesh_lo && b < mesh_hi;  // inside the prepared range of the bank
+  const int64_t ac = ok ? a : mesh_lo, bc = ok ? b : mesh_lo;
   in1[p] = bank_off[ac], in2[p] = bank_off[bc];
   if (!ok || bank_off[ac + 1] - bank_off[ac] != off1[p + 1] - off1[p] || bank_off[bc + 1] - bank_off[bc] != off2[p + 1] - off2[p])
     atomicExch(bad, 1);
@@ -885,10 +886,13 @@ size_t dm_bank_prepare_workspace_bytes(int n_meshes, int64_t total_n, int max_n,
 }
 
 int dm_bank_prepare(const float* F, int64_t ldF, const double* Phi, int64_t ldPhi, const double* area, const int64_t* off,
-                    int64_t total_n, int max_n, int n_meshes, int d, int k, void* state, size_t state_bytes, void* workspace,
-                    size_t workspace_bytes, dm_stream_t stream) {
+                    int64_t total_n, int max_n, int n_meshes, int d, int k, int mesh_lo, int mesh_hi, int64_t row_lo,
+                    int64_t row_hi, void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
+                    dm_stream_t stream) {
   if (n_meshes < 0 || total_n < 0 || max_n < 0 || d <= 0 || k < 2) DM_FAIL(DM_ERR_BADARG, "bad size (need k >= 2)");
-  if (n_meshes == 0 || total_n == 0) return DM_OK;
+  if (mesh_lo < 0 || mesh_hi > n_meshes || mesh_lo > mesh_hi || row_lo < 0 || row_hi > total_n || row_lo > row_hi)
+    DM_FAIL(DM_ERR_BADARG, "bad mesh / row range");
+  if (n_meshes == 0 || total_n == 0 || mesh_lo == mesh_hi || row_lo == row_hi) return DM_OK;
   if (!F || !Phi || !area || !off || !state) DM_FAIL(DM_ERR_BADARG, "null argument");
   if (ldF < d || ldPhi < k) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
   if (!proj_tc_supported(k, d) || !f2p_factored_applicable(k, k, 0))
@@ -902,12 +906,18 @@ int dm_bank_prepare(const float* F, int64_t ldF, const double* Phi, int64_t ldPh
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   // the same kernels, per row, as the per-pair preparation of dm_match_pairs / dm_fm_to_p2p: identical bits
-  if ((rc = nn_prep_side(F, 0, ldF, off, n_meshes, total_n, d, S.Fnorm, nullptr, 0, S.Fh, S.Fl, W.Fl2, nn_tc_kp(d), st))) return rc;
-  if ((rc = nn_prep_side(Phi, 1, ldPhi, off, n_meshes, total_n, k, S.Pnorm, nullptr, 0, S.Ph, S.Pm, S.Pl, nn_tc_kp(k), st)))
+  // (row-wise kernels: the range is addressed by shifting every array to its first row)
+  const size_t kpF = size_t(nn_tc_kp(d)), kpK = size_t(nn_tc_kp(k));
+  const int64_t nr = row_hi - row_lo;
+  if ((rc = nn_prep_side(F + row_lo * ldF, 0, ldF, off, 0, nr, d, S.Fnorm + row_lo, nullptr, 0, S.Fh + row_lo * kpF,
+                         S.Fl + row_lo * kpF, W.Fl2 + row_lo * kpF, int(kpF), st)))
+    return rc;
+  if ((rc = nn_prep_side(Phi + row_lo * ldPhi, 1, ldPhi, off, 0, nr, k, S.Pnorm + row_lo, nullptr, 0, S.Ph + row_lo * kpK,
+                         S.Pm + row_lo * kpK, S.Pl + row_lo * kpK, int(kpK), st)))
     return rc;
   const void* fs[3] = {S.Fh, S.Fl, W.Fl2};
-  for (int m0 = 0; m0 < n_meshes; m0 += kBankProjChunk) {
-    const int nb = n_meshes - m0 < kBankProjChunk ? n_meshes - m0 : kBankProjChunk;
+  for (int m0 = mesh_lo; m0 < mesh_hi; m0 += kBankProjChunk) {
+    const int nb = mesh_hi - m0 < kBankProjChunk ? mesh_hi - m0 : kBankProjChunk;
     // (the projection of a mesh sums fixed 256-vertex slices: it does not depend on the batch the mesh is in)
     if ((rc = proj_tc_run(Phi, ldPhi, area, F, nullptr, ldF, nullptr, nullptr, 0, nullptr, off + m0, total_n, max_n, nb, k, d,
                           S.A + size_t(m0) * k * d, W.proj_ws, W.proj_bytes, st, fs)))
@@ -924,7 +934,7 @@ size_t dm_match_bank_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_
 
 int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, int64_t ldF, const double* Phi, int64_t ldPhi,
                         const double* area, const double* evals, int64_t ld_evals, const int64_t* bank_off, int64_t total_n,
-                        int n_meshes, const int64_t* ids1, const int64_t* ids2, const int64_t* off1, int64_t total_n1,
+                        int n_meshes, int mesh_lo, int mesh_hi, const int64_t* ids1, const int64_t* ids2, const int64_t* off1, int64_t total_n1,
                         int max_n1, const int64_t* off2, int64_t total_n2, int max_n2, int n_pairs, int d, int k,
                         double w_descr, double w_lap, void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12,
                         void* dense_21, void* dense_12, int flags, void* workspace, size_t workspace_bytes,
@@ -936,6 +946,7 @@ int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, i
     DM_FAIL(DM_ERR_BADARG, "null argument");
   if (ldF < d || ldPhi < k || ld_evals < k) DM_FAIL(DM_ERR_BADARG, "leading dimension too small");
   if (total_n1 == 0 || total_n2 == 0) DM_FAIL(DM_ERR_BADARG, "empty meshes");
+  if (mesh_lo < 0 || mesh_hi > n_meshes || mesh_lo >= mesh_hi) DM_FAIL(DM_ERR_BADARG, "bad prepared range of meshes");
   if (!nn_use_tc(flags) || !proj_tc_supported(k, d) || !f2p_factored_applicable(k, k, flags))
     DM_FAIL(DM_ERR_UNSUPPORTED, "dm_match_bank_pairs needs the tensor-core engines (d <= 512, k <= 128)");
   if (!workspace) DM_FAIL(DM_ERR_WORKSPACE, "workspace is null");
@@ -966,8 +977,8 @@ int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, i
   }
   cudaStream_t sf = fk ? fk->side : st;
   DM_CUDA_OK(cudaMemsetAsync(L.bad, 0, 64 * sizeof(int), st));
-  bank_starts_kernel<<<unsigned((n_pairs + 255) / 256), 256, 0, st>>>(bank_off, n_meshes, ids1, ids2, off1, off2, n_pairs, L.in1,
-                                                                     L.in2, L.bad);
+  bank_starts_kernel<<<unsigned((n_pairs + 255) / 256), 256, 0, st>>>(bank_off, mesh_lo, mesh_hi, ids1, ids2, off1, off2, n_pairs,
+                                                                     L.in1, L.in2, L.bad);
   DM_LAUNCH_OK("bank_starts_kernel");
   if (fk) {
     DM_CUDA_OK(cudaEventRecord(fk->start, st));
@@ -1008,8 +1019,8 @@ int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, i
                           p2p_12, dense_21, dense_12, flags, L.p2p_ws, st, &b1, &b2);
 }
 
-// [0..3]: the solve stage's status words (dm_fmap_solve_read_status); [4] != 0: an id was out of range or the batch offsets
-// do not match the sizes of the meshes in the bank (results are then meaningless)
+// [0..3]: the solve stage's status words (dm_fmap_solve_read_status); [4] != 0: an id was outside the prepared range of meshes
+// or the batch offsets do not match the sizes of the meshes in the bank (results are then meaningless)
 int dm_match_bank_pairs_read_status(const void* workspace, int n_pairs, int d, int k, int* out_h /* [5] */, dm_stream_t stream) {
   if (!workspace || !out_h) DM_FAIL(DM_ERR_BADARG, "null argument");
   BankMatchLayout L = bank_match_carve(const_cast<void*>(workspace), n_pairs, 0, 0, 0, 0, d, k, 0);

@@ -376,7 +376,7 @@ def match_pairs(F1, F2, Phi1, Phi2, area1, area2, evals1, evals2, off1, off2, k,
 class BankState:
     """What ``dm_bank_prepare`` leaves in HBM for a bank of meshes: per-mesh operand splits, row norms and projections
     (opaque to Python), together with the matrices they were derived from (the per-pair call re-reads those for its
-    float64 re-evaluations)."""
+    float64 re-evaluations).  ``lo`` / ``hi``: the contiguous range of meshes prepared so far."""
 
     def __init__(self, F, Phi, area, evals, off_dev, off_host, k, state):
         self.F, self.Phi, self.area, self.evals = F, Phi, area, evals
@@ -384,35 +384,65 @@ class BankState:
         self.n_meshes = len(off_host) - 1
         self.sizes_h = np.diff(off_host)
         self.max_n = int(self.sizes_h.max()) if self.n_meshes else 0
+        self.lo = self.hi = 0
+
+    def covers(self, lo, hi):
+        return lo >= hi or (self.lo <= lo and hi <= self.hi)
 
 
-def bank_prepare(F, Phi, area, evals, off, k, workspace: Optional[Workspace] = None, state: Optional[torch.Tensor] = None):
-    """Once-per-mesh preparation of a bank of meshes (``dm_bank_prepare``): F [N, d] float32, Phi [N, K >= k] float64,
-    area [N], evals [M, K], off [M + 1] row offsets.  Returns a ``BankState`` for ``match_bank_pairs``."""
+def _bank_prepare_range(bank: BankState, lo, hi, workspace=None):
     lib = _lib.load()
-    dev = F.device
-    if dev.type != "cuda":
-        raise ValueError("bank_prepare needs CUDA tensors")
-    F = F if (F.dtype == torch.float32 and F.stride(1) == 1) else F.float().contiguous()
-    Phi, area, evals = _f64(Phi), _f64(area).contiguous(), _f64(evals)
-    k = int(k)
-    if k > Phi.shape[1] or k > evals.shape[1]:
-        raise AssertionError("At least k eigenvectors should be provided")
-    N, d = F.shape
-    od, oh, max_n = _offsets(off, N, dev)
-    M = len(oh) - 1
-    if Phi.shape[0] != N or area.numel() != N or evals.shape[0] != M:
-        raise ValueError("bank_prepare: rows of F / Phi / area, or the number of eigenvalue rows, do not agree")
-    need = lib.dm_bank_state_bytes(M, N, d, k)
-    if state is None or state.numel() < need:
-        state = torch.empty(max(int(need), 256), dtype=torch.uint8, device=dev)
-    wneed = lib.dm_bank_prepare_workspace_bytes(M, N, max_n, d, k)
+    dev = bank.F.device
+    N, d = bank.F.shape
+    wneed = lib.dm_bank_prepare_workspace_bytes(bank.n_meshes, N, bank.max_n, d, bank.k)
     ws = (workspace or default_workspace(dev, "bank_prep")).get(wneed)
     with torch.cuda.device(dev):
-        rc = lib.dm_bank_prepare(F.data_ptr(), F.stride(0), Phi.data_ptr(), Phi.stride(0), area.data_ptr(), od.data_ptr(), N,
-                                 max_n, M, d, k, state.data_ptr(), state.numel(), ws.data_ptr(), ws.numel(), _stream(dev))
+        rc = lib.dm_bank_prepare(bank.F.data_ptr(), bank.F.stride(0), bank.Phi.data_ptr(), bank.Phi.stride(0),
+                                 bank.area.data_ptr(), bank.off.data_ptr(), N, bank.max_n, bank.n_meshes, d, bank.k,
+                                 int(lo), int(hi), int(bank.off_h[lo]), int(bank.off_h[hi]), bank.state.data_ptr(),
+                                 bank.state.numel(), ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "dm_bank_prepare")
-    return BankState(F, Phi, area, evals, od, np.asarray(oh, np.int64), k, state)
+
+
+def bank_prepare(F, Phi, area, evals, off, k, workspace: Optional[Workspace] = None, state: Optional[torch.Tensor] = None,
+                 mesh_range=None, bank: Optional[BankState] = None):
+    """Once-per-mesh preparation of a bank of meshes (``dm_bank_prepare``): F [N, d] float32, Phi [N, K >= k] float64,
+    area [N], evals [M, K], off [M + 1] row offsets.  Returns a ``BankState`` for ``match_bank_pairs``.
+    ``mesh_range = (lo, hi)`` prepares only those meshes (a rank of a sharded job needs the ones its pairs touch); passing a
+    previous ``bank`` extends its prepared range to cover ``mesh_range`` -- only the missing meshes are worked on."""
+    lib = _lib.load()
+    if bank is None:
+        dev = F.device
+        if dev.type != "cuda":
+            raise ValueError("bank_prepare needs CUDA tensors")
+        F = F if (F.dtype == torch.float32 and F.stride(1) == 1) else F.float().contiguous()
+        Phi, area, evals = _f64(Phi), _f64(area).contiguous(), _f64(evals)
+        k = int(k)
+        if k > Phi.shape[1] or k > evals.shape[1]:
+            raise AssertionError("At least k eigenvectors should be provided")
+        N, d = F.shape
+        od, oh, _ = _offsets(off, N, dev)
+        M = len(oh) - 1
+        if Phi.shape[0] != N or area.numel() != N or evals.shape[0] != M:
+            raise ValueError("bank_prepare: rows of F / Phi / area, or the number of eigenvalue rows, do not agree")
+        need = lib.dm_bank_state_bytes(M, N, d, k)
+        if state is None or state.numel() < need:
+            state = torch.empty(max(int(need), 256), dtype=torch.uint8, device=dev)
+        bank = BankState(F, Phi, area, evals, od, np.asarray(oh, np.int64), k, state)
+    lo, hi = (0, bank.n_meshes) if mesh_range is None else (max(0, int(mesh_range[0])), min(bank.n_meshes, int(mesh_range[1])))
+    if lo >= hi or bank.covers(lo, hi):
+        return bank
+    if bank.lo == bank.hi:                      # nothing prepared yet
+        _bank_prepare_range(bank, lo, hi, workspace)
+        bank.lo, bank.hi = lo, hi
+        return bank
+    if lo < bank.lo:                            # extend to the left / right: the prepared range stays contiguous
+        _bank_prepare_range(bank, lo, bank.lo, workspace)
+        bank.lo = lo
+    if hi > bank.hi:
+        _bank_prepare_range(bank, bank.hi, hi, workspace)
+        bank.hi = hi
+    return bank
 
 
 def match_bank_pairs(bank: BankState, ids1, ids2, off1, off2, w_descr, w_lap, flags=0, out_dtype=torch.int32,
@@ -427,6 +457,8 @@ def match_bank_pairs(bank: BankState, ids1, ids2, off1, off2, w_descr, w_lap, fl
     P = int(ids1.numel())
     if int(ids2.numel()) != P or ids1.dtype != torch.int64 or ids2.dtype != torch.int64:
         raise ValueError("match_bank_pairs: ids1 / ids2 must be int64 device tensors of one length")
+    if bank.lo >= bank.hi and P > 0:
+        raise ValueError("match_bank_pairs: no mesh of the bank has been prepared")
     tot = lambda o: int((o.host if isinstance(o, Offsets) else np.asarray(o))[-1])
     o1, o1h, max1 = _offsets(off1, tot(off1), dev)
     o2, o2h, max2 = _offsets(off2, tot(off2), dev)
@@ -446,7 +478,7 @@ def match_bank_pairs(bank: BankState, ids1, ids2, off1, off2, w_descr, w_lap, fl
         rc = lib.dm_match_bank_pairs(
             bank.state.data_ptr(), bank.state.numel(), bank.F.data_ptr(), bank.F.stride(0), bank.Phi.data_ptr(),
             bank.Phi.stride(0), bank.area.data_ptr(), bank.evals.data_ptr(), bank.evals.stride(0), bank.off.data_ptr(),
-            bank.F.shape[0], bank.n_meshes, ids1.data_ptr(), ids2.data_ptr(), o1.data_ptr(), n1, max1, o2.data_ptr(), n2, max2,
+            bank.F.shape[0], bank.n_meshes, bank.lo, bank.hi, ids1.data_ptr(), ids2.data_ptr(), o1.data_ptr(), n1, max1, o2.data_ptr(), n2, max2,
             P, d, k, float(w_descr), float(w_lap), out["nn_p2p_21"].data_ptr(), out["nn_p2p_12"].data_ptr(),
             out["C"].data_ptr(), out["p2p_21_adjoint"].data_ptr(), out["p2p_12_adjoint"].data_ptr(),
             out["p2p_21"].data_ptr(), out["p2p_12"].data_ptr(), flags, ws.data_ptr(), ws.numel(), _stream(dev))
@@ -457,7 +489,8 @@ def match_bank_pairs(bank: BankState, ids1, ids2, off1, off2, w_descr, w_lap, fl
             rc = lib.dm_match_bank_pairs_read_status(ws.data_ptr(), P, d, k, st, _stream(dev))
         _lib.check(rc, "dm_match_bank_pairs_read_status")
         if st[4]:
-            raise ValueError("match_bank_pairs: a mesh id is out of range or off1 / off2 do not match the meshes' sizes")
+            raise ValueError("match_bank_pairs: a mesh id is outside the prepared range of the bank or off1 / off2 do not "
+                             "match the meshes' sizes")
         _raise_if_singular([int(v) for v in st[:4]], "dm_match_bank_pairs")
     else:
         out["status"] = ws[:16].view(torch.int32).clone()

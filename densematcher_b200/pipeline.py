@@ -331,15 +331,19 @@ class MeshBankDevice:
         return (self.Phi is not None and self.evals is not None and self.area is not None and self.F.shape[1] <= 512
                 and 2 <= int(k) <= 128 and not (flags & _lib.DM_ENGINE_FFMA))
 
-    def prepared(self, k):
-        """``fm.BankState`` for eigenbasis width k: the once-per-mesh preparation, made on first use and kept"""
+    def prepared(self, k, need=None):
+        """``fm.BankState`` for eigenbasis width k: the once-per-mesh preparation, made on first use and kept.
+        ``need = (lo, hi)``: only that range of meshes has to be prepared (what a rank's block of pairs touches); a state
+        that does not cover it yet is extended by the missing meshes.  Default: the whole bank."""
         k = int(k)
         st = getattr(self, "_states", None)
         if st is None:
             st = self._states = {}
         if k not in st:
             st[k] = _fm.bank_prepare(self.F, self.Phi, self.area, self.evals, _nn.Offsets(self.off, self.off_h), k,
-                                     state=getattr(self, "_state_buf", None))
+                                     state=getattr(self, "_state_buf", None), mesh_range=need)
+        elif not st[k].covers(*(need or (0, self.n_meshes))):
+            _fm.bank_prepare(None, None, None, None, None, k, mesh_range=need, bank=st[k])
         return st[k]
 
     def match(self, src_ids, dst_ids, k=None, w_descr: float = 1e4, w_lap: float = 1e3, out_dtype=torch.int32,
@@ -349,8 +353,11 @@ class MeshBankDevice:
         offsets of the packed outputs."""
         src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
         k = self.Phi.shape[1] if k is None else int(k)
-        bank = self.prepared(k)
         n = len(src_ids)
+        # the meshes these pairs touch must be prepared; a state that already exists is only extended (each mesh is
+        # prepared once), a fresh one covers the whole bank unless a driver asked for a range first (match_bank_pairs)
+        need = (int(min(src_ids.min(), dst_ids.min())), int(max(src_ids.max(), dst_ids.max())) + 1) if n else None
+        bank = self.prepared(k, need if k in getattr(self, "_states", {}) else None)
         o1 = np.concatenate([[0], np.cumsum(self.sizes_h[src_ids])]).astype(np.int64)
         o2 = np.concatenate([[0], np.cumsum(self.sizes_h[dst_ids])]).astype(np.int64)
         # one pinned staging buffer for ids and offsets: no host synchronisation
@@ -553,6 +560,11 @@ def match_bank_pairs(bank: MeshBankDevice, src_ids, dst_ids, chunk_pairs: int = 
     and packed in pair order."""
     src_ids, dst_ids = np.asarray(src_ids, np.int64), np.asarray(dst_ids, np.int64)
     lo, hi = shard_pairs(len(src_ids), rank, world)
+    k = kw.get("k") or (bank.Phi.shape[1] if bank.Phi is not None else None)
+    if hi > lo and k is not None and bank.bank_supported(k, kw.get("flags", 0)) and kw.get("functional_map", True):
+        # once-per-mesh preparation of the (contiguous) range of meshes this rank's block of pairs touches
+        ids = np.concatenate([src_ids[lo:hi], dst_ids[lo:hi]])
+        bank.prepared(k, (int(ids.min()), int(ids.max()) + 1))
     out = []
     for a in range(lo, hi, chunk_pairs):
         b = min(hi, a + chunk_pairs)

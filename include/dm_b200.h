@@ -342,20 +342,25 @@ int dm_match_pairs_read_status(const void* workspace, int* out_h /* [4] */, dm_s
  * ---------------------------------------------------------------------------------------- */
 size_t dm_bank_state_bytes(int n_meshes, int64_t total_n, int d, int k);
 size_t dm_bank_prepare_workspace_bytes(int n_meshes, int64_t total_n, int max_n, int d, int k);
+/* prepares meshes mesh_lo .. mesh_hi - 1, whose rows are row_lo .. row_hi - 1 (= bank_off[mesh_lo] .. bank_off[mesh_hi],
+ * which the host knows); the rest of `state` is left as it is, so a bank can be prepared piecewise -- a rank of a sharded
+ * job prepares only the meshes its block of pairs touches.  (0, n_meshes, 0, total_n) prepares everything. */
 int dm_bank_prepare(const float* F, int64_t ldF, const double* Phi, int64_t ldPhi, const double* area,
                     const int64_t* bank_off, int64_t total_n, int max_n, int n_meshes, int d, int k,
+                    int mesh_lo, int mesh_hi, int64_t row_lo, int64_t row_hi,
                     void* state, size_t state_bytes, void* workspace, size_t workspace_bytes, dm_stream_t stream);
 size_t dm_match_bank_pairs_workspace_bytes(int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2,
                                            int d, int k, int flags);
 int dm_match_bank_pairs(const void* state, size_t state_bytes, const float* F, int64_t ldF, const double* Phi,
                         int64_t ldPhi, const double* area, const double* evals, int64_t ld_evals,
-                        const int64_t* bank_off, int64_t total_n, int n_meshes, const int64_t* ids1,
-                        const int64_t* ids2, const int64_t* off1, int64_t total_n1, int max_n1, const int64_t* off2,
+                        const int64_t* bank_off, int64_t total_n, int n_meshes, int mesh_lo, int mesh_hi,
+                        const int64_t* ids1, const int64_t* ids2, const int64_t* off1, int64_t total_n1, int max_n1, const int64_t* off2,
                         int64_t total_n2, int max_n2, int n_pairs, int d, int k, double w_descr, double w_lap,
                         void* nn_p2p_21, void* nn_p2p_12, double* C, void* p2p_21, void* p2p_12, void* dense_21,
                         void* dense_12, int flags, void* workspace, size_t workspace_bytes, dm_stream_t stream);
-/* out_h[0..3]: the solve stage's status words (dm_fmap_solve_read_status); out_h[4] != 0: a mesh id was out of range or
- * off1 / off2 do not match the sizes of the meshes in the bank (the results are then meaningless).  Synchronises. */
+/* (mesh_lo, mesh_hi above: the range of meshes that dm_bank_prepare has prepared.)
+ * out_h[0..3]: the solve stage's status words (dm_fmap_solve_read_status); out_h[4] != 0: a mesh id was outside the prepared
+ * range or off1 / off2 do not match the sizes of the meshes in the bank (the results are then meaningless).  Synchronises. */
 int dm_match_bank_pairs_read_status(const void* workspace, int n_pairs, int d, int k, int* out_h /* [5] */,
                                     dm_stream_t stream);
 

@@ -105,3 +105,36 @@ def test_bank_host_entry_and_bad_ids():
     ids = torch.tensor([0, 2], dtype=torch.int64, device="cuda")
     with pytest.raises(ValueError):
         fm.match_bank_pairs(st, ids, ids, np.array([0, 256, 512]), np.array([0, 256, 512]), 1e4, 1e3)
+
+
+def test_bank_prepared_piecewise():
+    """A rank of a sharded job prepares only the meshes its block of pairs touches; later pairs extend the range, each
+    mesh is prepared once, and the results do not depend on how the bank was prepared."""
+    import torch
+    from densematcher_b200 import fm, pipeline
+    bank, _, _, _ = _bank([260, 300, 256, 384, 200, 310], 96, 32, seed=21)
+    k = 32
+    full = pipeline.MeshBankDevice(bank.F, bank.off_h, Phi=bank.Phi, evals=bank.evals, area=bank.area)
+    src, dst = np.array([2, 3, 3, 2]), np.array([3, 2, 3, 2])
+    st = bank.prepared(k, (2, 4))
+    assert (st.lo, st.hi) == (2, 4)
+    _same(bank.match(src, dst, k=k), full.match(src, dst, k=k))
+    assert (st.lo, st.hi) == (2, 4)
+    # ids outside the prepared range are refused by the library call itself
+    ids = torch.tensor([0, 2], dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):
+        fm.match_bank_pairs(st, ids, ids, np.array([0, 260, 516]), np.array([0, 260, 516]), 1e4, 1e3)
+    # pairs that reach further extend the prepared range on both sides
+    src2, dst2 = np.array([0, 5, 1, 4]), np.array([5, 0, 4, 1])
+    got = bank.match(src2, dst2, k=k)
+    assert (st.lo, st.hi) == (0, 6)
+    _same(got, full.match(src2, dst2, k=k))
+    _same(got, pipeline.match_pairs_device(bank.assemble(src2, dst2), k=k))
+    # the sharded driver prepares the range of its block
+    b2 = pipeline.MeshBankDevice(bank.F, bank.off_h, Phi=bank.Phi, evals=bank.evals, area=bank.area)
+    s_all, d_all = pipeline.intra_category_pairs(np.array([0, 0, 0, 1, 1, 1]))
+    chunks, (lo, hi) = pipeline.match_bank_pairs(b2, s_all, d_all, chunk_pairs=4, rank=1, world=2, k=k, to_host=False)
+    assert (b2._states[k].lo, b2._states[k].hi) == (3, 6) and (lo, hi) == (6, 12)
+    ref = full.match(s_all[lo:hi], d_all[lo:hi], k=k)
+    for n in NAMES:
+        assert np.array_equal(torch.cat([c[n] for c in chunks]).cpu().numpy(), ref[n].cpu().numpy()), n
