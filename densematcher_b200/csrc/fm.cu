@@ -566,6 +566,8 @@ struct MatchLayout {
   size_t solve_bytes;
   void* p2p_ws;
   size_t p2p_bytes, bytes;
+  uint16_t *p1h, *p1m, *p1l, *p2h, *p2m, *p2l;  // three-way splits of Phi1 / Phi2 [total, pad64(k)] for FM -> p2p
+  float *p1norm, *p2norm;
 };
 MatchLayout match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n2, int max_n1, int max_n2, int d, int k,
                         int flags) {
@@ -586,6 +588,11 @@ MatchLayout match_carve(void* ws, int n_pairs, int64_t total_n1, int64_t total_n
   L.proj_ws = c.take<char>(L.proj_bytes);
   L.p2p_bytes = dm_fm_to_p2p_workspace_bytes(n_pairs, total_n1, total_n2, max_n1, max_n2, k, k, flags);
   L.p2p_ws = c.take<char>(L.p2p_bytes);
+  const size_t kpK = f2p_factored_applicable(k, k, flags) ? size_t(nn_tc_kp(k)) : 0;
+  const size_t r1 = kpK ? size_t(total_n1) : 0, r2 = kpK ? size_t(total_n2) : 0;
+  L.p1h = c.take<uint16_t>(r1 * kpK), L.p1m = c.take<uint16_t>(r1 * kpK), L.p1l = c.take<uint16_t>(r1 * kpK);
+  L.p2h = c.take<uint16_t>(r2 * kpK), L.p2m = c.take<uint16_t>(r2 * kpK), L.p2l = c.take<uint16_t>(r2 * kpK);
+  L.p1norm = c.take<float>(r1), L.p2norm = c.take<float>(r2);
   L.bytes = c.bytes();
   return L;
 }
@@ -652,6 +659,17 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
   NNSplits sp{};
   if ((rc = nn_run(R, L.nn_ws, L.nn_bytes, st, &sp))) return rc;
   if (fk) DM_CUDA_OK(cudaStreamWaitEvent(sf, fk->prep, 0));
+  // The operand preparation of FM -> p2p (three-way splits + row norms of both eigenbases) does not depend on C: enqueued
+  // here, behind the feature search on the main stream, these HBM-bound kernels run beside the solve of the side stream
+  // instead of after it.  FM -> p2p then reads them like a mesh bank whose rows are the batch's own (in = off).
+  static const bool early_prep = [] { const char* e = getenv("DM_MATCH_LATE_PREP"); return !(e && e[0] == '1'); }();
+  const bool want_maps = p2p_21 || p2p_12 || dense_21 || dense_12;
+  const bool presplit = early_prep && want_maps && f2p_factored_applicable(k, k, flags);
+  if (presplit) {
+    const int kpK = nn_tc_kp(k);
+    if ((rc = nn_prep_side(Phi1, 1, ld1, off1, n_pairs, total_n1, k, L.p1norm, nullptr, 0, L.p1h, L.p1m, L.p1l, kpK, st))) return rc;
+    if ((rc = nn_prep_side(Phi2, 1, ld2, off2, n_pairs, total_n2, k, L.p2norm, nullptr, 0, L.p2h, L.p2m, L.p2l, kpK, st))) return rc;
+  }
   // 2. projections, reusing the feature splits (mesh 1 = database side, mesh 2 = query side)
   const void* s1[3] = {sp.xh, sp.xl, sp.xl2};
   const void* s2[3] = {sp.yh, sp.yl, sp.yl2};
@@ -672,7 +690,13 @@ int dm_match_pairs(const float* F1, int64_t ldF1, const float* F2, int64_t ldF2,
     DM_CUDA_OK(cudaStreamWaitEvent(st, fk->done, 0));
   }
   // 4. the four index maps
-  if (!p2p_21 && !p2p_12 && !dense_21 && !dense_12) return DM_OK;
+  if (!want_maps) return DM_OK;
+  if (presplit) {
+    const NNBankSide b1{off1, total_n1, L.p1h, L.p1m, L.p1l, L.p1norm}, b2{off2, total_n2, L.p2h, L.p2m, L.p2l, L.p2norm};
+    if (dense_21 && !area1) DM_FAIL(DM_ERR_BADARG, "dense_21 needs area1");
+    return f2p_factored_run(C, k, k, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs, p2p_21,
+                            p2p_12, dense_21, dense_12, flags, L.p2p_ws, st, &b1, &b2);
+  }
   return dm_fm_to_p2p(C, k, k, Phi1, ld1, off1, total_n1, max_n1, Phi2, ld2, off2, total_n2, max_n2, area1, n_pairs, p2p_21,
                       p2p_12, dense_21, dense_12, flags, L.p2p_ws, L.p2p_bytes, stream);
 }
