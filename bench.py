@@ -464,7 +464,7 @@ def main():
                 res.update(C_zo=Cz, p2p_zo=pz)
                 gather_all(res)
                 return res
-            launches_per_step = 37 + nit * 14 + 12     # 2382 launches per 170-rung ladder (gpurun_out/r4q_zo_launches.csv)
+            launches_per_step = 36 + nit * 11 + 11     # 11 launches per rung (profiles/r2_zoomout_launches.md minus the merged bookkeeping kernels)
         units_per_rank = P
     elif cfg == "cfg3":
         g = torch.Generator(device=device).manual_seed(3000 + rank)
@@ -514,7 +514,7 @@ def main():
             gather_all(res)
             return res
         n_chunks = (hi - lo + chunk - 1) // chunk
-        launches_per_step = n_chunks * (12 + nit * 14 + 12)
+        launches_per_step = n_chunks * (12 + nit * 11 + 11)
         units_per_rank = hi - lo
     else:  # cfg5
         bank, cats = make_device_bank_cfg5(device)

@@ -89,13 +89,12 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
-// c_fro[p] >= |C_p|_F from the chunk sums (fixed order)
-__global__ void __launch_bounds__(128) cfro_kernel(const double* __restrict__ fro_part, int n_pairs, float* __restrict__ c_fro) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+// |C_p|_F rounded up, from the chunk sums in fixed order (evaluated by the consumers: no kernel of its own)
+__device__ __forceinline__ float cfro_of(const double* __restrict__ fro_part, int p) {
   double ss = 0.0;
+#pragma unroll
   for (int c = 0; c < kCsplitChunks; ++c) ss += fro_part[p * kCsplitChunks + c];
-  c_fro[p] = __double2float_ru(sqrt(ss)) * 1.000001f;
+  return __double2float_ru(sqrt(ss)) * 1.000001f;
 }
 
 // ---------------------------------------------------------------- the embedding kernel
@@ -118,7 +117,7 @@ struct EbParams {
   __nv_bfloat16 *hi, *lo;   // [total, kp_out] split of the embedding (nullptr: norms / biases only)
   float* norm;              // inflated row norm (nullptr: not wanted)
   const float* a_norm;      // |Phi_i| (rounded up)
-  const float* c_fro;       // |C|_F per pair (rounded up)
+  const double* fro_part;   // [n_pairs, kCsplitChunks] sums of squares of C: |C|_F = cfro_of(fro_part, p)
   float eps_e;              // |d row_i| <= eps_e |Phi_i| |C|_F
   float inv_eps;            // 1 / eps of the score pass
   EbEpi epi[kMaxEpi];
@@ -142,6 +141,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
   const int n = int(P.off[p + 1] - r0);
   if (rt0 * EB_ROWS >= n) return;
   const int n_tiles = min(EB_TPC, (n - rt0 * EB_ROWS + EB_ROWS - 1) / EB_ROWS);
+  const float cfro_p = cfro_of(P.fro_part, p);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) embed_tc_kernel(const __grid_co
       if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
       // |row| rounded up (fp32 sum of squares: relative error <= (k_out + 2) 2^-24), embedding error e_i, inflated norm
       const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
-      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * P.c_fro[p] : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * cfro_p : 0.f;
       const float own = (nrm + e_i) + e_i * P.inv_eps;  // eps * own >= eps |row| + e_i
       if (ok && P.norm) P.norm[gi] = own;
       for (int e = 0; e < P.n_epi; ++e) {
@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1)
   const int n = int(P.off[p + 1] - r0);
   if (rt0 * EB_ROWS >= n) return;
   const int n_tiles = min(EB_TPC, (n - rt0 * EB_ROWS + EB_ROWS - 1) / EB_ROWS);
+  const float cfro_p = cfro_of(P.fro_part, p);
   const int n_units = n_tiles * n_half;
 
   extern __shared__ uint8_t smem_raw[];
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1)
         if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
       }
       const float nrm = ok ? __fsqrt_ru(ss * (1.f + float(P.k_out + 4) * 6.0e-8f)) * 1.000001f : 0.f;
-      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * P.c_fro[p] : 0.f;
+      const float e_i = ok ? P.eps_e * P.a_norm[P.a_in[p] + i] * cfro_p : 0.f;
       const float own = (nrm + e_i) + e_i * P.inv_eps;
       if (ok && P.norm) P.norm[gi] = own;
       for (int e = 0; e < P.n_epi; ++e) {
@@ -737,12 +738,11 @@ int f2p_prep_y(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
       X.C, X.k1, X.k2, X.kp2, X.kp1, reinterpret_cast<__nv_bfloat16*>(X.c0h), reinterpret_cast<__nv_bfloat16*>(X.c0m),
       reinterpret_cast<__nv_bfloat16*>(X.c0l), reinterpret_cast<__nv_bfloat16*>(X.c1h),
       reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.fro_part, 0, nullptr, EB_ROWS);
-  cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
   E.off = X.off2, E.a_in = X.in2, E.max_rt = (X.max_n2 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k1, E.kp_out = P.kp, E.n_epi = R.n_col;
   E.hi = reinterpret_cast<__nv_bfloat16*>(L.yh), E.lo = reinterpret_cast<__nv_bfloat16*>(L.yl);
-  E.norm = L.norm_q, E.a_norm = X.bank2 ? X.bank2->norm : X.p2norm, E.c_fro = X.c_fro;
+  E.norm = L.norm_q, E.a_norm = X.bank2 ? X.bank2->norm : X.p2norm, E.fro_part = X.fro_part;
   E.eps_e = eb_eps(X.kp2), E.inv_eps = 1.f / P.eps;
   for (int e = 0; e < R.n_col; ++e) {
     if (R.col[e].scale_mode == DM_SCALE_INVNORM || R.col[e].bias_mode == DM_BIAS_ARRAY)
@@ -766,7 +766,7 @@ int f2p_after_prep(void* vctx, const NNLayout& L, NNProblem& P, cudaStream_t st)
   EbParams E{};
   E.off = X.off1, E.a_in = X.in1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = X.kp2, E.n_epi = 1;
   E.hi = E.lo = nullptr, E.norm = nullptr;
-  E.a_norm = X.bank1 ? X.bank1->norm : L.norm_db, E.c_fro = X.c_fro;  // (L.norm_db is the batch-packed copy of the same values)
+  E.a_norm = X.bank1 ? X.bank1->norm : L.norm_db, E.fro_part = X.fro_part;  // (L.norm_db is the batch-packed copy of the same values)
   E.eps_e = eb_eps(X.kp1), E.inv_eps = 1.f / P.eps;
   // only bf / Bm of the bias epilogue change: the scale stays 1 (the kernel rewrites sf = 1) and G must stay
   // max_j |Phi1_j| from nn_prep_side, so the kernel's G (the norm of emb1, not wanted) goes to a scratch array
@@ -905,12 +905,11 @@ int p21_prep_x(void* vctx, const NNLayout& L, NNProblem& P, const NNRequest& R, 
       X.C, X.k1, X.k2, 0, X.kp1, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(X.c1h),
       reinterpret_cast<__nv_bfloat16*>(X.c1m), reinterpret_cast<__nv_bfloat16*>(X.c1l), X.fro_part, 1, X.Ct,
       wide ? eb_b_rows(X.k2) : EB_ROWS);
-  cfro_kernel<<<unsigned((X.n_pairs + 127) / 128), 128, 0, st>>>(X.fro_part, X.n_pairs, X.c_fro);
   DM_LAUNCH_OK("csplit_kernel");
   EbParams E{};
   E.off = X.off1, E.a_in = X.off1, E.max_rt = (X.max_n1 + EB_ROWS - 1) / EB_ROWS, E.k_out = X.k2, E.kp_out = P.kp, E.n_epi = 1;
   E.hi = reinterpret_cast<__nv_bfloat16*>(L.xh), E.lo = reinterpret_cast<__nv_bfloat16*>(L.xl);
-  E.norm = L.norm_db, E.a_norm = X.p1norm, E.c_fro = X.c_fro;
+  E.norm = L.norm_db, E.a_norm = X.p1norm, E.fro_part = X.fro_part;
   E.eps_e = eb_eps(X.kp1), E.inv_eps = 1.f / P.eps;
   if (R.n_row != 1 || R.row[0].bias_mode != DM_BIAS_NEG_HALF_SQNORM || R.row[0].scale_mode != DM_SCALE_NONE)
     DM_FAIL(DM_ERR_UNSUPPORTED, "factored database side: one Euclidean row epilogue expected");

@@ -42,7 +42,7 @@ __device__ __forceinline__ OpView resolve(const GemmOperand& o, int b) {
 
 __device__ __forceinline__ int ragged_k(const GemmOperand& o, int b) {
   if (o.trans != 1) return -1;
-  if (o.gather_off) return int(o.gather_off[b + 1] - o.gather_off[b]);
+  if (o.gather_off) return o.gather_cnt ? o.gather_cnt[b] : int(o.gather_off[b + 1] - o.gather_off[b]);
   if (o.off) return int(o.off[b + 1] - o.off[b]);
   return -1;
 }

@@ -23,6 +23,8 @@ struct GemmOperand {
   const void* gather = nullptr;  // trans == 1 only: matrix row k -> rows_of(gather_rows)[gather[goff + k]]
   int gather_i64 = 0;
   const int64_t* gather_off = nullptr;  // offsets of the gather index array (per batch), the gathered matrix uses `off`
+  const int* gather_cnt = nullptr;      // optional: batch b gathers gather_cnt[b] rows (segments of fixed capacity) instead of
+                                        // gather_off[b + 1] - gather_off[b]
   const double* kscale = nullptr;       // trans == 1 only: multiply by kscale[kbase + k] (kbase = gather_off or off)
 };
 

@@ -8,8 +8,9 @@
 // which changes by  sum_{n : p[n] != p_old[n]} Phi2[n]^T a2[n] (Phi1[p[n]] - Phi1[p_old[n]])  from rung to rung.  The ladder
 // keeps M resident, corrects it with the changed vertices only (|changed| K^2 instead of N k^2 multiply-adds), and hands
 // its leading (k2+s2) x (k1+s1) block to the next rung:
-//   delta_count / delta_scan / delta_fill   the changed vertices of every pair, in vertex order (deterministic), as
-//                                           interleaved (+a2, p) / (-a2, p_old) entries of a gather list
+//   delta_fill_kernel                       the changed vertices of every pair, in vertex order (deterministic), as
+//                                           interleaved (+a2, p) / (-a2, p_old) entries of a gather list (one fixed
+//                                           segment per pair: no count / scan pass over the pairs)
 //   gemm64_tt_kernel                        the correction as a gathered "both transposed" GEMM with M as its addend
 //   extract_block_kernel                    the dense leading block for the next conversion
 // The ladder re-anchors M with a full product every 64 rungs, and the last rung is always a fresh product, so the rounding
@@ -20,72 +21,17 @@
 namespace dm {
 namespace {
 
-__global__ void __launch_bounds__(256)
-    delta_count_kernel(const void* __restrict__ p_new, const void* __restrict__ p_old, int i64, const int64_t* __restrict__ off2,
-                       int* __restrict__ cnt) {
-  __shared__ int red[8];
-  const int b = blockIdx.x;
-  const int64_t r0 = off2[b];
-  const int n = int(off2[b + 1] - r0);
-  int c = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) c += load_index(p_new, r0 + i, i64 != 0) != load_index(p_old, r0 + i, i64 != 0);
-#pragma unroll
-  for (int sh = 16; sh > 0; sh >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sh);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) c += red[w];
-    cnt[b] = c;
-  }
-}
-
-// doff[b] = 2 * (cnt[0] + ... + cnt[b - 1]), doff[n_pairs] = total: one CTA, sequential carry over blocks of 1024
-__global__ void __launch_bounds__(1024) delta_scan_kernel(const int* __restrict__ cnt, int n_pairs, int64_t* __restrict__ doff) {
-  __shared__ int64_t wsum[32];
-  __shared__ int64_t carry_s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n_pairs; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int64_t v = i < n_pairs ? 2 * int64_t(cnt[i]) : 0;
-    int64_t x = v;
-#pragma unroll
-    for (int sh = 1; sh < 32; sh <<= 1) {
-      const int64_t y = __shfl_up_sync(0xffffffffu, x, sh);
-      if (lane >= sh) x += y;
-    }
-    if (lane == 31) wsum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int64_t w = wsum[lane];
-#pragma unroll
-      for (int sh = 1; sh < 32; sh <<= 1) {
-        const int64_t y = __shfl_up_sync(0xffffffffu, w, sh);
-        if (lane >= sh) w += y;
-      }
-      wsum[lane] = w;
-    }
-    __syncthreads();
-    const int64_t carry = carry_s;
-    const int64_t incl = x + (warp ? wsum[warp - 1] : 0) + carry;
-    if (i < n_pairs) doff[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) doff[n_pairs] = carry_s;
-}
-
-// entries 2 j, 2 j + 1 of pair b's segment: (vertex n_j, +a2, p_new) and (vertex n_j, -a2, p_old), n_j ascending
+// The changed vertices of pair b, in vertex order, as interleaved gather entries (vertex n, +a2, p_new) / (vertex n, -a2,
+// p_old).  Pair b owns the fixed segment [2 off2[b], 2 off2[b + 1]) of the lists (capacity: every vertex changed), so one
+// kernel does what needed a count, a scan over the pairs and a fill: seg[b] = start of the segment, cnt[b] = entries used.
 __global__ void __launch_bounds__(256)
     delta_fill_kernel(const void* __restrict__ p_new, const void* __restrict__ p_old, int i64, const int64_t* __restrict__ off2,
-                      const double* __restrict__ area2, const int64_t* __restrict__ doff, int32_t* __restrict__ ga,
-                      int32_t* __restrict__ gb, double* __restrict__ dscale) {
+                      const double* __restrict__ area2, int64_t* __restrict__ seg, int* __restrict__ cnt,
+                      int32_t* __restrict__ ga, int32_t* __restrict__ gb, double* __restrict__ dscale) {
   __shared__ int wcount[8];
   __shared__ int running_s;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = off2[b], o = doff[b];
+  const int64_t r0 = off2[b], o = 2 * r0;
   const int n = int(off2[b + 1] - r0);
   if (threadIdx.x == 0) running_s = 0;
   __syncthreads();
@@ -116,6 +62,7 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) seg[b] = o, cnt[b] = 2 * running_s;
 }
 
 // dense [n_pairs, k2, k1] copy of the leading block of M [n_pairs, K2, K1]
@@ -162,13 +109,12 @@ int p2p_to_fm_delta_run(const void* p_new, const void* p_old, int i64, const dou
                         const double* Phi2, int64_t ld2, const int64_t* off2, int64_t total_n2, int max_n2, const double* area2,
                         int n_pairs, int K1, int K2, double* M, void* ws, cudaStream_t st) {
   DeltaLayout L = delta_carve(ws, n_pairs, total_n2);
-  delta_count_kernel<<<n_pairs, 256, 0, st>>>(p_new, p_old, i64, off2, L.cnt);
-  delta_scan_kernel<<<1, 1024, 0, st>>>(L.cnt, n_pairs, L.doff);
-  delta_fill_kernel<<<n_pairs, 256, 0, st>>>(p_new, p_old, i64, off2, area2, L.doff, L.ga, L.gb, L.dscale);
+  delta_fill_kernel<<<n_pairs, 256, 0, st>>>(p_new, p_old, i64, off2, area2, L.doff, L.cnt, L.ga, L.gb, L.dscale);
   DM_LAUNCH_OK("delta_fill_kernel");
   GemmProblem G;
   G.A.d = Phi2, G.A.ld = ld2, G.A.off = off2, G.A.trans = 1, G.A.gather = L.ga, G.A.gather_off = L.doff, G.A.kscale = L.dscale;
-  G.B.d = Phi1, G.B.ld = ld1, G.B.off = off1, G.B.trans = 1, G.B.gather = L.gb, G.B.gather_off = L.doff;
+  G.A.gather_cnt = L.cnt;
+  G.B.d = Phi1, G.B.ld = ld1, G.B.off = off1, G.B.trans = 1, G.B.gather = L.gb, G.B.gather_off = L.doff, G.B.gather_cnt = L.cnt;
   G.M = K2, G.N = K1, G.maxM = K2, G.maxN = K1, G.maxK = 2 * max_n2, G.n_batch = n_pairs;
   G.C = M, G.ldc = K1, G.c_batch_stride = int64_t(K2) * K1;
   G.c_add = M, G.c_add_ld = K1, G.c_add_batch_stride = int64_t(K1) * K2;  // every entry is read and written by one thread
