@@ -144,7 +144,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, None
 
     def start(self):
         try:
@@ -157,13 +157,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def wait_ready(self, timeout=3.0):
+        """blocks until the first sample has arrived (NVML is up), at most ``timeout`` seconds"""
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+        return self
+
+    def begin(self):
+        """marks the start of the timed region: the process is started earlier (before the warm-up steps -- NVML takes
+        100-300 ms to come up on a multi-GPU box, longer than a short timed region) and only the samples that arrive from
+        here on are reported"""
+        self.t_begin = time.perf_counter()
+        return self
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.proc.terminate()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r[1:] for r in self.rows if t0 <= r[0] <= t_end + 0.03]  # a sample is printed up to one period late
+        self.rows = inside if inside else [r[1:] for r in self.rows if r[0] >= t0][:3]
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -538,10 +556,12 @@ def main():
     torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ timed steps (device-resident inputs)
+    sampler = ClockSampler(local_rank).start().wait_ready() if rank == 0 else None   # streaming before the warm-up, see begin()
     for _ in range(args.warmup):
         res = step()
     barrier()
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    if sampler:
+        sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -47,7 +47,7 @@ constexpr uint32_t kEbIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(EB_
 // ---------------------------------------------------------------- B operand: three-way bf16 split of C or C^T per pair
 // side 0: Bt[o][k] = C[k][o]   (rows o < k1, contraction k < k2: emb2 = Phi2 C)
 // side 1: Bt[o][k] = C[o][k]   (rows o < k2, contraction k < k1: emb1 = Phi1 C^T)
-// output rows are padded to rb (128 or 256) per pair and the contraction to kp (zeros); c_fro[p] >= |C|_F.
+// output rows are padded to rb (128 or 256) per pair and the contraction to kp (zeros); fro_part: chunk sums of |C|_F^2.
 constexpr int kCsplitChunks = 8;  // CTAs per (pair, side): the kernel is a latency-bound walk over <= 256 x 256 entries
 __global__ void __launch_bounds__(256)
     csplit_kernel(const double* __restrict__ C, int k1, int k2, int kp0, int kp1, __nv_bfloat16* __restrict__ h0,
@@ -712,8 +712,7 @@ struct F2PCtx {
   uint16_t *p2h, *p2m, *p2l;  // three-way split of Phi2 [total_n2, kp2]
   float* p2norm;
   uint16_t *c0h, *c0m, *c0l, *c1h, *c1m, *c1l;  // B operands [n_pairs * 128, kp]
-  float* c_fro;
-  double* fro_part;  // [n_pairs, kCsplitChunks] partial sums of squares of C
+  double* fro_part;  // [n_pairs, kCsplitChunks] partial sums of squares of C (|C|_F: cfro_of)
   float* g_scratch;
   double* emb2;   // [total_n2, k1] float64 query rows, filled on demand
   double* emb1;   // [total_n1, k2] float64, only for pairs that need every bias
@@ -840,7 +839,6 @@ F2PLayout f2p_carve(void* ws, int n_pairs, int64_t n1, int64_t n2, int max_n1, i
   const size_t cb0 = size_t(n_pairs) * EB_ROWS * kp2, cb1 = size_t(n_pairs) * EB_ROWS * kp1;
   L.c.c0h = c.take<uint16_t>(cb0), L.c.c0m = c.take<uint16_t>(cb0), L.c.c0l = c.take<uint16_t>(cb0);
   L.c.c1h = c.take<uint16_t>(cb1), L.c.c1m = c.take<uint16_t>(cb1), L.c.c1l = c.take<uint16_t>(cb1);
-  L.c.c_fro = c.take<float>(size_t(n_pairs));
   L.c.fro_part = c.take<double>(size_t(n_pairs) * kCsplitChunks);
   L.c.g_scratch = c.take<float>(size_t(n_pairs));
   L.c.emb2 = c.take<double>(size_t(n2) * k1);
@@ -864,7 +862,6 @@ struct P21Ctx {
   uint16_t *p1h, *p1m, *p1l;  // three-way split of Phi1 [total_n1, kp1] (resident across rungs)
   float* p1norm;
   uint16_t *c1h, *c1m, *c1l;  // split of C (rows o < k2, contraction k < k1) [n_pairs * 128, kp1]
-  float* c_fro;
   double* fro_part;           // [n_pairs, kCsplitChunks]
   double* Ct;                 // [n_pairs, k1, k2] float64 transpose of C
   double* emb1;               // [total_n1, lde] float64 database rows, filled on demand
@@ -958,7 +955,6 @@ P21Layout p21_carve(void* ws, int n_pairs, int64_t total_n1, int k1m, int k2m) {
   L.c.p1norm = c.take<float>(size_t(total_n1));
   const size_t cb = size_t(n_pairs) * rb * kp;
   L.c.c1h = c.take<uint16_t>(cb), L.c.c1m = c.take<uint16_t>(cb), L.c.c1l = c.take<uint16_t>(cb);
-  L.c.c_fro = c.take<float>(size_t(n_pairs));
   L.c.fro_part = c.take<double>(size_t(n_pairs) * kCsplitChunks);
   const int kt = k1m < kP21MaxK ? k1m : kP21MaxK, ku = k2m < kP21MaxK ? k2m : kP21MaxK;
   L.c.Ct = c.take<double>(size_t(n_pairs) * kt * ku);
