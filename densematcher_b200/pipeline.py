@@ -563,14 +563,22 @@ def match_bank_pairs(bank: MeshBankDevice, src_ids, dst_ids, chunk_pairs: int = 
     k = kw.get("k") or (bank.Phi.shape[1] if bank.Phi is not None else None)
     if hi > lo and k is not None and bank.bank_supported(k, kw.get("flags", 0)) and kw.get("functional_map", True):
         # once-per-mesh preparation of the (contiguous) range of meshes this rank's block of pairs touches
-        ids = np.concatenate([src_ids[lo:hi], dst_ids[lo:hi]])
-        bank.prepared(k, (int(ids.min()), int(ids.max()) + 1))
+        bank.prepared(k, pairs_mesh_range(src_ids, dst_ids, lo, hi))
     out = []
     for a in range(lo, hi, chunk_pairs):
         b = min(hi, a + chunk_pairs)
         res = _bank_chunk(bank, src_ids[a:b], dst_ids[a:b], **kw)
         out.append({n: (t.cpu().numpy() if to_host else t) for n, t in res.items()})
     return out, (lo, hi)
+
+
+def pairs_mesh_range(src_ids, dst_ids, lo: int, hi: int):
+    """(first, last + 1) of the mesh ids that the pairs lo .. hi - 1 touch: the contiguous range of a bank that a rank
+    owning that block has to prepare (pairs grouped by category touch ~1 / world of a category-sorted bank)."""
+    if hi <= lo:
+        return (0, 0)
+    a, b = np.asarray(src_ids)[lo:hi], np.asarray(dst_ids)[lo:hi]
+    return int(min(a.min(), b.min())), int(max(a.max(), b.max())) + 1
 
 
 def shard_pairs(n_pairs: int, rank: int, world: int):

@@ -59,3 +59,28 @@ def test_gather_results_world2_gloo(n_pairs):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True] and res[0][2] == res[1][2]
+
+
+def test_ranks_of_a_category_sorted_bank_prepare_disjoint_mesh_ranges():
+    """cfg5 shape: meshes sorted by category, every ordered intra-category pair, pairs sharded in contiguous blocks.
+    The range of meshes a rank has to prepare (``pairs_mesh_range``) covers the pairs of its block, the ranges of all
+    ranks cover the bank, and neighbouring ranks overlap by at most the one category their boundary cuts through."""
+    rng = np.random.default_rng(5000)
+    cats = np.sort(rng.integers(0, 24, size=599))
+    src, dst = pipeline.intra_category_pairs(cats)
+    assert len(src) == sum(c * (c - 1) for c in np.bincount(cats)) and np.all(cats[src] == cats[dst])
+    for world in (1, 2, 8):
+        ranges = []
+        for r in range(world):
+            lo, hi = pipeline.shard_pairs(len(src), r, world)
+            a, b = pipeline.pairs_mesh_range(src, dst, lo, hi)
+            ids = np.concatenate([src[lo:hi], dst[lo:hi]])
+            assert a == ids.min() and b == ids.max() + 1
+            ranges.append((a, b))
+        assert ranges[0][0] == 0 and ranges[-1][1] == 599
+        largest = int(np.bincount(cats).max())
+        for (a0, b0), (a1, b1) in zip(ranges[:-1], ranges[1:]):
+            assert a1 <= b0 and b0 - a1 <= largest          # contiguous cover, overlap within one category
+        if world == 8:
+            assert sum(b - a for a, b in ranges) <= 599 + 7 * largest
+    assert pipeline.pairs_mesh_range(src, dst, 5, 5) == (0, 0)
