@@ -77,6 +77,9 @@ SIGNATURES = {
     "dm_mapped_indicator_workspace_bytes": (c_sz, [c_int, c_int]),
     "dm_mapped_indicator": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64,
                                     c_vp, c_sz, c_vp]),
+    "dm_mapped_indicators_workspace_bytes": (c_sz, [c_i64, c_int]),
+    "dm_mapped_indicators": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_int, c_vp,
+                                     c_int, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "dm_p2p_to_fm_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "dm_p2p_to_fm": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp,
                              c_int, c_vp, c_sz, c_vp]),

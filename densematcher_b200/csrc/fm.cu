@@ -299,6 +299,43 @@ int dm_mapped_indicator(const double* C, int k1, int k2, const double* Phi1, int
   return gemm64_launch(H, st);
 }
 
+// the same for a ragged batch: MI rows of pair p are rows off2[p] .. off2[p + 1] of MI [total_n2, ldMI >= max_n1], columns
+// 0 .. n1_p - 1 (two ragged GEMMs for the whole batch; per pair the arithmetic of dm_mapped_indicator)
+size_t dm_mapped_indicators_workspace_bytes(int64_t total_n1, int k2) {
+  Carver c(nullptr);
+  c.take<double>(size_t(total_n1 > 0 ? total_n1 : 0) * (k2 > 0 ? k2 : 0));
+  return c.bytes();
+}
+
+int dm_mapped_indicators(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1,
+                         int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int max_n2,
+                         const double* area1, int n_pairs, double* MI, int64_t ldMI, void* workspace, size_t workspace_bytes,
+                         dm_stream_t stream) {
+  if (k1 <= 0 || k2 <= 0 || n_pairs < 0 || total_n1 < 0 || max_n1 < 0 || max_n2 < 0 || ldMI < max_n1)
+    DM_FAIL(DM_ERR_BADARG, "bad size");
+  if (n_pairs == 0 || total_n1 == 0 || max_n2 == 0) return DM_OK;
+  if (!C || !Phi1 || !Phi2 || !off1 || !off2 || !area1 || !MI) DM_FAIL(DM_ERR_BADARG, "null argument");
+  if (ld1 < k1 || ld2 < k2) DM_FAIL(DM_ERR_BADARG, "eigenbasis has fewer columns than the functional map");
+  if (!workspace || dm_mapped_indicators_workspace_bytes(total_n1, k2) > workspace_bytes)
+    DM_FAIL(DM_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(workspace);
+  double* W = c.take<double>(size_t(total_n1) * k2);  // W = Phi1 C^T, rows packed like Phi1
+  int rc;
+  GemmProblem G;
+  G.A.d = Phi1, G.A.ld = ld1, G.A.off = off1, G.A.trans = 0;
+  G.B.d = C, G.B.ld = k1, G.B.batch_stride = int64_t(k1) * k2, G.B.rows = k2, G.B.trans = 0;
+  G.N = k2, G.K = k1, G.maxM = max_n1, G.maxN = k2, G.maxK = k1, G.n_batch = n_pairs;
+  G.C = W, G.ldc = k2, G.c_off = off1;
+  if ((rc = gemm64_launch(G, st))) return rc;
+  GemmProblem H;
+  H.A.d = Phi2, H.A.ld = ld2, H.A.off = off2, H.A.trans = 0;
+  H.B.d = W, H.B.ld = k2, H.B.off = off1, H.B.trans = 0;
+  H.K = k2, H.maxM = max_n2, H.maxN = max_n1, H.maxK = k2, H.n_batch = n_pairs;
+  H.C = MI, H.ldc = ldMI, H.c_off = off2, H.c_colscale = area1, H.c_colscale_off = off1;
+  return gemm64_launch(H, st);
+}
+
 // ------------------------------------------------------------------ p2p -> FM
 size_t dm_p2p_to_fm_workspace_bytes(int n_pairs, int max_n2, int k1, int k2) {
   return p2p_to_fm_ws(n_pairs, max_n2, k1, k2);

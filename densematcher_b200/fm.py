@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .nn import Offsets, Workspace, as_offsets, default_workspace
 
-__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "p2p_to_fm", "spd_solve", "zoomout", "icp", "polar_factor",
+__all__ = ["project", "fmap_solve", "fm_to_p2p", "mapped_indicator", "mapped_indicators", "p2p_to_fm", "spd_solve", "zoomout", "icp", "polar_factor",
            "match_pairs", "bank_prepare", "match_bank_pairs", "BankState", "dense_energy", "fit_dense", "DENSE_TERMS",
            "PairBatch"]
 
@@ -186,6 +186,31 @@ def mapped_indicator(C, Phi1, Phi2, area1):
                                      ws.numel(), _stream(dev))
     _lib.check(rc, "dm_mapped_indicator")
     return MI
+
+
+def mapped_indicators(C, Phi1, Phi2, area1, off1, off2):
+    """Phi2 C Phi1^T A1 of every pair of a ragged batch in one call (``dm_mapped_indicators``).  Returns the list of the
+    pairs' float64 [n2_p, n1_p] matrices: views into one [total_n2, max_n1] buffer (contiguous when all meshes 1 have one
+    size)."""
+    lib = _lib.load()
+    dev = C.device
+    C, Phi1, Phi2, area1 = _f64(C).contiguous(), _f64(Phi1), _f64(Phi2), _f64(area1).contiguous()
+    P, k2, k1 = C.shape
+    if k1 > Phi1.shape[1] or k2 > Phi2.shape[1]:
+        raise AssertionError("At least k eigenvectors should be provided")
+    o1, o1h, max1 = _offsets(off1, Phi1.shape[0], dev)
+    o2, o2h, max2 = _offsets(off2, Phi2.shape[0], dev)
+    if len(o1h) - 1 != P or len(o2h) - 1 != P or area1.numel() != Phi1.shape[0]:
+        raise ValueError("mapped_indicators: C, the offsets and the per-vertex arrays describe different batches")
+    MI = torch.empty(Phi2.shape[0], max(max1, 1), dtype=torch.float64, device=dev)
+    need = lib.dm_mapped_indicators_workspace_bytes(Phi1.shape[0], k2)
+    ws = default_workspace(dev, "fm").get(max(need, 256))
+    with torch.cuda.device(dev):
+        rc = lib.dm_mapped_indicators(C.data_ptr(), k1, k2, Phi1.data_ptr(), Phi1.stride(0), o1.data_ptr(), Phi1.shape[0], max1,
+                                      Phi2.data_ptr(), Phi2.stride(0), o2.data_ptr(), max2, area1.data_ptr(), P, MI.data_ptr(),
+                                      MI.stride(0), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "dm_mapped_indicators")
+    return [MI[int(o2h[p]):int(o2h[p + 1]), :int(o1h[p + 1] - o1h[p])] for p in range(P)]
 
 
 def p2p_to_fm(p2p_21, Phi1, Phi2, area2=None, off1=None, off2=None, k1=None, k2=None,

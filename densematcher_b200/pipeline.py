@@ -157,11 +157,12 @@ def hungarian_pairs(batch: PairBatchDevice, C: torch.Tensor, chunk_pairs: Option
         chunk_pairs = int(max(1, min(256, max_bytes // max(per_pair, 1.0))))
     res = []
     for lo in range(0, batch.n_pairs, chunk_pairs):
-        mats = []
-        for p in range(lo, min(lo + chunk_pairs, batch.n_pairs)):
-            a, b = int(batch.off1_h[p]), int(batch.off1_h[p + 1])
-            c, d = int(batch.off2_h[p]), int(batch.off2_h[p + 1])
-            mats.append(_fm.mapped_indicator(C[p], batch.Phi1[a:b, :k1], batch.Phi2[c:d, :k2], batch.area1[a:b]))
+        hi = min(lo + chunk_pairs, batch.n_pairs)
+        a, b = int(batch.off1_h[lo]), int(batch.off1_h[hi])
+        c, d = int(batch.off2_h[lo]), int(batch.off2_h[hi])
+        # the chunk's indicators in ONE library call (two ragged GEMMs), no per-pair Python loop
+        mats = _fm.mapped_indicators(C[lo:hi], batch.Phi1[a:b, :k1], batch.Phi2[c:d, :k2], batch.area1[a:b],
+                                     batch.off1_h[lo:hi + 1] - a, batch.off2_h[lo:hi + 1] - c)
         res.extend(_fm.lap_solve(mats, maximize=True))
     return res
 

@@ -222,6 +222,14 @@ size_t dm_mapped_indicator_workspace_bytes(int n1, int k2);
 int dm_mapped_indicator(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, int n1,
                         const double* Phi2, int64_t ld2, int n2, const double* area1,
                         double* MI, int64_t ldMI, void* workspace, size_t workspace_bytes, dm_stream_t stream);
+/* The same for a ragged batch in one call (the Hungarian slots of compute_surface_map for many pairs,
+ * functional_map.py:57,66,78): the matrix of pair p occupies rows off2[p] .. off2[p + 1] of MI [total_n2, ldMI >= max_n1],
+ * columns 0 .. n1_p - 1; per pair the arithmetic of dm_mapped_indicator. */
+size_t dm_mapped_indicators_workspace_bytes(int64_t total_n1, int k2);
+int dm_mapped_indicators(const double* C, int k1, int k2, const double* Phi1, int64_t ld1, const int64_t* off1,
+                         int64_t total_n1, int max_n1, const double* Phi2, int64_t ld2, const int64_t* off2, int max_n2,
+                         const double* area1, int n_pairs, double* MI, int64_t ldMI, void* workspace,
+                         size_t workspace_bytes, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * p2p -> FM with the target mass:  C = Phi2[:, :k2]^T (area2 * Phi1[p2p_21, :k1])   float64

@@ -124,3 +124,31 @@ def test_batched_hungarian_and_precise_maps(golden_fm, golden_extras):
     for p in range(2):
         P = barycentric_to_precise(faces, face[642 * p:642 * (p + 1)], bary[642 * p:642 * (p + 1)], 642)
         assert abs(P - ref).max() < 1e-11
+
+
+def test_batched_mapped_indicators_ragged(golden_fm):
+    """dm_mapped_indicators (one call for a ragged batch) gives, bit for bit, the matrices of the per-pair
+    dm_mapped_indicator, and hungarian_pairs on the ragged batch the assignments of the per-pair solve."""
+    from densematcher_b200 import fm, pipeline
+    g = golden_fm
+    k = int(g["k"])
+    rng = np.random.default_rng(7)
+    n1s, n2s = [642, 300, 511], [642, 420, 200]
+    P1 = np.concatenate([g["Phi1"][:n, :k] for n in n1s]); P2 = np.concatenate([g["Phi2"][:n, :k] for n in n2s])
+    a1 = np.concatenate([g["area1"][:n] for n in n1s])
+    off1, off2 = np.concatenate([[0], np.cumsum(n1s)]), np.concatenate([[0], np.cumsum(n2s)])
+    C = np.stack([g["C_closed_form"], g["C_closed_form"] + 0.01 * rng.standard_normal((k, k)), np.eye(k)])
+    mats = fm.mapped_indicators(dev(C), dev(P1), dev(P2), dev(a1), off1, off2)
+    singles = []
+    for p in range(3):
+        one = fm.mapped_indicator(dev(C[p]), dev(P1[off1[p]:off1[p + 1]]), dev(P2[off2[p]:off2[p + 1]]), dev(a1[off1[p]:off1[p + 1]]))
+        assert mats[p].shape == one.shape and torch.equal(mats[p], one), p
+        singles.append(one)
+    batch = pipeline.PairBatchDevice(
+        dev(np.zeros((int(off1[-1]), 4), np.float32)), dev(np.zeros((int(off2[-1]), 4), np.float32)), off1, off2,
+        torch.device("cuda"), Phi1=dev(P1), Phi2=dev(P2), area1=dev(a1))
+    want = fm.lap_solve(singles, maximize=True)
+    for chunk in (None, 2):
+        got = pipeline.hungarian_pairs(batch, dev(C), chunk_pairs=chunk)
+        for (r, c), (rw, cw) in zip(got, want):
+            assert np.array_equal(r, rw) and np.array_equal(c, cw)
