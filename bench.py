@@ -466,11 +466,11 @@ def main():
                 res = pipeline.match_pairs_device(dev, k=K_EIG, w_descr=W_DESCR, w_lap=W_LAP, check=False)
                 gather_all(res)
                 return res
-            # launches of OUR kernels per step (profiles/launches_r2_step.csv, gpurun_out/r4h_step_launches.csv: 36 + the
-            # Frobenius finalise added since): feature NN 8 (2 prep, 2 per-pair maxima, score, column finalise, 2
-            # re-evaluation) + projection 2 x 3 + pinned entry 1 + solve 6 (2 Gram GEMMs, float32 pack, factor/refine, lazy
-            # float64 pack, float64 fallback) + FM->p2p 16 (2 splits, per-pair maxima, split of C + its norm, 2 embeddings,
-            # score pass, column finalise, on-demand fill, 2 flagged GEMMs + 2 bias passes, 2 re-evaluation)
+            # launches of OUR kernels per step (profiles/launches_r2_end_step.csv): feature NN 8 (2 prep, 2 per-pair maxima,
+            # score, column finalise, 2 re-evaluation) + projection 2 x 3 + pinned entry 1 + solve 6 (2 Gram GEMMs, float32
+            # pack, factor/refine, lazy float64 pack, float64 fallback) + FM->p2p 16 (2 eigenbasis splits enqueued beside the
+            # solve, per-row arrays of the database side + per-pair maxima, split of C, 2 embeddings, score pass, column
+            # finalise, on-demand fill, 2 flagged GEMMs + 2 bias passes, 2 re-evaluation)
             launches_per_step = 8 + 6 + 1 + 6 + 16
         else:
             nit = 70
