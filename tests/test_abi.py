@@ -87,3 +87,38 @@ def test_no_product_import_of_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/dm_b200.h must compile as C99 on its own (no C++, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run([gcc, "-std=c99", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_bank_state_grows_by_the_missing_meshes_only(monkeypatch):
+    """Host logic of the piecewise bank preparation (fm.bank_prepare with a previous state): the prepared range stays
+    contiguous, every mesh is prepared once, covered requests do nothing.  The library call is replaced by a recorder."""
+    import numpy as np
+    import torch
+    from densematcher_b200 import fm
+    off = np.array([0, 10, 25, 30, 50, 64, 80], dtype=np.int64)
+    st = fm.BankState(torch.zeros(80, 8), torch.zeros(80, 4, dtype=torch.float64), torch.zeros(80, dtype=torch.float64),
+                      torch.zeros(6, 4, dtype=torch.float64), torch.from_numpy(off), off, 4, torch.zeros(256, dtype=torch.uint8))
+    calls = []
+    monkeypatch.setattr(fm, "_bank_prepare_range", lambda bank, lo, hi, workspace=None: calls.append((lo, hi)))
+    assert not st.covers(0, 1) and st.covers(3, 3)
+    fm.bank_prepare(None, None, None, None, None, 4, mesh_range=(2, 4), bank=st)
+    assert calls == [(2, 4)] and (st.lo, st.hi) == (2, 4)
+    fm.bank_prepare(None, None, None, None, None, 4, mesh_range=(2, 3), bank=st)          # covered: nothing to do
+    assert calls == [(2, 4)]
+    fm.bank_prepare(None, None, None, None, None, 4, mesh_range=(1, 6), bank=st)          # both sides
+    assert calls == [(2, 4), (1, 2), (4, 6)] and (st.lo, st.hi) == (1, 6)
+    fm.bank_prepare(None, None, None, None, None, 4, mesh_range=None, bank=st)            # the whole bank
+    assert calls[-1] == (0, 1) and (st.lo, st.hi) == (0, 6) and len(calls) == 4
+    fm.bank_prepare(None, None, None, None, None, 4, mesh_range=(-3, 99), bank=st)        # clamped, covered
+    assert len(calls) == 4
